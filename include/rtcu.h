@@ -1,0 +1,172 @@
+/*
+ * rtcu.h -- C ABI of the B200 (sm_100a) path-tracing library behind marzer/rt's renderer plugin.
+ *
+ * This is the drop-in boundary for the reference's hot path: everything
+ * `rt::renderer_interface::render(const scene&, image_view&, muu::thread_pool&)`
+ * (reference src/renderer.hpp:9-14) does for `mg_ray_tracer` (src/renderers/mg_ray_tracer.cpp:178-205)
+ * and `sm_ray_tracer` (src/renderers/sm_ray_tracer.cpp:263-289) is reachable through these entry
+ * points with plain pointers and sizes.  The reference-side binding is plugin/cuda_path_tracer.cpp
+ * (see INTEGRATION.md); tests and bench.py bind the same symbols through ctypes.
+ *
+ * There is NO CPU fallback: every compute entry point returns RTCU_ERR_CUDA when no sm_100-class
+ * device is usable.
+ *
+ * Conventions: every function returning int returns RTCU_OK (0) or a negative RTCU_ERR_*; the
+ * message is available from rtcu_last_error() (thread-local).  Host pointers unless named d_*.
+ */
+#ifndef RTCU_H
+#define RTCU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTCU_ABI_VERSION 1
+
+enum {
+    RTCU_OK = 0,
+    RTCU_ERR_INVALID = -1, /* bad argument (null pointer, empty tile, material index out of range) */
+    RTCU_ERR_CUDA = -2,    /* CUDA runtime error, or no usable device                              */
+    RTCU_ERR_STATE = -3    /* call order (render before upload_scene)                              */
+};
+
+/* rt::material_type values, reference src/common.hpp:105-115 (ABI of the materials table) */
+enum {
+    RTCU_LAMBERT = 0, RTCU_METAL = 1, RTCU_DIELECTRIC = 2, RTCU_AIR = 3,
+    RTCU_VACUUM = 4, RTCU_WATER = 5, RTCU_ICE = 6, RTCU_DIAMOND = 7
+};
+
+/* which scatter_funcs table to apply:
+ *   RTCU_MODE_MG  mg_ray_tracer.cpp:142-152  (metal -> metal, everything else lambert)
+ *   RTCU_MODE_SM  sm_ray_tracer.cpp:221-236  (+ dielectric/air/vacuum/water/ice -> dielectric_scatter) */
+enum { RTCU_MODE_MG = 0, RTCU_MODE_SM = 1 };
+
+/* traversal selector for rtcu_view.flags / rtcu_intersect_batch */
+enum {
+    RTCU_ACCEL_AUTO = 0,   /* linear scan for small scenes, BVH above rtcu_bvh_threshold() spheres */
+    RTCU_ACCEL_LINEAR = 1, /* the reference's O(N) scan (mg_ray_tracer.cpp:62-87)                  */
+    RTCU_ACCEL_BVH = 2
+};
+/* pipeline selector, bits 4..7 of rtcu_view.flags */
+enum {
+    RTCU_PIPE_AUTO = 0 << 4,
+    RTCU_PIPE_MEGAKERNEL = 1 << 4, /* register-resident paths, per-pixel sample regeneration */
+    RTCU_PIPE_WAVEFRONT = 2 << 4   /* generate / intersect / shade / compact over HBM queues  */
+};
+
+/* one row of rt::materials (reference src/soa.hpp:157-170) minus the `name` column */
+typedef struct rtcu_material {
+    uint32_t type;         /* materials.type()                                             */
+    float    albedo[4];    /* materials.albedo(): rt::colour rgba                          */
+    float    roughness;    /* materials.roughness()                                        */
+    float    reflectivity; /* materials.reflectivity(); the IOR for dielectric-class types */
+} rtcu_material;
+
+/* a flattened rt::scene (reference src/scene.hpp:8-25).  The pointers are the reference's own
+ * soagen columns: spheres.value() is muu::bounding_sphere<float>[] = {cx,cy,cz,radius} (soa.hpp:194),
+ * planes.value() is muu::plane<float>[] = {nx,ny,nz,d}; boxes are never hit by either ray tracer
+ * (mg_ray_tracer.cpp:89-93) and are therefore not part of the ABI. */
+typedef struct rtcu_scene {
+    const float*         spheres;
+    const uint32_t*      sphere_material; /* spheres.material() */
+    uint32_t             n_spheres;
+    const float*         planes;
+    const uint32_t*      plane_material;
+    uint32_t             n_planes;
+    const rtcu_material* materials;
+    uint32_t             n_materials;
+} rtcu_scene;
+
+/* one render call.  inv_view_proj is viewport::inverse_view_projection (reference src/camera.hpp:17,
+ * :122-137), column-major (element (r,c) at [c*4+r]).  The call renders global sample indices
+ * [sample_begin, sample_end) of the pixel rectangle [tile_x0,tile_x1) x [tile_y0,tile_y1); the
+ * reference's single-call behaviour is sample range [0, samples_per_pixel) over the full image. */
+typedef struct rtcu_view {
+    float    inv_view_proj[16];
+    uint32_t width, height;
+    uint32_t samples_per_pixel; /* resolve divisor: scene::samples_per_pixel (scene.hpp:10) */
+    uint32_t max_bounces;       /* scene::max_bounces (scene.hpp:11)                        */
+    uint32_t sample_begin, sample_end;
+    uint32_t tile_x0, tile_y0, tile_x1, tile_y1;
+    uint64_t seed;
+    uint32_t material_mode; /* RTCU_MODE_* */
+    uint32_t flags;         /* RTCU_ACCEL_* | RTCU_PIPE_* */
+} rtcu_view;
+
+typedef struct rtcu_stats {
+    uint64_t segments;       /* path segments traced by the last render call (exact)         */
+    uint64_t samples;        /* pixel samples of the last render call                        */
+    uint64_t sphere_tests;   /* ray-sphere tests (linear: segments*n_spheres; BVH: counted)  */
+    uint64_t node_visits;    /* BVH nodes visited (0 for linear)                             */
+    float    ms_render;      /* device time of the trace kernels, CUDA events                */
+    float    ms_resolve;     /* device time of resolve/pack                                  */
+    float    ms_h2d, ms_d2h; /* copies of the host entry points                              */
+    uint32_t kernel_launches; /* kernels launched by the last call                           */
+    uint32_t pipeline;        /* RTCU_PIPE_* actually used                                   */
+    uint32_t accel;           /* RTCU_ACCEL_* actually used                                  */
+    uint32_t reserved;
+} rtcu_stats;
+
+typedef struct rtcu_ctx rtcu_ctx;
+
+/* ---- lifetime (one context per device; replaces `new T` in REGISTER_RENDERER, renderer.hpp:34-41) */
+int         rtcu_abi_version(void);
+int         rtcu_device_count(void);
+rtcu_ctx*   rtcu_create(int device);   /* NULL on failure, see rtcu_last_error() */
+void        rtcu_destroy(rtcu_ctx* ctx);
+const char* rtcu_last_error(void);
+uint32_t    rtcu_bvh_threshold(void);
+
+/* ---- scene upload: replaces the implicit `const scene&` argument of render (renderer.hpp:11).
+ * Copies the columns to the device (and builds the BVH when the sphere count calls for it).  The
+ * caller may free its buffers afterwards. */
+int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* scene);
+
+/* ---- render: replaces mg_ray_tracer::render / sm_ray_tracer::render.
+ * rgba8_out (nullable): width*height uint32 in image_view layout (row 0 = top, src/image.hpp:150-159),
+ *   packed as colour::operator uint32_t (colour.hpp:100-106); only the tile is written.
+ * accum_out (nullable): width*height*4 floats {sum_r,sum_g,sum_b,n_samples}; only the tile is written. */
+int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out);
+
+/* ---- device-resident variants (no host copies) for multi-GPU composition and benchmarking.
+ * d_accum: width*height float4 on ctx's device.  accumulate != 0 adds onto the existing contents.
+ * stream: a cudaStream_t (0 = the context's own stream). */
+int rtcu_render_device(rtcu_ctx* ctx, const rtcu_view* view, float* d_accum, int accumulate, void* stream);
+/* resolve: divide by samples_per_pixel, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200) */
+int rtcu_resolve_device(rtcu_ctx* ctx, const float* d_accum, uint32_t width, uint32_t height,
+                        uint32_t samples_per_pixel, uint32_t* d_rgba8, void* stream);
+int rtcu_sync(rtcu_ctx* ctx);
+
+/* ---- single-process multi-GPU render: sample ranges are split evenly over the contexts (one per
+ * device), each device accumulates its range, ctxs[0] sums the peers' fp32 buffers through NVLink peer
+ * loads inside its resolve kernel, and the host image is copied from ctxs[0]. */
+int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* view,
+                      uint32_t* rgba8_out, float* accum_out);
+
+/* ---- level-1 parity entry point: closest hit of n rays (o/d: n x {x,y,z}) against the uploaded
+ * scene; mirrors test_planes/test_spheres/select (mg_ray_tracer.cpp:35-102).
+ * hit[i] in {0,1}; prim[i] = sphere index | 0x80000000+plane index | 0xFFFFFFFF on miss;
+ * t[i] = hit distance or -1; normal (nullable) n x {x,y,z}.  accel: RTCU_ACCEL_*. */
+int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t n,
+                         uint8_t* hit, uint32_t* prim, float* t, float* normal, uint32_t accel);
+
+/* ---- step-wise parity entry points (device kernels run on n items, host buffers) */
+/* primary rays for n (pixel x, pixel y, sample) triples: mg_ray_tracer.cpp:189-193 */
+int rtcu_primary_rays(rtcu_ctx* ctx, const rtcu_view* view, const uint32_t* px, const uint32_t* py,
+                      const uint32_t* sample, uint32_t n, float* o, float* d);
+/* one scatter per item: mg_ray_tracer.cpp:109-140, sm_ray_tracer.cpp:181-219.
+ * scattered[i] = 1/0; att/o_out/d_out n x 3. */
+int rtcu_scatter_batch(rtcu_ctx* ctx, uint32_t material_mode, uint64_t seed, uint32_t n,
+                       const uint32_t* material, const float* o, const float* d, const float* t,
+                       const float* normal, const uint32_t* pixel, const uint32_t* sample,
+                       const uint32_t* block, uint8_t* scattered, float* att, float* o_out, float* d_out);
+/* Philox4x32-10 blocks for n counters (ctr n x 4, out n x 4) under one key */
+int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t key, uint32_t* out);
+
+int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""ctypes binding of the CPU oracle (oracle/rtref.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+module; nothing under rt_b200/ does.  PARITY UNPINNED against a reference binary (see rtref.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+
+HERE = pathlib.Path(__file__).resolve().parent
+PRIM_MISS, PRIM_PLANE = 0xFFFFFFFF, 0x80000000
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("albedo", C.c_float * 4), ("roughness", C.c_float), ("reflectivity", C.c_float)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("spheres", C.c_void_p), ("sphere_material", C.c_void_p), ("n_spheres", C.c_uint32),
+                ("planes", C.c_void_p), ("plane_material", C.c_void_p), ("n_planes", C.c_uint32),
+                ("materials", C.c_void_p), ("n_materials", C.c_uint32)]
+
+
+class View(C.Structure):
+    _fields_ = [("inv_view_proj", C.c_float * 16), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("samples_per_pixel", C.c_uint32), ("max_bounces", C.c_uint32),
+                ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
+                ("tile_x0", C.c_uint32), ("tile_y0", C.c_uint32), ("tile_x1", C.c_uint32), ("tile_y1", C.c_uint32),
+                ("seed", C.c_uint64), ("material_mode", C.c_uint32), ("flags", C.c_uint32)]
+
+
+def build(flavour: str = "strict") -> pathlib.Path:
+    out = HERE / "_build" / f"librtref_{flavour}.so"
+    r = subprocess.run(["make", "-C", str(HERE), flavour], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    return out
+
+
+_MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("albedo", "<f4", (4,)), ("roughness", "<f4"), ("reflectivity", "<f4")])
+
+
+class Oracle:
+    """flavour 'strict' = the parity checker; 'fast' = the CPU timing baseline (reference's -ffast-math flags)."""
+
+    def __init__(self, flavour: str = "strict"):
+        self.lib = C.CDLL(str(build(flavour)))
+        L, p, u32, u64, i = self.lib, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.rtref_philox4x32_10.argtypes = [p, p, p]
+        L.rtref_u01.restype = C.c_float
+        L.rtref_u01.argtypes = [u32]
+        L.rtref_intersect_batch.argtypes = [C.POINTER(SceneDesc), p, p, u32, p, p, p, p]
+        L.rtref_primary_ray.argtypes = [C.POINTER(View), u32, u32, u32, p, p]
+        L.rtref_scatter.argtypes = [C.POINTER(SceneDesc), u32, u32, p, p, C.c_float, p, u64, u32, u32, u32, p, p, p]
+        L.rtref_pack_pixel.restype = u32
+        L.rtref_pack_pixel.argtypes = [C.c_float, C.c_float, C.c_float, u32]
+        L.rtref_render.argtypes = [C.POINTER(SceneDesc), C.POINTER(View), p, p, p, i, u32]
+        L.rtref_trace_sample.restype = u32
+        L.rtref_trace_sample.argtypes = [C.POINTER(SceneDesc), C.POINTER(View), u32, u32, u32, p]
+        L.rtref_build_flavour.restype = C.c_char_p
+        assert L.rtref_build_flavour().decode() == flavour
+        self._keep = None
+
+    # ---- scene ------------------------------------------------------------------------------------
+    def scene_desc(self, scene) -> SceneDesc:
+        sph = np.ascontiguousarray(scene.spheres, np.float32).reshape(-1, 4)
+        smat = np.ascontiguousarray(scene.sphere_material, np.uint32)
+        pl = np.ascontiguousarray(scene.planes, np.float32).reshape(-1, 4)
+        pmat = np.ascontiguousarray(scene.plane_material, np.uint32)
+        mats = np.ascontiguousarray(scene.materials.astype(_MATERIAL_DTYPE))
+        self._keep = (sph, smat, pl, pmat, mats)
+        return SceneDesc(sph.ctypes.data if len(sph) else None, smat.ctypes.data if len(smat) else None, len(sph),
+                         pl.ctypes.data if len(pl) else None, pmat.ctypes.data if len(pmat) else None, len(pl),
+                         mats.ctypes.data, len(mats))
+
+    @staticmethod
+    def view_from(v) -> View:
+        """copy an rt_b200 View (same field layout) into the oracle's own struct"""
+        out = View()
+        for name, _ in View._fields_:
+            val = getattr(v, name)
+            if name == "inv_view_proj":
+                out.inv_view_proj[:] = list(val)
+            else:
+                setattr(out, name, val)
+        return out
+
+    # ---- entry points -------------------------------------------------------------------------------
+    def philox(self, ctr, key: int) -> np.ndarray:
+        c = (C.c_uint32 * 4)(*[int(x) for x in ctr])
+        k = (C.c_uint32 * 2)(key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF)
+        o = (C.c_uint32 * 4)()
+        self.lib.rtref_philox4x32_10(c, k, o)
+        return np.array(list(o), np.uint32)
+
+    def u01(self, x: int) -> float:
+        return float(self.lib.rtref_u01(int(x)))
+
+    def intersect_batch(self, scene, o, d):
+        sd = self.scene_desc(scene)
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = len(o)
+        hit = np.zeros(n, np.uint8); prim = np.zeros(n, np.uint32); t = np.zeros(n, np.float32); nrm = np.zeros((n, 3), np.float32)
+        rc = self.lib.rtref_intersect_batch(C.byref(sd), o.ctypes.data, d.ctypes.data, n, hit.ctypes.data, prim.ctypes.data, t.ctypes.data, nrm.ctypes.data)
+        assert rc == 0
+        return hit, prim, t, nrm
+
+    def primary_rays(self, view, px, py, sample):
+        v = self.view_from(view)
+        n = len(px)
+        o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32)
+        oo = (C.c_float * 3)(); dd = (C.c_float * 3)()
+        for i in range(n):
+            self.lib.rtref_primary_ray(C.byref(v), int(px[i]), int(py[i]), int(sample[i]), oo, dd)
+            o[i] = list(oo); d[i] = list(dd)
+        return o, d
+
+    def scatter_batch(self, scene, mode, seed, material, o, d, t, normal, pixel, sample, block):
+        sd = self.scene_desc(scene)
+        n = len(material)
+        o = np.ascontiguousarray(o, np.float32).reshape(n, 3); d = np.ascontiguousarray(d, np.float32).reshape(n, 3)
+        normal = np.ascontiguousarray(normal, np.float32).reshape(n, 3)
+        sc = np.zeros(n, np.uint8); att = np.zeros((n, 3), np.float32); oo = np.zeros((n, 3), np.float32); do = np.zeros((n, 3), np.float32)
+        for i in range(n):
+            sc[i] = self.lib.rtref_scatter(C.byref(sd), mode, int(material[i]), o[i].ctypes.data, d[i].ctypes.data, float(t[i]), normal[i].ctypes.data,
+                                           seed, int(pixel[i]), int(sample[i]), int(block[i]), att[i].ctypes.data, oo[i].ctypes.data, do[i].ctypes.data)
+        return sc, att, oo, do
+
+    def pack_pixel(self, r: float, g: float, b: float, spp: int) -> int:
+        return int(self.lib.rtref_pack_pixel(r, g, b, spp))
+
+    def render(self, scene, view, threads: int = 0, row_step: int = 1, want_rgba8: bool = True, want_accum: bool = True):
+        sd = self.scene_desc(scene)
+        v = self.view_from(view)
+        rgba8 = np.zeros((v.height, v.width), np.uint32) if want_rgba8 else None
+        accum = np.zeros((v.height, v.width, 4), np.float32) if want_accum else None
+        segs = C.c_uint64(0)
+        rc = self.lib.rtref_render(C.byref(sd), C.byref(v), rgba8.ctypes.data if want_rgba8 else None,
+                                   accum.ctypes.data if want_accum else None, C.byref(segs), threads, row_step)
+        if rc != 0:
+            raise RuntimeError(f"rtref_render failed: {rc}")
+        return rgba8, accum, int(segs.value)
+
+    def trace_sample(self, scene, view, px: int, py: int, sample: int):
+        sd = self.scene_desc(scene)
+        v = self.view_from(view)
+        out = (C.c_float * 3)()
+        nseg = self.lib.rtref_trace_sample(C.byref(sd), C.byref(v), px, py, sample, out)
+        return np.array(list(out), np.float32), int(nseg)

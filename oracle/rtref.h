@@ -1,0 +1,104 @@
+/*
+ * rtref.h -- CPU ORACLE for the marzer/rt path-tracing hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (rt_b200/, include/rtcu.h) never links, imports or calls it.
+ *
+ * PARITY STATUS: "parity unpinned" against a reference *binary*: marzer/rt cannot be built in
+ * this environment (its math library muu @06dbcecb, toml++, SDL2, imgui, argparse, magic_enum
+ * and meson are absent) and the reference ships no tests, golden vectors
+ * or fixtures.  This file restates the reference *source* line by line; the muu primitives it
+ * calls are restated from their published algorithms and written down as the numbered SPEC in
+ * rtref.c.  The pins that exist are the ones this repo creates (tests/golden/, hand-derived
+ * known-answer vectors, published Philox4x32-10 vectors).
+ *
+ * The data structures deliberately mirror include/rtcu.h field by field so one harness can feed
+ * both sides, but the two headers are independent files.
+ */
+#ifndef RTREF_H
+#define RTREF_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* material_type enum values, reference src/common.hpp:105-115 */
+enum {
+    RTREF_LAMBERT = 0, RTREF_METAL = 1, RTREF_DIELECTRIC = 2, RTREF_AIR = 3,
+    RTREF_VACUUM = 4, RTREF_WATER = 5, RTREF_ICE = 6, RTREF_DIAMOND = 7
+};
+
+/* scatter table selector: 0 = mg_ray_tracer.cpp:142-152, 1 = sm_ray_tracer.cpp:221-236 */
+enum { RTREF_MODE_MG = 0, RTREF_MODE_SM = 1 };
+
+typedef struct rtref_material {
+    uint32_t type;        /* material_type, soa.hpp materials.type      */
+    float    albedo[4];   /* rt::colour rgba, soa.hpp materials.albedo  */
+    float    roughness;
+    float    reflectivity; /* doubles as the IOR for dielectrics, scene.cpp:549-556 */
+} rtref_material;
+
+typedef struct rtref_scene {
+    const float*          spheres;          /* n_spheres x {cx,cy,cz,radius} == spheres.value() */
+    const uint32_t*       sphere_material;  /* spheres.material()                                */
+    uint32_t              n_spheres;
+    const float*          planes;           /* n_planes x {nx,ny,nz,d} == planes.value()         */
+    const uint32_t*       plane_material;
+    uint32_t              n_planes;
+    const rtref_material* materials;
+    uint32_t              n_materials;
+} rtref_scene;
+
+typedef struct rtref_view {
+    float    inv_view_proj[16]; /* viewport::inverse_view_projection, column-major m[c*4+r] */
+    uint32_t width, height;     /* full image size                                           */
+    uint32_t samples_per_pixel; /* divisor of the resolve step (scene::samples_per_pixel)    */
+    uint32_t max_bounces;
+    uint32_t sample_begin, sample_end; /* global sample indices rendered by this call       */
+    uint32_t tile_x0, tile_y0, tile_x1, tile_y1; /* pixel rectangle [x0,x1) x [y0,y1)        */
+    uint64_t seed;
+    uint32_t material_mode;     /* RTREF_MODE_MG / RTREF_MODE_SM */
+    uint32_t flags;             /* reserved, 0 */
+} rtref_view;
+
+/* --- RNG (replaces src/random.cpp on both sides) --------------------------------------- */
+void  rtref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+float rtref_u01(uint32_t x);                          /* (x >> 8) * 2^-24, in [0,1) */
+
+/* --- level-1 parity entry point: closest hit over planes + spheres ---------------------- */
+/* o/d: n x {x,y,z}.  hit[i] in {0,1}; prim[i] = sphere index, or 0x80000000|plane index,
+ * 0xFFFFFFFF on miss; t[i] = distance (-1 on miss); nrm (nullable) n x {x,y,z}.          */
+int rtref_intersect_batch(const rtref_scene* s, const float* o, const float* d, uint32_t n,
+                          uint8_t* hit, uint32_t* prim, float* t, float* nrm);
+
+/* --- unit entry points for step-wise parity --------------------------------------------- */
+void rtref_primary_ray(const rtref_view* v, uint32_t px, uint32_t py, uint32_t sample,
+                       float o[3], float d[3]);
+/* returns 1 if scattered, 0 if absorbed; block = philox block index (segment+1) */
+int  rtref_scatter(const rtref_scene* s, uint32_t mode, uint32_t material,
+                   const float o[3], const float d[3], float t, const float n[3],
+                   uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t block,
+                   float att[3], float o_out[3], float d_out[3]);
+uint32_t rtref_pack_pixel(float sum_r, float sum_g, float sum_b, uint32_t spp);
+
+/* --- the render call (mg_ray_tracer.cpp:178-205 / sm_ray_tracer.cpp:263-289) ------------ */
+/* accum (nullable): width*height*4 floats {sum_r,sum_g,sum_b,n_samples}, written inside the
+ * tile only.  rgba8 (nullable): width*height uint32, written inside the tile only, resolved
+ * as sum / samples_per_pixel.  segments (nullable): number of path segments traced.
+ * row_step > 1 renders only rows y0, y0+row_step, ... (bounded CPU-baseline samples).
+ * threads <= 0 means "all online cores".                                                  */
+int rtref_render(const rtref_scene* s, const rtref_view* v, uint32_t* rgba8, float* accum,
+                 uint64_t* segments, int threads, uint32_t row_step);
+
+/* per-sample radiance for one pixel (recursive trace, right-nested product); out[3]; returns
+ * the number of segments of that path */
+uint32_t rtref_trace_sample(const rtref_scene* s, const rtref_view* v, uint32_t px, uint32_t py,
+                            uint32_t sample, float out[3]);
+
+const char* rtref_build_flavour(void); /* "strict" or "fast" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

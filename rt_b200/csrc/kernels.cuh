@@ -1,0 +1,324 @@
+// kernels.cuh -- sm_100a kernels of the path-tracing hot path.
+//
+//   k_render_mega     register-resident paths: one thread owns one pixel and regenerates the next
+//                     sample of the same pixel when a path ends (mg_ray_tracer.cpp:182-201 per pixel,
+//                     :154-174 per path, iterated instead of recursed).  Scene primitives are staged
+//                     in shared memory and read as warp-uniform (broadcast) LDS.128.
+//   k_resolve         sum / spp, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200)
+//   k_intersect_batch / k_primary_rays / k_scatter_batch / k_philox_batch   step-wise parity kernels
+#pragma once
+#include "spec.cuh"
+
+namespace rtcu_dev {
+
+struct SceneDev {
+    const float4* spheres;   // {cx,cy,cz,r*r}
+    const uint32_t* sphere_material;
+    uint32_t n_spheres;
+    const float4* planes;    // {nx,ny,nz,d}
+    const uint32_t* plane_material;
+    uint32_t n_planes;
+    const MatRec* materials;
+    uint32_t n_materials;
+};
+
+struct RenderParams {
+    CameraConst cam;
+    uint32_t width, height;
+    uint32_t tile_x0, tile_y0, tile_x1, tile_y1;
+    uint32_t sample_begin, sample_end;
+    uint32_t max_bounces;
+    uint32_t mode;
+    uint2 key;
+    float spp_resolve;     // float(samples_per_pixel)
+    int accumulate;
+    float4* accum;         // width*height {sum_r,sum_g,sum_b,n}
+    uint32_t* rgba8;       // nullable
+    unsigned long long* counters; // [0] = segments
+};
+
+#define RTCU_PRIM_MISS 0xFFFFFFFFu
+#define RTCU_PRIM_PLANE 0x80000000u
+
+struct Hit { float t; uint32_t prim; }; // prim: sphere index | PLANE|index | MISS
+
+// closest hit over planes then spheres with the reference's tie rules
+// (mg_ray_tracer.cpp:35-102, :160-162).  s_sph / s_pl may point to shared or global memory.
+__device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_sph, const uint32_t n_sph,
+                                                  const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray& r)
+{
+    const float inf = __int_as_float(0x7f800000);
+    float ts = inf;
+    int is = -1;
+#pragma unroll 4
+    for (uint32_t i = 0; i < n_sph; i++)
+        sphere_test(s_sph[i], (int)i, r, ts, is);
+    Hit h;
+    h.t = ts;
+    h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS;
+    if (n_pl)
+    {
+        float tp = inf;
+        int ip = -1;
+        for (uint32_t i = 0; i < n_pl; i++)
+            plane_test(s_pl[i], (int)i, r, tp, ip);
+        // select(spheres, planes): the sphere wins when a.distance <= b.distance (:95-102)
+        if (ip >= 0 && !(is >= 0 && ts <= tp))
+        {
+            h.t = tp;
+            h.prim = RTCU_PRIM_PLANE | (uint32_t)ip;
+        }
+    }
+    if (h.prim == RTCU_PRIM_MISS)
+        h.t = -1.0f;
+    return h;
+}
+
+// hit normal + material (mg_ray_tracer.cpp:56-59, :84-86)
+__device__ __forceinline__ V3 hit_normal(const float4* __restrict__ s_sph, const float4* __restrict__ s_pl, const Ray& r, const Hit h)
+{
+    if (h.prim & RTCU_PRIM_PLANE)
+    {
+        const float4 pl = s_pl[h.prim & 0x7FFFFFFFu];
+        return v3(pl.x, pl.y, pl.z);
+    }
+    const float4 sp = s_sph[h.prim];
+    return normalize3(v3_sub(ray_at(r.o, r.d, h.t), v3(sp.x, sp.y, sp.z)));
+}
+
+__device__ __forceinline__ uint32_t hit_material(const SceneDev& sc, const Hit h)
+{
+    return (h.prim & RTCU_PRIM_PLANE) ? __ldg(sc.plane_material + (h.prim & 0x7FFFFFFFu)) : __ldg(sc.sphere_material + h.prim);
+}
+
+__device__ __forceinline__ MatRec load_material(const SceneDev& sc, uint32_t m)
+{
+    const float4* p = reinterpret_cast<const float4*>(sc.materials + m);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    MatRec r;
+    r.att_r = a.x; r.att_g = a.y; r.att_b = a.z; r.roughness = a.w;
+    r.ior = b.x; r.type = __float_as_uint(b.y); r.pad0 = 0; r.pad1 = 0;
+    return r;
+}
+
+// jittered screen position of (pixel, sample): mg_ray_tracer.cpp:189
+__device__ __forceinline__ Ray generate(const CameraConst& cam, const RngKey& key, uint32_t px, uint32_t py)
+{
+    float jx = 0.5f, jy = 0.5f;
+    if (key.sample != 0u)
+    {
+        const uint4 b = rng_block(key, 0u, 0u);
+        jx = u01(b.x);
+        jy = u01(b.y);
+    }
+    return primary_ray(cam, __fadd_rn(__uint2float_rn(px), jx), __fadd_rn(__uint2float_rn(py), jy));
+}
+
+constexpr int MEGA_TILE_W = 16, MEGA_TILE_H = 16, MEGA_THREADS = 256;
+
+// STAGE: primitives staged in dynamic shared memory (true) or read through L1 from global (false).
+template <bool STAGE>
+__global__ void __launch_bounds__(MEGA_THREADS) k_render_mega(const SceneDev sc, const RenderParams p)
+{
+    extern __shared__ float4 smem[];
+    const float4* s_sph = sc.spheres;
+    const float4* s_pl = sc.planes;
+    if (STAGE)
+    {
+        for (uint32_t i = threadIdx.x; i < sc.n_spheres; i += MEGA_THREADS)
+            smem[i] = __ldg(sc.spheres + i);
+        for (uint32_t i = threadIdx.x; i < sc.n_planes; i += MEGA_THREADS)
+            smem[sc.n_spheres + i] = __ldg(sc.planes + i);
+        __syncthreads();
+        s_sph = smem;
+        s_pl = smem + sc.n_spheres;
+    }
+
+    // a warp covers an 8x4 pixel patch; the block a 16x16 tile
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t px = p.tile_x0 + blockIdx.x * MEGA_TILE_W + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t py = p.tile_y0 + blockIdx.y * MEGA_TILE_H + (warp >> 1) * 4u + (lane >> 3);
+    const bool in_tile = px < p.tile_x1 && py < p.tile_y1;
+
+    unsigned long long segs = 0;
+    if (in_tile && p.sample_begin < p.sample_end)
+    {
+        RngKey key;
+        key.key = p.key;
+        key.pixel = py * p.width + px;
+        key.sample = p.sample_begin;
+
+        V3 sum = v3(0.0f, 0.0f, 0.0f);
+        V3 thr = v3(1.0f, 1.0f, 1.0f);
+        uint32_t seg = 0;
+        Ray ray = generate(p.cam, key, px, py);
+
+        for (;;)
+        {
+            segs++;
+            const Hit h = closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
+            bool ended;
+            if (h.prim == RTCU_PRIM_MISS)
+            {
+                sum = v3_add(sum, v3_mul(thr, sky(ray.d))); // S12: iterative throughput
+                ended = true;
+            }
+            else
+            {
+                const V3 n = hit_normal(s_sph, s_pl, ray, h);
+                const MatRec m = load_material(sc, hit_material(sc, h));
+                const uint4 rnd = rng_block(key, seg + 1u, 0u);
+                Ray next;
+                const bool scattered = scatter(scatter_kind(p.mode, m.type), m, ray, h.t, n, key, seg + 1u, rnd, next);
+                thr = v3_mul(thr, v3(m.att_r, m.att_g, m.att_b));
+                ray = next;
+                seg++;
+                // absorbed (:173) or bounce budget exhausted (:157-158): radiance 0
+                ended = !scattered || seg >= p.max_bounces;
+            }
+            if (ended)
+            {
+                key.sample++;
+                if (key.sample >= p.sample_end)
+                    break;
+                seg = 0;
+                thr = v3(1.0f, 1.0f, 1.0f);
+                ray = generate(p.cam, key, px, py);
+            }
+        }
+
+        const size_t idx = (size_t)key.pixel;
+        float4 acc = make_float4(sum.x, sum.y, sum.z, (float)(p.sample_end - p.sample_begin));
+        if (p.accumulate)
+        {
+            const float4 old = p.accum[idx];
+            acc.x = __fadd_rn(old.x, acc.x); acc.y = __fadd_rn(old.y, acc.y); acc.z = __fadd_rn(old.z, acc.z);
+            acc.w = __fadd_rn(old.w, acc.w);
+        }
+        p.accum[idx] = acc;
+        if (p.rgba8)
+            p.rgba8[idx] = pack_pixel(acc.x, acc.y, acc.z, p.spp_resolve);
+    }
+
+    // exact segment count: warp reduce, one atomic per warp
+    for (int off = 16; off > 0; off >>= 1)
+        segs += __shfl_down_sync(0xffffffffu, segs, off);
+    if (lane == 0 && segs)
+        atomicAdd(p.counters, segs);
+}
+
+// mg_ray_tracer.cpp:195-200 over a whole accumulation buffer
+__global__ void k_resolve(const float4* __restrict__ accum, uint32_t n, float spp, uint32_t* __restrict__ rgba8)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        const float4 a = accum[i];
+        rgba8[i] = pack_pixel(a.x, a.y, a.z, spp);
+    }
+}
+
+// resolve fused with the cross-GPU sum: peers[g] are the other devices' accumulation buffers, read
+// through NVLink peer mappings; the sum order is device 0, 1, 2, ... (deterministic).
+struct PeerList { const float4* ptr[8]; int n; };
+__global__ void k_reduce_resolve(float4* __restrict__ accum, const PeerList peers, uint32_t n, float spp, uint32_t* __restrict__ rgba8)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        float4 a = accum[i];
+        for (int g = 0; g < peers.n; g++)
+        {
+            const float4 b = peers.ptr[g][i];
+            a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+        }
+        accum[i] = a;
+        if (rgba8)
+            rgba8[i] = pack_pixel(a.x, a.y, a.z, spp);
+    }
+}
+
+// ---- step-wise parity kernels ----------------------------------------------------------------------
+template <bool STAGE>
+__global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, const float* __restrict__ o, const float* __restrict__ d,
+                                                         uint32_t n, uint8_t* __restrict__ hit, uint32_t* __restrict__ prim,
+                                                         float* __restrict__ t, float* __restrict__ nrm)
+{
+    extern __shared__ float4 smem[];
+    const float4* s_sph = sc.spheres;
+    const float4* s_pl = sc.planes;
+    if (STAGE)
+    {
+        for (uint32_t i = threadIdx.x; i < sc.n_spheres; i += blockDim.x)
+            smem[i] = __ldg(sc.spheres + i);
+        for (uint32_t i = threadIdx.x; i < sc.n_planes; i += blockDim.x)
+            smem[sc.n_spheres + i] = __ldg(sc.planes + i);
+        __syncthreads();
+        s_sph = smem;
+        s_pl = smem + sc.n_spheres;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        Ray r;
+        r.o = v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+        r.d = v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        const Hit h = closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, r);
+        hit[i] = h.prim != RTCU_PRIM_MISS;
+        prim[i] = h.prim;
+        t[i] = h.t;
+        if (nrm)
+        {
+            V3 nn = v3(0.0f, 0.0f, 0.0f);
+            if (h.prim != RTCU_PRIM_MISS)
+                nn = hit_normal(s_sph, s_pl, r, h);
+            nrm[3 * i] = nn.x; nrm[3 * i + 1] = nn.y; nrm[3 * i + 2] = nn.z;
+        }
+    }
+}
+
+__global__ void k_primary_rays(const CameraConst cam, uint32_t width, uint2 key, const uint32_t* __restrict__ px,
+                               const uint32_t* __restrict__ py, const uint32_t* __restrict__ sample, uint32_t n,
+                               float* __restrict__ o, float* __restrict__ d)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RngKey k;
+    k.key = key; k.pixel = py[i] * width + px[i]; k.sample = sample[i];
+    const Ray r = generate(cam, k, px[i], py[i]);
+    o[3 * i] = r.o.x; o[3 * i + 1] = r.o.y; o[3 * i + 2] = r.o.z;
+    d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z;
+}
+
+__global__ void k_scatter_batch(const SceneDev sc, uint32_t mode, uint2 key, uint32_t n, const uint32_t* __restrict__ material,
+                                const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ t,
+                                const float* __restrict__ nrm, const uint32_t* __restrict__ pixel, const uint32_t* __restrict__ sample,
+                                const uint32_t* __restrict__ block, uint8_t* __restrict__ scattered, float* __restrict__ att,
+                                float* __restrict__ o_out, float* __restrict__ d_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.o = v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+    r.d = v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    const V3 nn = v3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+    RngKey k;
+    k.key = key; k.pixel = pixel[i]; k.sample = sample[i];
+    const MatRec m = load_material(sc, material[i]);
+    const uint4 rnd = rng_block(k, block[i], 0u);
+    Ray out;
+    out.d = v3(0.0f, 0.0f, 0.0f);
+    const bool ok = scatter(scatter_kind(mode, m.type), m, r, t[i], nn, k, block[i], rnd, out);
+    scattered[i] = ok;
+    att[3 * i] = m.att_r; att[3 * i + 1] = m.att_g; att[3 * i + 2] = m.att_b;
+    o_out[3 * i] = out.o.x; o_out[3 * i + 1] = out.o.y; o_out[3 * i + 2] = out.o.z;
+    d_out[3 * i] = ok ? out.d.x : 0.0f; d_out[3 * i + 1] = ok ? out.d.y : 0.0f; d_out[3 * i + 2] = ok ? out.d.z : 0.0f;
+}
+
+__global__ void k_philox_batch(const uint4* __restrict__ ctr, uint32_t n, uint2 key, uint4* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = philox4x32_10(ctr[i], key);
+}
+
+} // namespace rtcu_dev

@@ -1,0 +1,687 @@
+// rtcu.cu -- host side of the C ABI declared in include/rtcu.h (context, scene upload, launches).
+// No CPU fallback: every compute entry point needs a CUDA device and says so when there is none.
+#include "../../include/rtcu.h"
+#include "kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace rtcu_dev;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        const cudaError_t e_ = (call);                                                                                 \
+        if (e_ != cudaSuccess)                                                                                         \
+            return fail(RTCU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+    } while (0)
+
+constexpr size_t MAX_STAGE_BYTES = 200 * 1024; // dynamic shared memory budget for staged primitives
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+bool is_device_accessible_host(const void* ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+} // namespace
+
+struct rtcu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    int sm_count = 0;
+
+    // scene (device)
+    DevBuf<float4> sph;        // {cx,cy,cz,r*r}
+    DevBuf<float4> sph_raw;    // {cx,cy,cz,r}
+    DevBuf<uint32_t> sph_mat;
+    DevBuf<float4> planes;
+    DevBuf<uint32_t> plane_mat;
+    DevBuf<MatRec> mats;
+    SceneDev scene = {};
+    bool have_scene = false;
+
+    // frame buffers owned by the host entry points
+    DevBuf<float4> accum;
+    DevBuf<uint32_t> rgba8;
+    PinnedBuf<uint32_t> h_rgba8;
+    PinnedBuf<float> h_accum;
+    DevBuf<unsigned long long> counters;
+    PinnedBuf<unsigned long long> h_counters;
+
+    // scratch for the batch entry points
+    DevBuf<unsigned char> scratch;
+
+    rtcu_stats stats = {};
+};
+
+namespace {
+
+int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
+{
+    if (!v) return fail(RTCU_ERR_INVALID, "view is null");
+    if (v->width == 0 || v->height == 0) return fail(RTCU_ERR_INVALID, "empty image");
+    if ((uint64_t)v->width * v->height > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "image too large");
+    if (v->tile_x0 >= v->tile_x1 || v->tile_y0 >= v->tile_y1 || v->tile_x1 > v->width || v->tile_y1 > v->height)
+        return fail(RTCU_ERR_INVALID, "bad tile [%u,%u)x[%u,%u) for %ux%u", v->tile_x0, v->tile_x1, v->tile_y0, v->tile_y1, v->width, v->height);
+    if (v->sample_end < v->sample_begin) return fail(RTCU_ERR_INVALID, "bad sample range");
+    if (v->samples_per_pixel == 0) return fail(RTCU_ERR_INVALID, "samples_per_pixel must be >= 1");
+    if (v->max_bounces == 0) return fail(RTCU_ERR_INVALID, "max_bounces must be >= 1 (scene.cpp:532 clamps to [1,1000])");
+    if (v->material_mode > RTCU_MODE_SM) return fail(RTCU_ERR_INVALID, "bad material_mode %u", v->material_mode);
+    (void)ctx;
+    memcpy(p.cam.m, v->inv_view_proj, sizeof p.cam.m);
+    p.cam.w = (float)v->width;
+    p.cam.h = (float)v->height;
+    p.width = v->width; p.height = v->height;
+    p.tile_x0 = v->tile_x0; p.tile_y0 = v->tile_y0; p.tile_x1 = v->tile_x1; p.tile_y1 = v->tile_y1;
+    p.sample_begin = v->sample_begin; p.sample_end = v->sample_end;
+    p.max_bounces = v->max_bounces;
+    p.mode = v->material_mode;
+    p.key = make_uint2((uint32_t)v->seed, (uint32_t)(v->seed >> 32));
+    p.spp_resolve = (float)v->samples_per_pixel;
+    p.accumulate = 0;
+    p.accum = nullptr;
+    p.rgba8 = nullptr;
+    p.counters = nullptr;
+    return RTCU_OK;
+}
+
+size_t stage_bytes(const rtcu_ctx* ctx) { return ((size_t)ctx->scene.n_spheres + ctx->scene.n_planes) * sizeof(float4); }
+
+// launches the trace kernels of one view on `st`; accum/rgba8 are device pointers
+int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st)
+{
+    if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
+    RenderParams p;
+    const int rc = make_params(ctx, v, p);
+    if (rc) return rc;
+    const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
+    if (accel == RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "BVH traversal is not available in this build");
+    if (pipe == RTCU_PIPE_WAVEFRONT) return fail(RTCU_ERR_INVALID, "wavefront pipeline is not available in this build");
+    p.accum = d_accum;
+    p.rgba8 = d_rgba8;
+    p.accumulate = accumulate;
+    p.counters = ctx->counters.p;
+
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
+    const dim3 grid((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W, (v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
+    const size_t sb = stage_bytes(ctx);
+    if (sb <= MAX_STAGE_BYTES)
+        k_render_mega<true><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, p);
+    else
+        k_render_mega<false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches = 1;
+    ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
+    ctx->stats.accel = RTCU_ACCEL_LINEAR;
+    ctx->stats.samples = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0) * (v->sample_end - v->sample_begin);
+    return RTCU_OK;
+}
+
+int fetch_counters(rtcu_ctx* ctx, cudaStream_t st)
+{
+    CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stats.segments = ctx->h_counters.p[0];
+    ctx->stats.sphere_tests = ctx->stats.segments * ctx->scene.n_spheres;
+    ctx->stats.node_visits = 0;
+    return RTCU_OK;
+}
+
+// device -> caller's host buffer; direct when the buffer is pinned/registered, staged otherwise
+template <typename T>
+int copy_out(rtcu_ctx* ctx, T* dst, const T* d_src, size_t n, PinnedBuf<T>& staging)
+{
+    if (is_device_accessible_host(dst))
+    {
+        CU(cudaMemcpyAsync(dst, d_src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    else
+    {
+        CU(staging.reserve(n));
+        CU(cudaMemcpyAsync(staging.p, d_src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        memcpy(dst, staging.p, n * sizeof(T));
+    }
+    return RTCU_OK;
+}
+
+} // namespace
+
+// ---- batch entry points: stage host arrays through one scratch allocation -----------------------
+namespace {
+struct Carver {
+    unsigned char* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+size_t padded(size_t bytes) { return ((bytes + 255) & ~(size_t)255) + 256; }
+} // namespace
+
+extern "C" {
+
+int rtcu_abi_version(void) { return RTCU_ABI_VERSION; }
+
+const char* rtcu_last_error(void) { return g_err; }
+
+uint32_t rtcu_bvh_threshold(void) { return 4096u; }
+
+int rtcu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+rtcu_ctx* rtcu_create(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+    {
+        fail(RTCU_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= n)
+    {
+        fail(RTCU_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    {
+        fail(RTCU_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (prop.major != 10)
+    {
+        fail(RTCU_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    rtcu_ctx* ctx = new (std::nothrow) rtcu_ctx;
+    if (!ctx)
+    {
+        fail(RTCU_ERR_INVALID, "out of host memory");
+        return nullptr;
+    }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 6; i++)
+        ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && ctx->counters.reserve(4) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_render_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_intersect_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
+    if (!ok)
+    {
+        fail(RTCU_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rtcu_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+void rtcu_destroy(rtcu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->sph.release(); ctx->sph_raw.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
+    ctx->mats.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
+    ctx->counters.release(); ctx->h_counters.release(); ctx->scratch.release();
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
+{
+    if (!ctx || !s) return fail(RTCU_ERR_INVALID, "null argument");
+    if (s->n_materials == 0 || !s->materials) return fail(RTCU_ERR_INVALID, "scene has no materials (scene.cpp:565-566 always provides one)");
+    if ((s->n_spheres && (!s->spheres || !s->sphere_material)) || (s->n_planes && (!s->planes || !s->plane_material)))
+        return fail(RTCU_ERR_INVALID, "null primitive column");
+    if (s->n_spheres >= 0x80000000u || s->n_planes >= 0x7FFFFFFFu) return fail(RTCU_ERR_INVALID, "too many primitives");
+    // scene.cpp:568-574 range-checks material indices at load; re-check at the boundary
+    for (uint32_t i = 0; i < s->n_spheres; i++)
+        if (s->sphere_material[i] >= s->n_materials) return fail(RTCU_ERR_INVALID, "sphere %u: material index %u out-of-range", i, s->sphere_material[i]);
+    for (uint32_t i = 0; i < s->n_planes; i++)
+        if (s->plane_material[i] >= s->n_materials) return fail(RTCU_ERR_INVALID, "plane %u: material index %u out-of-range", i, s->plane_material[i]);
+    for (uint32_t i = 0; i < s->n_materials; i++)
+        if (s->materials[i].type > RTCU_DIAMOND) return fail(RTCU_ERR_INVALID, "material %u: type %u is not a material_type", i, s->materials[i].type);
+
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float4> sph(s->n_spheres), raw(s->n_spheres);
+    for (uint32_t i = 0; i < s->n_spheres; i++)
+    {
+        const float* p = s->spheres + 4 * (size_t)i;
+        const float r = p[3];
+        const volatile float r2 = r * r; // S4: r2 = r*r, one IEEE multiply
+        raw[i] = make_float4(p[0], p[1], p[2], r);
+        sph[i] = make_float4(p[0], p[1], p[2], r2);
+    }
+    std::vector<MatRec> mats(s->n_materials);
+    for (uint32_t i = 0; i < s->n_materials; i++)
+    {
+        const rtcu_material& m = s->materials[i];
+        MatRec r;
+        const volatile float ar = m.albedo[0] * m.reflectivity, ag = m.albedo[1] * m.reflectivity, ab = m.albedo[2] * m.reflectivity;
+        r.att_r = ar; r.att_g = ag; r.att_b = ab;
+        r.roughness = m.roughness;
+        r.ior = m.reflectivity;
+        r.type = m.type;
+        r.pad0 = r.pad1 = 0;
+        mats[i] = r;
+    }
+    CU(ctx->sph.reserve(s->n_spheres ? s->n_spheres : 1));
+    CU(ctx->sph_raw.reserve(s->n_spheres ? s->n_spheres : 1));
+    CU(ctx->sph_mat.reserve(s->n_spheres ? s->n_spheres : 1));
+    CU(ctx->planes.reserve(s->n_planes ? s->n_planes : 1));
+    CU(ctx->plane_mat.reserve(s->n_planes ? s->n_planes : 1));
+    CU(ctx->mats.reserve(s->n_materials));
+    // make sure no kernel of a previous frame still reads the old scene
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (s->n_spheres)
+    {
+        CU(cudaMemcpyAsync(ctx->sph.p, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->sph_raw.p, raw.data(), raw.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->sph_mat.p, s->sphere_material, s->n_spheres * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (s->n_planes)
+    {
+        CU(cudaMemcpyAsync(ctx->planes.p, s->planes, s->n_planes * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->plane_mat.p, s->plane_material, s->n_planes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->mats.p, mats.data(), mats.size() * sizeof(MatRec), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // the staging vectors die here
+    ctx->scene.spheres = ctx->sph.p;
+    ctx->scene.sphere_material = ctx->sph_mat.p;
+    ctx->scene.n_spheres = s->n_spheres;
+    ctx->scene.planes = ctx->planes.p;
+    ctx->scene.plane_material = ctx->plane_mat.p;
+    ctx->scene.n_planes = s->n_planes;
+    ctx->scene.materials = ctx->mats.p;
+    ctx->scene.n_materials = s->n_materials;
+    ctx->have_scene = true;
+    return RTCU_OK;
+}
+
+int rtcu_render_device(rtcu_ctx* ctx, const rtcu_view* view, float* d_accum, int accumulate, void* stream)
+{
+    if (!ctx || !view || !d_accum) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    return launch_render(ctx, view, reinterpret_cast<float4*>(d_accum), nullptr, accumulate, st);
+}
+
+int rtcu_resolve_device(rtcu_ctx* ctx, const float* d_accum, uint32_t width, uint32_t height, uint32_t spp, uint32_t* d_rgba8, void* stream)
+{
+    if (!ctx || !d_accum || !d_rgba8 || !width || !height || !spp) return fail(RTCU_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t n = width * height;
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(d_accum), n, (float)spp, d_rgba8);
+    CU(cudaGetLastError());
+    return RTCU_OK;
+}
+
+int rtcu_sync(rtcu_ctx* ctx)
+{
+    if (!ctx) return fail(RTCU_ERR_INVALID, "null context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTCU_OK;
+}
+
+int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out)
+{
+    if (!ctx || !view) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)view->width * view->height;
+    if (npix == 0) return fail(RTCU_ERR_INVALID, "empty image");
+    CU(ctx->accum.reserve(npix));
+    CU(ctx->rgba8.reserve(npix));
+    const bool full = view->tile_x0 == 0 && view->tile_y0 == 0 && view->tile_x1 == view->width && view->tile_y1 == view->height;
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = launch_render(ctx, view, ctx->accum.p, rgba8_out ? ctx->rgba8.p : nullptr, 0, ctx->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    // copy the tile rows back (whole image when the tile is the image)
+    const size_t row0 = full ? 0 : view->tile_y0, rows = full ? view->height : view->tile_y1 - view->tile_y0;
+    const size_t off = row0 * view->width, cnt = rows * view->width;
+    if (rgba8_out)
+    {
+        if (full)
+            rc = copy_out(ctx, rgba8_out, ctx->rgba8.p, npix, ctx->h_rgba8);
+        else
+        {
+            CU(ctx->h_rgba8.reserve(npix));
+            CU(cudaMemcpyAsync(ctx->h_rgba8.p + off, ctx->rgba8.p + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t y = view->tile_y0; y < view->tile_y1; y++)
+                memcpy(rgba8_out + (size_t)y * view->width + view->tile_x0, ctx->h_rgba8.p + (size_t)y * view->width + view->tile_x0,
+                       (size_t)(view->tile_x1 - view->tile_x0) * sizeof(uint32_t));
+        }
+        if (rc) return rc;
+    }
+    if (accum_out)
+    {
+        if (full)
+            rc = copy_out(ctx, accum_out, reinterpret_cast<const float*>(ctx->accum.p), npix * 4, ctx->h_accum);
+        else
+        {
+            CU(ctx->h_accum.reserve(npix * 4));
+            CU(cudaMemcpyAsync(ctx->h_accum.p + off * 4, reinterpret_cast<const float*>(ctx->accum.p) + off * 4, cnt * 4 * sizeof(float),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t y = view->tile_y0; y < view->tile_y1; y++)
+                memcpy(accum_out + ((size_t)y * view->width + view->tile_x0) * 4, ctx->h_accum.p + ((size_t)y * view->width + view->tile_x0) * 4,
+                       (size_t)(view->tile_x1 - view->tile_x0) * 4 * sizeof(float));
+        }
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    rc = fetch_counters(ctx, ctx->stream);
+    if (rc) return rc;
+    CU(cudaEventElapsedTime(&ctx->stats.ms_render, ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(&ctx->stats.ms_d2h, ctx->ev[1], ctx->ev[2]));
+    ctx->stats.ms_resolve = 0.0f;
+    ctx->stats.ms_h2d = 0.0f;
+    return RTCU_OK;
+}
+
+int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out)
+{
+    if (!ctxs || n_ctx == 0 || n_ctx > 8 || !view) return fail(RTCU_ERR_INVALID, "bad argument");
+    if (n_ctx == 1) return rtcu_render(ctxs[0], view, rgba8_out, accum_out);
+    const size_t npix = (size_t)view->width * view->height;
+    const uint32_t s0 = view->sample_begin, total = view->sample_end - view->sample_begin;
+    // sample-range split: device g renders [s0 + g*total/G, s0 + (g+1)*total/G)
+    for (uint32_t g = 0; g < n_ctx; g++)
+    {
+        rtcu_ctx* c = ctxs[g];
+        if (!c) return fail(RTCU_ERR_INVALID, "null context %u", g);
+        CU(cudaSetDevice(c->device));
+        CU(c->accum.reserve(npix));
+        CU(cudaMemsetAsync(c->accum.p, 0, npix * sizeof(float4), c->stream)); // pixels outside the tile must add 0
+        rtcu_view v = *view;
+        v.sample_begin = s0 + (uint32_t)((uint64_t)total * g / n_ctx);
+        v.sample_end = s0 + (uint32_t)((uint64_t)total * (g + 1) / n_ctx);
+        if (g == 0) CU(cudaEventRecord(c->ev[0], c->stream));
+        if (v.sample_end > v.sample_begin)
+        {
+            const int rc = launch_render(c, &v, c->accum.p, nullptr, 0, c->stream);
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(c->ev[3], c->stream));
+    }
+    // root waits for every peer, then sums their buffers through peer loads inside the resolve kernel
+    rtcu_ctx* root = ctxs[0];
+    CU(cudaSetDevice(root->device));
+    PeerList peers;
+    peers.n = 0;
+    for (uint32_t g = 1; g < n_ctx; g++)
+    {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, root->device, ctxs[g]->device));
+        if (!can) return fail(RTCU_ERR_CUDA, "device %d cannot access peer %d", root->device, ctxs[g]->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[g]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RTCU_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        CU(cudaStreamWaitEvent(root->stream, ctxs[g]->ev[3], 0));
+        peers.ptr[peers.n++] = ctxs[g]->accum.p;
+    }
+    CU(root->rgba8.reserve(npix));
+    CU(cudaEventRecord(root->ev[1], root->stream));
+    k_reduce_resolve<<<(unsigned)((npix + 255) / 256), 256, 0, root->stream>>>(root->accum.p, peers, (uint32_t)npix, (float)view->samples_per_pixel,
+                                                                             rgba8_out ? root->rgba8.p : nullptr);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(root->ev[2], root->stream));
+    int rc = RTCU_OK;
+    if (rgba8_out) rc = copy_out(root, rgba8_out, root->rgba8.p, npix, root->h_rgba8);
+    if (!rc && accum_out) rc = copy_out(root, accum_out, reinterpret_cast<const float*>(root->accum.p), npix * 4, root->h_accum);
+    if (rc) return rc;
+    uint64_t segs = 0;
+    for (uint32_t g = 0; g < n_ctx; g++)
+    {
+        CU(cudaSetDevice(ctxs[g]->device));
+        rc = fetch_counters(ctxs[g], ctxs[g]->stream);
+        if (rc) return rc;
+        segs += ctxs[g]->stats.segments;
+    }
+    CU(cudaSetDevice(root->device));
+    CU(cudaStreamSynchronize(root->stream));
+    CU(cudaEventElapsedTime(&root->stats.ms_render, root->ev[0], root->ev[1]));
+    CU(cudaEventElapsedTime(&root->stats.ms_resolve, root->ev[1], root->ev[2]));
+    root->stats.segments = segs;
+    root->stats.sphere_tests = segs * root->scene.n_spheres;
+    root->stats.samples = (uint64_t)(view->tile_x1 - view->tile_x0) * (view->tile_y1 - view->tile_y0) * total;
+    root->stats.kernel_launches = n_ctx + 1;
+    return RTCU_OK;
+}
+
+int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t n, uint8_t* hit, uint32_t* prim, float* t, float* normal,
+                         uint32_t accel)
+{
+    if (!ctx || !o || !d || !hit || !prim || !t) return fail(RTCU_ERR_INVALID, "null argument");
+    if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
+    if (accel == RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "BVH traversal is not available in this build");
+    if (n == 0) return RTCU_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t need = 2 * padded((size_t)n * 12) + padded(n) + 2 * padded((size_t)n * 4) + padded((size_t)n * 12);
+    CU(ctx->scratch.reserve(need));
+    Carver c{ ctx->scratch.p };
+    float* d_o = c.take<float>((size_t)n * 3);
+    float* d_d = c.take<float>((size_t)n * 3);
+    uint8_t* d_hit = c.take<uint8_t>(n);
+    uint32_t* d_prim = c.take<uint32_t>(n);
+    float* d_t = c.take<float>(n);
+    float* d_n = c.take<float>((size_t)n * 3);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + 255) / 256 < (uint32_t)ctx->sm_count * 8 ? (n + 255) / 256 : ctx->sm_count * 8);
+    const size_t sb = stage_bytes(ctx);
+    CU(cudaEventRecord(ctx->ev[0], st));
+    if (sb <= MAX_STAGE_BYTES)
+        k_intersect_batch<true><<<blocks, 256, sb, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr);
+    else
+        k_intersect_batch<false><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(cudaMemcpyAsync(hit, d_hit, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(prim, d_prim, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (normal) CU(cudaMemcpyAsync(normal, d_n, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&ctx->stats.ms_render, ctx->ev[0], ctx->ev[1]));
+    ctx->stats.kernel_launches = 1;
+    ctx->stats.segments = n;
+    ctx->stats.sphere_tests = (uint64_t)n * ctx->scene.n_spheres;
+    ctx->stats.accel = RTCU_ACCEL_LINEAR;
+    return RTCU_OK;
+}
+
+int rtcu_primary_rays(rtcu_ctx* ctx, const rtcu_view* view, const uint32_t* px, const uint32_t* py, const uint32_t* sample, uint32_t n, float* o,
+                      float* d)
+{
+    if (!ctx || !view || !px || !py || !sample || !o || !d) return fail(RTCU_ERR_INVALID, "null argument");
+    if (n == 0) return RTCU_OK;
+    CU(cudaSetDevice(ctx->device));
+    RenderParams p;
+    rtcu_view v = *view;
+    if (v.max_bounces == 0) v.max_bounces = 1;
+    const int rc = make_params(ctx, &v, p);
+    if (rc) return rc;
+    CU(ctx->scratch.reserve(3 * padded((size_t)n * 4) + 2 * padded((size_t)n * 12)));
+    Carver c{ ctx->scratch.p };
+    uint32_t* d_px = c.take<uint32_t>(n);
+    uint32_t* d_py = c.take<uint32_t>(n);
+    uint32_t* d_s = c.take<uint32_t>(n);
+    float* d_o = c.take<float>((size_t)n * 3);
+    float* d_d = c.take<float>((size_t)n * 3);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_px, px, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_py, py, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_s, sample, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    k_primary_rays<<<(n + 255) / 256, 256, 0, st>>>(p.cam, p.width, p.key, d_px, d_py, d_s, n, d_o, d_d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(o, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d, d_d, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RTCU_OK;
+}
+
+int rtcu_scatter_batch(rtcu_ctx* ctx, uint32_t material_mode, uint64_t seed, uint32_t n, const uint32_t* material, const float* o, const float* d,
+                       const float* t, const float* normal, const uint32_t* pixel, const uint32_t* sample, const uint32_t* block,
+                       uint8_t* scattered, float* att, float* o_out, float* d_out)
+{
+    if (!ctx || !material || !o || !d || !t || !normal || !pixel || !sample || !block || !scattered || !att || !o_out || !d_out)
+        return fail(RTCU_ERR_INVALID, "null argument");
+    if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
+    if (material_mode > RTCU_MODE_SM) return fail(RTCU_ERR_INVALID, "bad material_mode");
+    for (uint32_t i = 0; i < n; i++)
+        if (material[i] >= ctx->scene.n_materials) return fail(RTCU_ERR_INVALID, "item %u: material index out-of-range", i);
+    if (n == 0) return RTCU_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->scratch.reserve(5 * padded((size_t)n * 4) + 6 * padded((size_t)n * 12) + padded(n)));
+    Carver c{ ctx->scratch.p };
+    uint32_t* d_mat = c.take<uint32_t>(n);
+    uint32_t* d_pix = c.take<uint32_t>(n);
+    uint32_t* d_smp = c.take<uint32_t>(n);
+    uint32_t* d_blk = c.take<uint32_t>(n);
+    float* d_t = c.take<float>(n);
+    float* d_o = c.take<float>((size_t)n * 3);
+    float* d_d = c.take<float>((size_t)n * 3);
+    float* d_n = c.take<float>((size_t)n * 3);
+    float* d_att = c.take<float>((size_t)n * 3);
+    float* d_oo = c.take<float>((size_t)n * 3);
+    float* d_do = c.take<float>((size_t)n * 3);
+    uint8_t* d_sc = c.take<uint8_t>(n);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_mat, material, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_pix, pixel, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_smp, sample, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_blk, block, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_t, t, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_n, normal, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    k_scatter_batch<<<(n + 255) / 256, 256, 0, st>>>(ctx->scene, material_mode, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), n, d_mat, d_o, d_d,
+                                                    d_t, d_n, d_pix, d_smp, d_blk, d_sc, d_att, d_oo, d_do);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(scattered, d_sc, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(att, d_att, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(o_out, d_oo, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d_out, d_do, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RTCU_OK;
+}
+
+int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t key, uint32_t* out)
+{
+    if (!ctx || !ctr || !out) return fail(RTCU_ERR_INVALID, "null argument");
+    if (n == 0) return RTCU_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->scratch.reserve(2 * padded((size_t)n * 16)));
+    Carver c{ ctx->scratch.p };
+    uint4* d_c = c.take<uint4>(n);
+    uint4* d_o = c.take<uint4>(n);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_c, ctr, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    k_philox_batch<<<(n + 255) / 256, 256, 0, st>>>(d_c, n, make_uint2((uint32_t)key, (uint32_t)(key >> 32)), d_o);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_o, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RTCU_OK;
+}
+
+int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out)
+{
+    if (!ctx || !out) return fail(RTCU_ERR_INVALID, "null argument");
+    *out = ctx->stats;
+    return RTCU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's renderer plugin interface, on top of the C ABI.
+
+Mirrors, with the same names and argument meaning:
+
+* `renderer_interface::render(const scene&, image_view&, muu::thread_pool&) noexcept` -- reference
+  src/renderer.hpp:9-14  -> `RendererInterface.render(scene, pixels, threads=None)`
+* `renderers::description / install / all / find_by_key / find_by_name` -- src/renderer.hpp:16-31,
+  src/renderer.cpp:21-69 -> `Description`, `renderers.install(...)` etc.
+* `REGISTER_RENDERER(T)` -- src/renderer.hpp:34-41 -> `@register_renderer`
+* `rt::image_view` -- src/image.hpp:112-163 -> `ImageView`
+
+`CudaPathTracer` is the Python twin of plugin/cuda_path_tracer.cpp: it flattens the scene into the POD
+descriptor, calls `rtcu_upload_scene` + `rtcu_render`, and like a `noexcept` C++ override it never raises
+from `render` -- it logs to stderr and leaves the (pre-cleared) image untouched ("Errors").
+The lower-level `Context` class raises `RtcuError` and is what tests and bench.py use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import hashlib
+import sys
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _native as nat
+from .camera import inverse_view_projection
+from .scene import MATERIAL_DTYPE, Scene
+
+DEFAULT_SEED = 0x5EED
+
+
+# --------------------------------------------------------------------------------------------------
+# rt::image_view
+class ImageView:
+    """Non-owning view over a row-major uint32 RGBA8888 buffer, row 0 = top (src/image.hpp:112-163)."""
+
+    def __init__(self, data: np.ndarray):
+        if data.dtype != np.uint32 or data.ndim != 2 or not data.flags.c_contiguous:
+            raise ValueError("ImageView needs a C-contiguous (height, width) uint32 array")
+        self.data = data
+
+    @classmethod
+    def allocate(cls, width: int, height: int) -> "ImageView":
+        return cls(np.zeros((height, width), np.uint32))
+
+    def size(self) -> tuple[int, int]:
+        return (self.data.shape[1], self.data.shape[0])  # vec2u{x, y}
+
+    def position_of(self, idx: int) -> tuple[int, int]:
+        w = self.data.shape[1]
+        return (idx % w, idx // w)  # src/image.hpp:156-159
+
+    def clear(self, colour: int = 0x000000FF) -> "ImageView":
+        self.data[...] = colour
+        return self
+
+    def __call__(self, x: int, y: int) -> int:
+        return int(self.data[y, x])
+
+
+# --------------------------------------------------------------------------------------------------
+# renderer_interface + registry
+class RendererInterface:
+    """src/renderer.hpp:9-14"""
+
+    def render(self, scene: Scene, pixels: ImageView, threads=None) -> None:  # noexcept in the reference
+        raise NotImplementedError
+
+
+@dataclasses.dataclass(frozen=True)
+class Description:
+    """renderers::description (src/renderer.hpp:18-25)"""
+    key: str
+    name: str
+    create: Callable[[], RendererInterface]
+
+
+class _Registry:
+    """src/renderer.cpp:9-69"""
+
+    def __init__(self) -> None:
+        self._all: list[Description] = []
+
+    def install(self, desc: Description) -> None:
+        assert desc.key and desc.name and desc.create
+        for i, r in enumerate(self._all):
+            if r.key == desc.key:  # same key overwrites (renderer.cpp:27-34)
+                self._all[i] = desc
+                return
+        self._all.append(desc)
+
+    def all(self) -> Sequence[Description]:
+        return tuple(self._all)
+
+    def find_by_key(self, key: str) -> Optional[Description]:
+        if not key:
+            return None
+        return next((r for r in self._all if r.key == key), None)
+
+    def find_by_name(self, name: str) -> Optional[Description]:
+        if not name:
+            return None
+        return next((r for r in self._all if r.name == name), None)
+
+    def find(self, name: str) -> Optional[Description]:
+        """CLI lookup: exact name, then prefix (src/main.cpp:68-81)."""
+        return self.find_by_name(name) or next((r for r in self._all if name and r.name.startswith(name)), None)
+
+
+renderers = _Registry()
+
+
+def register_renderer(cls):
+    """REGISTER_RENDERER(T): the CLI name is the type name (src/renderer.hpp:34-41)."""
+    renderers.install(Description(key=f"{cls.__module__}:{cls.__qualname__}", name=cls.__name__, create=cls))
+    return cls
+
+
+# --------------------------------------------------------------------------------------------------
+def make_view(scene: Scene, width: int, height: int, *, samples_per_pixel: Optional[int] = None,
+              max_bounces: Optional[int] = None, sample_range: Optional[tuple[int, int]] = None,
+              tile: Optional[tuple[int, int, int, int]] = None, seed: int = DEFAULT_SEED,
+              material_mode: int = nat.MODE_SM, flags: int = 0) -> nat.View:
+    """Fills an rtcu_view for `scene` (camera -> inverse_view_projection, defaults = the reference's single call)."""
+    v = nat.View()
+    v.inv_view_proj[:] = inverse_view_projection(scene.camera, width, height).tolist()
+    v.width, v.height = width, height
+    v.samples_per_pixel = scene.samples_per_pixel if samples_per_pixel is None else samples_per_pixel
+    v.max_bounces = scene.max_bounces if max_bounces is None else max_bounces
+    v.sample_begin, v.sample_end = (0, v.samples_per_pixel) if sample_range is None else sample_range
+    v.tile_x0, v.tile_y0, v.tile_x1, v.tile_y1 = (0, 0, width, height) if tile is None else tile
+    v.seed = seed
+    v.material_mode = material_mode
+    v.flags = flags
+    return v
+
+
+class Context:
+    """One rtcu_ctx (one device).  Raises RtcuError; no CPU fallback."""
+
+    def __init__(self, device: int = 0):
+        self._lib = nat.load_library()
+        self._h = self._lib.rtcu_create(device)
+        if not self._h:
+            raise nat.RtcuError(nat.RTCU_ERR_CUDA, nat.last_error())
+        self.device = device
+        self._keep: tuple = ()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.rtcu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self) -> int:
+        return self._h
+
+    # -- scene ----------------------------------------------------------------------------------
+    def upload_scene(self, scene: Scene) -> None:
+        sph = nat.contiguous(scene.spheres, np.float32).reshape(-1, 4)
+        smat = nat.contiguous(scene.sphere_material, np.uint32)
+        pl = nat.contiguous(scene.planes, np.float32).reshape(-1, 4)
+        pmat = nat.contiguous(scene.plane_material, np.uint32)
+        mats = np.ascontiguousarray(scene.materials.astype(MATERIAL_DTYPE))
+        d = nat.SceneDesc(nat.ptr(sph) if len(sph) else None, nat.ptr(smat) if len(smat) else None, len(sph),
+                          nat.ptr(pl) if len(pl) else None, nat.ptr(pmat) if len(pmat) else None, len(pl),
+                          nat.ptr(mats) if len(mats) else None, len(mats))
+        nat.check(self._lib.rtcu_upload_scene(self._h, C.byref(d)))
+
+    # -- render ---------------------------------------------------------------------------------
+    def render(self, view: nat.View, rgba8: Optional[np.ndarray] = None, accum: Optional[np.ndarray] = None,
+               want_rgba8: bool = True, want_accum: bool = False):
+        """rtcu_render into (new or caller-provided) host arrays; returns (rgba8 (H,W) u32, accum (H,W,4) f32)."""
+        h, w = view.height, view.width
+        if rgba8 is None and want_rgba8:
+            rgba8 = np.zeros((h, w), np.uint32)
+        if accum is None and want_accum:
+            accum = np.zeros((h, w, 4), np.float32)
+        nat.check(self._lib.rtcu_render(self._h, C.byref(view), nat.ptr(rgba8), nat.ptr(accum)))
+        return rgba8, accum
+
+    def render_device(self, view: nat.View, d_accum_ptr: int, accumulate: bool = False, stream: int = 0) -> None:
+        nat.check(self._lib.rtcu_render_device(self._h, C.byref(view), d_accum_ptr, int(accumulate), stream or None))
+
+    def resolve_device(self, d_accum_ptr: int, width: int, height: int, spp: int, d_rgba8_ptr: int, stream: int = 0) -> None:
+        nat.check(self._lib.rtcu_resolve_device(self._h, d_accum_ptr, width, height, spp, d_rgba8_ptr, stream or None))
+
+    def sync(self) -> None:
+        nat.check(self._lib.rtcu_sync(self._h))
+
+    def stats(self) -> dict:
+        s = nat.Stats()
+        nat.check(self._lib.rtcu_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    # -- step-wise parity entry points -------------------------------------------------------------
+    def intersect_batch(self, o: np.ndarray, d: np.ndarray, accel: int = nat.ACCEL_AUTO, want_normal: bool = True):
+        o = nat.contiguous(o, np.float32).reshape(-1, 3)
+        d = nat.contiguous(d, np.float32).reshape(-1, 3)
+        n = len(o)
+        hit = np.zeros(n, np.uint8)
+        prim = np.zeros(n, np.uint32)
+        t = np.zeros(n, np.float32)
+        nrm = np.zeros((n, 3), np.float32) if want_normal else None
+        nat.check(self._lib.rtcu_intersect_batch(self._h, nat.ptr(o), nat.ptr(d), n, nat.ptr(hit), nat.ptr(prim), nat.ptr(t), nat.ptr(nrm), accel))
+        return hit, prim, t, nrm
+
+    def primary_rays(self, view: nat.View, px, py, sample):
+        px = nat.contiguous(px, np.uint32); py = nat.contiguous(py, np.uint32); sample = nat.contiguous(sample, np.uint32)
+        n = len(px)
+        o = np.zeros((n, 3), np.float32)
+        d = np.zeros((n, 3), np.float32)
+        nat.check(self._lib.rtcu_primary_rays(self._h, C.byref(view), nat.ptr(px), nat.ptr(py), nat.ptr(sample), n, nat.ptr(o), nat.ptr(d)))
+        return o, d
+
+    def scatter_batch(self, mode: int, seed: int, material, o, d, t, normal, pixel, sample, block):
+        material = nat.contiguous(material, np.uint32)
+        n = len(material)
+        o = nat.contiguous(o, np.float32).reshape(n, 3); d = nat.contiguous(d, np.float32).reshape(n, 3)
+        t = nat.contiguous(t, np.float32); normal = nat.contiguous(normal, np.float32).reshape(n, 3)
+        pixel = nat.contiguous(pixel, np.uint32); sample = nat.contiguous(sample, np.uint32); block = nat.contiguous(block, np.uint32)
+        sc = np.zeros(n, np.uint8)
+        att = np.zeros((n, 3), np.float32); oo = np.zeros((n, 3), np.float32); do = np.zeros((n, 3), np.float32)
+        nat.check(self._lib.rtcu_scatter_batch(self._h, mode, seed, n, nat.ptr(material), nat.ptr(o), nat.ptr(d), nat.ptr(t), nat.ptr(normal),
+                                               nat.ptr(pixel), nat.ptr(sample), nat.ptr(block), nat.ptr(sc), nat.ptr(att), nat.ptr(oo), nat.ptr(do)))
+        return sc, att, oo, do
+
+    def philox_batch(self, ctr: np.ndarray, key: int) -> np.ndarray:
+        ctr = nat.contiguous(ctr, np.uint32).reshape(-1, 4)
+        out = np.zeros_like(ctr)
+        nat.check(self._lib.rtcu_philox_batch(self._h, nat.ptr(ctr), len(ctr), key, nat.ptr(out)))
+        return out
+
+
+def render_multi(contexts: Sequence[Context], view: nat.View, want_accum: bool = False):
+    """rtcu_render_multi: single-process sample-range split over several devices."""
+    lib = nat.load_library()
+    arr = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    rgba8 = np.zeros((view.height, view.width), np.uint32)
+    accum = np.zeros((view.height, view.width, 4), np.float32) if want_accum else None
+    nat.check(lib.rtcu_render_multi(arr, len(contexts), C.byref(view), nat.ptr(rgba8), nat.ptr(accum)))
+    return rgba8, accum
+
+
+def scene_fingerprint(scene: Scene) -> bytes:
+    """The reference scene has no dirty flag: detect changes by content."""
+    h = hashlib.blake2b(digest_size=16)
+    for a in (scene.spheres, scene.sphere_material, scene.planes, scene.plane_material, scene.materials):
+        h.update(np.ascontiguousarray(a).tobytes())
+        h.update(b"|")
+    return h.digest()
+
+
+@register_renderer
+class cuda_path_tracer(RendererInterface):  # noqa: N801 -- the CLI name is the type name (renderer.hpp:34-41)
+    """Drop-in for mg_ray_tracer / sm_ray_tracer behind the renderer interface.
+
+    `material_mode` picks the scatter table: MODE_SM (default; lambert/metal/dielectric, sm_ray_tracer.cpp:221-236)
+    or MODE_MG (mg_ray_tracer.cpp:142-152, no dielectric).  The two agree on scenes without dielectric-class
+    materials."""
+
+    material_mode = nat.MODE_SM
+    seed = DEFAULT_SEED
+    flags = 0
+
+    def __init__(self, device: int = 0):
+        self.ctx = Context(device)  # may raise, like a throwing C++ constructor inside create()
+        self._fingerprint: Optional[bytes] = None
+        self.last_error: Optional[str] = None
+
+    def render(self, scene: Scene, pixels: ImageView, threads=None) -> None:
+        try:
+            fp = scene_fingerprint(scene)
+            if fp != self._fingerprint:
+                self.ctx.upload_scene(scene)
+                self._fingerprint = fp
+            w, h = pixels.size()
+            view = make_view(scene, w, h, seed=self.seed, material_mode=self.material_mode, flags=self.flags)
+            self.ctx.render(view, rgba8=pixels.data, want_accum=False)
+            self.last_error = None
+        except Exception as e:  # noexcept: log, leave the pre-cleared image alone
+            self.last_error = str(e)
+            print(f"cuda_path_tracer: {e}", file=sys.stderr)
+
+
+CudaPathTracer = cuda_path_tracer

@@ -1,0 +1,311 @@
+"""Scene containers and the TOML scene loader (host side, feeds the C ABI).
+
+Restates the reference loader `scene::load` (reference src/scene.cpp:483-618) and the containers in
+src/scene.hpp:8-25 / src/soa.toml with the same defaults, clamps, aliases and error behaviour, so
+that `rt --scene <toml>` and this harness flatten a scene file to the same columns.  Quirks kept
+on purpose:
+
+* named colours are binarised: `colour(uint32)` clamps the integer byte to [0,1] without /255
+  (src/colour.hpp:72-98), so any non-zero byte becomes 1.0;
+* a colour given as an array starts from zero (not from the default) and gets alpha 1 when it has
+  fewer than four components (src/scene.cpp:347-356);
+* samples_per_pixel and max_bounces are clamped to [1,1000] (src/scene.cpp:531-532);
+* dielectric-class materials store their IOR in `reflectivity` (src/scene.cpp:546-556).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import pathlib
+import tomllib
+from typing import Any, Sequence
+
+import numpy as np
+
+from .colour_table import NAMED_COLOURS
+
+# rt::material_type, src/common.hpp:105-115
+MATERIAL_TYPES = ("lambert", "metal", "dielectric", "air", "vacuum", "water", "ice", "diamond")
+LAMBERT, METAL, DIELECTRIC, AIR, VACUUM, WATER, ICE, DIAMOND = range(8)
+
+# src/scene.cpp:546-556
+_DEFAULT_REFLECTIVITY = {
+    METAL: 0.8, DIELECTRIC: 1.52, AIR: 1.000293, VACUUM: 1.0, ICE: 1.31, WATER: 1.333,
+}
+
+# muu vector constants reachable through the loader's aliases (src/scene.cpp:113-144);
+# right-handed, forward = -Z (UNVERIFIED against muu, consistent with scenes/basic.toml)
+_VECTOR_ALIASES = {
+    "origin": (0, 0, 0), "zero": (0, 0, 0), "one": (1, 1, 1),
+    "forward": (0, 0, -1), "back": (0, 0, 1), "backward": (0, 0, 1),
+    "up": (0, 1, 0), "down": (0, -1, 0), "left": (-1, 0, 0), "right": (1, 0, 0),
+    "x": (1, 0, 0), "x_axis": (1, 0, 0), "y": (0, 1, 0), "y_axis": (0, 1, 0),
+    "z": (0, 0, 1), "z_axis": (0, 0, 1),
+}
+
+MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("albedo", "<f4", (4,)), ("roughness", "<f4"), ("reflectivity", "<f4")])
+assert MATERIAL_DTYPE.itemsize == 28
+
+
+class SceneError(RuntimeError):
+    """Mirrors the std::runtime_error thrown by the reference loader."""
+
+
+def named_colour(name: str) -> tuple[float, float, float, float]:
+    """colours::<name> as the reference constructs it: `colour{uint32}` -> to_component_value(int)
+    clamps the *byte value* to [0,1] (src/colour.hpp:72-98), i.e. byte != 0 -> 1.0."""
+    try:
+        rgb = NAMED_COLOURS[name]
+    except KeyError:
+        raise SceneError(f"unknown colour alias '{name}'") from None
+    comps = ((rgb >> 16) & 0xFF, (rgb >> 8) & 0xFF, rgb & 0xFF, 0xFF)
+    return tuple(min(max(float(c), 0.0), 1.0) for c in comps)  # type: ignore[return-value]
+
+
+def _finite_float(node: Any, what: str) -> float:
+    if isinstance(node, bool) or not isinstance(node, (int, float)):
+        raise SceneError(f"No mapping from TOML {type(node).__name__} to float ({what})")
+    v = float(node)
+    if math.isnan(v) or math.isinf(v):
+        raise SceneError("Infinities and NaNs are not allowed.")
+    return float(np.float32(v))
+
+
+def _vector(node: Any, default: Sequence[float], what: str) -> tuple[float, ...]:
+    """src/scene.cpp:113-166"""
+    n = len(default)
+    if node is None:
+        return tuple(float(x) for x in default)
+    if isinstance(node, str):
+        if node not in _VECTOR_ALIASES:
+            raise SceneError(f"unknown vector alias '{node}'")
+        return tuple(float(x) for x in _VECTOR_ALIASES[node][:n])
+    if isinstance(node, (int, float)) and not isinstance(node, bool):
+        return tuple(float(np.float32(node)) for _ in range(n))  # scalar broadcast (no NaN check, :146-157)
+    if not isinstance(node, list) or len(node) > n:
+        raise SceneError(f"No mapping from TOML {type(node).__name__} to vector<float, {n}> ({what})")
+    out = [float(x) for x in default]
+    for i, c in enumerate(node):
+        out[i] = _finite_float(c, what)
+    return tuple(out)
+
+
+def _colour(node: Any, default: tuple[float, float, float, float]) -> tuple[float, float, float, float]:
+    """src/scene.cpp:184-356"""
+    if node is None:
+        return default
+    if isinstance(node, str):
+        return named_colour(node)
+    if not isinstance(node, list) or len(node) > 4:
+        raise SceneError(f"No mapping from TOML {type(node).__name__} to colour")
+    out = [0.0, 0.0, 0.0, 0.0]
+    for i, c in enumerate(node):
+        out[i] = _finite_float(c, "colour")
+    if len(node) < 4:
+        out[3] = 1.0
+    return tuple(out)  # type: ignore[return-value]
+
+
+def _unsigned(node: Any, default: int, what: str) -> int:
+    if node is None:
+        return default
+    if isinstance(node, bool) or not isinstance(node, int):
+        raise SceneError(f"No mapping from TOML {type(node).__name__} to unsigned ({what})")
+    return int(node) & 0xFFFFFFFF  # toml++ value<unsigned>() narrows
+
+
+def _material_type(node: Any) -> int:
+    """src/scene.cpp:381-404 (magic_enum by integer or by name)"""
+    if node is None:
+        return LAMBERT
+    if isinstance(node, bool):
+        raise SceneError("No mapping from TOML boolean to material_type")
+    if isinstance(node, int):
+        if not 0 <= node < len(MATERIAL_TYPES):
+            raise SceneError(f"integer value {node} was not a member of enum material_type")
+        return node
+    if isinstance(node, str):
+        if node not in MATERIAL_TYPES:
+            raise SceneError(f"string value '{node}' was not a member of enum material_type")
+        return MATERIAL_TYPES.index(node)
+    raise SceneError(f"No mapping from TOML {type(node).__name__} to material_type")
+
+
+def _table_array(cfg: dict, key: str) -> list:
+    node = cfg.get(key)
+    if node is None:
+        return []
+    if not isinstance(node, list):
+        raise SceneError(f"expected array at key '{key}', got {type(node).__name__}")
+    return node
+
+
+def _f32(x: float) -> np.float32:
+    return np.float32(x)
+
+
+@dataclasses.dataclass
+class Camera:
+    """rt::camera (src/camera.hpp:51-138): vfov pi/4, near 0.01, far 1000 are fixed (private, no setter)."""
+    position: tuple[float, float, float] = (0.0, 1.0, 0.0)
+    direction: tuple[float, float, float] = (0.0, 0.0, -1.0)
+    vfov: float = math.pi / 4
+    near: float = 0.01
+    far: float = 1000.0
+
+
+@dataclasses.dataclass
+class Scene:
+    """rt::scene (src/scene.hpp:8-25) with the soagen tables as numpy columns (src/soa.toml)."""
+    samples_per_pixel: int = 30
+    max_bounces: int = 10
+    path: str = ""
+    camera: Camera = dataclasses.field(default_factory=Camera)
+    materials: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, MATERIAL_DTYPE))
+    material_names: list = dataclasses.field(default_factory=list)
+    spheres: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros((0, 4), np.float32))  # spheres.value()
+    sphere_material: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.uint32))
+    planes: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros((0, 4), np.float32))  # planes.value()
+    plane_material: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.uint32))
+    boxes: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros((0, 6), np.float32))  # centre, extents
+    box_material: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.uint32))
+
+    def validate(self) -> None:
+        if len(self.materials) == 0:
+            raise SceneError("scene has no materials")
+        for name, col in (("sphere", self.sphere_material), ("plane", self.plane_material)):
+            if len(col) and int(col.max()) >= len(self.materials):
+                raise SceneError(f"{name} material index {int(col.max())} out-of-range")
+
+
+def make_materials(rows: Sequence[tuple]) -> np.ndarray:
+    """rows of (type, albedo rgba, roughness, reflectivity)"""
+    m = np.zeros(len(rows), MATERIAL_DTYPE)
+    for i, (t, albedo, rough, refl) in enumerate(rows):
+        a = list(albedo) + [1.0] * (4 - len(albedo))
+        m[i] = (t, a, rough, refl)
+    return m
+
+
+def loads(text: str, path: str = "") -> Scene:
+    """scene::load on TOML text (src/scene.cpp:527-618)."""
+    try:
+        cfg = tomllib.loads(text)
+    except tomllib.TOMLDecodeError as e:
+        raise SceneError(f"TOML parse error: {e}") from None
+
+    s = Scene(path=path)
+    s.samples_per_pixel = min(max(_unsigned(cfg.get("samples_per_pixel"), 30, "samples_per_pixel"), 1), 1000)
+    s.max_bounces = min(max(_unsigned(cfg.get("max_bounces"), 10, "max_bounces"), 1), 1000)
+
+    cam = cfg.get("camera")
+    if cam is not None:
+        if not isinstance(cam, dict):
+            raise SceneError(f"expected table at key 'camera', got {type(cam).__name__}")
+        s.camera = Camera(position=_vector(cam.get("position"), (0, 1, 0), "camera.position"),
+                          direction=_vector(cam.get("direction"), (0, 0, -1), "camera.direction"))
+
+    rows, names = [], []
+    for tbl in _table_array(cfg, "materials"):
+        t = _material_type(tbl.get("type"))
+        refl_default = _DEFAULT_REFLECTIVITY.get(t, 0.5)
+        name = tbl.get("name", "")
+        if not isinstance(name, str):
+            raise SceneError("No mapping from TOML value to string (name)")
+        albedo = _colour(tbl.get("albedo"), named_colour("fuchsia"))
+        rough = _finite_float(tbl["roughness"], "roughness") if "roughness" in tbl else (0.0 if t == DIELECTRIC else 0.5)
+        refl = _finite_float(tbl["reflectivity"], "reflectivity") if "reflectivity" in tbl else refl_default
+        rows.append((t, albedo, rough, refl))
+        names.append(name)
+    if not rows:  # src/scene.cpp:565-566
+        rows.append((LAMBERT, named_colour("fuchsia"), 0.05, 0.5))
+        names.append("")
+    s.materials = make_materials(rows)
+    s.material_names = names
+
+    def material_of(tbl: dict) -> int:
+        m = _unsigned(tbl.get("material"), 0, "material")
+        if m >= len(rows):
+            raise SceneError(f"material index {m} out-of-range")
+        return m
+
+    planes, plane_mat = [], []
+    for tbl in _table_array(cfg, "planes"):
+        pos = np.array(_vector(tbl.get("position"), (0, 0, 0), "plane.position"), np.float32)
+        n = np.array(_vector(tbl.get("normal"), (0, 1, 0), "plane.normal"), np.float32)
+        n = (n * (_f32(1.0) / np.sqrt(np.dot(n, n), dtype=np.float32))).astype(np.float32)
+        d = -np.float32(np.dot(n, pos))  # muu plane{position, normal}: dot(n, p) + d == 0 (UNVERIFIED)
+        planes.append((n[0], n[1], n[2], d))
+        plane_mat.append(material_of(tbl))
+
+    spheres, sphere_mat = [], []
+    for tbl in _table_array(cfg, "spheres"):
+        pos = _vector(tbl.get("position"), (0, 1, -3), "sphere.position")
+        radius = _finite_float(tbl["radius"], "radius") if "radius" in tbl else 0.5
+        spheres.append((*pos, radius))
+        sphere_mat.append(material_of(tbl))
+
+    boxes, box_mat = [], []
+    for tbl in _table_array(cfg, "boxes"):
+        pos = _vector(tbl.get("position"), (0, 1, -3), "box.position")
+        ext = _vector(tbl.get("extents"), (0.5, 0.5, 0.5), "box.extents")
+        boxes.append((*pos, *ext))
+        box_mat.append(material_of(tbl))
+
+    s.planes = np.array(planes, np.float32).reshape(-1, 4)
+    s.plane_material = np.array(plane_mat, np.uint32)
+    s.spheres = np.array(spheres, np.float32).reshape(-1, 4)
+    s.sphere_material = np.array(sphere_mat, np.uint32)
+    s.boxes = np.array(boxes, np.float32).reshape(-1, 6)
+    s.box_material = np.array(box_mat, np.uint32)
+    return s
+
+
+_SEARCH_PREFIXES = ("scenes/", "../scenes/", "../../scenes/", "", "../", "../../")  # src/scene.cpp:479-480
+
+
+def load(path: str | pathlib.Path) -> Scene:
+    """scene::load(file) including the relative-path search (src/scene.cpp:483-525)."""
+    if not str(path):
+        raise SceneError("no scene file path provided")
+    p = pathlib.Path(path)
+    found = None
+    if not p.is_absolute():
+        for root in _SEARCH_PREFIXES:
+            q = pathlib.Path(root) / p if root else p
+            if q.is_file():
+                found = q
+                break
+    elif p.is_file():
+        found = p
+    if found is None:
+        raise SceneError(f"scene path '{p}' did not exist or was not a file")
+    return loads(found.read_text(), str(found))
+
+
+def dumps(s: Scene) -> str:
+    """Emit a scene as TOML the reference loader accepts (albedos as float arrays, types by name)."""
+    def fl(x: float) -> str:
+        r = repr(float(np.float32(x)))
+        return r if any(c in r for c in ".en") else r + ".0"
+
+    def vec(v: Sequence[float]) -> str:
+        return "[" + ", ".join(fl(x) for x in v) + "]"
+
+    out = [f"samples_per_pixel = {s.samples_per_pixel}", f"max_bounces = {s.max_bounces}", "",
+           f"camera = {{ position = {vec(s.camera.position)}, direction = {vec(s.camera.direction)} }}", "", "materials = ["]
+    for m in s.materials:
+        out.append(f"    {{ type = '{MATERIAL_TYPES[int(m['type'])]}', albedo = {vec(m['albedo'])}, "
+                   f"roughness = {fl(m['roughness'])}, reflectivity = {fl(m['reflectivity'])} }},")
+    out += ["]", "", "spheres = ["]
+    for sp, mat in zip(s.spheres, s.sphere_material):
+        out.append(f"    {{ material = {int(mat)}, position = {vec(sp[:3])}, radius = {fl(sp[3])} }},")
+    out += ["]", ""]
+    if len(s.planes):
+        out.append("planes = [")
+        for pl, mat in zip(s.planes, s.plane_material):
+            n = pl[:3].astype(np.float64)
+            pos = -float(pl[3]) * n  # a point on the plane
+            out.append(f"    {{ material = {int(mat)}, position = {vec(pos)}, normal = {vec(pl[:3])} }},")
+        out += ["]", ""]
+    return "\n".join(out)
