@@ -131,7 +131,8 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
 
 /* ---- device-resident variants (no host copies) for multi-GPU composition and benchmarking.
  * d_accum: width*height float4 on ctx's device.  accumulate != 0 adds onto the existing contents.
- * stream: a cudaStream_t (0 = the context's own stream). */
+ * stream: a cudaStream_t, passed through (NULL = CUDA's default stream, which is what torch's current
+ * stream usually is); the call is asynchronous, rtcu_get_stats() synchronises that stream to read counters. */
 int rtcu_render_device(rtcu_ctx* ctx, const rtcu_view* view, float* d_accum, int accumulate, void* stream);
 /* resolve: divide by samples_per_pixel, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200) */
 int rtcu_resolve_device(rtcu_ctx* ctx, const float* d_accum, uint32_t width, uint32_t height,
@@ -165,6 +166,10 @@ int rtcu_scatter_batch(rtcu_ctx* ctx, uint32_t material_mode, uint64_t seed, uin
 int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t key, uint32_t* out);
 
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out);
+
+/* ---- roofline calibration: achieved non-tensor FP32 TFLOP/s of an FFMA stream and of a packed FFMA2
+ * (fma.rn.f32x2) stream on ctx's device at the clocks it currently runs (no memory traffic). */
+int rtcu_measure_fp32_peak(rtcu_ctx* ctx, float* tflops_ffma, float* tflops_ffma2);
 
 #ifdef __cplusplus
 }

@@ -141,49 +141,51 @@ __global__ void __launch_bounds__(MEGA_THREADS) k_render_mega(const SceneDev sc,
     const bool in_tile = px < p.tile_x1 && py < p.tile_y1;
 
     unsigned long long segs = 0;
-    if (in_tile && p.sample_begin < p.sample_end)
+    if (in_tile)
     {
         RngKey key;
         key.key = p.key;
         key.pixel = py * p.width + px;
         key.sample = p.sample_begin;
-
         V3 sum = v3(0.0f, 0.0f, 0.0f);
-        V3 thr = v3(1.0f, 1.0f, 1.0f);
-        uint32_t seg = 0;
-        Ray ray = generate(p.cam, key, px, py);
 
-        for (;;)
+        if (p.sample_begin < p.sample_end)
         {
-            segs++;
-            const Hit h = closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
-            bool ended;
-            if (h.prim == RTCU_PRIM_MISS)
+            V3 thr = v3(1.0f, 1.0f, 1.0f);
+            uint32_t seg = 0;
+            Ray ray = generate(p.cam, key, px, py);
+            for (;;)
             {
-                sum = v3_add(sum, v3_mul(thr, sky(ray.d))); // S12: iterative throughput
-                ended = true;
-            }
-            else
-            {
-                const V3 n = hit_normal(s_sph, s_pl, ray, h);
-                const MatRec m = load_material(sc, hit_material(sc, h));
-                const uint4 rnd = rng_block(key, seg + 1u, 0u);
-                Ray next;
-                const bool scattered = scatter(scatter_kind(p.mode, m.type), m, ray, h.t, n, key, seg + 1u, rnd, next);
-                thr = v3_mul(thr, v3(m.att_r, m.att_g, m.att_b));
-                ray = next;
-                seg++;
-                // absorbed (:173) or bounce budget exhausted (:157-158): radiance 0
-                ended = !scattered || seg >= p.max_bounces;
-            }
-            if (ended)
-            {
-                key.sample++;
-                if (key.sample >= p.sample_end)
-                    break;
-                seg = 0;
-                thr = v3(1.0f, 1.0f, 1.0f);
-                ray = generate(p.cam, key, px, py);
+                segs++;
+                const Hit h = closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
+                bool ended;
+                if (h.prim == RTCU_PRIM_MISS)
+                {
+                    sum = v3_add(sum, v3_mul(thr, sky(ray.d))); // S12: iterative throughput
+                    ended = true;
+                }
+                else
+                {
+                    const V3 n = hit_normal(s_sph, s_pl, ray, h);
+                    const MatRec m = load_material(sc, hit_material(sc, h));
+                    const uint4 rnd = rng_block(key, seg + 1u, 0u);
+                    Ray next;
+                    const bool scattered = scatter(scatter_kind(p.mode, m.type), m, ray, h.t, n, key, seg + 1u, rnd, next);
+                    thr = v3_mul(thr, v3(m.att_r, m.att_g, m.att_b));
+                    ray = next;
+                    seg++;
+                    // absorbed (:173) or bounce budget exhausted (:157-158): radiance 0
+                    ended = !scattered || seg >= p.max_bounces;
+                }
+                if (ended)
+                {
+                    key.sample++;
+                    if (key.sample >= p.sample_end)
+                        break;
+                    seg = 0;
+                    thr = v3(1.0f, 1.0f, 1.0f);
+                    ray = generate(p.cam, key, px, py);
+                }
             }
         }
 
@@ -319,6 +321,41 @@ __global__ void k_philox_batch(const uint4* __restrict__ ctr, uint32_t n, uint2 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
         out[i] = philox4x32_10(ctr[i], key);
+}
+
+
+// ---- FP32 peak calibration: dependent-chain-free FFMA / FFMA2 streams, 16 independent accumulators per
+// thread, no memory traffic.  Used by bench.py to report the roofline denominator at the clocks actually seen.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) k_fp32_peak(float* __restrict__ out, int iters, float a, float b)
+{
+    float2 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        acc[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-4f - i);
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int it = 0; it < iters; it++)
+    {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                if (PACKED)
+                    acc[i] = __ffma2_rn(acc[i], a2, b2);
+                else
+                {
+                    acc[i].x = __fmaf_rn(acc[i].x, a, b);
+                    acc[i].y = __fmaf_rn(acc[i].y, a, b);
+                }
+            }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        s += acc[i].x + acc[i].y;
+    if (s == 123.456f) // never true; keeps the chain alive
+        out[0] = s;
 }
 
 } // namespace rtcu_dev

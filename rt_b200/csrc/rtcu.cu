@@ -119,6 +119,8 @@ struct rtcu_ctx {
     DevBuf<unsigned char> scratch;
 
     rtcu_stats stats = {};
+    cudaStream_t last_stream = nullptr; // stream of the last rtcu_render_device call
+    bool counters_pending = false;      // its counters have not been read back yet
 };
 
 namespace {
@@ -389,7 +391,9 @@ int rtcu_render_device(rtcu_ctx* ctx, const rtcu_view* view, float* d_accum, int
 {
     if (!ctx || !view || !d_accum) return fail(RTCU_ERR_INVALID, "null argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)stream; // passed through: NULL is CUDA's default stream, as torch uses it
+    ctx->last_stream = st;
+    ctx->counters_pending = true;
     return launch_render(ctx, view, reinterpret_cast<float4*>(d_accum), nullptr, accumulate, st);
 }
 
@@ -397,7 +401,7 @@ int rtcu_resolve_device(rtcu_ctx* ctx, const float* d_accum, uint32_t width, uin
 {
     if (!ctx || !d_accum || !d_rgba8 || !width || !height || !spp) return fail(RTCU_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     const uint32_t n = width * height;
     k_resolve<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(d_accum), n, (float)spp, d_rgba8);
     CU(cudaGetLastError());
@@ -677,9 +681,47 @@ int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t k
     return RTCU_OK;
 }
 
+int rtcu_measure_fp32_peak(rtcu_ctx* ctx, float* tflops_ffma, float* tflops_ffma2)
+{
+    if (!ctx || !tflops_ffma || !tflops_ffma2) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->scratch.reserve(256));
+    const int iters = 4096, blocks = ctx->sm_count * 8;
+    const double flop = (double)blocks * 256 * iters * 4 * 8 * 2 /*lanes of float2*/ * 2 /*fma*/;
+    float* results[2] = { tflops_ffma, tflops_ffma2 };
+    for (int variant = 0; variant < 2; variant++)
+    {
+        float best = 0.0f;
+        for (int rep = 0; rep < 4; rep++) // rep 0 warms up
+        {
+            CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+            if (variant == 0)
+                k_fp32_peak<false><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<float*>(ctx->scratch.p), iters, 0.999f, 0.001f);
+            else
+                k_fp32_peak<true><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<float*>(ctx->scratch.p), iters, 0.999f, 0.001f);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float ms = 0.0f;
+            CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+            const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+            if (rep > 0 && tf > best) best = tf;
+        }
+        *results[variant] = best;
+    }
+    return RTCU_OK;
+}
+
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out)
 {
     if (!ctx || !out) return fail(RTCU_ERR_INVALID, "null argument");
+    if (ctx->counters_pending)
+    {
+        CU(cudaSetDevice(ctx->device));
+        const int rc = fetch_counters(ctx, ctx->last_stream);
+        if (rc) return rc;
+        ctx->counters_pending = false;
+    }
     *out = ctx->stats;
     return RTCU_OK;
 }

@@ -207,6 +207,12 @@ class Context:
         nat.check(self._lib.rtcu_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def measure_fp32_peak(self) -> tuple[float, float]:
+        """(FFMA TFLOP/s, FFMA2 TFLOP/s) achieved by a register-only stream on this device right now."""
+        a, b = C.c_float(0), C.c_float(0)
+        nat.check(self._lib.rtcu_measure_fp32_peak(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     # -- step-wise parity entry points -------------------------------------------------------------
     def intersect_batch(self, o: np.ndarray, d: np.ndarray, accel: int = nat.ACCEL_AUTO, want_normal: bool = True):
         o = nat.contiguous(o, np.float32).reshape(-1, 3)

@@ -1,0 +1,136 @@
+"""The C-ABI library loads and exports every symbol include/rtcu.h declares; host-side mirrors of the
+reference interface (renderer registry, image_view, views, partitioning) behave like the reference's.
+No compute is launched here (these run without a GPU)."""
+import ctypes
+import pathlib
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from rt_b200 import _native as nat, build, dist, renderer as R, scene as S
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_cuda()
+    return nat.load_library()
+
+
+def test_header_symbols_are_all_exported(lib):
+    header = (ROOT / "include" / "rtcu.h").read_text()
+    declared = set(re.findall(r"\b(rtcu_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(nat.EXPORTS), declared ^ set(nat.EXPORTS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(nat.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (rtcu_[a-z0-9_]+)", nm))
+    assert declared <= exported, declared - exported
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(nat.Material) == 28
+    assert ctypes.sizeof(nat.View) == 64 + 4 * 10 + 8 + 8
+    assert nat.View.seed.offset == 104 and nat.View.material_mode.offset == 112
+    assert ctypes.sizeof(nat.SceneDesc) == 64
+    assert ctypes.sizeof(nat.Stats) == 64
+    assert S.MATERIAL_DTYPE.itemsize == ctypes.sizeof(nat.Material)
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", str(nat.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_abi_version_and_threshold(lib):
+    assert lib.rtcu_abi_version() == 1
+    assert lib.rtcu_bvh_threshold() > 0
+
+
+def test_null_arguments_are_rejected_without_a_device(lib):
+    # argument validation happens before any CUDA call
+    assert lib.rtcu_upload_scene(None, None) == nat.RTCU_ERR_INVALID
+    assert lib.rtcu_render(None, None, None, None) == nat.RTCU_ERR_INVALID
+    assert lib.rtcu_get_stats(None, None) == nat.RTCU_ERR_INVALID
+    assert b"null" in lib.rtcu_last_error()
+    lib.rtcu_destroy(None)  # no-op
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    if lib.rtcu_device_count() > 0:
+        pytest.skip("a device is present; the failure path is covered on CPU-only hosts")
+    assert not lib.rtcu_create(0)
+    assert b"no CPU fallback" in lib.rtcu_last_error()
+    with pytest.raises(nat.RtcuError):
+        R.Context(0)
+
+
+def test_registry_semantics():
+    reg = R._Registry()
+
+    class a(R.RendererInterface):
+        pass
+
+    class b(R.RendererInterface):
+        pass
+
+    reg.install(R.Description("k1", "alpha", a))
+    reg.install(R.Description("k2", "beta", b))
+    reg.install(R.Description("k1", "alpha2", b))  # same key overwrites in place (renderer.cpp:27-34)
+    assert [d.name for d in reg.all()] == ["alpha2", "beta"]
+    assert reg.find_by_key("k2").create is b and reg.find_by_key("") is None and reg.find_by_name("nope") is None
+    assert reg.find("be").name == "beta"  # prefix match like main.cpp:68-81
+    # the plugin registers under its type name
+    assert R.renderers.find_by_name("cuda_path_tracer") is not None
+    assert R.renderers.find("cuda").create is R.cuda_path_tracer
+
+
+def test_image_view():
+    img = R.ImageView.allocate(5, 3)
+    assert img.size() == (5, 3) and img.position_of(7) == (2, 1)
+    img.clear(0x000000FF)
+    assert img(4, 2) == 0xFF
+    with pytest.raises(ValueError):
+        R.ImageView(np.zeros((3, 5), np.float32))
+
+
+def test_make_view_defaults_follow_the_scene():
+    sc = S.load("scenes/dielectric.toml")
+    v = R.make_view(sc, 320, 200)
+    assert (v.samples_per_pixel, v.max_bounces) == (200, 10)
+    assert (v.sample_begin, v.sample_end) == (0, 200)
+    assert (v.tile_x0, v.tile_y0, v.tile_x1, v.tile_y1) == (0, 0, 320, 200)
+    assert v.seed == R.DEFAULT_SEED and v.material_mode == nat.MODE_SM
+    m = np.array(list(v.inv_view_proj), np.float32).reshape(4, 4).T  # column-major -> matrix
+    # the image centre at depth 0 unprojects onto the near plane in front of the camera
+    p = m @ np.array([0, 0, 0, 1], np.float32)
+    np.testing.assert_allclose(p[:3] / p[3], [0, 1, 7 - 0.01], atol=1e-4)
+    p = m @ np.array([0, 0, 1, 1], np.float32)
+    np.testing.assert_allclose(p[:3] / p[3], [0, 1, 7 - 1000], rtol=1e-3)
+
+
+def test_sample_range_partition_is_exact_cover():
+    for total, world in ((64, 1), (64, 8), (4096, 8), (7, 3), (3, 8)):
+        ranges = [dist.sample_range_for_rank(5, 5 + total, r, world) for r in range(world)]
+        assert ranges[0][0] == 5 and ranges[-1][1] == 5 + total
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        assert max(e - b for b, e in ranges) - min(e - b for b, e in ranges) <= 1
+    sc = S.load("scenes/basic.toml")
+    v = R.make_view(sc, 64, 48, samples_per_pixel=64)
+    parts = [dist.partition_view(v, r, 4) for r in range(4)]
+    assert [(p.sample_begin, p.sample_end) for p in parts] == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    assert all(p.samples_per_pixel == 64 and p.seed == v.seed for p in parts) and (v.sample_begin, v.sample_end) == (0, 64)
+    rows = [dist.partition_view(v, r, 4, by="rows") for r in range(4)]
+    assert [(p.tile_y0, p.tile_y1) for p in rows] == [(0, 12), (12, 24), (24, 36), (36, 48)]
+
+
+def test_scene_fingerprint_detects_changes():
+    a = S.load("scenes/basic.toml")
+    b = S.load("scenes/basic.toml")
+    assert R.scene_fingerprint(a) == R.scene_fingerprint(b)
+    b.spheres[1, 0] += 0.25
+    assert R.scene_fingerprint(a) != R.scene_fingerprint(b)

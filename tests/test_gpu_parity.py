@@ -1,0 +1,279 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden fixtures.
+
+Bars (BASELINE.json north_star): hit/miss flags and closest-hit primitive indices bit-exact, hit t within
+4 ulp (we observe and require 0: both sides implement the same numbered IEEE spec), images within a stated
+RMSE at equal spp with the same RNG streams.  Image tolerance: the paths are bit-identical (asserted through the
+exact segment count); only the radiance product differs -- the oracle nests it right-to-left like the reference's
+recursion (mg_ray_tracer.cpp:171), the kernel folds it left-to-right -- so the fp32 sums agree to ~1e-6 relative
+and the packed RGBA8 image may differ by 1 LSB in isolated pixels.  Stated bounds: accum rtol 2e-5, RGBA8
+max |diff| <= 1 on <= 0.5 % of channel values, RMSE on the sqrt-encoded [0,1] image <= 1e-4.
+"""
+import numpy as np
+import pytest
+
+from rt_b200 import _native as nat, scene as S, synth
+from rt_b200.renderer import ImageView, cuda_path_tracer, make_view
+
+from conftest import GOLDEN, ulp_diff, unpack_rgba
+
+pytestmark = pytest.mark.gpu
+
+ACCUM_RTOL = 2e-5
+RMSE_BOUND = 1e-4
+
+
+def assert_images_match(rgba_gpu, accum_gpu, rgba_ref, accum_ref, spp):
+    np.testing.assert_array_equal(accum_gpu[..., 3], accum_ref[..., 3])
+    np.testing.assert_allclose(accum_gpu[..., :3], accum_ref[..., :3], rtol=ACCUM_RTOL, atol=1e-6)
+    d = np.abs(unpack_rgba(rgba_gpu) - unpack_rgba(rgba_ref))
+    assert d.max() <= 1, f"RGBA8 differs by {d.max()} LSB"
+    assert (d > 0).mean() <= 0.005, f"{(d > 0).mean():.4%} of channel values differ"
+    enc = lambda a: np.sqrt(np.clip(a[..., :3] / spp, 0, 1))
+    rmse = float(np.sqrt(np.mean((enc(accum_gpu) - enc(accum_ref)) ** 2)))
+    assert rmse <= RMSE_BOUND, rmse
+
+
+# ---- level 0: RNG -------------------------------------------------------------------------------------
+def test_philox_matches_published_vectors_and_oracle(ctx, oracle):
+    from test_oracle_kat import PHILOX_KAT
+
+    for ctr, key, expect in PHILOX_KAT:
+        out = ctx.philox_batch(np.array([ctr], np.uint32), key[0] | (key[1] << 32))
+        assert tuple(int(x) for x in out[0]) == expect
+    rng = np.random.default_rng(3)
+    ctr = rng.integers(0, 2 ** 32, (4096, 4), dtype=np.uint64).astype(np.uint32)
+    out = ctx.philox_batch(ctr, 0x0123456789ABCDEF)
+    for i in range(0, 4096, 97):
+        np.testing.assert_array_equal(out[i], oracle.philox(ctr[i], 0x0123456789ABCDEF))
+
+
+# ---- level 1: closest hit on fixed ray batches ------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "planes"])
+def test_intersect_golden_batches(ctx, scenes, name):
+    g = np.load(GOLDEN / f"rays_{name}.npz")
+    ctx.upload_scene(scenes[name][0])
+    hit, prim, t, nrm = ctx.intersect_batch(g["o"], g["d"], accel=nat.ACCEL_LINEAR)
+    np.testing.assert_array_equal(hit, g["hit"])
+    np.testing.assert_array_equal(prim, g["prim"])
+    assert ulp_diff(t, g["t"]).max() == 0
+    np.testing.assert_array_equal(nrm, g["normal"])
+
+
+@pytest.mark.parametrize("name,n", [("c1", 1 << 20), ("c2", 1 << 20), ("c3", 1 << 18), ("planes", 1 << 18)])
+def test_intersect_large_seeded_batches_vs_oracle(ctx, oracle, scenes, name, n):
+    sc = scenes[name][0]
+    o, d = synth.random_rays(sc, n, seed=11)
+    ctx.upload_scene(sc)
+    hit, prim, t, nrm = ctx.intersect_batch(o, d, accel=nat.ACCEL_LINEAR)
+    rh, rp, rt, rn = oracle.intersect_batch(sc, o, d)
+    np.testing.assert_array_equal(hit, rh)
+    np.testing.assert_array_equal(prim, rp)
+    assert ulp_diff(t, rt).max() <= 4
+    assert ulp_diff(t, rt).max() == 0
+    np.testing.assert_array_equal(nrm, rn)
+    assert 0.2 < hit.mean() < 0.95
+
+
+def test_intersect_edge_cases(ctx, oracle):
+    from test_oracle_kat import _scene
+
+    # empty scene, ragged batch sizes (not a multiple of the block), n = 0
+    ctx.upload_scene(_scene([]))
+    hit, prim, t, _ = ctx.intersect_batch(np.zeros((5, 3), np.float32), np.tile(np.float32([0, 0, -1]), (5, 1)))
+    assert not hit.any() and (prim == nat.PRIM_MISS).all() and (t == -1).all()
+    hit, prim, t, _ = ctx.intersect_batch(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert len(hit) == 0
+    # ties, inside / behind / tangent cases: identical to the oracle
+    sc = _scene([(0, 0, -5, 1), (0, 0, -5, 1), (0, 0, -9, 1), (0, 0, 0, 2), (0, 0.5, 0, 0.5)], planes=[(0, 1, 0, 3), (0, 1, 0, 3)])
+    ctx.upload_scene(sc)
+    o = np.float32([(0, 0, 0), (0, 0, 0), (0, 1, 3), (0, 0, 10), (0, 0, 2.0001), (0, 20, 0), (1, 1, 1)])
+    d = np.float32([(0, 0, -1), (1, 0, 0), (0, 0, -1), (0, 0, 1), (0, 0, -1), (0, -1, 0), (0, -1, 0)])
+    got = ctx.intersect_batch(o, d)
+    ref = oracle.intersect_batch(sc, o, d)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_many_spheres_fall_back_to_global_memory_scan(ctx, oracle):
+    # more primitives than the shared-memory staging budget (200 KB / 16 B): the unstaged kernel variant
+    sc = synth.grid_scene(nx=130, nz=100, seed=5)
+    assert len(sc.spheres) * 16 > 200 * 1024
+    o, d = synth.random_rays(sc, 2048, seed=5, spread=30.0)
+    ctx.upload_scene(sc)
+    got = ctx.intersect_batch(o, d, accel=nat.ACCEL_LINEAR)
+    ref = oracle.intersect_batch(sc, o, d)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
+
+
+# ---- level 1b: primary rays and scatter events, bit-exact --------------------------------------------------
+def test_primary_rays_bit_exact(ctx, oracle, scenes):
+    sc = scenes["c2"][0]
+    v = make_view(sc, 1920, 1080, samples_per_pixel=64, max_bounces=50)
+    rng = np.random.default_rng(5)
+    n = 3000
+    px = rng.integers(0, 1920, n); py = rng.integers(0, 1080, n); smp = rng.integers(0, 64, n)
+    smp[:200] = 0  # pixel-centre rule
+    o, d = ctx.primary_rays(v, px, py, smp)
+    ro, rd = oracle.primary_rays(v, px, py, smp)
+    np.testing.assert_array_equal(o, ro)
+    np.testing.assert_array_equal(d, rd)
+
+
+@pytest.mark.parametrize("mode", [nat.MODE_MG, nat.MODE_SM])
+def test_scatter_bit_exact(ctx, oracle, scenes, mode):
+    sc = scenes["c2"][0]
+    ctx.upload_scene(sc)
+    rng = np.random.default_rng(8 + mode)
+    n = 4000
+    # realistic inputs: rays that hit something, with the oracle's t / normal / material
+    o, d = synth.random_rays(sc, 4 * n, seed=21)
+    hit, prim, t, nrm = oracle.intersect_batch(sc, o, d)
+    sel = np.flatnonzero(hit)[:n]
+    o, d, t, nrm, prim = o[sel], d[sel], t[sel], nrm[sel], prim[sel]
+    mat = sc.sphere_material[prim]
+    d = (d * rng.uniform(0.5, 2.0, (len(sel), 1))).astype(np.float32)  # dielectric bounces do not renormalise
+    pixel = rng.integers(0, 2 ** 21, len(sel)); smp = rng.integers(0, 64, len(sel)); blk = rng.integers(1, 50, len(sel))
+    s, att, oo, do = ctx.scatter_batch(mode, 0x5EED, mat, o, d, t, nrm, pixel, smp, blk)
+    rs, ratt, roo, rdo = oracle.scatter_batch(sc, mode, 0x5EED, mat, o, d, t, nrm, pixel, smp, blk)
+    np.testing.assert_array_equal(s, rs)
+    np.testing.assert_array_equal(att, ratt)
+    ok = s.astype(bool)
+    np.testing.assert_array_equal(oo[ok], roo[ok])
+    np.testing.assert_array_equal(do[ok], rdo[ok])
+    kinds = {int(k) for k in np.unique(sc.materials["type"][mat])}
+    assert {S.LAMBERT, S.METAL, S.DIELECTRIC} <= kinds
+
+
+# ---- level 2: images --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "planes"])
+@pytest.mark.parametrize("mode", ["mg", "sm"])
+def test_render_matches_golden_images(ctx, scenes, name, mode):
+    g = np.load(GOLDEN / f"image_{name}_{mode}.npz")
+    sc = scenes[name][0]
+    ctx.upload_scene(sc)
+    v = make_view(sc, int(g["width"]), int(g["height"]), samples_per_pixel=int(g["spp"]), max_bounces=int(g["max_bounces"]),
+                  material_mode=int(g["mode"]), seed=int(g["seed"]))
+    rgba8, accum = ctx.render(v, want_accum=True)
+    st = ctx.stats()
+    assert st["segments"] == int(g["segments"])  # identical paths, segment for segment
+    assert st["samples"] == int(g["width"]) * int(g["height"]) * int(g["spp"])
+    assert_images_match(rgba8, accum, g["rgba8"], g["accum"], int(g["spp"]))
+
+
+def test_render_c1_default_frame_vs_oracle(ctx, oracle, scenes):
+    # BASELINE configs[0] at its real size: 800x600, 30 spp, depth 10, mg table
+    sc = scenes["c1"][0]
+    ctx.upload_scene(sc)
+    v = make_view(sc, 800, 600, material_mode=nat.MODE_MG)
+    rgba8, accum = ctx.render(v, want_accum=True)
+    r_rgba8, r_accum, r_segs = oracle.render(sc, v)
+    assert ctx.stats()["segments"] == r_segs
+    assert_images_match(rgba8, accum, r_rgba8, r_accum, 30)
+
+
+def test_render_c2_full_size_properties(ctx, oracle, scenes):
+    # BASELINE configs[1] at full size (1920x1080, 64 spp, depth 50, sm table): size-independent properties
+    sc = scenes["c2"][0]
+    ctx.upload_scene(sc)
+    v = make_view(sc, 1920, 1080, samples_per_pixel=64, max_bounces=50, material_mode=nat.MODE_SM)
+    rgba_a, accum_a = ctx.render(v, want_accum=True)
+    segs_a = ctx.stats()["segments"]
+    rgba_b, accum_b = ctx.render(v, want_accum=True)
+    # (1) deterministic: bit-identical repeat, identical segment count
+    np.testing.assert_array_equal(accum_a, accum_b)
+    np.testing.assert_array_equal(rgba_a, rgba_b)
+    assert ctx.stats()["segments"] == segs_a
+    assert (accum_a[..., 3] == 64).all() and np.isfinite(accum_a).all() and ((rgba_a & 0xFF) == 0xFF).all()
+    # (2) tiles compose exactly: a tile render equals the same pixels of the full frame
+    vt = make_view(sc, 1920, 1080, samples_per_pixel=64, max_bounces=50, material_mode=nat.MODE_SM, tile=(1000, 500, 1100, 540))
+    rgba_t, accum_t = ctx.render(vt, want_accum=True)
+    np.testing.assert_array_equal(accum_t[500:540, 1000:1100], accum_a[500:540, 1000:1100])
+    np.testing.assert_array_equal(rgba_t[500:540, 1000:1100], rgba_a[500:540, 1000:1100])
+    assert (rgba_t[:500] == 0).all()
+    # (3) a strided row subset against the oracle at the full spp / depth
+    r_rgba8, r_accum, r_segs = oracle.render(sc, v, row_step=90)
+    rows = np.arange(0, 1080, 90)
+    assert_images_match(rgba_a[rows], accum_a[rows], r_rgba8[rows], r_accum[rows], 64)
+    # (4) every sample is bounded by the brightest possible radiance (attenuations > 1 exist: IOR quirk)
+    assert accum_a[..., :3].min() >= 0
+
+
+def test_sample_ranges_compose(ctx, scenes):
+    sc = scenes["c2"][0]
+    ctx.upload_scene(sc)
+    full = make_view(sc, 160, 90, samples_per_pixel=16, max_bounces=50)
+    _, accum = ctx.render(full, want_accum=True)
+    total = np.zeros_like(accum)
+    segs = 0
+    for b, e in ((0, 5), (5, 6), (6, 16)):
+        v = make_view(sc, 160, 90, samples_per_pixel=16, max_bounces=50, sample_range=(b, e))
+        _, part = ctx.render(v, want_accum=True)
+        assert (part[..., 3] == e - b).all()
+        total += part
+        segs += ctx.stats()["segments"]
+    ctx.render(full, want_rgba8=False, want_accum=False)
+    assert segs == ctx.stats()["segments"]  # same paths, partitioned
+    np.testing.assert_allclose(total, accum, rtol=2e-6, atol=1e-7)  # only the summation order differs
+    # an empty sample range renders nothing
+    v = make_view(sc, 160, 90, samples_per_pixel=16, sample_range=(4, 4))
+    _, part = ctx.render(v, want_accum=True)
+    assert (part == 0).all() and ctx.stats()["segments"] == 0
+
+
+def test_odd_sizes_and_one_pixel(ctx, oracle, scenes):
+    sc = scenes["c1"][0]
+    ctx.upload_scene(sc)
+    for w, h in ((1, 1), (17, 5), (33, 31)):
+        v = make_view(sc, w, h, samples_per_pixel=3, max_bounces=4, material_mode=nat.MODE_MG)
+        rgba8, accum = ctx.render(v, want_accum=True)
+        r_rgba8, r_accum, r_segs = oracle.render(sc, v)
+        assert ctx.stats()["segments"] == r_segs
+        assert_images_match(rgba8, accum, r_rgba8, r_accum, 3)
+
+
+# ---- the boundary: plugin-style calls and error behaviour -------------------------------------------------
+def test_plugin_render_into_image_view(ctx, oracle, scenes):
+    r = cuda_path_tracer(0)
+    r.material_mode = nat.MODE_MG
+    sc = S.load("scenes/basic.toml")
+    sc.samples_per_pixel = 4
+    img = ImageView.allocate(96, 64).clear(0x000000FF)
+    r.render(sc, img)
+    assert r.last_error is None
+    v = make_view(sc, 96, 64, material_mode=nat.MODE_MG)
+    ref, _, _ = oracle.render(sc, v)
+    d = np.abs(unpack_rgba(img.data) - unpack_rgba(ref))
+    assert d.max() <= 1
+    # scene change is detected by content (no dirty flag in the reference, main.cpp:123-125)
+    sc.spheres[1, 1] += 1.0
+    before = img.data.copy()
+    r.render(sc, img)
+    assert (img.data != before).any()
+
+
+def test_plugin_render_is_noexcept_and_leaves_image_black(ctx, capsys):
+    r = cuda_path_tracer(0)
+    sc = S.load("scenes/basic.toml")
+    sc.sphere_material = np.array([0, 1, 9], np.uint32)  # out-of-range material
+    img = ImageView.allocate(32, 16).clear(0x000000FF)
+    r.render(sc, img)  # must not raise
+    assert r.last_error and "out-of-range" in r.last_error
+    assert (img.data == 0x000000FF).all()
+    assert "cuda_path_tracer" in capsys.readouterr().err
+
+
+def test_error_codes(ctx, scenes):
+    from rt_b200.renderer import Context
+
+    fresh = Context(0)
+    v = make_view(scenes["c1"][0], 16, 16)
+    with pytest.raises(nat.RtcuError) as e:
+        fresh.render(v)
+    assert e.value.code == nat.RTCU_ERR_STATE
+    fresh.upload_scene(scenes["c1"][0])
+    for bad in (dict(tile=(4, 4, 4, 8)), dict(tile=(0, 0, 17, 16)), dict(sample_range=(3, 2)), dict(max_bounces=0), dict(samples_per_pixel=0)):
+        with pytest.raises(nat.RtcuError) as e:
+            fresh.render(make_view(scenes["c1"][0], 16, 16, **bad))
+        assert e.value.code == nat.RTCU_ERR_INVALID
+    fresh.close()

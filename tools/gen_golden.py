@@ -1,0 +1,53 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the strict CPU oracle (oracle/rtref.c).
+
+The reference ships no golden vectors, so these fixtures pin the oracle's own
+output: a change to either the oracle or the CUDA path that alters results shows up against them.
+Run from the repo root: `python tools/gen_golden.py`.
+"""
+import pathlib, sys
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle.binding import Oracle  # noqa: E402
+from rt_b200 import scene as S, synth  # noqa: E402
+from rt_b200.renderer import make_view  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+OUT.mkdir(parents=True, exist_ok=True)
+O = Oracle("strict")
+
+
+def planes_scene():
+    s = S.loads("""
+camera = { position = [0, 1.5, 6], direction = [0, -0.1, -1] }
+materials = [ { type = 'lambert', albedo = [0.8, 0.8, 0.2] }, { type = 'metal', albedo = [0.9,0.9,0.9], roughness = 0.1 },
+              { type = 'dielectric', albedo = [0.6, 0.6, 0.6] } ]
+planes = [ { material = 0 }, { material = 1, position = [0, 0, -6], normal = [0, 0, 1] }, { material = 0, position = [0, 0.25, 0] } ]
+spheres = [ { material = 2, position = [0, 1, 0], radius = 1.0 }, { material = 1, position = [2.2, 0.5, 0.5] }, { material = 0, position = [-2, 0.5, 1] } ]
+""")
+    return s
+
+
+SCENES = {
+    "c1": (S.load(ROOT / "scenes" / "basic.toml"), 10),
+    "c2": (S.load(ROOT / "scenes" / "dielectric.toml"), 50),
+    "c3": (synth.rtiow_scene(), 50),
+    "planes": (planes_scene(), 12),
+}
+
+if __name__ == "__main__":
+    for name, (sc, depth) in SCENES.items():
+        o, d = synth.random_rays(sc, 4096, seed=7)
+        hit, prim, t, nrm = O.intersect_batch(sc, o, d)
+        np.savez_compressed(OUT / f"rays_{name}.npz", o=o, d=d, hit=hit, prim=prim, t=t, normal=nrm)
+        print(name, "rays hit fraction", hit.mean())
+        w, h, spp = (64, 48, 8) if name != "c3" else (64, 36, 4)
+        for mode in (0, 1):
+            v = make_view(sc, w, h, samples_per_pixel=spp, max_bounces=depth, material_mode=mode, seed=0x5EED)
+            rgba8, accum, segs = O.render(sc, v, threads=0)
+            np.savez_compressed(OUT / f"image_{name}_{'mg' if mode == 0 else 'sm'}.npz", rgba8=rgba8, accum=accum, segments=np.uint64(segs),
+                                width=w, height=h, spp=spp, max_bounces=depth, mode=mode, seed=np.uint64(0x5EED))
+            print(name, mode, "segments/sample", segs / (w * h * spp))
