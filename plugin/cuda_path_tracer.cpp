@@ -1,0 +1,146 @@
+// cuda_path_tracer.cpp -- renderer plugin for marzer/rt: drop this file into src/renderers/, add it to
+// src/renderers/meson.build next to mg_ray_tracer.cpp, and link librtcu.so.
+//
+// `rt --scene <toml> --renderer cuda_path_tracer` then renders through the B200 library instead of the CPU
+// loops of mg_ray_tracer.cpp:178-205 / sm_ray_tracer.cpp:263-289.  The plugin only flattens rt::scene into
+// the POD descriptor of include/rtcu.h and calls the C ABI; scene.hpp, image.cpp and the window stay untouched.
+//
+// Behaviour at the boundary (reference src/renderer.hpp:9-14, src/main.cpp:315-321):
+//  * render() is noexcept and has no error channel: on failure it logs to stderr and leaves the image as the
+//    caller cleared it (black, main.cpp:318).
+//  * the constructor runs inside create() under main's try/catch (main.cpp:329-379), so it may throw.
+//  * rt::scene has no dirty flag and is replaced wholesale on reload (main.cpp:123-125): the scene columns are
+//    compared by content against the last upload and re-uploaded when they differ.
+//  * RT_CUDA_MATERIAL_MODE=mg selects mg_ray_tracer's scatter table (no dielectric); default is sm_ray_tracer's.
+#ifdef RTCU_PLUGIN_STUB_CHECK
+	#include "rt_stub.hpp" // minimal stand-ins for the accessors used below (compile check without muu)
+#else
+	#include "../scene.hpp"
+	#include "../image.hpp"
+	#include "../colour.hpp"
+	#include "../renderer.hpp"
+MUU_DISABLE_WARNINGS;
+	#include <muu/thread_pool.h>
+MUU_ENABLE_WARNINGS;
+#endif
+
+#include <rtcu.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace rt;
+
+namespace
+{
+	struct cuda_path_tracer final : renderer_interface
+	{
+		rtcu_ctx* ctx_ = nullptr;
+		uint32_t material_mode_ = RTCU_MODE_SM;
+
+		// last uploaded scene columns (content comparison, see header comment)
+		std::vector<float> spheres_, planes_;
+		std::vector<uint32_t> sphere_mat_, plane_mat_;
+		std::vector<rtcu_material> materials_;
+		bool uploaded_ = false;
+
+		cuda_path_tracer()
+		{
+			ctx_ = rtcu_create(0);
+			if (!ctx_)
+				throw std::runtime_error{ std::string{ "cuda_path_tracer: " } + rtcu_last_error() };
+			if (const char* mode = std::getenv("RT_CUDA_MATERIAL_MODE"); mode && std::strcmp(mode, "mg") == 0)
+				material_mode_ = RTCU_MODE_MG;
+		}
+
+		~cuda_path_tracer() noexcept override
+		{
+			rtcu_destroy(ctx_);
+		}
+
+		template <typename T>
+		static bool assign_if_changed(std::vector<T>& cache, const T* src, size_t count)
+		{
+			if (cache.size() == count && (count == 0 || std::memcmp(cache.data(), src, count * sizeof(T)) == 0))
+				return false;
+			cache.assign(src, src + count);
+			return true;
+		}
+
+		bool sync_scene(const rt::scene& scene) noexcept
+		{
+			// spheres.value() is muu::bounding_sphere<float>[] = {center.xyz, radius}: already a float4 array
+			static_assert(sizeof(scene.spheres.value()[0]) == 4 * sizeof(float));
+			static_assert(sizeof(scene.planes.value()[0]) == 4 * sizeof(float));
+
+			bool changed = !uploaded_;
+			changed |= assign_if_changed(spheres_, reinterpret_cast<const float*>(scene.spheres.value()), scene.spheres.size() * 4);
+			changed |= assign_if_changed(sphere_mat_, scene.spheres.material(), scene.spheres.size());
+			changed |= assign_if_changed(planes_, reinterpret_cast<const float*>(scene.planes.value()), scene.planes.size() * 4);
+			changed |= assign_if_changed(plane_mat_, scene.planes.material(), scene.planes.size());
+
+			std::vector<rtcu_material> mats(scene.materials.size());
+			for (size_t i = 0; i < mats.size(); i++)
+			{
+				mats[i].type = static_cast<uint32_t>(scene.materials.type()[i]);
+				std::memcpy(mats[i].albedo, &scene.materials.albedo()[i], sizeof(float) * 4);
+				mats[i].roughness	 = scene.materials.roughness()[i];
+				mats[i].reflectivity = scene.materials.reflectivity()[i];
+			}
+			changed |= assign_if_changed(materials_, mats.data(), mats.size());
+			if (!changed)
+				return true;
+
+			rtcu_scene desc{};
+			desc.spheres		 = spheres_.data();
+			desc.sphere_material = sphere_mat_.data();
+			desc.n_spheres		 = static_cast<uint32_t>(sphere_mat_.size());
+			desc.planes			 = planes_.data();
+			desc.plane_material	 = plane_mat_.data();
+			desc.n_planes		 = static_cast<uint32_t>(plane_mat_.size());
+			desc.materials		 = materials_.data();
+			desc.n_materials	 = static_cast<uint32_t>(materials_.size());
+			uploaded_			 = rtcu_upload_scene(ctx_, &desc) == RTCU_OK;
+			return uploaded_;
+		}
+
+		void render(const rt::scene& scene, image_view& pixels, muu::thread_pool& /*threads*/) noexcept override
+		{
+			if (!sync_scene(scene))
+			{
+				std::fprintf(stderr, "cuda_path_tracer: %s\n", rtcu_last_error());
+				return;
+			}
+
+			const auto view = scene.camera.viewport(pixels.size());
+
+			rtcu_view v{};
+			for (int c = 0; c < 4; c++)
+				for (int r = 0; r < 4; r++)
+					v.inv_view_proj[c * 4 + r] = view.inverse_view_projection(static_cast<size_t>(r), static_cast<size_t>(c));
+			v.width				= pixels.size().x;
+			v.height			= pixels.size().y;
+			v.samples_per_pixel = scene.samples_per_pixel;
+			v.max_bounces		= scene.max_bounces;
+			v.sample_begin		= 0;
+			v.sample_end		= scene.samples_per_pixel;
+			v.tile_x0			= 0;
+			v.tile_y0			= 0;
+			v.tile_x1			= v.width;
+			v.tile_y1			= v.height;
+			v.seed				= 0x5EEDull;
+			v.material_mode		= material_mode_;
+			v.flags				= RTCU_ACCEL_AUTO | RTCU_PIPE_AUTO;
+
+			// image_view memory is pageable host memory (image.cpp:9-13); rtcu_render stages through pinned memory
+			if (rtcu_render(ctx_, &v, pixels.data(), nullptr) != RTCU_OK)
+				std::fprintf(stderr, "cuda_path_tracer: %s\n", rtcu_last_error());
+		}
+	};
+
+	REGISTER_RENDERER(cuda_path_tracer);
+}
