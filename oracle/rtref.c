@@ -530,19 +530,22 @@ static void* render_rows(void* arg)
         {
             const uint32_t pixel = y * v->width + x;
             v3 colour = { 0, 0, 0 };
+            uint64_t pixel_segs = 0;
             for (uint32_t i = v->sample_begin; i < v->sample_end; i++)
             {
                 const rng_key k = { v->seed, pixel, i };
                 uint32_t nseg = 0;
                 const v3 c = trace(j->s, v->material_mode, primary_ray(v, x, y, &k), v->max_bounces, &k, 0, &nseg);
                 colour = v3_add(colour, c);
-                segs += nseg;
+                pixel_segs += nseg;
             }
+            segs += pixel_segs;
             if (j->accum)
             {
                 float* a = j->accum + 4 * (size_t)pixel;
                 a[0] = colour.x; a[1] = colour.y; a[2] = colour.z;
-                a[3] = (float)(v->sample_end - v->sample_begin);
+                /* flags bit 8 (oracle-only diagnostic): report the pixel's segment count instead of its sample count */
+                a[3] = (v->flags & 0x100u) ? (float)pixel_segs : (float)(v->sample_end - v->sample_begin);
             }
             if (j->rgba8)
                 j->rgba8[pixel] = rtref_pack_pixel(colour.x, colour.y, colour.z, v->samples_per_pixel);

@@ -9,7 +9,10 @@ import pathlib
 
 import numpy as np
 
-LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "librtcu.so"
+import os
+
+# RTCU_LIB overrides the library path (kernel-variant experiments only; the default is the in-tree build)
+LIB_PATH = pathlib.Path(os.environ.get("RTCU_LIB") or (pathlib.Path(__file__).resolve().parent / "lib" / "librtcu.so"))
 
 RTCU_OK, RTCU_ERR_INVALID, RTCU_ERR_CUDA, RTCU_ERR_STATE = 0, -1, -2, -3
 MODE_MG, MODE_SM = 0, 1

@@ -114,11 +114,17 @@ __device__ __forceinline__ Ray generate(const CameraConst& cam, const RngKey& ke
     return primary_ray(cam, __fadd_rn(__uint2float_rn(px), jx), __fadd_rn(__uint2float_rn(py), jy));
 }
 
-constexpr int MEGA_TILE_W = 16, MEGA_TILE_H = 16, MEGA_THREADS = 256;
+#ifndef RTCU_MEGA_TILE_H
+#define RTCU_MEGA_TILE_H 16 // 16 -> 256 threads, 8 -> 128 threads
+#endif
+#ifndef RTCU_MEGA_MIN_BLOCKS
+#define RTCU_MEGA_MIN_BLOCKS 1
+#endif
+constexpr int MEGA_TILE_W = 16, MEGA_TILE_H = RTCU_MEGA_TILE_H, MEGA_THREADS = MEGA_TILE_W * MEGA_TILE_H;
 
 // STAGE: primitives staged in dynamic shared memory (true) or read through L1 from global (false).
 template <bool STAGE>
-__global__ void __launch_bounds__(MEGA_THREADS) k_render_mega(const SceneDev sc, const RenderParams p)
+__global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_mega(const SceneDev sc, const RenderParams p)
 {
     extern __shared__ float4 smem[];
     const float4* s_sph = sc.spheres;
