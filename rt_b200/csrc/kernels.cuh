@@ -13,6 +13,7 @@ namespace rtcu_dev {
 
 struct SceneDev {
     const float4* spheres;   // {cx,cy,cz,r*r}
+    const float4* pairs;     // 2*ceil(n/2)+2 float4 (one never-hit sentinel pair at the end): {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1} (packed-FP32 scan layout)
     const uint32_t* sphere_material;
     uint32_t n_spheres;
     const float4* planes;    // {nx,ny,nz,d}
@@ -43,16 +44,25 @@ struct RenderParams {
 struct Hit { float t; uint32_t prim; }; // prim: sphere index | PLANE|index | MISS
 
 // closest hit over planes then spheres with the reference's tie rules
-// (mg_ray_tracer.cpp:35-102, :160-162).  s_sph / s_pl may point to shared or global memory.
-__device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_sph, const uint32_t n_sph,
+// (mg_ray_tracer.cpp:35-102, :160-162).  s_pairs / s_pl may point to shared or global memory.
+__device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_pairs, const uint32_t n_sph,
                                                   const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray& r)
 {
     const float inf = __int_as_float(0x7f800000);
     float ts = inf;
     int is = -1;
+    const uint32_t n_pairs = (n_sph + 1u) >> 1;
+    // software pipeline: the next pair is loaded (warp-uniform LDS.128 x2) before the current one is tested, so the
+    // shared-memory latency hides behind ~20 arithmetic instructions.  The array carries one sentinel pair at the end.
+    float4 A = s_pairs[0], B = s_pairs[1];
 #pragma unroll 4
-    for (uint32_t i = 0; i < n_sph; i++)
-        sphere_test(s_sph[i], (int)i, r, ts, is);
+    for (uint32_t j = 0; j < n_pairs; j++)
+    {
+        const float4 An = s_pairs[2 * j + 2], Bn = s_pairs[2 * j + 3];
+        sphere_pair_test(A, B, (int)j, r, ts, is);
+        A = An;
+        B = Bn;
+    }
     Hit h;
     h.t = ts;
     h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS;
@@ -74,16 +84,16 @@ __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_s
     return h;
 }
 
-// hit normal + material (mg_ray_tracer.cpp:56-59, :84-86)
-__device__ __forceinline__ V3 hit_normal(const float4* __restrict__ s_sph, const float4* __restrict__ s_pl, const Ray& r, const Hit h)
+// hit normal (mg_ray_tracer.cpp:56-59, :84-86); the sphere centre is read back from the pair layout
+__device__ __forceinline__ V3 hit_normal(const float4* __restrict__ s_pairs, const float4* __restrict__ s_pl, const Ray& r, const Hit h)
 {
     if (h.prim & RTCU_PRIM_PLANE)
     {
         const float4 pl = s_pl[h.prim & 0x7FFFFFFFu];
         return v3(pl.x, pl.y, pl.z);
     }
-    const float4 sp = s_sph[h.prim];
-    return normalize3(v3_sub(ray_at(r.o, r.d, h.t), v3(sp.x, sp.y, sp.z)));
+    const float* base = reinterpret_cast<const float*>(s_pairs) + 8u * (h.prim >> 1) + (h.prim & 1u);
+    return normalize3(v3_sub(ray_at(r.o, r.d, h.t), v3(base[0], base[2], base[4])));
 }
 
 __device__ __forceinline__ uint32_t hit_material(const SceneDev& sc, const Hit h)
@@ -115,10 +125,10 @@ __device__ __forceinline__ Ray generate(const CameraConst& cam, const RngKey& ke
 }
 
 #ifndef RTCU_MEGA_TILE_H
-#define RTCU_MEGA_TILE_H 16 // 16 -> 256 threads, 8 -> 128 threads
+#define RTCU_MEGA_TILE_H 8 // 16 -> 256 threads, 8 -> 128 threads
 #endif
 #ifndef RTCU_MEGA_MIN_BLOCKS
-#define RTCU_MEGA_MIN_BLOCKS 1
+#define RTCU_MEGA_MIN_BLOCKS 8
 #endif
 constexpr int MEGA_TILE_W = 16, MEGA_TILE_H = RTCU_MEGA_TILE_H, MEGA_THREADS = MEGA_TILE_W * MEGA_TILE_H;
 
@@ -127,20 +137,21 @@ template <bool STAGE>
 __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_mega(const SceneDev sc, const RenderParams p)
 {
     extern __shared__ float4 smem[];
-    const float4* s_sph = sc.spheres;
+    const float4* s_sph = sc.pairs;
     const float4* s_pl = sc.planes;
     if (STAGE)
     {
-        for (uint32_t i = threadIdx.x; i < sc.n_spheres; i += MEGA_THREADS)
-            smem[i] = __ldg(sc.spheres + i);
+        const uint32_t n4 = ((sc.n_spheres + 1u) & ~1u) + 2u; // float4 count of the pair layout + sentinel pair
+        for (uint32_t i = threadIdx.x; i < n4; i += MEGA_THREADS)
+            smem[i] = __ldg(sc.pairs + i);
         for (uint32_t i = threadIdx.x; i < sc.n_planes; i += MEGA_THREADS)
-            smem[sc.n_spheres + i] = __ldg(sc.planes + i);
+            smem[n4 + i] = __ldg(sc.planes + i);
         __syncthreads();
         s_sph = smem;
-        s_pl = smem + sc.n_spheres;
+        s_pl = smem + n4;
     }
 
-    // a warp covers an 8x4 pixel patch; the block a 16x16 tile
+    // a warp covers an 8x4 pixel patch; the block a 16 x MEGA_TILE_H tile
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t px = p.tile_x0 + blockIdx.x * MEGA_TILE_W + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t py = p.tile_y0 + blockIdx.y * MEGA_TILE_H + (warp >> 1) * 4u + (lane >> 3);
@@ -253,17 +264,18 @@ __global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, cons
                                                          float* __restrict__ t, float* __restrict__ nrm)
 {
     extern __shared__ float4 smem[];
-    const float4* s_sph = sc.spheres;
+    const float4* s_sph = sc.pairs;
     const float4* s_pl = sc.planes;
     if (STAGE)
     {
-        for (uint32_t i = threadIdx.x; i < sc.n_spheres; i += blockDim.x)
-            smem[i] = __ldg(sc.spheres + i);
+        const uint32_t n4 = ((sc.n_spheres + 1u) & ~1u) + 2u;
+        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x)
+            smem[i] = __ldg(sc.pairs + i);
         for (uint32_t i = threadIdx.x; i < sc.n_planes; i += blockDim.x)
-            smem[sc.n_spheres + i] = __ldg(sc.planes + i);
+            smem[n4 + i] = __ldg(sc.planes + i);
         __syncthreads();
         s_sph = smem;
-        s_pl = smem + sc.n_spheres;
+        s_pl = smem + n4;
     }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {

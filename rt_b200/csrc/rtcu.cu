@@ -100,6 +100,7 @@ struct rtcu_ctx {
     // scene (device)
     DevBuf<float4> sph;        // {cx,cy,cz,r*r}
     DevBuf<float4> sph_raw;    // {cx,cy,cz,r}
+    DevBuf<float4> pairs;      // packed-scan layout, see SceneDev::pairs
     DevBuf<uint32_t> sph_mat;
     DevBuf<float4> planes;
     DevBuf<uint32_t> plane_mat;
@@ -154,7 +155,7 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     return RTCU_OK;
 }
 
-size_t stage_bytes(const rtcu_ctx* ctx) { return ((size_t)ctx->scene.n_spheres + ctx->scene.n_planes) * sizeof(float4); }
+size_t stage_bytes(const rtcu_ctx* ctx) { return ((((size_t)ctx->scene.n_spheres + 1) & ~(size_t)1) + 2 + ctx->scene.n_planes) * sizeof(float4); }
 
 // launches the trace kernels of one view on `st`; accum/rgba8 are device pointers
 int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st)
@@ -307,7 +308,7 @@ void rtcu_destroy(rtcu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    ctx->sph.release(); ctx->sph_raw.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
+    ctx->sph.release(); ctx->sph_raw.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
     ctx->mats.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
     ctx->counters.release(); ctx->h_counters.release(); ctx->scratch.release();
     for (auto& e : ctx->ev)
@@ -341,6 +342,17 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         raw[i] = make_float4(p[0], p[1], p[2], r);
         sph[i] = make_float4(p[0], p[1], p[2], r2);
     }
+    // packed-scan layout: pair j = spheres 2j, 2j+1 as {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}; odd tail padded with r2 = -inf
+    const size_t n_pairs = ((size_t)s->n_spheres + 1) / 2;
+    std::vector<float4> pairs(2 * n_pairs + 2, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // + sentinel pair (prefetch target, never tested)
+    pairs[2 * n_pairs + 1] = make_float4(0.0f, 0.0f, -__builtin_inff(), -__builtin_inff());
+    for (size_t j = 0; j < n_pairs; j++)
+    {
+        const float4 s0 = sph[2 * j];
+        const float4 s1 = (2 * j + 1 < s->n_spheres) ? sph[2 * j + 1] : make_float4(0.0f, 0.0f, 0.0f, -__builtin_inff());
+        pairs[2 * j] = make_float4(s0.x, s1.x, s0.y, s1.y);
+        pairs[2 * j + 1] = make_float4(s0.z, s1.z, s0.w, s1.w);
+    }
     std::vector<MatRec> mats(s->n_materials);
     for (uint32_t i = 0; i < s->n_materials; i++)
     {
@@ -356,6 +368,7 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     }
     CU(ctx->sph.reserve(s->n_spheres ? s->n_spheres : 1));
     CU(ctx->sph_raw.reserve(s->n_spheres ? s->n_spheres : 1));
+    CU(ctx->pairs.reserve(pairs.empty() ? 2 : pairs.size()));
     CU(ctx->sph_mat.reserve(s->n_spheres ? s->n_spheres : 1));
     CU(ctx->planes.reserve(s->n_planes ? s->n_planes : 1));
     CU(ctx->plane_mat.reserve(s->n_planes ? s->n_planes : 1));
@@ -366,6 +379,7 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     {
         CU(cudaMemcpyAsync(ctx->sph.p, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->sph_raw.p, raw.data(), raw.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), pairs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->sph_mat.p, s->sphere_material, s->n_spheres * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (s->n_planes)
@@ -376,6 +390,7 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     CU(cudaMemcpyAsync(ctx->mats.p, mats.data(), mats.size() * sizeof(MatRec), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream)); // the staging vectors die here
     ctx->scene.spheres = ctx->sph.p;
+    ctx->scene.pairs = ctx->pairs.p;
     ctx->scene.sphere_material = ctx->sph_mat.p;
     ctx->scene.n_spheres = s->n_spheres;
     ctx->scene.planes = ctx->planes.p;
