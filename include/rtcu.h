@@ -167,6 +167,14 @@ int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t k
 
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out);
 
+/* ---- host-only: the BVH builder used by rtcu_upload_scene (binned SAH, two children per node), exposed so its
+ * invariants can be checked without a device.  The reference has no acceleration structure (mg_ray_tracer.cpp:62-87
+ * scans all spheres); traversal returns the scan's exact result.
+ * nodes_out (nullable): max_nodes x 16 words {x[4], y[4], z[4] = l.lo,l.hi,r.lo,r.hi per axis; int32 child[2] (>= 0 inner
+ * node, < 0 leaf starting at ~child in order_out); uint32 count[2]}.  order_out (nullable): n original sphere indices. */
+int rtcu_bvh_build_host(const float* spheres, uint32_t n, float* nodes_out, uint32_t* order_out, uint32_t max_nodes,
+                        uint32_t* n_nodes, uint32_t* depth);
+
 /* ---- roofline calibration: achieved non-tensor FP32 TFLOP/s of an FFMA stream and of a packed FFMA2
  * (fma.rn.f32x2) stream on ctx's device at the clocks it currently runs (no memory traffic). */
 int rtcu_measure_fp32_peak(rtcu_ctx* ctx, float* tflops_ffma, float* tflops_ffma2);

@@ -24,7 +24,7 @@ PRIM_MISS, PRIM_PLANE = 0xFFFFFFFF, 0x80000000
 EXPORTS = (
     "rtcu_abi_version", "rtcu_device_count", "rtcu_create", "rtcu_destroy", "rtcu_last_error", "rtcu_bvh_threshold",
     "rtcu_upload_scene", "rtcu_render", "rtcu_render_device", "rtcu_resolve_device", "rtcu_sync", "rtcu_render_multi",
-    "rtcu_intersect_batch", "rtcu_primary_rays", "rtcu_scatter_batch", "rtcu_philox_batch", "rtcu_get_stats", "rtcu_measure_fp32_peak",
+    "rtcu_intersect_batch", "rtcu_primary_rays", "rtcu_scatter_batch", "rtcu_philox_batch", "rtcu_get_stats", "rtcu_measure_fp32_peak", "rtcu_bvh_build_host",
 )
 
 
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
         "rtcu_philox_batch": (i, [p, p, u32, u64, p]),
         "rtcu_get_stats": (i, [p, C.POINTER(Stats)]),
         "rtcu_measure_fp32_peak": (i, [p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "rtcu_bvh_build_host": (i, [p, u32, p, p, u32, C.POINTER(u32), C.POINTER(u32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -21,6 +21,13 @@ struct SceneDev {
     uint32_t n_planes;
     const MatRec* materials;
     uint32_t n_materials;
+    // BVH over the spheres (built when the scene size calls for it, see bvh.h); nodes = 4 float4 per node:
+    // {l.lo.x,l.hi.x,r.lo.x,r.hi.x}, same for y and z, then {ref_left, ref_right, -, -} as bit patterns.
+    // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | first << 3 | count over leaf_sph / leaf_idx.
+    const float4* bvh_nodes;
+    const float4* leaf_sph;   // {cx,cy,cz,r*r} in leaf order
+    const uint32_t* leaf_idx; // original sphere index
+    uint32_t n_bvh_nodes;
 };
 
 struct RenderParams {
@@ -36,6 +43,7 @@ struct RenderParams {
     float4* accum;         // width*height {sum_r,sum_g,sum_b,n}
     uint32_t* rgba8;       // nullable
     unsigned long long* counters; // [0] = segments
+    uint32_t regen_threshold;     // regenerate ended lanes once this many lanes of the warp are idle (1 = immediately)
 };
 
 #define RTCU_PRIM_MISS 0xFFFFFFFFu
@@ -96,6 +104,177 @@ __device__ __forceinline__ V3 hit_normal(const float4* __restrict__ s_pairs, con
     return normalize3(v3_sub(ray_at(r.o, r.d, h.t), v3(base[0], base[2], base[4])));
 }
 
+// ---- BVH traversal with the linear scan's exact result ------------------------------------------------------
+// The answer must equal closest_hit_linear bit for bit: the lexicographic minimum (t, index) over all spheres whose
+// S4 test yields t >= 0.001.  Spheres are tested with the same S4 arithmetic, so only *culling* can change the result;
+// it is made conservative against the rounding of S4 itself: the computed discriminant differs from the geometric one
+// by at most ~(16 eps + 2|d.d - 1|) * |c-o|^2, i.e. a computed hit means the line passes within
+// sqrt(r^2 + kappa^2 |e|^2) of the centre and the computed t is within kappa*|e| of the true entry point.  Every child
+// box is therefore inflated by m = kappa * E, E = L1 distance from the ray origin to the box's farthest corner
+// (>= |e| of any sphere inside), before the slab test and the `tmin <= best_t` ordering cull.
+struct BvhStats { uint32_t nodes, tests; };
+
+__device__ __forceinline__ void bvh_leaf_test(const float4 sph, const int index, const Ray& r, float& best_t, int& best_i)
+{
+    const float ex = __fsub_rn(sph.x, r.o.x), ey = __fsub_rn(sph.y, r.o.y), ez = __fsub_rn(sph.z, r.o.z);
+    const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+    const float a = __fmaf_rn(ez, r.d.z, __fmaf_rn(ey, r.d.y, __fmul_rn(ex, r.d.x)));
+    const float disc = __fsub_rn(sph.w, __fmaf_rn(-a, a, e2));
+    if (!(disc < 0.0f))
+    {
+        const float f = __fsqrt_rn(disc);
+        const float t = (e2 < sph.w) ? __fadd_rn(a, f) : __fsub_rn(a, f);
+        // leaves are visited in traversal order, not index order: (t, index) lexicographic == "lowest index wins ties"
+        if (!(t < 0.001f) && (t < best_t || (t == best_t && index < best_i)))
+        {
+            best_t = t;
+            best_i = index;
+        }
+    }
+}
+
+constexpr int BVH_STACK = 64;
+
+// returns false when the ray direction is too far from unit length for the conservative margins (caller falls back
+// to the linear scan); otherwise (best_t, best_i) hold the closest sphere hit or (inf, -1)
+__device__ __forceinline__ bool closest_sphere_bvh(const SceneDev& sc, const Ray& r, float& best_t, int& best_i, BvhStats& st)
+{
+    const float inf = __int_as_float(0x7f800000);
+    best_t = inf;
+    best_i = 0x7fffffff;
+    const float dd = dot3(r.d, r.d);
+    const float eps_d = fabsf(dd - 1.0f);
+    if (!(eps_d <= 1e-3f))
+        return false;
+    const float kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
+    const float ix = __frcp_rn(r.d.x), iy = __frcp_rn(r.d.y), iz = __frcp_rn(r.d.z);
+
+    uint32_t stack_ref[BVH_STACK];
+    float stack_t[BVH_STACK];
+    int sp = 0;
+    uint32_t node = 0;
+    for (;;)
+    {
+        st.nodes++;
+        const float4* np = sc.bvh_nodes + 4 * (size_t)node;
+        const float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2), meta = __ldg(np + 3);
+        uint32_t ref[2] = { __float_as_uint(meta.x), __float_as_uint(meta.y) };
+        float tn[2];
+        bool hit[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+        {
+            const float lox = (c ? bx.z : bx.x) - r.o.x, hix = (c ? bx.w : bx.y) - r.o.x;
+            const float loy = (c ? by.z : by.x) - r.o.y, hiy = (c ? by.w : by.y) - r.o.y;
+            const float loz = (c ? bz.z : bz.x) - r.o.z, hiz = (c ? bz.w : bz.y) - r.o.z;
+            const float m = kappa * (fmaxf(fabsf(lox), fabsf(hix)) + fmaxf(fabsf(loy), fabsf(hiy)) + fmaxf(fabsf(loz), fabsf(hiz)));
+            const float t1x = (lox - m) * ix, t2x = (hix + m) * ix;
+            const float t1y = (loy - m) * iy, t2y = (hiy + m) * iy;
+            const float t1z = (loz - m) * iz, t2z = (hiz + m) * iz;
+            const float tmin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+            const float tmax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+            tn[c] = tmin;
+            hit[c] = tmax >= fmaxf(tmin, 0.0f) && tmin <= best_t; // empty boxes (lo > hi) fail the first test
+        }
+        // leaves are tested immediately, inner children are descended near-first
+        uint32_t next = 0xffffffffu;
+        float next_t = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+        {
+            if (!hit[c]) continue;
+            if (ref[c] & 0x80000000u)
+            {
+                const uint32_t first = (ref[c] & 0x7fffffffu) >> 3, count = ref[c] & 7u;
+                for (uint32_t k = 0; k < count; k++)
+                {
+                    st.tests++;
+                    bvh_leaf_test(__ldg(sc.leaf_sph + first + k), (int)__ldg(sc.leaf_idx + first + k), r, best_t, best_i);
+                }
+            }
+            else if (next == 0xffffffffu)
+            {
+                next = ref[c];
+                next_t = tn[c];
+            }
+            else
+            {
+                // both children are inner nodes: continue with the nearer, push the farther
+                const bool swap = tn[c] < next_t;
+                stack_ref[sp] = swap ? next : ref[c];
+                stack_t[sp] = swap ? next_t : tn[c];
+                sp++;
+                if (swap) { next = ref[c]; next_t = tn[c]; }
+            }
+        }
+        if (next != 0xffffffffu && next_t <= best_t)
+        {
+            node = next;
+            continue;
+        }
+        // pop, skipping entries that the current best already excludes
+        bool found = false;
+        while (sp > 0)
+        {
+            sp--;
+            if (stack_t[sp] <= best_t)
+            {
+                node = stack_ref[sp];
+                found = true;
+                break;
+            }
+        }
+        if (!found)
+            break;
+    }
+    if (best_i == 0x7fffffff)
+        best_i = -1;
+    return true;
+}
+
+// closest hit: spheres through the BVH (or the global-memory linear scan when the ray is not unit length), planes linear
+__device__ __forceinline__ Hit closest_hit_bvh(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, BvhStats& st)
+{
+    float ts;
+    int is;
+    if (!closest_sphere_bvh(sc, r, ts, is, st))
+    {
+        st.tests += sc.n_spheres;
+        return closest_hit_linear(sc.pairs, sc.n_spheres, s_pl, sc.n_planes, r);
+    }
+    Hit h;
+    h.t = ts;
+    h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS;
+    if (sc.n_planes)
+    {
+        const float inf = __int_as_float(0x7f800000);
+        float tp = inf;
+        int ip = -1;
+        for (uint32_t i = 0; i < sc.n_planes; i++)
+            plane_test(s_pl[i], (int)i, r, tp, ip);
+        if (ip >= 0 && !(is >= 0 && ts <= tp))
+        {
+            h.t = tp;
+            h.prim = RTCU_PRIM_PLANE | (uint32_t)ip;
+        }
+    }
+    if (h.prim == RTCU_PRIM_MISS)
+        h.t = -1.0f;
+    return h;
+}
+
+// hit normal when primitives are not staged: centre from the global {cx,cy,cz,r*r} array
+__device__ __forceinline__ V3 hit_normal_global(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, const Hit h)
+{
+    if (h.prim & RTCU_PRIM_PLANE)
+    {
+        const float4 pl = s_pl[h.prim & 0x7FFFFFFFu];
+        return v3(pl.x, pl.y, pl.z);
+    }
+    const float4 sp = __ldg(sc.spheres + h.prim);
+    return normalize3(v3_sub(ray_at(r.o, r.d, h.t), v3(sp.x, sp.y, sp.z)));
+}
+
 __device__ __forceinline__ uint32_t hit_material(const SceneDev& sc, const Hit h)
 {
     return (h.prim & RTCU_PRIM_PLANE) ? __ldg(sc.plane_material + (h.prim & 0x7FFFFFFFu)) : __ldg(sc.sphere_material + h.prim);
@@ -132,8 +311,37 @@ __device__ __forceinline__ Ray generate(const CameraConst& cam, const RngKey& ke
 #endif
 constexpr int MEGA_TILE_W = 16, MEGA_TILE_H = RTCU_MEGA_TILE_H, MEGA_THREADS = MEGA_TILE_W * MEGA_TILE_H;
 
+// One path segment (mg_ray_tracer.cpp:154-174, one level of the recursion): closest hit, then sky on a miss or one
+// scatter event on a hit.  Returns true when the path ended (miss, absorbed, or bounce budget exhausted).
+template <bool BVH>
+__device__ __forceinline__ bool segment_step(const SceneDev& sc, const RenderParams& p, const float4* __restrict__ s_sph,
+                                             const float4* __restrict__ s_pl, const RngKey& key, Ray& ray, V3& thr, V3& sum, uint32_t& seg,
+                                             BvhStats& bst)
+{
+    const Hit h = BVH ? closest_hit_bvh(sc, s_pl, ray, bst) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
+    if (h.prim == RTCU_PRIM_MISS)
+    {
+        sum = v3_add(sum, v3_mul(thr, sky(ray.d))); // S12: iterative throughput
+        return true;
+    }
+    const V3 n = BVH ? hit_normal_global(sc, s_pl, ray, h) : hit_normal(s_sph, s_pl, ray, h);
+    const MatRec m = load_material(sc, hit_material(sc, h));
+    const uint4 rnd = rng_block(key, seg + 1u, 0u);
+    Ray next;
+    const bool scattered = scatter(scatter_kind(p.mode, m.type), m, ray, h.t, n, key, seg + 1u, rnd, next);
+    thr = v3_mul(thr, v3(m.att_r, m.att_g, m.att_b));
+    ray = next;
+    seg++;
+    // absorbed (:173) or bounce budget exhausted (:157-158): radiance 0
+    return !scattered || seg >= p.max_bounces;
+}
+
 // STAGE: primitives staged in dynamic shared memory (true) or read through L1 from global (false).
-template <bool STAGE>
+// FLAT: lanes regenerate inside a warp-vote loop (all lanes reconverge every segment; best when the O(N) sweep
+// dominates).  !FLAT: plain per-thread loop, which the compiler nests as {generate; bounce until every lane's path
+// ended} -- generate and shade then run at full lane occupancy, best for tiny N where they dominate.
+// BVH: spheres are reached through the BVH (STAGE must be false; the structure lives in L1/L2).
+template <bool STAGE, bool FLAT, bool BVH>
 __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_mega(const SceneDev sc, const RenderParams p)
 {
     extern __shared__ float4 smem[];
@@ -157,55 +365,78 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
     const uint32_t py = p.tile_y0 + blockIdx.y * MEGA_TILE_H + (warp >> 1) * 4u + (lane >> 3);
     const bool in_tile = px < p.tile_x1 && py < p.tile_y1;
 
+    // (measured on C3, 484 spheres: the plain loop keeps 23/32 lanes active in the sweep, the vote loop ~29/32;
+    //  on C2, 7 spheres, the plain loop is ~10 % faster because generate/shade dominate)
     unsigned long long segs = 0;
-    if (in_tile)
+    BvhStats bst;
+    bst.nodes = 0;
+    bst.tests = 0;
+    RngKey key;
+    key.key = p.key;
+    key.pixel = py * p.width + px;
+    key.sample = p.sample_begin;
+    V3 sum = v3(0.0f, 0.0f, 0.0f);
+    V3 thr = v3(1.0f, 1.0f, 1.0f);
+    uint32_t seg = 0;
+    if (FLAT)
     {
-        RngKey key;
-        key.key = p.key;
-        key.pixel = py * p.width + px;
-        key.sample = p.sample_begin;
-        V3 sum = v3(0.0f, 0.0f, 0.0f);
-
-        if (p.sample_begin < p.sample_end)
+        // lane state: `more` = the pixel still has samples to start, `live` = a path is in flight
+        bool more = in_tile && p.sample_begin < p.sample_end;
+        bool live = false;
+        Ray ray;
+        ray.o = v3(0.0f, 0.0f, 0.0f);
+        ray.d = v3(0.0f, 0.0f, 1.0f);
+        for (;;)
         {
-            V3 thr = v3(1.0f, 1.0f, 1.0f);
-            uint32_t seg = 0;
-            Ray ray = generate(p.cam, key, px, py);
-            for (;;)
+            // (1) regeneration, decided by a warp vote so every lane reconverges here each iteration: lanes whose path
+            // ended start the next sample of their pixel once `regen_threshold` lanes are idle (or nothing is in flight)
+            const unsigned idle = __ballot_sync(0xffffffffu, more && !live);
+            const unsigned flying = __ballot_sync(0xffffffffu, live);
+            if (!idle && !flying)
+                break;
+            if (idle && (!flying || __popc(idle) >= (int)p.regen_threshold))
             {
-                segs++;
-                const Hit h = closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
-                bool ended;
-                if (h.prim == RTCU_PRIM_MISS)
+                if (more && !live)
                 {
-                    sum = v3_add(sum, v3_mul(thr, sky(ray.d))); // S12: iterative throughput
-                    ended = true;
-                }
-                else
-                {
-                    const V3 n = hit_normal(s_sph, s_pl, ray, h);
-                    const MatRec m = load_material(sc, hit_material(sc, h));
-                    const uint4 rnd = rng_block(key, seg + 1u, 0u);
-                    Ray next;
-                    const bool scattered = scatter(scatter_kind(p.mode, m.type), m, ray, h.t, n, key, seg + 1u, rnd, next);
-                    thr = v3_mul(thr, v3(m.att_r, m.att_g, m.att_b));
-                    ray = next;
-                    seg++;
-                    // absorbed (:173) or bounce budget exhausted (:157-158): radiance 0
-                    ended = !scattered || seg >= p.max_bounces;
-                }
-                if (ended)
-                {
-                    key.sample++;
-                    if (key.sample >= p.sample_end)
-                        break;
                     seg = 0;
                     thr = v3(1.0f, 1.0f, 1.0f);
                     ray = generate(p.cam, key, px, py);
+                    live = true;
+                }
+            }
+            // (2) one path segment for every lane in flight
+            if (live)
+            {
+                segs++;
+                if (segment_step<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, bst))
+                {
+                    live = false;
+                    key.sample++;
+                    more = key.sample < p.sample_end;
                 }
             }
         }
+    }
+    else if (in_tile && p.sample_begin < p.sample_end)
+    {
+        Ray ray = generate(p.cam, key, px, py);
+        for (;;)
+        {
+            segs++;
+            if (segment_step<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, bst))
+            {
+                key.sample++;
+                if (key.sample >= p.sample_end)
+                    break;
+                seg = 0;
+                thr = v3(1.0f, 1.0f, 1.0f);
+                ray = generate(p.cam, key, px, py);
+            }
+        }
+    }
 
+    if (in_tile)
+    {
         const size_t idx = (size_t)key.pixel;
         float4 acc = make_float4(sum.x, sum.y, sum.z, (float)(p.sample_end - p.sample_begin));
         if (p.accumulate)
@@ -219,11 +450,26 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
             p.rgba8[idx] = pack_pixel(acc.x, acc.y, acc.z, p.spp_resolve);
     }
 
-    // exact segment count: warp reduce, one atomic per warp
+    // exact counters: warp reduce, one atomic per warp
+    unsigned long long nodes = bst.nodes, tests = bst.tests;
     for (int off = 16; off > 0; off >>= 1)
+    {
         segs += __shfl_down_sync(0xffffffffu, segs, off);
+        if (BVH)
+        {
+            nodes += __shfl_down_sync(0xffffffffu, nodes, off);
+            tests += __shfl_down_sync(0xffffffffu, tests, off);
+        }
+    }
     if (lane == 0 && segs)
+    {
         atomicAdd(p.counters, segs);
+        if (BVH)
+        {
+            atomicAdd(p.counters + 1, nodes);
+            atomicAdd(p.counters + 2, tests);
+        }
+    }
 }
 
 // mg_ray_tracer.cpp:195-200 over a whole accumulation buffer
@@ -258,10 +504,10 @@ __global__ void k_reduce_resolve(float4* __restrict__ accum, const PeerList peer
 }
 
 // ---- step-wise parity kernels ----------------------------------------------------------------------
-template <bool STAGE>
+template <bool STAGE, bool BVH>
 __global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, const float* __restrict__ o, const float* __restrict__ d,
                                                          uint32_t n, uint8_t* __restrict__ hit, uint32_t* __restrict__ prim,
-                                                         float* __restrict__ t, float* __restrict__ nrm)
+                                                         float* __restrict__ t, float* __restrict__ nrm, unsigned long long* counters)
 {
     extern __shared__ float4 smem[];
     const float4* s_sph = sc.pairs;
@@ -282,7 +528,10 @@ __global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, cons
         Ray r;
         r.o = v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]);
         r.d = v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-        const Hit h = closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, r);
+        BvhStats bst;
+        bst.nodes = 0;
+        bst.tests = 0;
+        const Hit h = BVH ? closest_hit_bvh(sc, s_pl, r, bst) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, r);
         hit[i] = h.prim != RTCU_PRIM_MISS;
         prim[i] = h.prim;
         t[i] = h.t;
@@ -290,8 +539,13 @@ __global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, cons
         {
             V3 nn = v3(0.0f, 0.0f, 0.0f);
             if (h.prim != RTCU_PRIM_MISS)
-                nn = hit_normal(s_sph, s_pl, r, h);
+                nn = BVH ? hit_normal_global(sc, s_pl, r, h) : hit_normal(s_sph, s_pl, r, h);
             nrm[3 * i] = nn.x; nrm[3 * i + 1] = nn.y; nrm[3 * i + 2] = nn.z;
+        }
+        if (BVH)
+        {
+            atomicAdd(counters + 1, (unsigned long long)bst.nodes);
+            atomicAdd(counters + 2, (unsigned long long)bst.tests);
         }
     }
 }

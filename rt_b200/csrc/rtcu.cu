@@ -2,9 +2,12 @@
 // No CPU fallback: every compute entry point needs a CUDA device and says so when there is none.
 #include "../../include/rtcu.h"
 #include "kernels.cuh"
+#include "bvh.h"
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -105,6 +108,11 @@ struct rtcu_ctx {
     DevBuf<float4> planes;
     DevBuf<uint32_t> plane_mat;
     DevBuf<MatRec> mats;
+    DevBuf<float4> bvh_nodes, leaf_sph;
+    DevBuf<uint32_t> leaf_idx;
+    bool have_bvh = false;
+    uint32_t bvh_depth = 0;
+    float ms_bvh_build = 0.0f;
     SceneDev scene = {};
     bool have_scene = false;
 
@@ -155,6 +163,25 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     return RTCU_OK;
 }
 
+// lanes idle before ended paths are regenerated (see k_render_mega); RTCU_REGEN_THRESHOLD overrides for tuning runs
+uint32_t regen_threshold_for(uint32_t n_prims)
+{
+    if (const char* e = getenv("RTCU_REGEN_THRESHOLD"))
+    {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) return (uint32_t)v;
+    }
+    (void)n_prims;
+    return 1u;
+}
+
+// loop structure of k_render_mega: the warp-vote (flat) loop pays off once the O(N) sweep dominates a segment
+bool flat_loop_for(uint32_t n_prims)
+{
+    if (const char* e = getenv("RTCU_FLAT_LOOP")) return atoi(e) != 0;
+    return n_prims >= 32;
+}
+
 size_t stage_bytes(const rtcu_ctx* ctx) { return ((((size_t)ctx->scene.n_spheres + 1) & ~(size_t)1) + 2 + ctx->scene.n_planes) * sizeof(float4); }
 
 // launches the trace kernels of one view on `st`; accum/rgba8 are device pointers
@@ -165,24 +192,33 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     const int rc = make_params(ctx, v, p);
     if (rc) return rc;
     const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
-    if (accel == RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "BVH traversal is not available in this build");
+    if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
+    if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or tree deeper than %d)", BVH_STACK - 2);
     if (pipe == RTCU_PIPE_WAVEFRONT) return fail(RTCU_ERR_INVALID, "wavefront pipeline is not available in this build");
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
     p.accum = d_accum;
     p.rgba8 = d_rgba8;
     p.accumulate = accumulate;
     p.counters = ctx->counters.p;
+    p.regen_threshold = regen_threshold_for(ctx->scene.n_spheres + ctx->scene.n_planes);
 
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
     const dim3 grid((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W, (v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
     const size_t sb = stage_bytes(ctx);
-    if (sb <= MAX_STAGE_BYTES)
-        k_render_mega<true><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, p);
+    const bool flat = flat_loop_for(ctx->scene.n_spheres + ctx->scene.n_planes);
+    if (use_bvh)
+        k_render_mega<false, true, true><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
+    else if (sb <= MAX_STAGE_BYTES)
+    {
+        if (flat) k_render_mega<true, true, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, p);
+        else k_render_mega<true, false, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, p);
+    }
     else
-        k_render_mega<false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
+        k_render_mega<false, true, false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
     CU(cudaGetLastError());
     ctx->stats.kernel_launches = 1;
     ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
-    ctx->stats.accel = RTCU_ACCEL_LINEAR;
+    ctx->stats.accel = use_bvh ? RTCU_ACCEL_BVH : RTCU_ACCEL_LINEAR;
     ctx->stats.samples = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0) * (v->sample_end - v->sample_begin);
     return RTCU_OK;
 }
@@ -192,8 +228,16 @@ int fetch_counters(rtcu_ctx* ctx, cudaStream_t st)
     CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->stats.segments = ctx->h_counters.p[0];
-    ctx->stats.sphere_tests = ctx->stats.segments * ctx->scene.n_spheres;
-    ctx->stats.node_visits = 0;
+    if (ctx->stats.accel == RTCU_ACCEL_BVH)
+    {
+        ctx->stats.node_visits = ctx->h_counters.p[1];
+        ctx->stats.sphere_tests = ctx->h_counters.p[2];
+    }
+    else
+    {
+        ctx->stats.sphere_tests = ctx->stats.segments * ctx->scene.n_spheres;
+        ctx->stats.node_visits = 0;
+    }
     return RTCU_OK;
 }
 
@@ -241,7 +285,11 @@ int rtcu_abi_version(void) { return RTCU_ABI_VERSION; }
 
 const char* rtcu_last_error(void) { return g_err; }
 
-uint32_t rtcu_bvh_threshold(void) { return 4096u; }
+uint32_t rtcu_bvh_threshold(void)
+{
+    if (const char* e = getenv("RTCU_BVH_THRESHOLD")) return (uint32_t)strtoul(e, nullptr, 10);
+    return 64u; // measured crossover, see DESIGN.md
+}
 
 int rtcu_device_count(void)
 {
@@ -292,8 +340,9 @@ rtcu_ctx* rtcu_create(int device)
     for (int i = 0; ok && i < 6; i++)
         ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && ctx->counters.reserve(4) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_render_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_intersect_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_render_mega<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess
+         && cudaFuncSetAttribute(k_render_mega<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_intersect_batch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
     if (!ok)
     {
         fail(RTCU_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -309,7 +358,7 @@ void rtcu_destroy(rtcu_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->sph.release(); ctx->sph_raw.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
-    ctx->mats.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
+    ctx->mats.release(); ctx->bvh_nodes.release(); ctx->leaf_sph.release(); ctx->leaf_idx.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
     ctx->counters.release(); ctx->h_counters.release(); ctx->scratch.release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -388,6 +437,56 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         CU(cudaMemcpyAsync(ctx->plane_mat.p, s->plane_material, s->n_planes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     CU(cudaMemcpyAsync(ctx->mats.p, mats.data(), mats.size() * sizeof(MatRec), cudaMemcpyHostToDevice, ctx->stream));
+    // BVH: built whenever there are spheres (cheap for small scenes; lets ACCEL_BVH be requested explicitly for parity
+    // tests); RTCU_ACCEL_AUTO uses it from rtcu_bvh_threshold() spheres up
+    ctx->have_bvh = false;
+    ctx->scene.bvh_nodes = nullptr;
+    ctx->scene.leaf_sph = nullptr;
+    ctx->scene.leaf_idx = nullptr;
+    ctx->scene.n_bvh_nodes = 0;
+    std::vector<float4> nodes_dev, leaf_sph;
+    std::vector<uint32_t> leaf_idx;
+    if (s->n_spheres)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const rtcu_bvh::Result bvh = rtcu_bvh::build(s->spheres, s->n_spheres);
+        ctx->ms_bvh_build = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        ctx->bvh_depth = bvh.max_depth;
+        if (bvh.max_depth + 2 <= (uint32_t)BVH_STACK && s->n_spheres < (1u << 28))
+        {
+            nodes_dev.resize(4 * bvh.nodes.size());
+            for (size_t i = 0; i < bvh.nodes.size(); i++)
+            {
+                const rtcu_bvh::Node& nd = bvh.nodes[i];
+                nodes_dev[4 * i + 0] = make_float4(nd.x[0], nd.x[1], nd.x[2], nd.x[3]);
+                nodes_dev[4 * i + 1] = make_float4(nd.y[0], nd.y[1], nd.y[2], nd.y[3]);
+                nodes_dev[4 * i + 2] = make_float4(nd.z[0], nd.z[1], nd.z[2], nd.z[3]);
+                uint32_t ref[2];
+                for (int c = 0; c < 2; c++)
+                    ref[c] = nd.child[c] >= 0 ? (uint32_t)nd.child[c] : (0x80000000u | ((uint32_t)(~nd.child[c]) << 3) | nd.count[c]);
+                float4 meta;
+                memcpy(&meta.x, &ref[0], 4);
+                memcpy(&meta.y, &ref[1], 4);
+                meta.z = meta.w = 0.0f;
+                nodes_dev[4 * i + 3] = meta;
+            }
+            leaf_sph.resize(s->n_spheres);
+            leaf_idx = bvh.order;
+            for (uint32_t k = 0; k < s->n_spheres; k++)
+                leaf_sph[k] = sph[bvh.order[k]];
+            CU(ctx->bvh_nodes.reserve(nodes_dev.size()));
+            CU(ctx->leaf_sph.reserve(leaf_sph.size()));
+            CU(ctx->leaf_idx.reserve(leaf_idx.size()));
+            CU(cudaMemcpyAsync(ctx->bvh_nodes.p, nodes_dev.data(), nodes_dev.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->leaf_sph.p, leaf_sph.data(), leaf_sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->leaf_idx.p, leaf_idx.data(), leaf_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->scene.bvh_nodes = ctx->bvh_nodes.p;
+            ctx->scene.leaf_sph = ctx->leaf_sph.p;
+            ctx->scene.leaf_idx = ctx->leaf_idx.p;
+            ctx->scene.n_bvh_nodes = (uint32_t)bvh.nodes.size();
+            ctx->have_bvh = true;
+        }
+    }
     CU(cudaStreamSynchronize(ctx->stream)); // the staging vectors die here
     ctx->scene.spheres = ctx->sph.p;
     ctx->scene.pairs = ctx->pairs.p;
@@ -565,7 +664,9 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
 {
     if (!ctx || !o || !d || !hit || !prim || !t) return fail(RTCU_ERR_INVALID, "null argument");
     if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
-    if (accel == RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "BVH traversal is not available in this build");
+    if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
+    if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene");
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
     if (n == 0) return RTCU_OK;
     CU(cudaSetDevice(ctx->device));
     const size_t need = 2 * padded((size_t)n * 12) + padded(n) + 2 * padded((size_t)n * 4) + padded((size_t)n * 12);
@@ -582,11 +683,14 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
     CU(cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     const unsigned blocks = (unsigned)((n + 255) / 256 < (uint32_t)ctx->sm_count * 8 ? (n + 255) / 256 : ctx->sm_count * 8);
     const size_t sb = stage_bytes(ctx);
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
     CU(cudaEventRecord(ctx->ev[0], st));
-    if (sb <= MAX_STAGE_BYTES)
-        k_intersect_batch<true><<<blocks, 256, sb, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr);
+    if (use_bvh)
+        k_intersect_batch<false, true><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
+    else if (sb <= MAX_STAGE_BYTES)
+        k_intersect_batch<true, false><<<blocks, 256, sb, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
     else
-        k_intersect_batch<false><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr);
+        k_intersect_batch<false, false><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], st));
     CU(cudaMemcpyAsync(hit, d_hit, n, cudaMemcpyDeviceToHost, st));
@@ -596,9 +700,11 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
     CU(cudaStreamSynchronize(st));
     CU(cudaEventElapsedTime(&ctx->stats.ms_render, ctx->ev[0], ctx->ev[1]));
     ctx->stats.kernel_launches = 1;
+    ctx->stats.accel = use_bvh ? RTCU_ACCEL_BVH : RTCU_ACCEL_LINEAR;
+    const int rc = fetch_counters(ctx, st);
+    if (rc) return rc;
     ctx->stats.segments = n;
-    ctx->stats.sphere_tests = (uint64_t)n * ctx->scene.n_spheres;
-    ctx->stats.accel = RTCU_ACCEL_LINEAR;
+    if (!use_bvh) ctx->stats.sphere_tests = (uint64_t)n * ctx->scene.n_spheres;
     return RTCU_OK;
 }
 
@@ -724,6 +830,22 @@ int rtcu_measure_fp32_peak(rtcu_ctx* ctx, float* tflops_ffma, float* tflops_ffma
         }
         *results[variant] = best;
     }
+    return RTCU_OK;
+}
+
+int rtcu_bvh_build_host(const float* spheres, uint32_t n, float* nodes_out, uint32_t* order_out, uint32_t max_nodes, uint32_t* n_nodes,
+                        uint32_t* depth)
+{
+    if ((n && !spheres) || !n_nodes || !depth) return fail(RTCU_ERR_INVALID, "null argument");
+    const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n);
+    *n_nodes = (uint32_t)bvh.nodes.size();
+    *depth = bvh.max_depth;
+    if (nodes_out)
+    {
+        if (bvh.nodes.size() > max_nodes) return fail(RTCU_ERR_INVALID, "nodes_out too small: need %zu", bvh.nodes.size());
+        memcpy(nodes_out, bvh.nodes.data(), bvh.nodes.size() * sizeof(rtcu_bvh::Node));
+    }
+    if (order_out && n) memcpy(order_out, bvh.order.data(), n * sizeof(uint32_t));
     return RTCU_OK;
 }
 

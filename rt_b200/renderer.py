@@ -252,6 +252,22 @@ class Context:
         return out
 
 
+BVH_NODE_DTYPE = np.dtype([("x", "<f4", (4,)), ("y", "<f4", (4,)), ("z", "<f4", (4,)), ("child", "<i4", (2,)), ("count", "<u4", (2,))])
+
+
+def bvh_build_host(spheres: np.ndarray):
+    """The library's host BVH builder (no device needed): returns (nodes structured array, order, depth)."""
+    lib = nat.load_library()
+    sph = nat.contiguous(spheres, np.float32).reshape(-1, 4)
+    n = len(sph)
+    n_nodes, depth = C.c_uint32(0), C.c_uint32(0)
+    nat.check(lib.rtcu_bvh_build_host(nat.ptr(sph) if n else None, n, None, None, 0, C.byref(n_nodes), C.byref(depth)))
+    nodes = np.zeros(n_nodes.value, BVH_NODE_DTYPE)
+    order = np.zeros(n, np.uint32)
+    nat.check(lib.rtcu_bvh_build_host(nat.ptr(sph) if n else None, n, nat.ptr(nodes), nat.ptr(order) if n else None, len(nodes), C.byref(n_nodes), C.byref(depth)))
+    return nodes, order, int(depth.value)
+
+
 def render_multi(contexts: Sequence[Context], view: nat.View, want_accum: bool = False):
     """rtcu_render_multi: single-process sample-range split over several devices."""
     lib = nat.load_library()

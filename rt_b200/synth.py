@@ -94,3 +94,26 @@ def random_rays(scene: Scene, n: int, seed: int = 1, spread: float = 12.0) -> tu
         scale = np.where(rng.random(k) < 0.3, 0.5, 1.0)[:, None]  # some origins strictly inside
         o[:k] = sp[:, :3] + nrm * sp[:, 3:4] * scale
     return o.astype(np.float32), d.astype(np.float32)
+
+
+def grazing_rays(scene: Scene, n: int, seed: int = 3) -> tuple[np.ndarray, np.ndarray]:
+    """Adversarial batch for traversal parity: rays aimed at points on (or a hair inside / outside) the silhouette of
+    randomly chosen spheres, from origins 0.3 to 400 units away, plus origins exactly on sphere surfaces.  These are the
+    rays for which the rounding of the sphere test decides hit or miss."""
+    rng = np.random.default_rng(seed)
+    sp = scene.spheres[rng.integers(0, len(scene.spheres), n)].astype(np.float64)
+    c, r = sp[:, :3], sp[:, 3:4]
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)      # direction origin -> centre
+    dist = r + np.exp(rng.uniform(np.log(0.3), np.log(400.0), (n, 1)))
+    o = c - u * dist
+    # a unit vector perpendicular to u
+    w = np.cross(u, rng.normal(size=(n, 3))); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    offs = rng.choice([0.0, 1e-7, -1e-7, 1e-6, -1e-6, 1e-5, -1e-5, 1e-4, -1e-4, 1e-3, -1e-3], (n, 1))
+    # tangent point direction: angle between u and the tangent line is asin(r / dist)
+    sin_a = np.clip(r * (1.0 + offs) / dist, -1.0, 1.0)
+    cos_a = np.sqrt(1.0 - sin_a ** 2)
+    d = u * cos_a + w * sin_a
+    k = n // 8  # some origins on the surface, pointing in or out
+    o[:k] = c[:k] + w[:k] * r[:k]
+    d[:k] = rng.normal(size=(k, 3)); d[:k] /= np.linalg.norm(d[:k], axis=1, keepdims=True)
+    return o.astype(np.float32), (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)

@@ -134,3 +134,57 @@ def test_scene_fingerprint_detects_changes():
     assert R.scene_fingerprint(a) == R.scene_fingerprint(b)
     b.spheres[1, 0] += 0.25
     assert R.scene_fingerprint(a) != R.scene_fingerprint(b)
+
+
+# ---- host BVH builder (no device): every sphere in exactly one leaf, child boxes enclose their subtrees ------------
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 9, 484, 5000])
+def test_bvh_builder_invariants(lib, n):
+    from rt_b200 import synth
+
+    if n == 484:
+        sph = synth.rtiow_scene().spheres
+    else:
+        rng = np.random.default_rng(n)
+        sph = np.concatenate([rng.uniform(-20, 20, (n, 3)), rng.uniform(0.05, 2.0, (n, 1))], axis=1).astype(np.float32)
+        if n >= 5:
+            sph[0] = [0, -1000, 0, 1000]   # a huge ground sphere like the benchmark scenes
+            sph[1] = sph[2]                # duplicates (identical centroids)
+    n = len(sph)
+    nodes, order, depth = R.bvh_build_host(sph)
+    assert sorted(order.tolist()) == list(range(n))
+    assert depth <= 62 and len(nodes) >= 1
+    seen = np.zeros(n, bool)
+
+    def check(node_index):
+        nd = nodes[node_index]
+        lo_hi = []
+        for side in range(2):
+            lo = np.array([nd["x"][2 * side], nd["y"][2 * side], nd["z"][2 * side]])
+            hi = np.array([nd["x"][2 * side + 1], nd["y"][2 * side + 1], nd["z"][2 * side + 1]])
+            child, count = int(nd["child"][side]), int(nd["count"][side])
+            if child < 0:
+                first = ~child
+                assert count <= 4
+                prims = order[first:first + count]
+                assert list(prims) == sorted(prims)  # ascending original index inside a leaf
+                for p in prims:
+                    assert not seen[p]
+                    seen[p] = True
+                    assert (lo <= sph[p, :3] - sph[p, 3]).all() and (hi >= sph[p, :3] + sph[p, 3]).all()
+                sub = (lo, hi) if count else None
+            else:
+                sub = check(child)
+                assert (lo <= sub[0]).all() and (hi >= sub[1]).all()
+                sub = (lo, hi)
+            if sub is not None:
+                lo_hi.append(sub)
+        if not lo_hi:
+            return np.full(3, np.inf), np.full(3, -np.inf)
+        los = np.min([b[0] for b in lo_hi], axis=0)
+        his = np.max([b[1] for b in lo_hi], axis=0)
+        return los, his
+
+    import sys
+    sys.setrecursionlimit(10000)
+    check(0)
+    assert seen.all()

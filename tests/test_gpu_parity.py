@@ -277,3 +277,63 @@ def test_error_codes(ctx, scenes):
             fresh.render(make_view(scenes["c1"][0], 16, 16, **bad))
         assert e.value.code == nat.RTCU_ERR_INVALID
     fresh.close()
+
+
+# ---- BVH traversal: the linear scan's exact result ----------------------------------------------------------
+def _grid():
+    return synth.grid_scene(nx=120, nz=80, seed=9)  # 9601 spheres + ground
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "planes", "grid"])
+def test_bvh_matches_linear_scan_exactly(ctx, oracle, scenes, name):
+    sc = _grid() if name == "grid" else scenes[name][0]
+    ctx.upload_scene(sc)
+    batches = [synth.random_rays(sc, 1 << 17, seed=31, spread=40.0 if name == "grid" else 12.0), synth.grazing_rays(sc, 1 << 17, seed=32)]
+    for o, d in batches:
+        lin = ctx.intersect_batch(o, d, accel=nat.ACCEL_LINEAR)
+        bvh = ctx.intersect_batch(o, d, accel=nat.ACCEL_BVH)
+        st = ctx.stats()
+        for a, b in zip(bvh, lin):
+            np.testing.assert_array_equal(a, b)
+        assert st["accel"] == nat.ACCEL_BVH and st["node_visits"] > 0
+        if len(sc.spheres) > 400:
+            assert st["sphere_tests"] < 0.2 * len(o) * len(sc.spheres)  # it actually culls
+    # and against the oracle on a subset (the linear kernel is already pinned to it)
+    o, d = batches[1][0][:20000], batches[1][1][:20000]
+    got = ctx.intersect_batch(o, d, accel=nat.ACCEL_BVH)
+    ref = oracle.intersect_batch(sc, o, d)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_bvh_non_unit_directions_fall_back_to_the_scan(ctx, scenes):
+    sc = scenes["c3"][0]
+    ctx.upload_scene(sc)
+    o, d = synth.random_rays(sc, 4096, seed=5)
+    d = (d * np.float32(1.7)).astype(np.float32)
+    lin = ctx.intersect_batch(o, d, accel=nat.ACCEL_LINEAR)
+    bvh = ctx.intersect_batch(o, d, accel=nat.ACCEL_BVH)
+    for a, b in zip(bvh, lin):
+        np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,mode", [("c3", nat.MODE_SM), ("c2", nat.MODE_SM), ("planes", nat.MODE_SM), ("grid", nat.MODE_SM), ("grid", nat.MODE_MG)])
+def test_bvh_render_is_bit_identical_to_linear_render(ctx, scenes, name, mode):
+    sc = _grid() if name == "grid" else scenes[name][0]
+    ctx.upload_scene(sc)
+    kw = dict(samples_per_pixel=4, max_bounces=20, material_mode=mode)
+    _, lin = ctx.render(make_view(sc, 192, 108, flags=nat.ACCEL_LINEAR, **kw), want_accum=True)
+    segs_lin = ctx.stats()["segments"]
+    rgba, bvh = ctx.render(make_view(sc, 192, 108, flags=nat.ACCEL_BVH, **kw), want_accum=True)
+    st = ctx.stats()
+    assert st["accel"] == nat.ACCEL_BVH and st["segments"] == segs_lin
+    np.testing.assert_array_equal(bvh, lin)  # same paths, same arithmetic, same sums
+
+
+def test_bvh_auto_threshold(ctx, scenes):
+    thr = nat.load_library().rtcu_bvh_threshold()
+    for name in ("c2", "c3"):
+        sc = scenes[name][0]
+        ctx.upload_scene(sc)
+        ctx.render(make_view(sc, 32, 32, samples_per_pixel=1, max_bounces=2), want_accum=False)
+        assert ctx.stats()["accel"] == (nat.ACCEL_BVH if len(sc.spheres) >= thr else nat.ACCEL_LINEAR)
