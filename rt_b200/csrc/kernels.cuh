@@ -44,6 +44,11 @@ struct RenderParams {
     uint32_t* rgba8;       // nullable
     unsigned long long* counters; // [0] = segments
     uint32_t regen_threshold;     // regenerate ended lanes once this many lanes of the warp are idle (1 = immediately)
+    // straggler hand-off: a thread that has traced `segment_budget` segments stops at the next sample boundary and
+    // queues {pixel, next sample} for k_render_stragglers (one warp per queued pixel).  0 = no budget.
+    uint32_t segment_budget;
+    uint2* stragglers;            // queue storage, width*height entries
+    unsigned int* straggler_count;
 };
 
 #define RTCU_PRIM_MISS 0xFFFFFFFFu
@@ -413,6 +418,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
                     live = false;
                     key.sample++;
                     more = key.sample < p.sample_end;
+                    if (more && p.segment_budget && segs >= p.segment_budget)
+                    {
+                        p.stragglers[atomicAdd(p.straggler_count, 1u)] = make_uint2(key.pixel, key.sample);
+                        more = false;
+                    }
                 }
             }
         }
@@ -428,6 +438,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
                 key.sample++;
                 if (key.sample >= p.sample_end)
                     break;
+                if (p.segment_budget && segs >= p.segment_budget)
+                {
+                    p.stragglers[atomicAdd(p.straggler_count, 1u)] = make_uint2(key.pixel, key.sample);
+                    break;
+                }
                 seg = 0;
                 thr = v3(1.0f, 1.0f, 1.0f);
                 ray = generate(p.cam, key, px, py);
@@ -437,8 +452,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
 
     if (in_tile)
     {
-        const size_t idx = (size_t)key.pixel;
-        float4 acc = make_float4(sum.x, sum.y, sum.z, (float)(p.sample_end - p.sample_begin));
+        const size_t idx = (size_t)(py * p.width + px);
+        // n = samples finished by this thread (key.sample has advanced past them); stragglers add the rest
+        float4 acc = make_float4(sum.x, sum.y, sum.z, (float)(key.sample - p.sample_begin));
         if (p.accumulate)
         {
             const float4 old = p.accum[idx];
@@ -469,6 +485,74 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
             atomicAdd(p.counters + 1, nodes);
             atomicAdd(p.counters + 2, tests);
         }
+    }
+}
+
+// Second pass of a render call: the few pixels whose paths are far longer than the frame average (a crevice between
+// two bright spheres can take 20x the mean) would otherwise each keep one lane -- and its whole CTA slot -- busy long
+// after the rest of the grid has drained.  Here one warp takes one queued pixel: lane l traces samples next+l, next+l+32,
+// ...; the 32 partial sums are combined in a fixed butterfly order (deterministic) and added to the pixel's partial
+// result from the first pass.  Primitives are read from global memory (L1-resident for the scenes that reach this path).
+template <bool BVH>
+__global__ void __launch_bounds__(128) k_render_stragglers(const SceneDev sc, const RenderParams p)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t count = *p.straggler_count;
+    unsigned long long segs = 0;
+    BvhStats bst;
+    bst.nodes = 0;
+    bst.tests = 0;
+    for (uint32_t item = warp_global; item < count; item += n_warps)
+    {
+        const uint2 w = p.stragglers[item];
+        const uint32_t px = w.x % p.width, py = w.x / p.width;
+        RngKey key;
+        key.key = p.key;
+        key.pixel = w.x;
+        V3 sum = v3(0.0f, 0.0f, 0.0f);
+        for (key.sample = w.y + lane; key.sample < p.sample_end; key.sample += 32u)
+        {
+            V3 thr = v3(1.0f, 1.0f, 1.0f);
+            uint32_t seg = 0;
+            Ray ray = generate(p.cam, key, px, py);
+            do
+                segs++;
+            while (!segment_step<BVH>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+        {
+            sum.x = __fadd_rn(sum.x, __shfl_xor_sync(0xffffffffu, sum.x, off));
+            sum.y = __fadd_rn(sum.y, __shfl_xor_sync(0xffffffffu, sum.y, off));
+            sum.z = __fadd_rn(sum.z, __shfl_xor_sync(0xffffffffu, sum.z, off));
+        }
+        if (lane == 0)
+        {
+            float4 acc = p.accum[w.x];
+            acc.x = __fadd_rn(acc.x, sum.x); acc.y = __fadd_rn(acc.y, sum.y); acc.z = __fadd_rn(acc.z, sum.z);
+            acc.w = __fadd_rn(acc.w, (float)(p.sample_end - w.y));
+            p.accum[w.x] = acc;
+            if (p.rgba8)
+                p.rgba8[w.x] = pack_pixel(acc.x, acc.y, acc.z, p.spp_resolve);
+        }
+    }
+    unsigned long long nodes = bst.nodes, tests = bst.tests;
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        segs += __shfl_down_sync(0xffffffffu, segs, off);
+        nodes += __shfl_down_sync(0xffffffffu, nodes, off);
+        tests += __shfl_down_sync(0xffffffffu, tests, off);
+    }
+    if (lane == 0 && segs)
+    {
+        atomicAdd(p.counters, segs);
+        if (BVH)
+        {
+            atomicAdd(p.counters + 1, nodes);
+            atomicAdd(p.counters + 2, tests);
+        }
+        atomicAdd(p.counters + 3, 1ull); // warps that had straggler work (diagnostic)
     }
 }
 

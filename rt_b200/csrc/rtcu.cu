@@ -122,6 +122,8 @@ struct rtcu_ctx {
     PinnedBuf<uint32_t> h_rgba8;
     PinnedBuf<float> h_accum;
     DevBuf<unsigned long long> counters;
+    DevBuf<uint2> stragglers;            // straggler queue of the last render (width*height entries)
+    DevBuf<unsigned int> straggler_count;
     PinnedBuf<unsigned long long> h_counters;
 
     // scratch for the batch entry points
@@ -175,6 +177,16 @@ uint32_t regen_threshold_for(uint32_t n_prims)
     return 1u;
 }
 
+// per-thread segment budget before a pixel is handed to k_render_stragglers (0 disables; RTCU_STRAGGLER_BUDGET overrides
+// with a multiple of the call's samples per pixel)
+uint32_t straggler_budget_for(uint32_t n_samples)
+{
+    int mult = 3;
+    if (const char* e = getenv("RTCU_STRAGGLER_BUDGET")) mult = atoi(e);
+    if (mult <= 0 || n_samples < 2) return 0;
+    return (uint32_t)mult * n_samples + 64u;
+}
+
 // loop structure of k_render_mega: the warp-vote (flat) loop pays off once the O(N) sweep dominates a segment
 bool flat_loop_for(uint32_t n_prims)
 {
@@ -201,6 +213,13 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     p.accumulate = accumulate;
     p.counters = ctx->counters.p;
     p.regen_threshold = regen_threshold_for(ctx->scene.n_spheres + ctx->scene.n_planes);
+    // straggler hand-off (see k_render_stragglers): budget = 3x the samples of this call + 64 segments per pixel
+    const uint32_t n_samples = v->sample_end - v->sample_begin;
+    p.segment_budget = straggler_budget_for(n_samples);
+    CU(ctx->stragglers.reserve((size_t)v->width * v->height));
+    p.stragglers = ctx->stragglers.p;
+    p.straggler_count = ctx->straggler_count.p;
+    CU(cudaMemsetAsync(ctx->straggler_count.p, 0, sizeof(unsigned int), st));
 
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
     const dim3 grid((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W, (v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
@@ -217,6 +236,15 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
         k_render_mega<false, true, false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
     CU(cudaGetLastError());
     ctx->stats.kernel_launches = 1;
+    if (p.segment_budget)
+    {
+        // the accumulate flag only applies to the first pass: the second adds onto what the first wrote
+        const unsigned blocks = (unsigned)ctx->sm_count * 4;
+        if (use_bvh) k_render_stragglers<true><<<blocks, 128, 0, st>>>(ctx->scene, p);
+        else k_render_stragglers<false><<<blocks, 128, 0, st>>>(ctx->scene, p);
+        CU(cudaGetLastError());
+        ctx->stats.kernel_launches = 2;
+    }
     ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
     ctx->stats.accel = use_bvh ? RTCU_ACCEL_BVH : RTCU_ACCEL_LINEAR;
     ctx->stats.samples = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0) * (v->sample_end - v->sample_begin);
@@ -339,7 +367,7 @@ rtcu_ctx* rtcu_create(int device)
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 6; i++)
         ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
-    ok = ok && ctx->counters.reserve(4) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess;
+    ok = ok && ctx->counters.reserve(4) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess && ctx->straggler_count.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_render_mega<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess
          && cudaFuncSetAttribute(k_render_mega<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_intersect_batch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
@@ -359,7 +387,7 @@ void rtcu_destroy(rtcu_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->sph.release(); ctx->sph_raw.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
     ctx->mats.release(); ctx->bvh_nodes.release(); ctx->leaf_sph.release(); ctx->leaf_idx.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
-    ctx->counters.release(); ctx->h_counters.release(); ctx->scratch.release();
+    ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
