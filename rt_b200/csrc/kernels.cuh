@@ -13,7 +13,7 @@ namespace rtcu_dev {
 
 struct SceneDev {
     const float4* spheres;   // {cx,cy,cz,r*r}
-    const float4* pairs;     // 2*ceil(n/2)+2 float4 (one never-hit sentinel pair at the end): {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1} (packed-FP32 scan layout)
+    const float4* pairs;     // pair_float4_count(n) float4 (padded with never-hit pairs): {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1} (packed-FP32 scan layout)
     const uint32_t* sphere_material;
     uint32_t n_spheres;
     const float4* planes;    // {nx,ny,nz,d}
@@ -37,7 +37,7 @@ struct RenderParams {
     uint32_t sample_begin, sample_end;
     uint32_t max_bounces;
     uint32_t mode;
-    uint2 key;
+    PhiloxKeys rk;         // Philox round keys of the view's seed
     float spp_resolve;     // float(samples_per_pixel)
     int accumulate;
     float4* accum;         // width*height {sum_r,sum_g,sum_b,n}
@@ -56,6 +56,10 @@ struct RenderParams {
 
 struct Hit { float t; uint32_t prim; }; // prim: sphere index | PLANE|index | MISS
 
+// packed-scan layout sizes: pairs padded to an even count, plus two trailing never-hit pairs (prefetch target)
+__host__ __device__ __forceinline__ uint32_t pair_count_padded(uint32_t n_spheres) { return ((n_spheres + 3u) >> 2) << 1; }
+__host__ __device__ __forceinline__ uint32_t pair_float4_count(uint32_t n_spheres) { return 2u * (pair_count_padded(n_spheres) + 2u); }
+
 // closest hit over planes then spheres with the reference's tie rules
 // (mg_ray_tracer.cpp:35-102, :160-162).  s_pairs / s_pl may point to shared or global memory.
 __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_pairs, const uint32_t n_sph,
@@ -64,9 +68,11 @@ __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_p
     const float inf = __int_as_float(0x7f800000);
     float ts = inf;
     int is = -1;
-    const uint32_t n_pairs = (n_sph + 1u) >> 1;
     // software pipeline: the next pair is loaded (warp-uniform LDS.128 x2) before the current one is tested, so the
-    // shared-memory latency hides behind ~20 arithmetic instructions.  The array carries one sentinel pair at the end.
+    // shared-memory latency hides behind ~20 arithmetic instructions.  The array ends with never-hit pairs (r2 = -inf),
+    // so the prefetch of the pair after the last one is always in bounds.  (Testing two pairs per iteration with a
+    // two-pair prefetch was measured slower: 16 more live registers under the 64-register cap.)
+    const uint32_t n_pairs = (n_sph + 1u) >> 1;
     float4 A = s_pairs[0], B = s_pairs[1];
 #pragma unroll 4
     for (uint32_t j = 0; j < n_pairs; j++)
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
     const float4* s_pl = sc.planes;
     if (STAGE)
     {
-        const uint32_t n4 = ((sc.n_spheres + 1u) & ~1u) + 2u; // float4 count of the pair layout + sentinel pair
+        const uint32_t n4 = pair_float4_count(sc.n_spheres);
         for (uint32_t i = threadIdx.x; i < n4; i += MEGA_THREADS)
             smem[i] = __ldg(sc.pairs + i);
         for (uint32_t i = threadIdx.x; i < sc.n_planes; i += MEGA_THREADS)
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
     bst.nodes = 0;
     bst.tests = 0;
     RngKey key;
-    key.key = p.key;
+    key.ks = &p.rk;
     key.pixel = py * p.width + px;
     key.sample = p.sample_begin;
     V3 sum = v3(0.0f, 0.0f, 0.0f);
@@ -508,7 +514,7 @@ __global__ void __launch_bounds__(128) k_render_stragglers(const SceneDev sc, co
         const uint2 w = p.stragglers[item];
         const uint32_t px = w.x % p.width, py = w.x / p.width;
         RngKey key;
-        key.key = p.key;
+        key.ks = &p.rk;
         key.pixel = w.x;
         V3 sum = v3(0.0f, 0.0f, 0.0f);
         for (key.sample = w.y + lane; key.sample < p.sample_end; key.sample += 32u)
@@ -598,7 +604,7 @@ __global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, cons
     const float4* s_pl = sc.planes;
     if (STAGE)
     {
-        const uint32_t n4 = ((sc.n_spheres + 1u) & ~1u) + 2u;
+        const uint32_t n4 = pair_float4_count(sc.n_spheres);
         for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x)
             smem[i] = __ldg(sc.pairs + i);
         for (uint32_t i = threadIdx.x; i < sc.n_planes; i += blockDim.x)
@@ -634,20 +640,20 @@ __global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, cons
     }
 }
 
-__global__ void k_primary_rays(const CameraConst cam, uint32_t width, uint2 key, const uint32_t* __restrict__ px,
+__global__ void k_primary_rays(const CameraConst cam, uint32_t width, const PhiloxKeys rk, const uint32_t* __restrict__ px,
                                const uint32_t* __restrict__ py, const uint32_t* __restrict__ sample, uint32_t n,
                                float* __restrict__ o, float* __restrict__ d)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     RngKey k;
-    k.key = key; k.pixel = py[i] * width + px[i]; k.sample = sample[i];
+    k.ks = &rk; k.pixel = py[i] * width + px[i]; k.sample = sample[i];
     const Ray r = generate(cam, k, px[i], py[i]);
     o[3 * i] = r.o.x; o[3 * i + 1] = r.o.y; o[3 * i + 2] = r.o.z;
     d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z;
 }
 
-__global__ void k_scatter_batch(const SceneDev sc, uint32_t mode, uint2 key, uint32_t n, const uint32_t* __restrict__ material,
+__global__ void k_scatter_batch(const SceneDev sc, uint32_t mode, const PhiloxKeys rk, uint32_t n, const uint32_t* __restrict__ material,
                                 const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ t,
                                 const float* __restrict__ nrm, const uint32_t* __restrict__ pixel, const uint32_t* __restrict__ sample,
                                 const uint32_t* __restrict__ block, uint8_t* __restrict__ scattered, float* __restrict__ att,
@@ -660,7 +666,7 @@ __global__ void k_scatter_batch(const SceneDev sc, uint32_t mode, uint2 key, uin
     r.d = v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
     const V3 nn = v3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
     RngKey k;
-    k.key = key; k.pixel = pixel[i]; k.sample = sample[i];
+    k.ks = &rk; k.pixel = pixel[i]; k.sample = sample[i];
     const MatRec m = load_material(sc, material[i]);
     const uint4 rnd = rng_block(k, block[i], 0u);
     Ray out;
@@ -672,11 +678,11 @@ __global__ void k_scatter_batch(const SceneDev sc, uint32_t mode, uint2 key, uin
     d_out[3 * i] = ok ? out.d.x : 0.0f; d_out[3 * i + 1] = ok ? out.d.y : 0.0f; d_out[3 * i + 2] = ok ? out.d.z : 0.0f;
 }
 
-__global__ void k_philox_batch(const uint4* __restrict__ ctr, uint32_t n, uint2 key, uint4* __restrict__ out)
+__global__ void k_philox_batch(const uint4* __restrict__ ctr, uint32_t n, const PhiloxKeys rk, uint4* __restrict__ out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
-        out[i] = philox4x32_10(ctr[i], key);
+        out[i] = philox4x32_10(ctr[i], rk);
 }
 
 

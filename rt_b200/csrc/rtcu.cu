@@ -156,7 +156,7 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     p.sample_begin = v->sample_begin; p.sample_end = v->sample_end;
     p.max_bounces = v->max_bounces;
     p.mode = v->material_mode;
-    p.key = make_uint2((uint32_t)v->seed, (uint32_t)(v->seed >> 32));
+    p.rk = philox_keys(make_uint2((uint32_t)v->seed, (uint32_t)(v->seed >> 32)));
     p.spp_resolve = (float)v->samples_per_pixel;
     p.accumulate = 0;
     p.accum = nullptr;
@@ -194,7 +194,7 @@ bool flat_loop_for(uint32_t n_prims)
     return n_prims >= 32;
 }
 
-size_t stage_bytes(const rtcu_ctx* ctx) { return ((((size_t)ctx->scene.n_spheres + 1) & ~(size_t)1) + 2 + ctx->scene.n_planes) * sizeof(float4); }
+size_t stage_bytes(const rtcu_ctx* ctx) { return ((size_t)pair_float4_count(ctx->scene.n_spheres) + ctx->scene.n_planes) * sizeof(float4); }
 
 // launches the trace kernels of one view on `st`; accum/rgba8 are device pointers
 int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st)
@@ -419,14 +419,14 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         raw[i] = make_float4(p[0], p[1], p[2], r);
         sph[i] = make_float4(p[0], p[1], p[2], r2);
     }
-    // packed-scan layout: pair j = spheres 2j, 2j+1 as {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}; odd tail padded with r2 = -inf
-    const size_t n_pairs = ((size_t)s->n_spheres + 1) / 2;
-    std::vector<float4> pairs(2 * n_pairs + 2, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // + sentinel pair (prefetch target, never tested)
-    pairs[2 * n_pairs + 1] = make_float4(0.0f, 0.0f, -__builtin_inff(), -__builtin_inff());
-    for (size_t j = 0; j < n_pairs; j++)
+    // packed-scan layout: pair j = spheres 2j, 2j+1 as {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}; everything past the last
+    // sphere (odd tail, padding to an even pair count, two prefetch pairs) is a never-hit entry: centre 0, r2 = -inf
+    const float4 never = make_float4(0.0f, 0.0f, 0.0f, -__builtin_inff());
+    std::vector<float4> pairs(pair_float4_count(s->n_spheres));
+    for (size_t j = 0; 2 * j < pairs.size(); j++)
     {
-        const float4 s0 = sph[2 * j];
-        const float4 s1 = (2 * j + 1 < s->n_spheres) ? sph[2 * j + 1] : make_float4(0.0f, 0.0f, 0.0f, -__builtin_inff());
+        const float4 s0 = (2 * j < s->n_spheres) ? sph[2 * j] : never;
+        const float4 s1 = (2 * j + 1 < s->n_spheres) ? sph[2 * j + 1] : never;
         pairs[2 * j] = make_float4(s0.x, s1.x, s0.y, s1.y);
         pairs[2 * j + 1] = make_float4(s0.z, s1.z, s0.w, s1.w);
     }
@@ -445,18 +445,18 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     }
     CU(ctx->sph.reserve(s->n_spheres ? s->n_spheres : 1));
     CU(ctx->sph_raw.reserve(s->n_spheres ? s->n_spheres : 1));
-    CU(ctx->pairs.reserve(pairs.empty() ? 2 : pairs.size()));
+    CU(ctx->pairs.reserve(pairs.size()));
     CU(ctx->sph_mat.reserve(s->n_spheres ? s->n_spheres : 1));
     CU(ctx->planes.reserve(s->n_planes ? s->n_planes : 1));
     CU(ctx->plane_mat.reserve(s->n_planes ? s->n_planes : 1));
     CU(ctx->mats.reserve(s->n_materials));
     // make sure no kernel of a previous frame still reads the old scene
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), pairs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     if (s->n_spheres)
     {
         CU(cudaMemcpyAsync(ctx->sph.p, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->sph_raw.p, raw.data(), raw.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), pairs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->sph_mat.p, s->sphere_material, s->n_spheres * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (s->n_planes)
@@ -758,7 +758,7 @@ int rtcu_primary_rays(rtcu_ctx* ctx, const rtcu_view* view, const uint32_t* px, 
     CU(cudaMemcpyAsync(d_px, px, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_py, py, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_s, sample, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    k_primary_rays<<<(n + 255) / 256, 256, 0, st>>>(p.cam, p.width, p.key, d_px, d_py, d_s, n, d_o, d_d);
+    k_primary_rays<<<(n + 255) / 256, 256, 0, st>>>(p.cam, p.width, p.rk, d_px, d_py, d_s, n, d_o, d_d);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(o, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(d, d_d, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
@@ -801,7 +801,7 @@ int rtcu_scatter_batch(rtcu_ctx* ctx, uint32_t material_mode, uint64_t seed, uin
     CU(cudaMemcpyAsync(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_n, normal, (size_t)n * 12, cudaMemcpyHostToDevice, st));
-    k_scatter_batch<<<(n + 255) / 256, 256, 0, st>>>(ctx->scene, material_mode, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), n, d_mat, d_o, d_d,
+    k_scatter_batch<<<(n + 255) / 256, 256, 0, st>>>(ctx->scene, material_mode, philox_keys(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), n, d_mat, d_o, d_d,
                                                     d_t, d_n, d_pix, d_smp, d_blk, d_sc, d_att, d_oo, d_do);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(scattered, d_sc, n, cudaMemcpyDeviceToHost, st));
@@ -823,7 +823,7 @@ int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t k
     uint4* d_o = c.take<uint4>(n);
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(d_c, ctr, (size_t)n * 16, cudaMemcpyHostToDevice, st));
-    k_philox_batch<<<(n + 255) / 256, 256, 0, st>>>(d_c, n, make_uint2((uint32_t)key, (uint32_t)(key >> 32)), d_o);
+    k_philox_batch<<<(n + 255) / 256, 256, 0, st>>>(d_c, n, philox_keys(make_uint2((uint32_t)key, (uint32_t)(key >> 32))), d_o);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, d_o, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
