@@ -13,8 +13,9 @@ work per GPU), the fp32 accumulation buffers are reduced onto rank 0 over NCCL, 
          wall clock around K steps.
   roofline      dominant kernel (k_render_mega) against the non-tensor FP32 peak: SURVEY.md 8d names the FP32
                 pipe, not HBM or tensor cores, as the bound of this path.
-  cpu_baseline  the oracle's fast build ("port": the reference cannot be compiled here) on the host cores,
-                bounded row subset of the same frame.  `--impl reference` prints that arm as its own line.
+  cpu_baseline  the reference's own sm_ray_tracer.cpp compiled against the muu stand-in (oracle/_ref, kind "reference";
+                the oracle port when that library is absent) on the host cores, bounded row subset of the same frame.
+                `--impl reference` prints that arm as its own line.
 """
 from __future__ import annotations
 
@@ -107,34 +108,51 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------------
 def cpu_baseline(scene, view, target_seconds: float, steps: int = 1, warmup: int = 0):
-    """Times the oracle's fast build (reference flags, all host cores) on a bounded row subset of the frame.
-    Returns (Msamples/s, cores, description, ms_per_step)."""
-    from oracle.binding import Oracle
+    """Times the reference's CPU implementation of the path on all host cores, on a bounded row subset of the frame.
 
-    oracle = Oracle("fast")
+    kind "reference": oracle/_ref/librt_ref_fast.so -- marzer/rt's own sm_ray_tracer.cpp compiled (in the dev container,
+    with the reference's -O3 -ffast-math flags, x86-64-v3) against the muu stand-in; used whenever that library travelled.
+    kind "port": the oracle's fast build (oracle/rtref.c), when it did not.
+    Returns (mean Msamples/s, best Msamples/s, cores, kind, description, ms_per_step)."""
+    from oracle.binding import Oracle, ReferenceBuild
+
     cores = os.cpu_count() or 1
-    # probe: every 120th row
+    spp = view.sample_end - view.sample_begin
+    if ReferenceBuild.FAST_PATH.exists():
+        ref = ReferenceBuild("fast")
+        kind = "reference"
+        what = "marzer/rt sm_ray_tracer.cpp compiled against the muu stand-in (oracle/_ref, -O3 -march=x86-64-v3 -ffast-math)"
+
+        def run(row_step):
+            ref.render(scene, view.width, view.height, spp, view.max_bounces, view.seed, "sm_ray_tracer", threads=cores, row_step=row_step)
+    else:
+        oracle = Oracle("fast")
+        kind = "port"
+        what = "oracle fast build (oracle/rtref.c, -O3 -march=native -ffast-math)"
+
+        def run(row_step):
+            oracle.render(scene, view, threads=cores, row_step=row_step, want_rgba8=True, want_accum=False)
+
     t0 = time.perf_counter()
-    oracle.render(scene, view, threads=cores, row_step=120, want_rgba8=True, want_accum=False)
+    run(120)  # probe: every 120th row
     probe = time.perf_counter() - t0
-    probe_rows = len(range(0, view.height, 120))
-    per_row = probe / probe_rows
+    per_row = probe / len(range(0, view.height, 120))
     rows_wanted = max(1, min(view.height, int(target_seconds / max(per_row, 1e-6))))
     row_step = max(1, view.height // rows_wanted)
     rows = len(range(0, view.height, row_step))
-    samples = rows * view.width * (view.sample_end - view.sample_begin)
+    samples = rows * view.width * spp
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        oracle.render(scene, view, threads=cores, row_step=row_step, want_rgba8=True, want_accum=False)
+        run(row_step)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     best = min(times)
     mean = sum(times) / len(times)
-    desc = (f"oracle fast build (-O3 -march=native -ffast-math, {cores} threads), rows 0::{row_step} of the {view.width}x{view.height} frame "
+    desc = (f"{what}, {cores} threads, rows 0::{row_step} of the {view.width}x{view.height} frame "
             f"({rows} rows, {samples / 1e6:.1f} Msamples per step), same RNG streams")
-    return samples / mean / 1e6, samples / best / 1e6, cores, desc, mean * 1e3
+    return samples / mean / 1e6, samples / best / 1e6, cores, kind, desc, mean * 1e3
 
 
 def run_reference(args):
@@ -148,12 +166,12 @@ def run_reference(args):
     scene = load_scene()
     view = make_view(scene, WIDTH, HEIGHT, samples_per_pixel=SPP, max_bounces=MAX_BOUNCES, material_mode=nat.MODE_SM)
     budget = 150.0 / max(1, args.steps + args.warmup)
-    mean_v, best_v, cores, desc, ms = cpu_baseline(scene, view, target_seconds=min(20.0, budget), steps=args.steps, warmup=args.warmup)
+    mean_v, best_v, cores, kind, desc, ms = cpu_baseline(scene, view, target_seconds=min(20.0, budget), steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(mean_v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": desc},
-        "cpu_baseline": {"value": round(mean_v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": round(mean_v, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": round(mean_v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -311,8 +329,8 @@ def run_gpu(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cview = make_view(scene, WIDTH, HEIGHT, samples_per_pixel=SPP, max_bounces=MAX_BOUNCES, material_mode=nat.MODE_SM)
-            mean_v, best_v, cores, desc, _ = cpu_baseline(scene, cview, target_seconds=12.0, steps=1, warmup=0)
-            cpu = {"value": round(mean_v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            mean_v, best_v, cores, kind, desc, _ = cpu_baseline(scene, cview, target_seconds=12.0, steps=1, warmup=0)
+            cpu = {"value": round(mean_v, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

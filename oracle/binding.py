@@ -152,3 +152,68 @@ class Oracle:
         out = (C.c_float * 3)()
         nseg = self.lib.rtref_trace_sample(C.byref(sd), C.byref(v), px, py, sample, out)
         return np.array(list(out), np.float32), int(nseg)
+
+
+class ReferenceBuild:
+    """oracle/_ref/librt_ref.so: marzer/rt's own mg_ray_tracer.cpp / sm_ray_tracer.cpp / renderer.cpp compiled against the
+    ref_shim stand-in for muu (see oracle/Makefile `ref`).  TEST INFRASTRUCTURE.  The library is built in the dev
+    container (where /root/reference exists) and travels to the GPU box prebuilt."""
+
+    PATH = HERE / "_ref" / "librt_ref.so"
+    FAST_PATH = HERE / "_ref" / "librt_ref_fast.so"  # -O3 -ffast-math flavour for CPU timing
+
+    @classmethod
+    def available(cls, build_if_possible: bool = True) -> bool:
+        if build_if_possible and pathlib.Path("/root/reference/src/renderers/mg_ray_tracer.cpp").exists():
+            r = subprocess.run(["make", "-C", str(HERE), "ref"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("reference build failed:\n" + r.stdout + r.stderr)
+        return cls.PATH.exists()
+
+    def __init__(self, flavour: str = "strict"):
+        if not self.available():
+            raise RuntimeError(f"{self.PATH} is missing and /root/reference is not present to build it")
+        path = self.FAST_PATH if flavour == "fast" else self.PATH
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing")
+        self.lib = C.CDLL(str(path))
+        p, u32 = C.c_void_p, C.c_uint32
+        self.lib.refbin_list.argtypes = [C.c_char_p, u32]
+        self.lib.refbin_render.argtypes = [C.POINTER(SceneDesc), p, p, u32, u32, u32, u32, C.c_uint64, C.c_char_p, p, C.c_int, u32, p]
+        self._keep = None
+
+    def renderers(self) -> list:
+        buf = C.create_string_buffer(1024)
+        self.lib.refbin_list(buf, 1024)
+        return [x for x in buf.value.decode().split("\n") if x]
+
+    def _desc(self, scene) -> SceneDesc:
+        sph = np.ascontiguousarray(scene.spheres, np.float32).reshape(-1, 4)
+        smat = np.ascontiguousarray(scene.sphere_material, np.uint32)
+        pl = np.ascontiguousarray(scene.planes, np.float32).reshape(-1, 4)
+        pmat = np.ascontiguousarray(scene.plane_material, np.uint32)
+        mats = np.ascontiguousarray(scene.materials.astype(_MATERIAL_DTYPE))
+        self._keep = (sph, smat, pl, pmat, mats)
+        return SceneDesc(sph.ctypes.data if len(sph) else None, smat.ctypes.data if len(smat) else None, len(sph),
+                         pl.ctypes.data if len(pl) else None, pmat.ctypes.data if len(pmat) else None, len(pl), mats.ctypes.data, len(mats))
+
+    def inverse_view_projection(self, scene, width: int, height: int) -> np.ndarray:
+        """the matrix the reference's own camera::viewport produces (through the stand-in matrix code)"""
+        sd = self._desc(scene)
+        pos = np.array(scene.camera.position, np.float32); d = np.array(scene.camera.direction, np.float32)
+        out = np.zeros(16, np.float32)
+        rc = self.lib.refbin_render(C.byref(sd), pos.ctypes.data, d.ctypes.data, width, height, 1, 1, 0, b"mg_ray_tracer", None, 1, 1, out.ctypes.data)
+        assert rc == 0
+        return out
+
+    def render(self, scene, width: int, height: int, spp: int, max_bounces: int, seed: int, renderer: str = "mg_ray_tracer",
+               threads: int = 0, row_step: int = 1):
+        sd = self._desc(scene)
+        pos = np.array(scene.camera.position, np.float32); d = np.array(scene.camera.direction, np.float32)
+        rgba8 = np.zeros((height, width), np.uint32)
+        ivp = np.zeros(16, np.float32)
+        rc = self.lib.refbin_render(C.byref(sd), pos.ctypes.data, d.ctypes.data, width, height, spp, max_bounces, seed, renderer.encode(),
+                                    rgba8.ctypes.data, threads, row_step, ivp.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"reference has no renderer named {renderer!r}")
+        return rgba8, ivp

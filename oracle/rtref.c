@@ -14,6 +14,11 @@
  * so its own contraction is compiler-chosen; this spec fixes one legal choice.  The strict
  * build of this file uses -ffp-contract=off so only the fmaf() written below fuses.
  *
+ *  R   expressions written in the reference's own source (reflect, the metal and lambert sums, refract, the
+ *      Schlick polynomial, attenuation products, the per-pixel sum) are evaluated exactly as written, left to
+ *      right, one rounding per operator, NO contraction.  Only the muu primitives below (which the reference calls
+ *      but does not contain) use fused multiply-adds; oracle/ref_shim implements them identically so that the
+ *      reference's renderer sources, compiled against the stand-in, reproduce this file bit for bit.
  *  S1  dot3(a,b)      = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x))
  *  S2  normalize(v)   = v * (1.0f / sqrtf(dot3(v,v)))        (one division, three multiplies)
  *  S3  at(o,d,t)      = fma(d, t, o) per component            (muu ray::at = origin + dir*t)
@@ -243,7 +248,7 @@ static hit_result closest_hit(const rtref_scene* s, const ray_t* r)
 static inline v3 reflect3(v3 v, v3 n)
 {
     const float k = 2.0f * dot3(v, n);
-    return v3_make(FMA(-k, n.x, v.x), FMA(-k, n.y, v.y), FMA(-k, n.z, v.z));
+    return v3_sub(v, v3_scale(n, k)); /* source expression, evaluated without contraction (SPEC rule R) */
 }
 
 /* attenuation = vec3{albedo * reflectivity}: mg_ray_tracer.cpp:115,:131, sm_ray_tracer.cpp:194 */
@@ -275,7 +280,7 @@ static int metal_scatter(const rtref_material* m, const ray_t* r, const hit_resu
     *att = attenuation_of(m);
     const v3 refl = reflect3(normalize3(r->d), hit->normal);
     const v3 u = random_unit_vector(k, block);
-    v3 s = v3_make(FMA(m->roughness, u.x, refl.x), FMA(m->roughness, u.y, refl.y), FMA(m->roughness, u.z, refl.z));
+    v3 s = v3_add(refl, v3_scale(u, m->roughness)); /* reflect(...) + roughness * random_unit_vector(), rule R */
     if (dot3(s, hit->normal) <= 0.0f)
         return 0;
     s = normalize3(s);
@@ -288,12 +293,12 @@ static int metal_scatter(const rtref_material* m, const ray_t* r, const hit_resu
 static int refract3(v3 v, v3 n, float eta, v3* refracted)
 {
     const float cos_i = -dot3(v, n);
-    const float sin2_t = (eta * eta) * FMA(-cos_i, cos_i, 1.0f);
+    const float sin2_t = (eta * eta) * (1.0f - cos_i * cos_i); /* rule R: eta * eta * (1 - cos_i * cos_i) */
     if (sin2_t > 1.0f)
         return 0;
     const float cos_t = sqrtf(1.0f - sin2_t);
-    const float k = FMA(eta, cos_i, -cos_t);
-    *refracted = v3_make(FMA(k, n.x, eta * v.x), FMA(k, n.y, eta * v.y), FMA(k, n.z, eta * v.z));
+    const float k = eta * cos_i - cos_t;
+    *refracted = v3_add(v3_scale(v, eta), v3_scale(n, k)); /* eta * v + (eta * cos_i - cos_t) * n */
     return 1;
 }
 

@@ -80,7 +80,19 @@ def build_oracle(fast: bool = False) -> pathlib.Path:
     return ROOT / "oracle" / "_build" / f"librtref_{target}.so"
 
 
+def build_reference() -> bool:
+    """oracle/_ref/librt_ref*.so from the reference's own sources (oracle/Makefile `ref`); a no-op where the reference
+    tree is absent (the prebuilt libraries travel with the repo snapshot)."""
+    if not pathlib.Path("/root/reference/src/renderers/mg_ray_tracer.cpp").exists():
+        return False
+    r = subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference build failed:\n" + r.stdout + r.stderr)
+    return True
+
+
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
     build_plugin_check()
     print(build_oracle())
+    print("reference build:", build_reference())

@@ -38,7 +38,36 @@ SCENES = {
     "planes": (planes_scene(), 12),
 }
 
+REFBUILD_CASES = [  # (scene, reference renderer, material mode, width, height, spp, max_bounces)
+    ("c1", "mg_ray_tracer", 0, 160, 120, 8, 10),
+    ("c2", "sm_ray_tracer", 1, 192, 108, 16, 50),
+    ("c2", "mg_ray_tracer", 0, 192, 108, 16, 50),
+    ("planes", "sm_ray_tracer", 1, 128, 96, 8, 12),
+    ("planes", "mg_ray_tracer", 0, 128, 96, 8, 12),
+    ("c3", "sm_ray_tracer", 1, 96, 54, 4, 50),
+]
+
+
+def gen_reference_build_goldens():
+    """Outputs of the reference's OWN renderer sources (oracle/_ref/librt_ref.so: mg_ray_tracer.cpp / sm_ray_tracer.cpp
+    compiled where they lie against the muu stand-in, RNG replaced by the counter-based stream).  Only possible where
+    /root/reference exists; the fixtures are committed so the pin travels."""
+    from oracle.binding import ReferenceBuild
+
+    if not ReferenceBuild.available():
+        print("reference build unavailable: refbuild_* fixtures not regenerated")
+        return
+    ref = ReferenceBuild()
+    for name, renderer, mode, w, h, spp, depth in REFBUILD_CASES:
+        sc = SCENES[name][0]
+        rgba8, ivp = ref.render(sc, w, h, spp, depth, 0x5EED, renderer, threads=0)
+        np.savez_compressed(OUT / f"refbuild_{name}_{renderer}.npz", rgba8=rgba8, inv_view_proj=ivp, width=w, height=h, spp=spp,
+                            max_bounces=depth, mode=mode, seed=np.uint64(0x5EED))
+        print("reference build", name, renderer, rgba8.shape)
+
+
 if __name__ == "__main__":
+    gen_reference_build_goldens()
     for name, (sc, depth) in SCENES.items():
         o, d = synth.random_rays(sc, 4096, seed=7)
         hit, prim, t, nrm = O.intersect_batch(sc, o, d)
