@@ -146,113 +146,126 @@ __device__ __forceinline__ void bvh_leaf_test(const float4 sph, const int index,
 
 constexpr int BVH_STACK = 64;
 
-// returns false when the ray direction is too far from unit length for the conservative margins (caller falls back
-// to the linear scan); otherwise (best_t, best_i) hold the closest sphere hit or (inf, -1)
-__device__ __forceinline__ bool closest_sphere_bvh(const SceneDev& sc, const Ray& r, float& best_t, int& best_i, BvhStats& st)
-{
-    const float inf = __int_as_float(0x7f800000);
-    best_t = inf;
-    best_i = 0x7fffffff;
-    const float dd = dot3(r.d, r.d);
-    const float eps_d = fabsf(dd - 1.0f);
-    if (!(eps_d <= 1e-3f))
-        return false;
-    const float kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
-    const float ix = __frcp_rn(r.d.x), iy = __frcp_rn(r.d.y), iz = __frcp_rn(r.d.z);
+// traversal state of one ray; the node stack lives in (L1-cached) local memory of the calling kernel
+struct Trav {
+    uint32_t node;
+    int sp;
+    float best_t;
+    int best_i;
+    float ix, iy, iz; // 1 / d
+    float kappa;      // margin factor, see above
+};
 
-    uint32_t stack_ref[BVH_STACK];
-    float stack_t[BVH_STACK];
-    int sp = 0;
-    uint32_t node = 0;
-    for (;;)
+// returns false when the ray direction is too far from unit length for the conservative margins (caller falls back
+// to the linear scan)
+__device__ __forceinline__ bool trav_init(const Ray& r, Trav& tv)
+{
+    tv.node = 0;
+    tv.sp = 0;
+    tv.best_t = __int_as_float(0x7f800000);
+    tv.best_i = 0x7fffffff;
+    const float eps_d = fabsf(dot3(r.d, r.d) - 1.0f);
+    tv.kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
+    tv.ix = __frcp_rn(r.d.x);
+    tv.iy = __frcp_rn(r.d.y);
+    tv.iz = __frcp_rn(r.d.z);
+    return eps_d <= 1e-3f;
+}
+
+// one node visit: slab-test both children, test leaf children immediately, descend near-first / push / pop.
+// Returns true when the traversal is complete.
+__device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav& tv, uint32_t* __restrict__ stack_ref,
+                                          float* __restrict__ stack_t, BvhStats& st)
+{
+    st.nodes++;
+    const float4* np = sc.bvh_nodes + 4 * (size_t)tv.node;
+    const float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2), meta = __ldg(np + 3);
+    const uint32_t ref[2] = { __float_as_uint(meta.x), __float_as_uint(meta.y) };
+    float tn[2];
+    bool hit[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
     {
-        st.nodes++;
-        const float4* np = sc.bvh_nodes + 4 * (size_t)node;
-        const float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2), meta = __ldg(np + 3);
-        uint32_t ref[2] = { __float_as_uint(meta.x), __float_as_uint(meta.y) };
-        float tn[2];
-        bool hit[2];
-#pragma unroll
-        for (int c = 0; c < 2; c++)
-        {
-            const float lox = (c ? bx.z : bx.x) - r.o.x, hix = (c ? bx.w : bx.y) - r.o.x;
-            const float loy = (c ? by.z : by.x) - r.o.y, hiy = (c ? by.w : by.y) - r.o.y;
-            const float loz = (c ? bz.z : bz.x) - r.o.z, hiz = (c ? bz.w : bz.y) - r.o.z;
-            const float m = kappa * (fmaxf(fabsf(lox), fabsf(hix)) + fmaxf(fabsf(loy), fabsf(hiy)) + fmaxf(fabsf(loz), fabsf(hiz)));
-            const float t1x = (lox - m) * ix, t2x = (hix + m) * ix;
-            const float t1y = (loy - m) * iy, t2y = (hiy + m) * iy;
-            const float t1z = (loz - m) * iz, t2z = (hiz + m) * iz;
-            const float tmin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
-            const float tmax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
-            tn[c] = tmin;
-            hit[c] = tmax >= fmaxf(tmin, 0.0f) && tmin <= best_t; // empty boxes (lo > hi) fail the first test
-        }
-        // leaves are tested immediately, inner children are descended near-first
-        uint32_t next = 0xffffffffu;
-        float next_t = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 2; c++)
-        {
-            if (!hit[c]) continue;
-            if (ref[c] & 0x80000000u)
-            {
-                const uint32_t first = (ref[c] & 0x7fffffffu) >> 3, count = ref[c] & 7u;
-                for (uint32_t k = 0; k < count; k++)
-                {
-                    st.tests++;
-                    bvh_leaf_test(__ldg(sc.leaf_sph + first + k), (int)__ldg(sc.leaf_idx + first + k), r, best_t, best_i);
-                }
-            }
-            else if (next == 0xffffffffu)
-            {
-                next = ref[c];
-                next_t = tn[c];
-            }
-            else
-            {
-                // both children are inner nodes: continue with the nearer, push the farther
-                const bool swap = tn[c] < next_t;
-                stack_ref[sp] = swap ? next : ref[c];
-                stack_t[sp] = swap ? next_t : tn[c];
-                sp++;
-                if (swap) { next = ref[c]; next_t = tn[c]; }
-            }
-        }
-        if (next != 0xffffffffu && next_t <= best_t)
-        {
-            node = next;
-            continue;
-        }
-        // pop, skipping entries that the current best already excludes
-        bool found = false;
-        while (sp > 0)
-        {
-            sp--;
-            if (stack_t[sp] <= best_t)
-            {
-                node = stack_ref[sp];
-                found = true;
-                break;
-            }
-        }
-        if (!found)
-            break;
+        const float lox = (c ? bx.z : bx.x) - r.o.x, hix = (c ? bx.w : bx.y) - r.o.x;
+        const float loy = (c ? by.z : by.x) - r.o.y, hiy = (c ? by.w : by.y) - r.o.y;
+        const float loz = (c ? bz.z : bz.x) - r.o.z, hiz = (c ? bz.w : bz.y) - r.o.z;
+        const float m = tv.kappa * (fmaxf(fabsf(lox), fabsf(hix)) + fmaxf(fabsf(loy), fabsf(hiy)) + fmaxf(fabsf(loz), fabsf(hiz)));
+        const float t1x = (lox - m) * tv.ix, t2x = (hix + m) * tv.ix;
+        const float t1y = (loy - m) * tv.iy, t2y = (hiy + m) * tv.iy;
+        const float t1z = (loz - m) * tv.iz, t2z = (hiz + m) * tv.iz;
+        const float tmin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+        const float tmax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+        tn[c] = tmin;
+        hit[c] = tmax >= fmaxf(tmin, 0.0f) && tmin <= tv.best_t; // empty boxes (lo > hi) fail the first test
     }
-    if (best_i == 0x7fffffff)
-        best_i = -1;
+    // leaves are tested immediately, inner children are descended near-first
+    uint32_t next = 0xffffffffu;
+    float next_t = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+    {
+        if (!hit[c]) continue;
+        if (ref[c] & 0x80000000u)
+        {
+            const uint32_t first = (ref[c] & 0x7fffffffu) >> 3, count = ref[c] & 7u;
+            for (uint32_t k = 0; k < count; k++)
+            {
+                st.tests++;
+                bvh_leaf_test(__ldg(sc.leaf_sph + first + k), (int)__ldg(sc.leaf_idx + first + k), r, tv.best_t, tv.best_i);
+            }
+        }
+        else if (next == 0xffffffffu)
+        {
+            next = ref[c];
+            next_t = tn[c];
+        }
+        else
+        {
+            // both children are inner nodes: continue with the nearer, push the farther
+            const bool swap = tn[c] < next_t;
+            stack_ref[tv.sp] = swap ? next : ref[c];
+            stack_t[tv.sp] = swap ? next_t : tn[c];
+            tv.sp++;
+            if (swap) { next = ref[c]; next_t = tn[c]; }
+        }
+    }
+    if (next != 0xffffffffu && next_t <= tv.best_t)
+    {
+        tv.node = next;
+        return false;
+    }
+    // pop, skipping entries that the current best already excludes
+    while (tv.sp > 0)
+    {
+        tv.sp--;
+        if (stack_t[tv.sp] <= tv.best_t)
+        {
+            tv.node = stack_ref[tv.sp];
+            return false;
+        }
+    }
     return true;
 }
 
-// closest hit: spheres through the BVH (or the global-memory linear scan when the ray is not unit length), planes linear
-__device__ __forceinline__ Hit closest_hit_bvh(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, BvhStats& st)
+// whole traversal for one ray; (best_t, best_i) = closest sphere hit or (inf, -1)
+__device__ __forceinline__ bool closest_sphere_bvh(const SceneDev& sc, const Ray& r, float& best_t, int& best_i, BvhStats& st)
 {
-    float ts;
-    int is;
-    if (!closest_sphere_bvh(sc, r, ts, is, st))
+    Trav tv;
+    if (!trav_init(r, tv))
+        return false;
+    uint32_t stack_ref[BVH_STACK];
+    float stack_t[BVH_STACK];
+    while (!trav_step(sc, r, tv, stack_ref, stack_t, st))
     {
-        st.tests += sc.n_spheres;
-        return closest_hit_linear(sc.pairs, sc.n_spheres, s_pl, sc.n_planes, r);
     }
+    best_t = tv.best_t;
+    best_i = tv.best_i == 0x7fffffff ? -1 : tv.best_i;
+    return true;
+}
+
+// sphere result of a traversal + the planes (linear) -> Hit, with the reference's select rule (mg_ray_tracer.cpp:95-102)
+__device__ __forceinline__ Hit combine_with_planes(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, const float ts, const int is)
+{
     Hit h;
     h.t = ts;
     h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS;
@@ -272,6 +285,19 @@ __device__ __forceinline__ Hit closest_hit_bvh(const SceneDev& sc, const float4*
     if (h.prim == RTCU_PRIM_MISS)
         h.t = -1.0f;
     return h;
+}
+
+// closest hit: spheres through the BVH (or the global-memory linear scan when the ray is not unit length), planes linear
+__device__ __forceinline__ Hit closest_hit_bvh(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, BvhStats& st)
+{
+    float ts;
+    int is;
+    if (!closest_sphere_bvh(sc, r, ts, is, st))
+    {
+        st.tests += sc.n_spheres;
+        return closest_hit_linear(sc.pairs, sc.n_spheres, s_pl, sc.n_planes, r);
+    }
+    return combine_with_planes(sc, s_pl, r, ts, is);
 }
 
 // hit normal when primitives are not staged: centre from the global {cx,cy,cz,r*r} array
@@ -322,6 +348,11 @@ __device__ __forceinline__ Ray generate(const CameraConst& cam, const RngKey& ke
 #endif
 constexpr int MEGA_TILE_W = 16, MEGA_TILE_H = RTCU_MEGA_TILE_H, MEGA_THREADS = MEGA_TILE_W * MEGA_TILE_H;
 
+template <bool BVH>
+__device__ __forceinline__ bool shade_segment(const SceneDev& sc, const RenderParams& p, const float4* __restrict__ s_sph,
+                                              const float4* __restrict__ s_pl, const RngKey& key, Ray& ray, V3& thr, V3& sum, uint32_t& seg,
+                                              const Hit h);
+
 // One path segment (mg_ray_tracer.cpp:154-174, one level of the recursion): closest hit, then sky on a miss or one
 // scatter event on a hit.  Returns true when the path ended (miss, absorbed, or bounce budget exhausted).
 template <bool BVH>
@@ -330,6 +361,15 @@ __device__ __forceinline__ bool segment_step(const SceneDev& sc, const RenderPar
                                              BvhStats& bst)
 {
     const Hit h = BVH ? closest_hit_bvh(sc, s_pl, ray, bst) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
+    return shade_segment<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, h);
+}
+
+// the part of a segment after the closest hit is known: sky on a miss, one scatter event on a hit
+template <bool BVH>
+__device__ __forceinline__ bool shade_segment(const SceneDev& sc, const RenderParams& p, const float4* __restrict__ s_sph,
+                                              const float4* __restrict__ s_pl, const RngKey& key, Ray& ray, V3& thr, V3& sum, uint32_t& seg,
+                                              const Hit h)
+{
     if (h.prim == RTCU_PRIM_MISS)
     {
         sum = v3_add(sum, v3_mul(thr, sky(ray.d))); // S12: iterative throughput

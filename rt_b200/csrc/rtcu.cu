@@ -226,7 +226,11 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     const size_t sb = stage_bytes(ctx);
     const bool flat = flat_loop_for(ctx->scene.n_spheres + ctx->scene.n_planes);
     if (use_bvh)
+    {
+        // flat (warp-vote) loop; the nested form measures the same on C3/C4.  A warp-level state machine that runs one
+        // node visit per iteration and lets finished lanes shade/regenerate early was measured 20-25 % slower.
         k_render_mega<false, true, true><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
+    }
     else if (sb <= MAX_STAGE_BYTES)
     {
         if (flat) k_render_mega<true, true, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, p);
