@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device and says so when there is none.
 #include "../../include/rtcu.h"
 #include "kernels.cuh"
+#include "wavefront.cuh"
 #include "bvh.h"
 
 #include <cstdarg>
@@ -126,6 +127,12 @@ struct rtcu_ctx {
     DevBuf<unsigned int> straggler_count;
     PinnedBuf<unsigned long long> h_counters;
 
+    // wavefront pipeline queues (allocated on first use)
+    DevBuf<float4> wf_o[2], wf_d[2], wf_thr[2], wf_rad, wf_sum;
+    DevBuf<uint2> wf_hit;
+    DevBuf<uint32_t> wf_list[4], wf_counts;
+    PinnedBuf<uint32_t> h_wf_counts;
+
     // scratch for the batch entry points
     DevBuf<unsigned char> scratch;
 
@@ -196,6 +203,91 @@ bool flat_loop_for(uint32_t n_prims)
 
 size_t stage_bytes(const rtcu_ctx* ctx) { return ((size_t)pair_float4_count(ctx->scene.n_spheres) + ctx->scene.n_planes) * sizeof(float4); }
 
+// Wavefront pipeline (RTCU_PIPE_WAVEFRONT): generate / intersect(+material sort) / shade(+compact) / advance per bounce
+// over HBM queues, one wave = all tile pixels x S consecutive samples.  Results are bit-identical to the megakernel's
+// first pass (same paths, per-pixel sums in sample order).
+int launch_wavefront(rtcu_ctx* ctx, const rtcu_view* v, RenderParams p, bool use_bvh, cudaStream_t st)
+{
+    const uint32_t tw = v->tile_x1 - v->tile_x0, th = v->tile_y1 - v->tile_y0, npix = tw * th;
+    size_t target = 8u << 20; // rays per wave
+    if (const char* e = getenv("RTCU_WF_RAYS")) target = strtoull(e, nullptr, 10);
+    uint32_t slots = (uint32_t)(target / npix);
+    if (slots < 1) slots = 1;
+    if (slots > 4096) slots = 4096;
+    const uint32_t n_samples = v->sample_end - v->sample_begin;
+    if (slots > n_samples && n_samples) slots = n_samples;
+    const size_t cap = (size_t)npix * slots;
+    if (cap > 0x7fffffffull) return fail(RTCU_ERR_INVALID, "wave too large");
+    for (int i = 0; i < 2; i++)
+    {
+        CU(ctx->wf_o[i].reserve(cap)); CU(ctx->wf_d[i].reserve(cap)); CU(ctx->wf_thr[i].reserve(cap));
+    }
+    for (auto& l : ctx->wf_list) CU(l.reserve(cap));
+    CU(ctx->wf_hit.reserve(cap));
+    CU(ctx->wf_rad.reserve(cap));
+    CU(ctx->wf_sum.reserve((size_t)v->width * v->height));
+    CU(ctx->wf_counts.reserve(8));
+    CU(ctx->h_wf_counts.reserve(8));
+    WfQueues q;
+    for (int i = 0; i < 2; i++) { q.q_o[i] = ctx->wf_o[i].p; q.q_d[i] = ctx->wf_d[i].p; q.q_thr[i] = ctx->wf_thr[i].p; }
+    for (int k = 0; k < 4; k++) q.list[k] = ctx->wf_list[k].p;
+    q.q_hit = ctx->wf_hit.p;
+    q.rad = ctx->wf_rad.p;
+    q.counts = ctx->wf_counts.p;
+    q.capacity = (uint32_t)cap;
+
+    const unsigned blocks = (unsigned)ctx->sm_count * 8;
+    const size_t sb = stage_bytes(ctx);
+    const bool stage = !use_bvh && sb <= MAX_STAGE_BYTES;
+    uint32_t launches = 0;
+    int first = 1;
+    for (uint32_t s0 = v->sample_begin; s0 < v->sample_end; s0 += slots)
+    {
+        WfWave w;
+        w.sample0 = s0;
+        w.n_slots = v->sample_end - s0 < slots ? v->sample_end - s0 : slots;
+        w.tile_w = tw;
+        w.tile_h = th;
+        w.cur = 0;
+        k_wf_generate<<<blocks, 256, 0, st>>>(p, q, w);
+        launches++;
+        for (uint32_t b = 0; b < v->max_bounces; b++)
+        {
+            w.cur = (int)(b & 1u);
+            if (use_bvh) k_wf_intersect<false, true><<<blocks, 256, 0, st>>>(ctx->scene, p, q, w.cur);
+            else if (stage) k_wf_intersect<true, false><<<blocks, 256, sb, st>>>(ctx->scene, p, q, w.cur);
+            else k_wf_intersect<false, false><<<blocks, 256, 0, st>>>(ctx->scene, p, q, w.cur);
+            k_wf_shade<<<blocks, 256, 0, st>>>(ctx->scene, p, q, w);
+            k_wf_advance<<<1, 32, 0, st>>>(q);
+            launches += 3;
+            CU(cudaGetLastError());
+            if (b >= 1 && b + 1 < v->max_bounces)
+            {
+                // how many paths are still alive?  (one small synchronous read per bounce; paths die fast)
+                CU(cudaMemcpyAsync(ctx->h_wf_counts.p, ctx->wf_counts.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (ctx->h_wf_counts.p[0] == 0) break;
+            }
+        }
+        k_wf_accumulate<<<blocks, 256, 0, st>>>(p, q, w, ctx->wf_sum.p, first);
+        launches++;
+        first = 0;
+    }
+    if (first)
+    {
+        WfWave w;
+        w.sample0 = v->sample_begin; w.n_slots = 0; w.tile_w = tw; w.tile_h = th; w.cur = 0;
+        k_wf_accumulate<<<blocks, 256, 0, st>>>(p, q, w, ctx->wf_sum.p, 1);
+        launches++;
+    }
+    k_wf_finish<<<blocks, 256, 0, st>>>(p, ctx->wf_sum.p, tw, th);
+    launches++;
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches = launches;
+    ctx->stats.pipeline = RTCU_PIPE_WAVEFRONT;
+    return RTCU_OK;
+}
+
 // launches the trace kernels of one view on `st`; accum/rgba8 are device pointers
 int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st)
 {
@@ -206,7 +298,7 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
     if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
     if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or tree deeper than %d)", BVH_STACK - 2);
-    if (pipe == RTCU_PIPE_WAVEFRONT) return fail(RTCU_ERR_INVALID, "wavefront pipeline is not available in this build");
+    if (pipe > RTCU_PIPE_WAVEFRONT) return fail(RTCU_ERR_INVALID, "bad pipeline selector %u", pipe);
     const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
     p.accum = d_accum;
     p.rgba8 = d_rgba8;
@@ -222,6 +314,10 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     CU(cudaMemsetAsync(ctx->straggler_count.p, 0, sizeof(unsigned int), st));
 
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
+    ctx->stats.accel = use_bvh ? RTCU_ACCEL_BVH : RTCU_ACCEL_LINEAR;
+    ctx->stats.samples = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0) * (v->sample_end - v->sample_begin);
+    if (pipe == RTCU_PIPE_WAVEFRONT)
+        return launch_wavefront(ctx, v, p, use_bvh, st); // PIPE_AUTO = megakernel: measured faster on every config
     const dim3 grid((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W, (v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
     const size_t sb = stage_bytes(ctx);
     const bool flat = flat_loop_for(ctx->scene.n_spheres + ctx->scene.n_planes);
@@ -374,7 +470,8 @@ rtcu_ctx* rtcu_create(int device)
     ok = ok && ctx->counters.reserve(4) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess && ctx->straggler_count.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_render_mega<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess
          && cudaFuncSetAttribute(k_render_mega<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_intersect_batch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_wf_intersect<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess
+         && cudaFuncSetAttribute(k_intersect_batch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
     if (!ok)
     {
         fail(RTCU_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -391,6 +488,9 @@ void rtcu_destroy(rtcu_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->sph.release(); ctx->sph_raw.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
     ctx->mats.release(); ctx->bvh_nodes.release(); ctx->leaf_sph.release(); ctx->leaf_idx.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
+    for (int i = 0; i < 2; i++) { ctx->wf_o[i].release(); ctx->wf_d[i].release(); ctx->wf_thr[i].release(); }
+    for (auto& l : ctx->wf_list) l.release();
+    ctx->wf_rad.release(); ctx->wf_sum.release(); ctx->wf_hit.release(); ctx->wf_counts.release(); ctx->h_wf_counts.release();
     ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);

@@ -356,3 +356,45 @@ def test_render_matches_reference_build_fixtures(ctx, scenes):
         # identical paths; only the left- vs right-nested radiance product differs (S12): isolated 1-LSB differences
         assert d.max() <= 1, (name, renderer, int(d.max()))
         assert (d > 0).mean() <= 0.005, (name, renderer, float((d > 0).mean()))
+
+
+# ---- wavefront pipeline (generate / intersect + material sort / shade + compact over HBM queues) ------------------
+@pytest.mark.parametrize("name,mode,accel", [("c2", nat.MODE_SM, nat.ACCEL_LINEAR), ("c1", nat.MODE_MG, nat.ACCEL_LINEAR),
+                                             ("planes", nat.MODE_SM, nat.ACCEL_LINEAR), ("c3", nat.MODE_SM, nat.ACCEL_BVH),
+                                             ("c3", nat.MODE_MG, nat.ACCEL_LINEAR)])
+def test_wavefront_is_bit_identical_to_the_megakernel(ctx, scenes, monkeypatch, name, mode, accel):
+    # same paths, and per-pixel sums in sample order in both pipelines (the megakernel's straggler pass, which re-orders the
+    # sum of the few pixels it takes over, is switched off for this comparison)
+    monkeypatch.setenv("RTCU_STRAGGLER_BUDGET", "0")
+    monkeypatch.setenv("RTCU_WF_RAYS", str(200 * 120 * 3))  # 3 samples per wave: 6 spp = 2 waves, 7 spp = 2 full + 1 partial
+    sc = scenes[name][0]
+    ctx.upload_scene(sc)
+    for spp in (6, 7):
+        kw = dict(samples_per_pixel=spp, max_bounces=scenes[name][1], material_mode=mode)
+        rgba_m, acc_m = ctx.render(make_view(sc, 200, 120, flags=accel | nat.PIPE_MEGAKERNEL, **kw), want_accum=True)
+        st_m = ctx.stats()
+        rgba_w, acc_w = ctx.render(make_view(sc, 200, 120, flags=accel | nat.PIPE_WAVEFRONT, **kw), want_accum=True)
+        st_w = ctx.stats()
+        assert st_w["pipeline"] == nat.PIPE_WAVEFRONT and st_m["pipeline"] == nat.PIPE_MEGAKERNEL
+        assert st_w["segments"] == st_m["segments"] and st_w["kernel_launches"] > 5
+        np.testing.assert_array_equal(acc_w, acc_m)
+        np.testing.assert_array_equal(rgba_w, rgba_m)
+
+
+def test_wavefront_tiles_sample_ranges_and_golden(ctx, scenes):
+    g = np.load(GOLDEN / "image_c2_sm.npz")
+    sc = scenes["c2"][0]
+    ctx.upload_scene(sc)
+    w, h, spp = int(g["width"]), int(g["height"]), int(g["spp"])
+    kw = dict(samples_per_pixel=spp, max_bounces=int(g["max_bounces"]), material_mode=nat.MODE_SM, seed=int(g["seed"]), flags=nat.PIPE_WAVEFRONT)
+    rgba8, accum = ctx.render(make_view(sc, w, h, **kw), want_accum=True)
+    assert ctx.stats()["segments"] == int(g["segments"])
+    assert_images_match(rgba8, accum, g["rgba8"], g["accum"], spp)
+    # odd tile (not a multiple of the 8x4 patch) and a partial sample range
+    _, part = ctx.render(make_view(sc, w, h, tile=(3, 5, 40, 31), sample_range=(2, 7), **kw), want_accum=True)
+    _, ref = ctx.render(make_view(sc, w, h, tile=(3, 5, 40, 31), sample_range=(2, 7), **{**kw, "flags": nat.PIPE_MEGAKERNEL}), want_accum=True)
+    np.testing.assert_allclose(part, ref, rtol=2e-6, atol=1e-7)
+    assert (part[5:31, 3:40, 3] == 5).all() and (part[:5] == 0).all()
+    # empty range
+    _, none = ctx.render(make_view(sc, w, h, sample_range=(3, 3), **kw), want_accum=True)
+    assert (none == 0).all()
