@@ -3,7 +3,7 @@
 
   cuobjdump -xelf all rt_b200/lib/librtcu.so && nvdisasm --print-line-info-inline rtcu.sm_100a.cubin > dis.txt
   ncu -i rep.ncu-rep --page source --csv > src.csv
-  python tools/ncu_lines.py src.csv dis.txt <mangled-kernel-substring> [--lines]
+  python tools/ncu_lines.py src.csv dis.txt <mangled-kernel-substring> [--lines] [--kernel=N]   (N-th kernel section of the csv)
 
 Every SASS instruction is charged to the innermost source line nvdisasm reports for it (through inlining) and,
 from there, to the enclosing __device__/__global__ function found by scanning the source file.
@@ -15,6 +15,13 @@ by_line = "--lines" in sys.argv
 
 # ---- executed counts per instruction offset from ncu
 rows = list(csv.reader(open(src_csv)))
+which = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--kernel=")), 0)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if starts:
+    lo = starts[which]
+    hi = starts[which + 1] if which + 1 < len(starts) else len(rows)
+    print(rows[lo][1][:110])
+    rows = rows[lo:hi]
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]; ci = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[hdr_i + 1:] if len(r) >= len(hdr) and r[0].startswith("0x")]
