@@ -4,7 +4,8 @@
 Workload (BASELINE.json configs[1], "C2"): scenes/dielectric.toml at 1920x1080, 64 spp, max depth 50,
 sm scatter table (lambert / metal / dielectric with Schlick).  A *step* is one frame.  At N > 1 the frame
 is split by sample range: every rank renders 64 samples per pixel of a 64*N-spp frame (weak scaling, fixed
-work per GPU), the fp32 accumulation buffers are reduced onto rank 0 over NCCL, rank 0 resolves.
+work per GPU), the fp32 accumulation buffers are reduce-scattered by row band over NCCL, every rank resolves its band and
+rank 0 gathers the packed bands.
 
   value  whole-job Msamples/s with the scene resident on the device, timed with CUDA events per step on the
          launching stream; L2 is flushed between steps (outside the events); max over ranks.
@@ -212,16 +213,16 @@ def run_gpu(args):
     total_spp = SPP * world
     view = make_view(scene, WIDTH, HEIGHT, samples_per_pixel=total_spp, max_bounces=MAX_BOUNCES, material_mode=nat.MODE_SM)
     mine = rdist.partition_view(view, rank, world, by="samples")
-    gr = rdist.GpuRank(ctx, WIDTH, HEIGHT, dev)
+    gr = rdist.GpuRank(ctx, WIDTH, HEIGHT, dev, world=world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
     def step_device():
-        accum = gr.render_accum(mine)
         if world > 1:
-            tdist.reduce(accum, dst=0, op=tdist.ReduceOp.SUM)
-        if rank == 0:
-            gr.resolve(accum, total_spp)
+            # trace -> reduce-scatter fp32 row bands (NCCL) -> resolve the band on every rank -> gather RGBA8 bands on rank 0
+            gr.render_reduce_resolve(mine, rank, total_spp)
+        else:
+            gr.resolve(gr.render_accum(mine), total_spp)
 
     # ---- value: device-resident, CUDA events per step, L2 flushed between steps ----
     for _ in range(max(3, args.warmup)):
@@ -245,8 +246,9 @@ def run_gpu(args):
         accum = gr.render_accum(mine)
         kev[i][1].record(stream)
         if world > 1:
-            tdist.reduce(accum, dst=0, op=tdist.ReduceOp.SUM)
-        if rank == 0:
+            band = rdist.sum_row_bands(gr.accum_padded, rank, world)
+            rdist.gather_bands(gr.resolve_band(band, total_spp), HEIGHT, rank, world)
+        else:
             gr.resolve(accum, total_spp)
         ev[i][1].record(stream)
     torch.cuda.synchronize(dev)
@@ -278,10 +280,9 @@ def run_gpu(args):
         if world == 1:
             ctx.render(view, rgba8=host_np, want_accum=False)  # rtcu_render: launch + D2H into the pinned buffer + sync
         else:
-            accum = gr.render_accum(mine)
-            tdist.reduce(accum, dst=0, op=tdist.ReduceOp.SUM)
+            img = gr.render_reduce_resolve(mine, rank, total_spp)
             if rank == 0:
-                host_rgba.copy_(gr.resolve(accum, total_spp), non_blocking=False)
+                host_rgba.copy_(img, non_blocking=False)
             torch.cuda.synchronize(dev)
 
     for _ in range(max(3, args.warmup)):
@@ -340,7 +341,7 @@ def run_gpu(args):
                        "l2": "flushed between steps (256 MiB fill, outside the per-step CUDA events)",
                        "pipeline": "megakernel", "accel": "linear"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
-            "gpu_launches": args.steps * (world + 1),  # k_render_mega on every rank + k_resolve on rank 0, per step
+            "gpu_launches": args.steps * 3 * world,  # per step and rank: k_render_mega, k_render_stragglers, k_resolve (band)
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "wall_ms_per_step_incl_flush": round(wall * 1e3 / args.steps, 3),
             "segments_per_sample": round(segments_all / samples_per_step, 4),

@@ -58,17 +58,59 @@ def render_distributed(render_accum: Callable[[nat.View], "object"], view: nat.V
     return accum, None
 
 
+def band_rows(height: int, world: int) -> int:
+    """rows per rank when the frame is cut into `world` equal row bands (the last band may hang over the frame)"""
+    return -(-height // world)
+
+
+def sum_row_bands(accum_padded, rank: int, world: int, group=None):
+    """Sum the ranks' accumulation buffers and leave each rank with *its* row band of the total: a reduce-scatter
+    (NCCL; over NVSwitch every rank sends and receives (world-1)/world of the buffer, instead of rank 0 receiving all of
+    it), or all-reduce + slice on backends without reduce-scatter (gloo, CPU tests).  accum_padded: (world*band, W, 4)."""
+    import torch
+    import torch.distributed as dist
+
+    band = accum_padded.shape[0] // world
+    if world == 1:
+        return accum_padded[:band]
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty_like(accum_padded[:band])
+        dist.reduce_scatter_tensor(out, accum_padded, op=dist.ReduceOp.SUM, group=group)
+        return out
+    dist.all_reduce(accum_padded, op=dist.ReduceOp.SUM, group=group)
+    return accum_padded[rank * band:(rank + 1) * band].clone()
+
+
+def gather_bands(band_rgba8, height: int, rank: int, world: int, dst: int = 0, group=None):
+    """Gather the packed row bands onto `dst` (4x fewer bytes than the fp32 buffers); returns (H, W) there, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return band_rgba8[:height]
+    parts = [torch.empty_like(band_rgba8) for _ in range(world)] if rank == dst else None
+    dist.gather(band_rgba8, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat(parts, dim=0)[:height]
+
+
 class GpuRank:
     """One rank's device state for bench.py / multi-GPU runs: a Context plus torch-owned frame buffers."""
 
-    def __init__(self, ctx, width: int, height: int, device=None):
+    def __init__(self, ctx, width: int, height: int, device=None, world: int = 1):
         import torch
 
         self.torch = torch
         self.ctx = ctx
         self.device = torch.device("cuda", ctx.device) if device is None else device
-        self.accum = torch.zeros((height, width, 4), dtype=torch.float32, device=self.device)
+        self.world = world
+        self.band = band_rows(height, world)
+        # the buffer is padded to world equal row bands (rows past the frame stay zero) for the reduce-scatter
+        self.accum_padded = torch.zeros((self.band * world, width, 4), dtype=torch.float32, device=self.device)
+        self.accum = self.accum_padded[:height]
         self.rgba8 = torch.zeros((height, width), dtype=torch.int32, device=self.device)  # bit pattern of uint32
+        self.band_rgba8 = torch.zeros((self.band, width), dtype=torch.int32, device=self.device)
         self.width, self.height = width, height
 
     def render_accum(self, view: nat.View):
@@ -84,3 +126,17 @@ class GpuRank:
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
         self.ctx.resolve_device(accum.data_ptr(), self.width, self.height, spp, self.rgba8.data_ptr(), stream=stream)
         return self.rgba8
+
+    def resolve_band(self, band_accum, spp: int):
+        """divide / sqrt / pack this rank's summed row band (mg_ray_tracer.cpp:195-200 over band rows)"""
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.resolve_device(band_accum.data_ptr(), self.width, self.band, spp, self.band_rgba8.data_ptr(), stream=stream)
+        return self.band_rgba8
+
+    def render_reduce_resolve(self, view: nat.View, rank: int, spp_total: int, dst: int = 0):
+        """One multi-GPU frame: trace this rank's share, reduce-scatter the fp32 sums by row band, resolve the band here,
+        gather the packed bands on `dst`.  Returns the (H, W) packed image on dst, None elsewhere."""
+        self.render_accum(view)
+        band = sum_row_bands(self.accum_padded, rank, self.world)
+        packed = self.resolve_band(band, spp_total)
+        return gather_bands(packed, self.height, rank, self.world, dst)
