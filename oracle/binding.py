@@ -161,6 +161,7 @@ class ReferenceBuild:
 
     PATH = HERE / "_ref" / "librt_ref.so"
     FAST_PATH = HERE / "_ref" / "librt_ref_fast.so"  # -O3 -ffast-math flavour for CPU timing
+    PLUGIN_PATH = HERE / "_ref" / "librt_ref_plugin.so"  # + plugin/cuda_path_tracer.cpp against the reference's headers, linked to librtcu.so
 
     @classmethod
     def available(cls, build_if_possible: bool = True) -> bool:
@@ -173,12 +174,13 @@ class ReferenceBuild:
     def __init__(self, flavour: str = "strict"):
         if not self.available():
             raise RuntimeError(f"{self.PATH} is missing and /root/reference is not present to build it")
-        path = self.FAST_PATH if flavour == "fast" else self.PATH
+        path = {"fast": self.FAST_PATH, "plugin": self.PLUGIN_PATH}.get(flavour, self.PATH)
         if not path.exists():
             raise RuntimeError(f"{path} is missing")
         self.lib = C.CDLL(str(path))
         p, u32 = C.c_void_p, C.c_uint32
         self.lib.refbin_list.argtypes = [C.c_char_p, u32]
+        self.lib.refbin_last_error.restype = C.c_char_p
         self.lib.refbin_render.argtypes = [C.POINTER(SceneDesc), p, p, u32, u32, u32, u32, C.c_uint64, C.c_char_p, p, C.c_int, u32, p]
         self._keep = None
 
@@ -214,6 +216,8 @@ class ReferenceBuild:
         ivp = np.zeros(16, np.float32)
         rc = self.lib.refbin_render(C.byref(sd), pos.ctypes.data, d.ctypes.data, width, height, spp, max_bounces, seed, renderer.encode(),
                                     rgba8.ctypes.data, threads, row_step, ivp.ctypes.data)
+        if rc == -2:
+            raise RuntimeError("renderer construction failed: " + self.lib.refbin_last_error().decode(errors="replace"))
         if rc != 0:
             raise RuntimeError(f"reference has no renderer named {renderer!r}")
         return rgba8, ivp

@@ -16,7 +16,9 @@
 #include "renderer.hpp"
 #include <muu/thread_pool.h>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <string>
 
@@ -34,6 +36,7 @@ namespace
 	};
 	thread_local rng_state g_rng;
 	uint64_t g_seed = 0;
+	char g_last_error[512] = "";
 	uint32_t g_sample_begin = 0;
 }
 
@@ -107,6 +110,8 @@ extern "C"
 		uint32_t n_materials;
 	};
 
+	const char* refbin_last_error() { return g_last_error; }
+
 	// names of the renderers registered by the compiled reference sources, '\n'-separated
 	int refbin_list(char* buf, uint32_t size)
 	{
@@ -170,7 +175,16 @@ extern "C"
 		g_sample_begin			= 0;
 		muu::shim::row_step		= row_step ? row_step : 1;
 		muu::shim::row_width	= width;
-		std::unique_ptr<rt::renderer_interface> renderer{ desc->create() };
+		std::unique_ptr<rt::renderer_interface> renderer;
+		try
+		{
+			renderer.reset(desc->create()); // a plugin constructor may throw (main.cpp:329-379 catches it in the real app)
+		}
+		catch (const std::exception& e)
+		{
+			std::snprintf(g_last_error, sizeof g_last_error, "%s", e.what());
+			return -2;
+		}
 		rt::image_view pixels{ rgba8, rt::vec2u{ width, height } };
 		muu::thread_pool pool{ threads > 0 ? static_cast<unsigned>(threads) : 0u };
 		renderer->render(scene, pixels, pool);

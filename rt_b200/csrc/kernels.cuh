@@ -22,7 +22,8 @@ struct SceneDev {
     const MatRec* materials;
     uint32_t n_materials;
     // BVH over the spheres (built when the scene size calls for it, see bvh.h); nodes = 4 float4 per node:
-    // {l.lo.x,l.hi.x,r.lo.x,r.hi.x}, same for y and z, then {ref_left, ref_right, -, -} as bit patterns.
+    // {l.lo.x,r.lo.x,l.hi.x,r.hi.x}, same for y and z (left/right interleaved for the packed FP32 slab test), then
+    // {ref_left, ref_right, -, -} as bit patterns.
     // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | first << 3 | count over leaf_sph / leaf_idx.
     const float4* bvh_nodes;
     const float4* leaf_sph;   // {cx,cy,cz,r*r} in leaf order
@@ -183,20 +184,31 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
     const uint32_t ref[2] = { __float_as_uint(meta.x), __float_as_uint(meta.y) };
     float tn[2];
     bool hit[2];
-#pragma unroll
-    for (int c = 0; c < 2; c++)
     {
-        const float lox = (c ? bx.z : bx.x) - r.o.x, hix = (c ? bx.w : bx.y) - r.o.x;
-        const float loy = (c ? by.z : by.x) - r.o.y, hiy = (c ? by.w : by.y) - r.o.y;
-        const float loz = (c ? bz.z : bz.x) - r.o.z, hiz = (c ? bz.w : bz.y) - r.o.z;
-        const float m = tv.kappa * (fmaxf(fabsf(lox), fabsf(hix)) + fmaxf(fabsf(loy), fabsf(hiy)) + fmaxf(fabsf(loz), fabsf(hiz)));
-        const float t1x = (lox - m) * tv.ix, t2x = (hix + m) * tv.ix;
-        const float t1y = (loy - m) * tv.iy, t2y = (hiy + m) * tv.iy;
-        const float t1z = (loz - m) * tv.iz, t2z = (hiz + m) * tv.iz;
-        const float tmin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
-        const float tmax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
-        tn[c] = tmin;
-        hit[c] = tmax >= fmaxf(tmin, 0.0f) && tmin <= tv.best_t; // empty boxes (lo > hi) fail the first test
+        // Both children at once on the packed FP32 pipe: the device node stores {l.lo, r.lo, l.hi, r.hi} per axis, so the
+        // left and right slab tests are the two halves of FADD2 / FMUL2 instructions (the kernel is issue-bound; only the
+        // min / max / abs steps stay scalar).  Rounding is irrelevant here: the boxes are inflated by the margin m.
+        const float2 nox = make_float2(-r.o.x, -r.o.x), noy = make_float2(-r.o.y, -r.o.y), noz = make_float2(-r.o.z, -r.o.z);
+        const float2 lox = __fadd2_rn(make_float2(bx.x, bx.y), nox), hix = __fadd2_rn(make_float2(bx.z, bx.w), nox);
+        const float2 loy = __fadd2_rn(make_float2(by.x, by.y), noy), hiy = __fadd2_rn(make_float2(by.z, by.w), noy);
+        const float2 loz = __fadd2_rn(make_float2(bz.x, bz.y), noz), hiz = __fadd2_rn(make_float2(bz.z, bz.w), noz);
+        const float2 ax = make_float2(fmaxf(fabsf(lox.x), fabsf(hix.x)), fmaxf(fabsf(lox.y), fabsf(hix.y)));
+        const float2 ay = make_float2(fmaxf(fabsf(loy.x), fabsf(hiy.x)), fmaxf(fabsf(loy.y), fabsf(hiy.y)));
+        const float2 az = make_float2(fmaxf(fabsf(loz.x), fabsf(hiz.x)), fmaxf(fabsf(loz.y), fabsf(hiz.y)));
+        const float2 m = __fmul2_rn(__fadd2_rn(__fadd2_rn(ax, ay), az), make_float2(tv.kappa, tv.kappa));
+        const float2 nm = make_float2(-m.x, -m.y);
+        const float2 ix2 = make_float2(tv.ix, tv.ix), iy2 = make_float2(tv.iy, tv.iy), iz2 = make_float2(tv.iz, tv.iz);
+        const float2 t1x = __fmul2_rn(__fadd2_rn(lox, nm), ix2), t2x = __fmul2_rn(__fadd2_rn(hix, m), ix2);
+        const float2 t1y = __fmul2_rn(__fadd2_rn(loy, nm), iy2), t2y = __fmul2_rn(__fadd2_rn(hiy, m), iy2);
+        const float2 t1z = __fmul2_rn(__fadd2_rn(loz, nm), iz2), t2z = __fmul2_rn(__fadd2_rn(hiz, m), iz2);
+        const float tmin_l = fmaxf(fmaxf(fminf(t1x.x, t2x.x), fminf(t1y.x, t2y.x)), fminf(t1z.x, t2z.x));
+        const float tmax_l = fminf(fminf(fmaxf(t1x.x, t2x.x), fmaxf(t1y.x, t2y.x)), fmaxf(t1z.x, t2z.x));
+        const float tmin_r = fmaxf(fmaxf(fminf(t1x.y, t2x.y), fminf(t1y.y, t2y.y)), fminf(t1z.y, t2z.y));
+        const float tmax_r = fminf(fminf(fmaxf(t1x.y, t2x.y), fmaxf(t1y.y, t2y.y)), fmaxf(t1z.y, t2z.y));
+        tn[0] = tmin_l;
+        tn[1] = tmin_r;
+        hit[0] = tmax_l >= fmaxf(tmin_l, 0.0f) && tmin_l <= tv.best_t; // empty boxes (lo > hi) fail the first test
+        hit[1] = tmax_r >= fmaxf(tmin_r, 0.0f) && tmin_r <= tv.best_t;
     }
     // leaves are tested immediately, inner children are descended near-first
     uint32_t next = 0xffffffffu;

@@ -590,9 +590,10 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
             for (size_t i = 0; i < bvh.nodes.size(); i++)
             {
                 const rtcu_bvh::Node& nd = bvh.nodes[i];
-                nodes_dev[4 * i + 0] = make_float4(nd.x[0], nd.x[1], nd.x[2], nd.x[3]);
-                nodes_dev[4 * i + 1] = make_float4(nd.y[0], nd.y[1], nd.y[2], nd.y[3]);
-                nodes_dev[4 * i + 2] = make_float4(nd.z[0], nd.z[1], nd.z[2], nd.z[3]);
+                // host node: {l.lo, l.hi, r.lo, r.hi} per axis -> device: {l.lo, r.lo, l.hi, r.hi} (packed slab test)
+                nodes_dev[4 * i + 0] = make_float4(nd.x[0], nd.x[2], nd.x[1], nd.x[3]);
+                nodes_dev[4 * i + 1] = make_float4(nd.y[0], nd.y[2], nd.y[1], nd.y[3]);
+                nodes_dev[4 * i + 2] = make_float4(nd.z[0], nd.z[2], nd.z[1], nd.z[3]);
                 uint32_t ref[2];
                 for (int c = 0; c < 2; c++)
                     ref[c] = nd.child[c] >= 0 ? (uint32_t)nd.child[c] : (0x80000000u | ((uint32_t)(~nd.child[c]) << 3) | nd.count[c]);
