@@ -8,7 +8,7 @@ fails loudly when the library or a B200-class device is missing (there is no CPU
 """
 from .scene import Scene, Camera, SceneError, load as load_scene, loads as loads_scene  # noqa: F401
 from .renderer import (Context, ImageView, RendererInterface, Description, renderers, register_renderer,  # noqa: F401
-                       cuda_path_tracer, CudaPathTracer, make_view, render_multi, DEFAULT_SEED)
+                       cuda_path_tracer, CudaPathTracer, ProgressiveRenderer, make_view, render_multi, DEFAULT_SEED)
 from ._native import (RtcuError, MODE_MG, MODE_SM, ACCEL_AUTO, ACCEL_LINEAR, ACCEL_BVH,  # noqa: F401
                       PIPE_AUTO, PIPE_MEGAKERNEL, PIPE_WAVEFRONT, PRIM_MISS, PRIM_PLANE)
 

@@ -278,6 +278,46 @@ def render_multi(contexts: Sequence[Context], view: nat.View, want_accum: bool =
     return rgba8, accum
 
 
+class ProgressiveRenderer:
+    """Progressive refinement behind the same boundary: every `refine()` call traces the next
+    `samples_per_step` global samples of the frame into the context's fp32 accumulation buffer and returns the image
+    resolved over the samples so far -- what an interactive `render()` would show while the camera rests.  Because sample
+    indices are global (counter-based RNG), the image after k steps equals a single render of k*samples_per_step samples
+    up to fp32 summation order."""
+
+    def __init__(self, ctx: "Context", scene: Scene, width: int, height: int, *, samples_per_step: int = 4, max_bounces: Optional[int] = None,
+                 material_mode: int = nat.MODE_SM, seed: int = DEFAULT_SEED, flags: int = 0):
+        self.ctx, self.scene, self.width, self.height = ctx, scene, width, height
+        self.samples_per_step, self.max_bounces = samples_per_step, max_bounces
+        self.material_mode, self.seed, self.flags = material_mode, seed, flags
+        self.samples_done = 0
+        self.accum = np.zeros((height, width, 4), np.float32)
+        ctx.upload_scene(scene)
+
+    def reset(self) -> None:
+        """camera moved / scene reloaded (main.cpp:233-313): start over"""
+        self.samples_done = 0
+        self.accum[...] = 0
+        self.ctx.upload_scene(self.scene)
+
+    def refine(self) -> np.ndarray:
+        begin, end = self.samples_done, self.samples_done + self.samples_per_step
+        view = make_view(self.scene, self.width, self.height, samples_per_pixel=end, max_bounces=self.max_bounces,
+                         sample_range=(begin, end), seed=self.seed, material_mode=self.material_mode, flags=self.flags)
+        _, part = self.ctx.render(view, want_rgba8=False, want_accum=True)
+        self.accum += part
+        self.samples_done = end
+        return self.resolve()
+
+    def resolve(self) -> np.ndarray:
+        """divide / sqrt / pack over the samples so far (mg_ray_tracer.cpp:195-200), on the host copy"""
+        n = np.float32(max(self.samples_done, 1))
+        c = np.sqrt(self.accum[..., :3] / n, dtype=np.float32)
+        c = np.minimum(np.maximum(c, np.float32(0)), np.float32(1))
+        b = (c * np.float32(255.99999)).astype(np.uint32)
+        return (b[..., 0] << 24) | (b[..., 1] << 16) | (b[..., 2] << 8) | np.uint32(255)
+
+
 def scene_fingerprint(scene: Scene) -> bytes:
     """The reference scene has no dirty flag: detect changes by content."""
     h = hashlib.blake2b(digest_size=16)

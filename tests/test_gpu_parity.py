@@ -398,3 +398,19 @@ def test_wavefront_tiles_sample_ranges_and_golden(ctx, scenes):
     # empty range
     _, none = ctx.render(make_view(sc, w, h, sample_range=(3, 3), **kw), want_accum=True)
     assert (none == 0).all()
+
+
+def test_progressive_refinement_converges_to_the_single_render(ctx, scenes):
+    from rt_b200.renderer import ProgressiveRenderer
+
+    sc = scenes["c2"][0]
+    prog = ProgressiveRenderer(ctx, sc, 160, 90, samples_per_step=4, max_bounces=50)
+    first = prog.refine()
+    for _ in range(3):
+        img = prog.refine()
+    assert prog.samples_done == 16 and (img != first).any()
+    rgba8, accum = ctx.render(make_view(sc, 160, 90, samples_per_pixel=16, max_bounces=50), want_accum=True)
+    np.testing.assert_allclose(prog.accum, accum, rtol=2e-6, atol=1e-7)
+    assert np.abs(unpack_rgba(img) - unpack_rgba(rgba8)).max() <= 1
+    prog.reset()
+    assert prog.samples_done == 0 and (prog.refine() == first).all()
