@@ -80,6 +80,23 @@ def build_oracle(fast: bool = False) -> pathlib.Path:
     return ROOT / "oracle" / "_build" / f"librtref_{target}.so"
 
 
+HOST_BIN = ROOT / "rt_b200" / "host" / "rt_headless"
+
+
+def build_host() -> pathlib.Path:
+    """The headless C++ host (scene loader + CLI over the C ABI): rt_b200/host/rt_headless, linked to librtcu.so."""
+    src = ROOT / "rt_b200" / "host" / "rt_headless.cpp"
+    deps = [src, src.with_name("scene_loader.hpp"), src.with_name("toml_lite.hpp"), src.with_name("colour_table.inc"), ROOT / "include" / "rtcu.h"]
+    if HOST_BIN.exists() and all(d.stat().st_mtime <= HOST_BIN.stat().st_mtime for d in deps):
+        return HOST_BIN
+    cmd = ["g++", "-std=c++20", "-O2", "-Wall", "-Wextra", f"-I{ROOT / 'include'}", "-o", str(HOST_BIN), str(src),
+           f"-L{LIBDIR}", "-lrtcu", "-Wl,-rpath,$ORIGIN/../lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build failed:\n" + r.stdout + r.stderr)
+    return HOST_BIN
+
+
 def build_reference() -> bool:
     """oracle/_ref/librt_ref*.so from the reference's own sources (oracle/Makefile `ref`); a no-op where the reference
     tree is absent (the prebuilt libraries travel with the repo snapshot)."""
@@ -94,5 +111,6 @@ def build_reference() -> bool:
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
     build_plugin_check()
+    print(build_host())
     print(build_oracle())
     print("reference build:", build_reference())

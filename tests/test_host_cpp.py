@@ -1,0 +1,177 @@
+"""The C++ host (rt_b200/host: TOML reader, scene loader restating scene.cpp, viewport, rt_headless CLI) against its Python
+twin (rt_b200/scene.py, camera.py) and, on a GPU, against the Python path through the same C ABI."""
+import json
+import subprocess
+
+import numpy as np
+import pytest
+
+from rt_b200 import build, scene as S, synth
+from rt_b200.camera import inverse_view_projection
+
+
+@pytest.fixture(scope="module")
+def cli():
+    build.build_cuda()
+    return str(build.build_host())
+
+
+def run(cli, *args, check=True):
+    r = subprocess.run([cli, *args], capture_output=True, text=True)
+    if check:
+        assert r.returncode == 0, r.stderr
+    return r
+
+
+def dumped(cli, path) -> dict:
+    return json.loads(run(cli, "--scene", str(path), "--dump-scene").stdout)
+
+
+def assert_same_scene(d: dict, s: S.Scene):
+    assert d["samples_per_pixel"] == s.samples_per_pixel and d["max_bounces"] == s.max_bounces
+    np.testing.assert_array_equal(np.float32(d["camera"]["position"]), np.float32(s.camera.position))
+    np.testing.assert_array_equal(np.float32(d["camera"]["direction"]), np.float32(s.camera.direction))
+    assert len(d["materials"]) == len(s.materials)
+    for a, b in zip(d["materials"], s.materials):
+        assert a["type"] == int(b["type"])
+        np.testing.assert_array_equal(np.float32(a["albedo"]), b["albedo"])
+        assert np.float32(a["roughness"]) == b["roughness"] and np.float32(a["reflectivity"]) == b["reflectivity"]
+    np.testing.assert_array_equal(np.float32(d["spheres"]).reshape(-1, 4), s.spheres)
+    np.testing.assert_array_equal(np.uint32(d["sphere_material"]), s.sphere_material)
+    np.testing.assert_array_equal(np.float32(d["planes"]).reshape(-1, 4), s.planes)
+    np.testing.assert_array_equal(np.uint32(d["plane_material"]), s.plane_material)
+    np.testing.assert_array_equal(np.float32(d["boxes"]).reshape(-1, 6), s.boxes)
+
+
+def test_list_and_renderer_lookup(cli):
+    assert run(cli, "--list").stdout.split() == ["cuda_path_tracer"]
+    r = run(cli, "--scene", "scenes/basic.toml", "--renderer", "nope", check=False)
+    assert r.returncode == 1 and "error: unknown renderer 'nope'" in r.stderr
+    assert run(cli, "--scene", "scenes/basic.toml", "--renderer", "cuda", "--dump-view").returncode == 0  # prefix match (main.cpp:68-81)
+
+
+@pytest.mark.parametrize("name", ["basic.toml", "dielectric.toml"])
+def test_shipped_scenes_load_like_the_python_loader(cli, name):
+    assert_same_scene(dumped(cli, f"scenes/{name}"), S.load(f"scenes/{name}"))
+
+
+def test_synthetic_scene_toml_round_trip(cli, tmp_path):
+    sc = synth.rtiow_scene()
+    p = tmp_path / "c3.toml"
+    p.write_text(S.dumps(sc))
+    assert_same_scene(dumped(cli, p), S.loads(p.read_text()))
+    g = synth.grid_scene(nx=60, nz=40)
+    p2 = tmp_path / "grid.toml"
+    p2.write_text(S.dumps(g))
+    d = dumped(cli, p2)
+    assert len(d["spheres"]) == 2401
+    assert_same_scene(d, S.loads(p2.read_text()))
+
+
+SYNTAX = '''
+# every value syntax the loader accepts (scene.cpp:113-166, :184-356, :381-404)
+samples_per_pixel = 4_096        # clamps to 1000
+max_bounces = 0                  # clamps to 1
+camera.position = 'up'
+camera.direction = [0.25, -1]    # missing z keeps the default (-1)
+
+[[materials]]
+type = 2
+albedo = [0.5]                   # starts from zero, alpha 1
+[[materials]]
+type = 'metal'
+albedo = "teal"
+roughness = 1e-1
+[[materials]]
+name = "default-everything"
+
+[[spheres]]
+position = 2                     # scalar broadcast
+material = 1
+[[spheres]]
+radius = 0x2
+
+[[planes]]
+normal = [0, 2.0, 0]
+position = [0, 3, 0]
+
+[[boxes]]
+extents = 2
+'''
+
+
+def test_value_syntax_matches_the_python_loader(cli, tmp_path):
+    p = tmp_path / "syntax.toml"
+    p.write_text(SYNTAX)
+    d = dumped(cli, p)
+    assert_same_scene(d, S.loads(SYNTAX))
+    assert d["samples_per_pixel"] == 1000 and d["max_bounces"] == 1
+    assert d["camera"]["direction"] == [0.25, -1, -1]
+
+
+@pytest.mark.parametrize("text,message", [
+    ("spheres = [ {material = 3} ]", "material index 3 out-of-range"),
+    ("spheres = [ {radius = nan} ]", "Infinities and NaNs are not allowed."),
+    ("spheres = [ {position = 'sideways'} ]", "unknown vector alias 'sideways'"),
+    ("materials = [ {albedo = 'octarine'} ]", "unknown colour alias 'octarine'"),
+    ("materials = [ {type = 'glass'} ]", "was not a member of enum material_type"),
+    ("materials = [ {type = 8} ]", "integer value 8 was not a member of enum material_type"),
+    ("spheres = 3", "expected array at key 'spheres'"),
+    ("spheres = [ {position = [1,2,3,4]} ]", "No mapping from TOML array"),
+    ("spheres = [ {radius = 1 ]", "TOML parse error"),
+])
+def test_loader_errors_exit_1_with_the_reference_messages(cli, tmp_path, text, message):
+    p = tmp_path / "bad.toml"
+    p.write_text(text)
+    r = run(cli, "--scene", str(p), "--dump-scene", check=False)
+    assert r.returncode == 1 and r.stderr.strip().splitlines()[-1].startswith("error: ") and message in r.stderr
+    with pytest.raises(S.SceneError):
+        S.loads(text)
+
+
+def test_viewport_matrix_matches_the_python_camera(cli):
+    for name, size in (("scenes/basic.toml", (800, 600)), ("scenes/dielectric.toml", (1920, 1080))):
+        m = np.float32(json.loads(run(cli, "--scene", name, "--size", f"{size[0]}x{size[1]}", "--dump-view").stdout))
+        ref = inverse_view_projection(S.load(name).camera, *size)
+        np.testing.assert_allclose(m, ref, rtol=2e-6, atol=2e-6)
+
+
+def test_no_device_fails_loudly(cli):
+    from rt_b200 import _native as nat
+
+    if nat.load_library().rtcu_device_count() > 0:
+        pytest.skip("device present")
+    r = run(cli, "--scene", "scenes/basic.toml", "--size", "32x24", check=False)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_render_equals_the_python_path_byte_for_byte(cli, ctx, tmp_path):
+    from rt_b200.renderer import make_view
+
+    out = tmp_path / "img.ppm"
+    r = run(cli, "--scene", "scenes/dielectric.toml", "--size", "320x180", "--spp", "8", "--bounces", "50", "--out", str(out))
+    assert "Msamples/s" in r.stderr
+    data = out.read_bytes()
+    header = b"P6\n320 180\n255\n"
+    assert data.startswith(header)
+    img = np.frombuffer(data[len(header):], np.uint8).reshape(180, 320, 3)
+    sc = S.load("scenes/dielectric.toml")
+    v = make_view(sc, 320, 180, samples_per_pixel=8, max_bounces=50)
+    v.inv_view_proj[:] = json.loads(run(cli, "--scene", "scenes/dielectric.toml", "--size", "320x180", "--dump-view").stdout)
+    ctx.upload_scene(sc)
+    rgba8, _ = ctx.render(v)
+    ref = np.stack([(rgba8 >> 24) & 255, (rgba8 >> 16) & 255, (rgba8 >> 8) & 255], axis=-1).astype(np.uint8)
+    np.testing.assert_array_equal(img, ref)
+    # two GPUs when present: the sample-range split changes only the summation order
+    if nat_device_count() >= 2:
+        out2 = tmp_path / "img2.ppm"
+        run(cli, "--scene", "scenes/dielectric.toml", "--size", "320x180", "--spp", "8", "--bounces", "50", "--gpus", "2", "--out", str(out2))
+        img2 = np.frombuffer(out2.read_bytes()[len(header):], np.uint8).reshape(180, 320, 3)
+        assert np.abs(img2.astype(int) - img.astype(int)).max() <= 1
+
+
+def nat_device_count() -> int:
+    from rt_b200 import _native as nat
+
+    return nat.load_library().rtcu_device_count()
