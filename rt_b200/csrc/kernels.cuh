@@ -128,21 +128,8 @@ struct BvhStats { uint32_t nodes, tests; };
 
 __device__ __forceinline__ void bvh_leaf_test(const float4 sph, const int index, const Ray& r, float& best_t, int& best_i)
 {
-    const float ex = __fsub_rn(sph.x, r.o.x), ey = __fsub_rn(sph.y, r.o.y), ez = __fsub_rn(sph.z, r.o.z);
-    const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
-    const float a = __fmaf_rn(ez, r.d.z, __fmaf_rn(ey, r.d.y, __fmul_rn(ex, r.d.x)));
-    const float disc = __fsub_rn(sph.w, __fmaf_rn(-a, a, e2));
-    if (!(disc < 0.0f))
-    {
-        const float f = __fsqrt_rn(disc);
-        const float t = (e2 < sph.w) ? __fadd_rn(a, f) : __fsub_rn(a, f);
-        // leaves are visited in traversal order, not index order: (t, index) lexicographic == "lowest index wins ties"
-        if (!(t < 0.001f) && (t < best_t || (t == best_t && index < best_i)))
-        {
-            best_t = t;
-            best_i = index;
-        }
-    }
+    // leaves are visited in traversal order, not index order: (t, index) lexicographic == "lowest index wins ties"
+    sphere_test<true>(sph, index, r, best_t, best_i);
 }
 
 constexpr int BVH_STACK = 64;

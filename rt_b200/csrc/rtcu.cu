@@ -103,7 +103,6 @@ struct rtcu_ctx {
 
     // scene (device)
     DevBuf<float4> sph;        // {cx,cy,cz,r*r}
-    DevBuf<float4> sph_raw;    // {cx,cy,cz,r}
     DevBuf<float4> pairs;      // packed-scan layout, see SceneDev::pairs
     DevBuf<uint32_t> sph_mat;
     DevBuf<float4> planes;
@@ -486,7 +485,7 @@ void rtcu_destroy(rtcu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    ctx->sph.release(); ctx->sph_raw.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
+    ctx->sph.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
     ctx->mats.release(); ctx->bvh_nodes.release(); ctx->leaf_sph.release(); ctx->leaf_idx.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
     for (int i = 0; i < 2; i++) { ctx->wf_o[i].release(); ctx->wf_d[i].release(); ctx->wf_thr[i].release(); }
     for (auto& l : ctx->wf_list) l.release();
@@ -514,13 +513,12 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         if (s->materials[i].type > RTCU_DIAMOND) return fail(RTCU_ERR_INVALID, "material %u: type %u is not a material_type", i, s->materials[i].type);
 
     CU(cudaSetDevice(ctx->device));
-    std::vector<float4> sph(s->n_spheres), raw(s->n_spheres);
+    std::vector<float4> sph(s->n_spheres);
     for (uint32_t i = 0; i < s->n_spheres; i++)
     {
         const float* p = s->spheres + 4 * (size_t)i;
         const float r = p[3];
         const volatile float r2 = r * r; // S4: r2 = r*r, one IEEE multiply
-        raw[i] = make_float4(p[0], p[1], p[2], r);
         sph[i] = make_float4(p[0], p[1], p[2], r2);
     }
     // packed-scan layout: pair j = spheres 2j, 2j+1 as {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}; everything past the last
@@ -548,7 +546,6 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         mats[i] = r;
     }
     CU(ctx->sph.reserve(s->n_spheres ? s->n_spheres : 1));
-    CU(ctx->sph_raw.reserve(s->n_spheres ? s->n_spheres : 1));
     CU(ctx->pairs.reserve(pairs.size()));
     CU(ctx->sph_mat.reserve(s->n_spheres ? s->n_spheres : 1));
     CU(ctx->planes.reserve(s->n_planes ? s->n_planes : 1));
@@ -560,7 +557,6 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     if (s->n_spheres)
     {
         CU(cudaMemcpyAsync(ctx->sph.p, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->sph_raw.p, raw.data(), raw.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->sph_mat.p, s->sphere_material, s->n_spheres * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (s->n_planes)
