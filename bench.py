@@ -40,6 +40,10 @@ SCENE_FILE = "scenes/dielectric.toml"
 WORKLOAD = "C2: scenes/dielectric.toml 1920x1080 64spp depth50 sm-table (lambert/metal/dielectric)"
 METRIC, UNIT = "Msamples/sec (paths*spp/s)", "Msamples/s"
 FLOP_PER_TEST, FLOP_PER_SEGMENT, FLOP_PER_SAMPLE = 18, 60, 60  # SURVEY.md 8d algorithmic work unit
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_render_mega launch on this workload, from the committed
+# `ncu --set full` capture (profiles/r1_final_ncu_summary.txt: 0.039 MB read + 0.80 MB written; the 33 MB accumulation
+# buffer stays in the 126 MB L2 for the duration of the launch)
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 39_170 + 802_000
 
 
 def load_scene():
@@ -316,7 +320,7 @@ def run_gpu(args):
         alg_bytes = WIDTH * HEIGHT * 16
         roofline = {
             "bound": "fp32", "kernel": "k_render_mega", "achieved": round(achieved, 3), "peak": round(peak_nominal, 2), "unit": "TFLOP/s",
-            "frac": round(achieved / peak_nominal, 4), "traffic": None,
+            "frac": round(achieved / peak_nominal, 4), "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
             "peak_source": f"non-tensor FP32: {sm_count} SMs x 128 lanes x 2 x sm_max_mhz {sm_max_mhz:.0f} (MEASURED_PEAKS.json clock{'' if peaks else ', fallback'}); "
                            "SURVEY.md 8d: this path is FP32-pipe bound, not HBM/tensor",
             "peak_measured_ffma": round(ffma_tf, 2), "peak_measured_ffma2": round(ffma2_tf, 2),

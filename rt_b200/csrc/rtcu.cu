@@ -132,6 +132,8 @@ struct rtcu_ctx {
     DevBuf<uint32_t> wf_list[4], wf_counts;
     PinnedBuf<uint32_t> h_wf_counts;
 
+    std::vector<cudaEvent_t> copy_events; // per-chunk completion events of staged device -> host copies
+
     // scratch for the batch entry points
     DevBuf<unsigned char> scratch;
 
@@ -379,10 +381,29 @@ int copy_out(rtcu_ctx* ctx, T* dst, const T* d_src, size_t n, PinnedBuf<T>& stag
     }
     else
     {
+        // pageable destination (the reference's image buffer, image.cpp:9-13): DMA into pinned staging in chunks and
+        // copy chunk k to the caller while chunk k+1 is still in flight
         CU(staging.reserve(n));
-        CU(cudaMemcpyAsync(staging.p, d_src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        memcpy(dst, staging.p, n * sizeof(T));
+        const size_t chunk = (size_t)(1u << 20) / sizeof(T); // 1 MiB
+        const size_t n_chunks = (n + chunk - 1) / chunk;
+        if (ctx->copy_events.size() < n_chunks)
+        {
+            const size_t old = ctx->copy_events.size();
+            ctx->copy_events.resize(n_chunks, nullptr);
+            for (size_t k = old; k < n_chunks; k++) CU(cudaEventCreateWithFlags(&ctx->copy_events[k], cudaEventDisableTiming));
+        }
+        for (size_t k = 0; k < n_chunks; k++)
+        {
+            const size_t off = k * chunk, cnt = n - off < chunk ? n - off : chunk;
+            CU(cudaMemcpyAsync(staging.p + off, d_src + off, cnt * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaEventRecord(ctx->copy_events[k], ctx->stream));
+        }
+        for (size_t k = 0; k < n_chunks; k++)
+        {
+            const size_t off = k * chunk, cnt = n - off < chunk ? n - off : chunk;
+            CU(cudaEventSynchronize(ctx->copy_events[k]));
+            memcpy(dst + off, staging.p + off, cnt * sizeof(T));
+        }
     }
     return RTCU_OK;
 }
@@ -492,6 +513,8 @@ void rtcu_destroy(rtcu_ctx* ctx)
     ctx->wf_rad.release(); ctx->wf_sum.release(); ctx->wf_hit.release(); ctx->wf_counts.release(); ctx->h_wf_counts.release();
     ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
     for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->copy_events)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
