@@ -436,7 +436,7 @@ const char* rtcu_last_error(void) { return g_err; }
 uint32_t rtcu_bvh_threshold(void)
 {
     if (const char* e = getenv("RTCU_BVH_THRESHOLD")) return (uint32_t)strtoul(e, nullptr, 10);
-    return 64u; // measured crossover, see DESIGN.md
+    return 32u; // measured crossover (profiles/bvh_crossover_r1.jsonl): BVH is ahead from ~24 spheres, 20 % at 32, 2x at 64
 }
 
 int rtcu_device_count(void)
