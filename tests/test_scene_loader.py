@@ -120,3 +120,16 @@ def test_synthetic_scenes_round_trip_through_toml():
     assert len(g.spheres) == 201 and int(g.sphere_material.max()) < len(g.materials)
     # determinism of the generators
     np.testing.assert_array_equal(synth.rtiow_scene().spheres, sc.spheres)
+
+
+def test_scene_files_describe_the_reference_scenes():
+    # the two shipped scene files restate the reference's scenes by value (they are written in a different TOML style);
+    # expected values read off reference scenes/basic.toml:1-19 and scenes/dielectric.toml:1-30
+    b = S.load("scenes/basic.toml")
+    np.testing.assert_array_equal(b.spheres, np.float32([[0, -1000, 0, 1000], [0, 0.5, 0, 0.5], [1, 0.5, 0, 0.5]]))
+    assert [int(t) for t in b.materials["type"]] == [S.LAMBERT, S.LAMBERT, S.METAL] and (b.samples_per_pixel, b.max_bounces) == (30, 10)
+    d = S.load("scenes/dielectric.toml")
+    np.testing.assert_array_equal(d.spheres[:, :3], np.float32([[0, -1000, 0], [-3, 0.5, 0], [-3, 2, 0], [-1, 0.5, 0], [-1, 2, 0], [1, 0.5, 0], [1, 2, 0]]))
+    assert [int(t) for t in d.materials["type"]] == [S.LAMBERT, S.VACUUM, S.METAL, S.DIELECTRIC, S.AIR, S.WATER, S.ICE]
+    np.testing.assert_array_equal(d.sphere_material, np.arange(7))
+    assert d.samples_per_pixel == 200 and d.camera.position == (0.0, 1.0, 7.0)
