@@ -119,11 +119,14 @@ __device__ __forceinline__ V3 hit_normal(const float4* __restrict__ s_pairs, con
 // ---- BVH traversal with the linear scan's exact result ------------------------------------------------------
 // The answer must equal closest_hit_linear bit for bit: the lexicographic minimum (t, index) over all spheres whose
 // S4 test yields t >= 0.001.  Spheres are tested with the same S4 arithmetic, so only *culling* can change the result;
-// it is made conservative against the rounding of S4 itself: the computed discriminant differs from the geometric one
-// by at most ~(16 eps + 2|d.d - 1|) * |c-o|^2, i.e. a computed hit means the line passes within
-// sqrt(r^2 + kappa^2 |e|^2) of the centre and the computed t is within kappa*|e| of the true entry point.  Every child
-// box is therefore inflated by m = kappa * E, E = L1 distance from the ray origin to the box's farthest corner
-// (>= |e| of any sphere inside), before the slab test and the `tmin <= best_t` ordering cull.
+// it is made conservative against the rounding of S4 itself.  With u = 2^-24: e = c - o carries u|e| per component, e2 and
+// a = e.d carry <= 5u e2 and <= 4u|e||d|, a^2 <= 8u e2, the fused e2 - a^2 one more u e2, so the computed discriminant
+// differs from the geometric one by Delta <= (16u + 2|d.d - 1|) |e|^2 =: kappa^2 |e|^2.  A computed hit therefore means the
+// line passes within sqrt(r^2 + Delta) <= r + kappa|e| of the centre, and the computed t is >= (entry of the ray into that
+// inflated ball) - 4u|e|.  Every child box is therefore inflated by m = kappa * E, E = L1 distance from the ray origin to the
+// box's farthest corner (>= |e| of any sphere inside), before the slab test and the `tmin <= best_t` ordering cull.
+// (The tighter m = sqrt(r_min^2 + kappa^2 E^2) - r_min with the subtree's smallest radius was measured: 13-15 % fewer
+// sphere tests but 2-7 % slower -- the extra per-node arithmetic costs more than the visits it saves.)
 struct BvhStats { uint32_t nodes, tests; };
 
 __device__ __forceinline__ void bvh_leaf_test(const float4 sph, const int index, const Ray& r, float& best_t, int& best_i)
