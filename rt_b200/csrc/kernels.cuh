@@ -24,10 +24,11 @@ struct SceneDev {
     // BVH over the spheres (built when the scene size calls for it, see bvh.h); nodes = 4 float4 per node:
     // {l.lo.x,r.lo.x,l.hi.x,r.hi.x}, same for y and z (left/right interleaved for the packed FP32 slab test), then
     // {ref_left, ref_right, -, -} as bit patterns.
-    // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | first << 3 | count over leaf_sph / leaf_idx.
+    // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | leaf number; leaf L owns leaf_sph[4L..4L+3] (two packed
+    // pairs {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}, padded with never-hit spheres) and leaf_idx[4L..4L+3].
     const float4* bvh_nodes;
-    const float4* leaf_sph;   // {cx,cy,cz,r*r} in leaf order
-    const uint32_t* leaf_idx; // original sphere index
+    const float4* leaf_sph;
+    const uint32_t* leaf_idx; // original sphere indices (0x7fffffff = padding)
     uint32_t n_bvh_nodes;
 };
 
@@ -129,10 +130,36 @@ __device__ __forceinline__ V3 hit_normal(const float4* __restrict__ s_pairs, con
 // sphere tests but 2-7 % slower -- the extra per-node arithmetic costs more than the visits it saves.)
 struct BvhStats { uint32_t nodes, tests; };
 
-__device__ __forceinline__ void bvh_leaf_test(const float4 sph, const int index, const Ray& r, float& best_t, int& best_i)
+// two spheres of a leaf on the packed FP32 pipe (same arithmetic as sphere_pair_test, hence as the scan); candidates are
+// accepted by (t, index) lexicographic order because leaves are visited in traversal order, not index order
+__device__ __forceinline__ void bvh_leaf_candidate(const float a, const float e2, const float r2, const float disc, const int index,
+                                                   float& best_t, int& best_i)
 {
-    // leaves are visited in traversal order, not index order: (t, index) lexicographic == "lowest index wins ties"
-    sphere_test<true>(sph, index, r, best_t, best_i);
+    const float f = __fsqrt_rn(disc);
+    const float t = (e2 < r2) ? __fadd_rn(a, f) : __fsub_rn(a, f);
+    if (!(t < 0.001f) && (t < best_t || (t == best_t && index < best_i)))
+    {
+        best_t = t;
+        best_i = index;
+    }
+}
+
+__device__ __forceinline__ void bvh_leaf_pair_test(const float4 A, const float4 B, const int i0, const int i1, const Ray& r, float& best_t, int& best_i)
+{
+    const float2 ex = __fadd2_rn(make_float2(A.x, A.y), make_float2(-r.o.x, -r.o.x));
+    const float2 ey = __fadd2_rn(make_float2(A.z, A.w), make_float2(-r.o.y, -r.o.y));
+    const float2 ez = __fadd2_rn(make_float2(B.x, B.y), make_float2(-r.o.z, -r.o.z));
+    const float2 e2 = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
+    const float2 a = __ffma2_rn(ez, make_float2(r.d.z, r.d.z), __ffma2_rn(ey, make_float2(r.d.y, r.d.y), __fmul2_rn(ex, make_float2(r.d.x, r.d.x))));
+    const float2 t1 = __ffma2_rn(make_float2(-a.x, -a.y), a, e2);
+    const float2 disc = __fadd2_rn(make_float2(B.z, B.w), make_float2(-t1.x, -t1.y));
+    if (!(disc.x < 0.0f) || !(disc.y < 0.0f))
+    {
+        if (!(disc.x < 0.0f))
+            bvh_leaf_candidate(a.x, e2.x, B.z, disc.x, i0, best_t, best_i);
+        if (!(disc.y < 0.0f))
+            bvh_leaf_candidate(a.y, e2.y, B.w, disc.y, i1, best_t, best_i);
+    }
 }
 
 constexpr int BVH_STACK = 64;
@@ -209,12 +236,12 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
         if (!hit[c]) continue;
         if (ref[c] & 0x80000000u)
         {
-            const uint32_t first = (ref[c] & 0x7fffffffu) >> 3, count = ref[c] & 7u;
-            for (uint32_t k = 0; k < count; k++)
-            {
-                st.tests++;
-                bvh_leaf_test(__ldg(sc.leaf_sph + first + k), (int)__ldg(sc.leaf_idx + first + k), r, tv.best_t, tv.best_i);
-            }
+            const uint32_t leaf = ref[c] & 0x7fffffffu;
+            const float4* lp = sc.leaf_sph + 4 * (size_t)leaf;
+            const uint4 idx = __ldg(reinterpret_cast<const uint4*>(sc.leaf_idx) + leaf);
+            st.tests += 4; // sphere test slots (a leaf holds 1-4 spheres)
+            bvh_leaf_pair_test(__ldg(lp), __ldg(lp + 1), (int)idx.x, (int)idx.y, r, tv.best_t, tv.best_i);
+            bvh_leaf_pair_test(__ldg(lp + 2), __ldg(lp + 3), (int)idx.z, (int)idx.w, r, tv.best_t, tv.best_i);
         }
         else if (next == 0xffffffffu)
         {

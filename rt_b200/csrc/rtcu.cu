@@ -3,6 +3,7 @@
 #include "../../include/rtcu.h"
 #include "kernels.cuh"
 #include "wavefront.cuh"
+#include "pool.cuh"
 #include "bvh.h"
 
 #include <cstdarg>
@@ -324,9 +325,17 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     const bool flat = flat_loop_for(ctx->scene.n_spheres + ctx->scene.n_planes);
     if (use_bvh)
     {
-        // flat (warp-vote) loop; the nested form measures the same on C3/C4.  A warp-level state machine that runs one
-        // node visit per iteration and lets finished lanes shade/regenerate early was measured 20-25 % slower.
-        k_render_mega<false, true, true><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
+        // default: the one-segment-per-iteration loop (flat; the nested form measures the same on C3/C4).
+        // RTCU_BVH_KERNEL=pool selects the warp-local ray pool (pool.cuh): correct and deterministic, but measured 20-30 %
+        // slower, so it is not the default.
+        const char* which = getenv("RTCU_BVH_KERNEL");
+        if (which && strcmp(which, "pool") == 0)
+        {
+            p.segment_budget = 0; // work is shared by the 32 lanes of a warp: no per-thread stragglers
+            k_render_pool<<<grid, 32 * POOL_WARPS, 0, st>>>(ctx->scene, p);
+        }
+        else
+            k_render_mega<false, true, true><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
     }
     else if (sb <= MAX_STAGE_BYTES)
     {
@@ -603,7 +612,7 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         const rtcu_bvh::Result bvh = rtcu_bvh::build(s->spheres, s->n_spheres);
         ctx->ms_bvh_build = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ctx->bvh_depth = bvh.max_depth;
-        if (bvh.max_depth + 2 <= (uint32_t)BVH_STACK && s->n_spheres < (1u << 28))
+        if (bvh.max_depth + 2 <= (uint32_t)BVH_STACK && s->n_spheres < (1u << 29))
         {
             nodes_dev.resize(4 * bvh.nodes.size());
             for (size_t i = 0; i < bvh.nodes.size(); i++)
@@ -613,19 +622,40 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
                 nodes_dev[4 * i + 0] = make_float4(nd.x[0], nd.x[2], nd.x[1], nd.x[3]);
                 nodes_dev[4 * i + 1] = make_float4(nd.y[0], nd.y[2], nd.y[1], nd.y[3]);
                 nodes_dev[4 * i + 2] = make_float4(nd.z[0], nd.z[2], nd.z[1], nd.z[3]);
+                // leaves become fixed 4-sphere blocks in the packed pair layout of the sweep (two pairs = 4 float4, padded with
+                // never-hit spheres) + their 4 original indices: a leaf visit is two straight-line FFMA2 pair tests
                 uint32_t ref[2];
                 for (int c = 0; c < 2; c++)
-                    ref[c] = nd.child[c] >= 0 ? (uint32_t)nd.child[c] : (0x80000000u | ((uint32_t)(~nd.child[c]) << 3) | nd.count[c]);
+                {
+                    if (nd.child[c] >= 0)
+                    {
+                        ref[c] = (uint32_t)nd.child[c];
+                        continue;
+                    }
+                    const uint32_t leaf = (uint32_t)(leaf_idx.size() / 4);
+                    ref[c] = 0x80000000u | leaf;
+                    const float4 never = make_float4(0.0f, 0.0f, 0.0f, -__builtin_inff());
+                    float4 sp[4];
+                    for (uint32_t k = 0; k < 4; k++)
+                    {
+                        const bool real = k < nd.count[c];
+                        const uint32_t orig = real ? bvh.order[(size_t)(~nd.child[c]) + k] : 0x7fffffffu;
+                        sp[k] = real ? sph[orig] : never;
+                        leaf_idx.push_back(orig);
+                    }
+                    for (int pr = 0; pr < 2; pr++)
+                    {
+                        leaf_sph.push_back(make_float4(sp[2 * pr].x, sp[2 * pr + 1].x, sp[2 * pr].y, sp[2 * pr + 1].y));
+                        leaf_sph.push_back(make_float4(sp[2 * pr].z, sp[2 * pr + 1].z, sp[2 * pr].w, sp[2 * pr + 1].w));
+                    }
+                }
                 float4 meta;
                 memcpy(&meta.x, &ref[0], 4);
                 memcpy(&meta.y, &ref[1], 4);
                 meta.z = meta.w = 0.0f;
                 nodes_dev[4 * i + 3] = meta;
             }
-            leaf_sph.resize(s->n_spheres);
-            leaf_idx = bvh.order;
-            for (uint32_t k = 0; k < s->n_spheres; k++)
-                leaf_sph[k] = sph[bvh.order[k]];
+            if (leaf_idx.empty()) { leaf_idx.assign(4, 0x7fffffffu); leaf_sph.assign(4, make_float4(0.0f, 0.0f, -__builtin_inff(), -__builtin_inff())); }
             CU(ctx->bvh_nodes.reserve(nodes_dev.size()));
             CU(ctx->leaf_sph.reserve(leaf_sph.size()));
             CU(ctx->leaf_idx.reserve(leaf_idx.size()));

@@ -317,17 +317,48 @@ def test_bvh_non_unit_directions_fall_back_to_the_scan(ctx, scenes):
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("kernel", ["pool", "mega"])
 @pytest.mark.parametrize("name,mode", [("c3", nat.MODE_SM), ("c2", nat.MODE_SM), ("planes", nat.MODE_SM), ("grid", nat.MODE_SM), ("grid", nat.MODE_MG)])
-def test_bvh_render_is_bit_identical_to_linear_render(ctx, scenes, name, mode):
+def test_bvh_render_matches_linear_render(ctx, scenes, monkeypatch, name, mode, kernel):
+    # Both BVH kernels trace exactly the linear scan's paths (same segment count).  "mega" (one segment per iteration) also
+    # sums every pixel's samples in the same order -> bit-identical buffers; "pool" (warp-local ray pool, not the default) sums
+    # them in completion order -> identical up to fp32 summation order, and deterministic.
+    monkeypatch.setenv("RTCU_BVH_KERNEL", kernel)
     sc = _grid() if name == "grid" else scenes[name][0]
     ctx.upload_scene(sc)
-    kw = dict(samples_per_pixel=4, max_bounces=20, material_mode=mode)
-    _, lin = ctx.render(make_view(sc, 192, 108, flags=nat.ACCEL_LINEAR, **kw), want_accum=True)
-    segs_lin = ctx.stats()["segments"]
-    rgba, bvh = ctx.render(make_view(sc, 192, 108, flags=nat.ACCEL_BVH, **kw), want_accum=True)
-    st = ctx.stats()
-    assert st["accel"] == nat.ACCEL_BVH and st["segments"] == segs_lin
-    np.testing.assert_array_equal(bvh, lin)  # same paths, same arithmetic, same sums
+    for w, h, spp in ((192, 108, 4), (61, 37, 9)):  # the second size leaves partial 8x4 patches and partial CTAs
+        kw = dict(samples_per_pixel=spp, max_bounces=20, material_mode=mode)
+        _, lin = ctx.render(make_view(sc, w, h, flags=nat.ACCEL_LINEAR, **kw), want_accum=True)
+        segs_lin = ctx.stats()["segments"]
+        rgba, bvh = ctx.render(make_view(sc, w, h, flags=nat.ACCEL_BVH, **kw), want_accum=True)
+        st = ctx.stats()
+        assert st["accel"] == nat.ACCEL_BVH and st["segments"] == segs_lin
+        if kernel == "mega":
+            np.testing.assert_array_equal(bvh, lin)
+        else:
+            np.testing.assert_array_equal(bvh[..., 3], lin[..., 3])
+            np.testing.assert_allclose(bvh[..., :3], lin[..., :3], rtol=2e-6, atol=1e-6)
+            rgba2, bvh2 = ctx.render(make_view(sc, w, h, flags=nat.ACCEL_BVH, **kw), want_accum=True)
+            np.testing.assert_array_equal(bvh2, bvh)  # deterministic
+
+
+def test_bvh_pool_tiles_and_sample_ranges(ctx, scenes, monkeypatch):
+    monkeypatch.setenv("RTCU_BVH_KERNEL", "pool")
+    sc = scenes["c3"][0]
+    ctx.upload_scene(sc)
+    kw = dict(samples_per_pixel=12, max_bounces=50, material_mode=nat.MODE_SM, flags=nat.ACCEL_BVH)
+    _, full = ctx.render(make_view(sc, 160, 96, **kw), want_accum=True)
+    segs = ctx.stats()["segments"]
+    _, tile = ctx.render(make_view(sc, 160, 96, tile=(21, 10, 77, 59), **kw), want_accum=True)
+    np.testing.assert_allclose(tile[10:59, 21:77], full[10:59, 21:77], rtol=2e-6, atol=1e-6)
+    assert (tile[:10] == 0).all() and (tile[:, :21] == 0).all() and (tile[59:] == 0).all()
+    total, s = np.zeros_like(full), 0
+    for rng in ((0, 5), (5, 12)):
+        _, part = ctx.render(make_view(sc, 160, 96, sample_range=rng, **kw), want_accum=True)
+        total += part
+        s += ctx.stats()["segments"]
+    assert s == segs
+    np.testing.assert_allclose(total, full, rtol=2e-6, atol=1e-6)
 
 
 def test_bvh_auto_threshold(ctx, scenes):

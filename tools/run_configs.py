@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--depth", type=int, default=0, help="override max_bounces (0 = the config's own)")
     args = ap.parse_args()
     cfgs = configs()
     ctx = Context(0)
@@ -45,6 +46,8 @@ def main():
         t0 = time.perf_counter()
         ctx.upload_scene(sc)
         upload_ms = (time.perf_counter() - t0) * 1e3
+        if args.depth:
+            c = dict(c, depth=args.depth)
         v = make_view(sc, c["width"], c["height"], samples_per_pixel=c["spp"], max_bounces=c["depth"], material_mode=c["mode"],
                       sample_range=c.get("sample_range"), flags=args.flags)
         best, st = None, None
