@@ -1,11 +1,14 @@
 // kernels.cuh -- sm_100a kernels of the path-tracing hot path.
 //
-//   k_render_mega     register-resident paths: one thread owns one pixel and regenerates the next
-//                     sample of the same pixel when a path ends (mg_ray_tracer.cpp:182-201 per pixel,
-//                     :154-174 per path, iterated instead of recursed).  Scene primitives are staged
-//                     in shared memory and read as warp-uniform (broadcast) LDS.128.
-//   k_resolve         sum / spp, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200)
+//   k_render_mega<STAGE,FLAT,BVH>   register-resident paths: one thread owns one pixel and regenerates the next sample of
+//                     the same pixel when a path ends (mg_ray_tracer.cpp:182-201 per pixel, :154-174 per path, iterated
+//                     instead of recursed).  Linear scenes: primitives staged in shared memory as packed pairs, read as
+//                     warp-uniform LDS.128, two spheres per FFMA2.  BVH scenes: closest_hit_bvh (exact, conservative culls).
+//   k_render_stragglers<BVH>        second pass: one warp per pixel that exceeded its per-thread segment budget
+//   k_resolve / k_reduce_resolve    sum / spp, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200), the latter + NVLink peer sums
 //   k_intersect_batch / k_primary_rays / k_scatter_batch / k_philox_batch   step-wise parity kernels
+//   k_fp32_peak                     FFMA / FFMA2 calibration stream for the roofline denominator
+// (wavefront.cuh: the queue-based pipeline; pool.cuh: the warp-local ray pool; both selectable, neither the default)
 #pragma once
 #include "spec.cuh"
 

@@ -22,6 +22,9 @@ namespace rtcu_dev {
 #ifndef RTCU_POOL_K
 #define RTCU_POOL_K 4 // BVH node visits per loop iteration
 #endif
+#ifndef RTCU_POOL_REFILL
+#define RTCU_POOL_REFILL 16 // idle lanes that trigger a refill (swept 4..16 x K 1..4: 16 / 4 is the fastest on C3s / C4s)
+#endif
 #ifndef RTCU_POOL_BLOCKS
 #define RTCU_POOL_BLOCKS 6
 #endif
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, RTCU_POOL_BLOCKS) k_render_po
         // ---- refill: idle lanes take READY records -------------------------------------------------------------------
         const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
         bool finished = false; // this lane's traversal completed in this iteration
-        if (idle && ready_count)
+        // refills are batched: the refill path (6 LDS + trav_init) otherwise runs almost every iteration for ~2 lanes
+        if (ready_count && (__popc(idle) >= RTCU_POOL_REFILL || idle == 0xffffffffu || (__popc(idle) && ready_count + pend_count < 32u)))
         {
             const uint32_t n_take = min((uint32_t)__popc(idle), ready_count);
             const uint32_t rank = __popc(idle & lanemask_lt());
