@@ -722,15 +722,37 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     CU(ctx->rgba8.reserve(npix));
     const bool full = view->tile_x0 == 0 && view->tile_y0 == 0 && view->tile_x1 == view->width && view->tile_y1 == view->height;
 
+    // Zero-copy output: when the caller's image is pinned / registered host memory and the whole frame is rendered, the
+    // kernels store the packed pixels straight into it over PCIe as each pixel finishes, so the read-back overlaps the
+    // frame instead of following it (RTCU_ZERO_COPY=0 disables; pageable buffers -- the reference's image.cpp -- are staged).
+    uint32_t* d_out = rgba8_out ? ctx->rgba8.p : nullptr;
+    bool zero_copy = false;
+    if (rgba8_out && full && is_device_accessible_host(rgba8_out))
+    {
+        const char* e = getenv("RTCU_ZERO_COPY");
+        void* mapped = nullptr;
+        if (!(e && e[0] == '0') && cudaHostGetDevicePointer(&mapped, rgba8_out, 0) == cudaSuccess && mapped)
+        {
+            d_out = static_cast<uint32_t*>(mapped);
+            zero_copy = true;
+        }
+        else
+            cudaGetLastError();
+    }
+
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int rc = launch_render(ctx, view, ctx->accum.p, rgba8_out ? ctx->rgba8.p : nullptr, 0, ctx->stream);
+    int rc = launch_render(ctx, view, ctx->accum.p, d_out, 0, ctx->stream);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 
     // copy the tile rows back (whole image when the tile is the image)
     const size_t row0 = full ? 0 : view->tile_y0, rows = full ? view->height : view->tile_y1 - view->tile_y0;
     const size_t off = row0 * view->width, cnt = rows * view->width;
-    if (rgba8_out)
+    if (rgba8_out && zero_copy)
+    {
+        CU(cudaStreamSynchronize(ctx->stream)); // the pixels are already in the caller's buffer
+    }
+    else if (rgba8_out)
     {
         if (full)
             rc = copy_out(ctx, rgba8_out, ctx->rgba8.p, npix, ctx->h_rgba8);
