@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -160,6 +161,14 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     memcpy(p.cam.m, v->inv_view_proj, sizeof p.cam.m);
     p.cam.w = (float)v->width;
     p.cam.h = (float)v->height;
+    {
+        // perspective-divide reciprocals as frame constants when h.w is pixel-independent (see CameraConst)
+        const float* m = v->inv_view_proj;
+        p.cam.w_const = m[3] == 0.0f && m[7] == 0.0f && std::isfinite(m[11]) && std::isfinite(m[15]);
+        const volatile float b3 = m[15], f3 = b3 + m[11];
+        p.cam.iwn = 1.0f / b3;
+        p.cam.iwf = 1.0f / f3;
+    }
     p.width = v->width; p.height = v->height;
     p.tile_x0 = v->tile_x0; p.tile_y0 = v->tile_y0; p.tile_x1 = v->tile_x1; p.tile_y1 = v->tile_y1;
     p.sample_begin = v->sample_begin; p.sample_end = v->sample_end;
