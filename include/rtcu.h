@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTCU_ABI_VERSION 1
+#define RTCU_ABI_VERSION 2
 
 enum {
     RTCU_OK = 0,
@@ -55,6 +55,11 @@ enum {
     RTCU_PIPE_WAVEFRONT = 2 << 4   /* generate / intersect / shade / compact over HBM queues  */
 };
 
+/* primitive ids reported by rtcu_intersect_batch / rtcu_rasterize: a sphere index, or one of these */
+#define RTCU_PRIM_MISS  0xFFFFFFFFu
+#define RTCU_PRIM_PLANE 0x80000000u /* | plane index */
+#define RTCU_PRIM_BOX   0x40000000u /* | box index (rasterizer only) */
+
 /* one row of rt::materials (reference src/soa.hpp:157-170) minus the `name` column */
 typedef struct rtcu_material {
     uint32_t type;         /* materials.type()                                             */
@@ -65,8 +70,9 @@ typedef struct rtcu_material {
 
 /* a flattened rt::scene (reference src/scene.hpp:8-25).  The pointers are the reference's own
  * soagen columns: spheres.value() is muu::bounding_sphere<float>[] = {cx,cy,cz,radius} (soa.hpp:194),
- * planes.value() is muu::plane<float>[] = {nx,ny,nz,d}; boxes are never hit by either ray tracer
- * (mg_ray_tracer.cpp:89-93) and are therefore not part of the ABI. */
+ * planes.value() is muu::plane<float>[] = {nx,ny,nz,d}; boxes.value() is muu::bounding_box<float>[] =
+ * {cx,cy,cz,ex,ey,ez} (soa.hpp:138-150).  Boxes are never hit by either ray tracer
+ * (mg_ray_tracer.cpp:89-93): only rtcu_rasterize reads them, and they may be NULL / 0. */
 typedef struct rtcu_scene {
     const float*         spheres;
     const uint32_t*      sphere_material; /* spheres.material() */
@@ -76,6 +82,9 @@ typedef struct rtcu_scene {
     uint32_t             n_planes;
     const rtcu_material* materials;
     uint32_t             n_materials;
+    const float*         boxes;           /* ABI 2 */
+    const uint32_t*      box_material;    /* boxes.material() */
+    uint32_t             n_boxes;
 } rtcu_scene;
 
 /* one render call.  inv_view_proj is viewport::inverse_view_projection (reference src/camera.hpp:17,
@@ -128,6 +137,15 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* scene);
  *   packed as colour::operator uint32_t (colour.hpp:100-106); only the tile is written.
  * accum_out (nullable): width*height*4 floats {sum_r,sum_g,sum_b,n_samples}; only the tile is written. */
 int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out);
+
+/* ---- preview: replaces rasterizer::render (reference src/renderers/rasterizer.cpp:22-88): one ray per pixel through the
+ * pixel centre, nearest of planes, boxes, spheres (strict '<' in that order, no minimum distance), N.L shading against
+ * the eye, no gamma.  Uses inv_view_proj, width, height and the tile of the view; every other field is ignored.
+ * rgba8_out as in rtcu_render.  prim_out / depth_out (nullable, width*height each): per pixel the sphere index,
+ * RTCU_PRIM_PLANE|index, RTCU_PRIM_BOX|index or RTCU_PRIM_MISS, and the accepted distance -- the parity hooks. */
+int rtcu_rasterize(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, uint32_t* prim_out, float* depth_out);
+/* the same into DEVICE memory, asynchronously on `stream` (cudaStream_t as void*; NULL = legacy default stream) */
+int rtcu_rasterize_device(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* d_rgba8, void* stream);
 
 /* ---- device-resident variants (no host copies) for multi-GPU composition and benchmarking.
  * d_accum: width*height float4 on ctx's device.  accumulate != 0 adds onto the existing contents.

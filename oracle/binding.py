@@ -22,7 +22,8 @@ class Material(C.Structure):
 class SceneDesc(C.Structure):
     _fields_ = [("spheres", C.c_void_p), ("sphere_material", C.c_void_p), ("n_spheres", C.c_uint32),
                 ("planes", C.c_void_p), ("plane_material", C.c_void_p), ("n_planes", C.c_uint32),
-                ("materials", C.c_void_p), ("n_materials", C.c_uint32)]
+                ("materials", C.c_void_p), ("n_materials", C.c_uint32),
+                ("boxes", C.c_void_p), ("box_material", C.c_void_p), ("n_boxes", C.c_uint32)]
 
 
 class View(C.Structure):
@@ -44,6 +45,22 @@ def build(flavour: str = "strict") -> pathlib.Path:
 _MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("albedo", "<f4", (4,)), ("roughness", "<f4"), ("reflectivity", "<f4")])
 
 
+def _scene_desc(scene):
+    """(SceneDesc, arrays that must outlive it)"""
+    sph = np.ascontiguousarray(scene.spheres, np.float32).reshape(-1, 4)
+    smat = np.ascontiguousarray(scene.sphere_material, np.uint32)
+    pl = np.ascontiguousarray(scene.planes, np.float32).reshape(-1, 4)
+    pmat = np.ascontiguousarray(scene.plane_material, np.uint32)
+    bx = np.ascontiguousarray(getattr(scene, "boxes", np.zeros((0, 6))), np.float32).reshape(-1, 6)
+    bmat = np.ascontiguousarray(getattr(scene, "box_material", np.zeros(0)), np.uint32)
+    mats = np.ascontiguousarray(scene.materials.astype(_MATERIAL_DTYPE))
+    sd = SceneDesc(sph.ctypes.data if len(sph) else None, smat.ctypes.data if len(smat) else None, len(sph),
+                   pl.ctypes.data if len(pl) else None, pmat.ctypes.data if len(pmat) else None, len(pl),
+                   mats.ctypes.data, len(mats),
+                   bx.ctypes.data if len(bx) else None, bmat.ctypes.data if len(bmat) else None, len(bx))
+    return sd, (sph, smat, pl, pmat, mats, bx, bmat)
+
+
 class Oracle:
     """flavour 'strict' = the parity checker; 'fast' = the CPU timing baseline (reference's -ffast-math flags)."""
 
@@ -61,21 +78,16 @@ class Oracle:
         L.rtref_render.argtypes = [C.POINTER(SceneDesc), C.POINTER(View), p, p, p, i, u32]
         L.rtref_trace_sample.restype = u32
         L.rtref_trace_sample.argtypes = [C.POINTER(SceneDesc), C.POINTER(View), u32, u32, u32, p]
+        L.rtref_rasterize.argtypes = [C.POINTER(SceneDesc), C.POINTER(View), p, p, p, i, u32]
+        L.rtref_ray_hits_box.argtypes = [p, p, p, p]
         L.rtref_build_flavour.restype = C.c_char_p
         assert L.rtref_build_flavour().decode() == flavour
         self._keep = None
 
     # ---- scene ------------------------------------------------------------------------------------
     def scene_desc(self, scene) -> SceneDesc:
-        sph = np.ascontiguousarray(scene.spheres, np.float32).reshape(-1, 4)
-        smat = np.ascontiguousarray(scene.sphere_material, np.uint32)
-        pl = np.ascontiguousarray(scene.planes, np.float32).reshape(-1, 4)
-        pmat = np.ascontiguousarray(scene.plane_material, np.uint32)
-        mats = np.ascontiguousarray(scene.materials.astype(_MATERIAL_DTYPE))
-        self._keep = (sph, smat, pl, pmat, mats)
-        return SceneDesc(sph.ctypes.data if len(sph) else None, smat.ctypes.data if len(smat) else None, len(sph),
-                         pl.ctypes.data if len(pl) else None, pmat.ctypes.data if len(pmat) else None, len(pl),
-                         mats.ctypes.data, len(mats))
+        sd, self._keep = _scene_desc(scene)
+        return sd
 
     @staticmethod
     def view_from(v) -> View:
@@ -146,6 +158,24 @@ class Oracle:
             raise RuntimeError(f"rtref_render failed: {rc}")
         return rgba8, accum, int(segs.value)
 
+    def rasterize(self, scene, view, threads: int = 0, row_step: int = 1):
+        """rasterizer.cpp:22-88 -> (rgba8, prim, depth)"""
+        sd = self.scene_desc(scene)
+        v = self.view_from(view)
+        rgba8 = np.zeros((v.height, v.width), np.uint32)
+        prim = np.full((v.height, v.width), 0xFFFFFFFF, np.uint32)
+        depth = np.zeros((v.height, v.width), np.float32)
+        rc = self.lib.rtref_rasterize(C.byref(sd), C.byref(v), rgba8.ctypes.data, prim.ctypes.data, depth.ctypes.data, threads, row_step)
+        if rc != 0:
+            raise RuntimeError(f"rtref_rasterize failed: {rc}")
+        return rgba8, prim, depth
+
+    def ray_hits_box(self, o, d, box):
+        o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32); box = np.ascontiguousarray(box, np.float32)
+        t = C.c_float(0)
+        hit = self.lib.rtref_ray_hits_box(o.ctypes.data, d.ctypes.data, box.ctypes.data, C.byref(t))
+        return bool(hit), float(t.value)
+
     def trace_sample(self, scene, view, px: int, py: int, sample: int):
         sd = self.scene_desc(scene)
         v = self.view_from(view)
@@ -190,14 +220,8 @@ class ReferenceBuild:
         return [x for x in buf.value.decode().split("\n") if x]
 
     def _desc(self, scene) -> SceneDesc:
-        sph = np.ascontiguousarray(scene.spheres, np.float32).reshape(-1, 4)
-        smat = np.ascontiguousarray(scene.sphere_material, np.uint32)
-        pl = np.ascontiguousarray(scene.planes, np.float32).reshape(-1, 4)
-        pmat = np.ascontiguousarray(scene.plane_material, np.uint32)
-        mats = np.ascontiguousarray(scene.materials.astype(_MATERIAL_DTYPE))
-        self._keep = (sph, smat, pl, pmat, mats)
-        return SceneDesc(sph.ctypes.data if len(sph) else None, smat.ctypes.data if len(smat) else None, len(sph),
-                         pl.ctypes.data if len(pl) else None, pmat.ctypes.data if len(pmat) else None, len(pl), mats.ctypes.data, len(mats))
+        sd, self._keep = _scene_desc(scene)
+        return sd
 
     def inverse_view_projection(self, scene, width: int, height: int) -> np.ndarray:
         """the matrix the reference's own camera::viewport produces (through the stand-in matrix code)"""

@@ -133,7 +133,13 @@ namespace muu
 
 		// SPEC S1
 		[[nodiscard]] static constexpr T dot(vector a, vector b) noexcept { return shim_fma(a.z, b.z, shim_fma(a.y, b.y, a.x * b.x)); }
+		[[nodiscard]] constexpr T dot(vector b) const noexcept { return dot(*this, b); }
 		[[nodiscard]] constexpr T length() const noexcept { return __builtin_sqrtf(dot(*this, *this)); }
+		[[nodiscard]] static constexpr T distance(vector a, vector b) noexcept { return (b - a).length(); }
+		[[nodiscard]] static constexpr vector min(vector a, vector b) noexcept
+		{
+			return { a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z < b.z ? a.z : b.z };
+		}
 		// SPEC S2
 		[[nodiscard]] static constexpr vector normalize(vector v) noexcept
 		{

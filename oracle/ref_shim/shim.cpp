@@ -108,6 +108,9 @@ extern "C"
 		uint32_t n_planes;
 		const refbin_material* materials;
 		uint32_t n_materials;
+		const float* boxes; // n x {cx,cy,cz,ex,ey,ez}; only the rasterizer tests them
+		const uint32_t* box_material;
+		uint32_t n_boxes;
 	};
 
 	const char* refbin_last_error() { return g_last_error; }
@@ -161,6 +164,12 @@ extern "C"
 			const float* s = sc->spheres + 4 * i;
 			const rt::sphere sp{ rt::vec3{ s[0], s[1], s[2] }, s[3] };
 			scene.spheres.push_back(sp, sc->sphere_material[i], s[0], s[1], s[2], s[3]);
+		}
+		for (uint32_t i = 0; i < sc->n_boxes; i++)
+		{
+			const float* b = sc->boxes + 6 * i;
+			const rt::box bx{ rt::vec3{ b[0], b[1], b[2] }, rt::vec3{ b[3], b[4], b[5] } };
+			scene.boxes.push_back(bx, sc->box_material[i], b[0], b[1], b[2], b[3], b[4], b[5]);
 		}
 		if (inv_view_proj_out)
 		{

@@ -603,6 +603,180 @@ int rtref_render(const rtref_scene* s, const rtref_view* v, uint32_t* rgba8, flo
     return 0;
 }
 
+/* ==== rasterizer (rasterizer.cpp:22-88) ======================================================================== */
+
+/* S13: muu ray::hits(bounding_box), called at rasterizer.cpp:47.  Game-Physics-Cookbook slab form like S4/S5
+ * (UNVERIFIED against muu): lo = c - e, hi = c + e; per axis t1 = (lo - o)/d, t2 = (hi - o)/d (IEEE division, a zero
+ * direction component gives +-inf or NaN; fminf/fmaxf drop a NaN operand); tmin = max of the per-axis minima,
+ * tmax = min of the maxima; tmax < 0 or tmin > tmax -> miss; tmin < 0 (origin inside) -> tmax, else tmin.           */
+int rtref_ray_hits_box(const float o[3], const float d[3], const float box[6], float* t)
+{
+    float tmin = -INFINITY, tmax = INFINITY;
+    for (int k = 0; k < 3; k++)
+    {
+        const float lo = box[k] - box[3 + k], hi = box[k] + box[3 + k];
+        const float t1 = (lo - o[k]) / d[k], t2 = (hi - o[k]) / d[k];
+        tmin = fmaxf(tmin, fminf(t1, t2));
+        tmax = fminf(tmax, fmaxf(t1, t2));
+    }
+    if (tmax < 0.0f || tmin > tmax)
+        return 0;
+    *t = (tmin < 0.0f) ? tmax : tmin;
+    return 1;
+}
+
+#define PRIM_BOX 0x40000000u
+
+/* the worker lambda, rasterizer.cpp:28-83 */
+static uint32_t raster_pixel(const rtref_scene* s, const rtref_view* v, uint32_t px, uint32_t py, uint32_t* prim_out,
+                             float* depth_out)
+{
+    const float sx = (float)px + 0.5f, sy = (float)py + 0.5f;
+    const v3 near_p = screen_to_world(v, sx, sy, 0.0f); /* :31 */
+    const v3 far_p = screen_to_world(v, sx, sy, 1.0f);  /* :32 */
+    const v3 span = v3_sub(far_p, near_p);
+    const float max_dist = sqrtf(dot3(span, span));     /* vec3::distance, :33 */
+    float dist = max_dist + 1.0f;                       /* :35 */
+    uint32_t prim = PRIM_MISS, material = 0;
+    v3 hit_pos = { 0, 0, 0 };
+    v3 hit_normal = { 0.0f, 1.0f, 0.0f };               /* vec3::constants::up, :38 */
+    ray_t r;
+    r.o = near_p;
+    r.d = normalize3(span);                             /* :39 */
+
+    /* hit_tests(scene.planes), :61 */
+    for (uint32_t i = 0; i < s->n_planes; i++)
+    {
+        const float* pl = s->planes + 4 * (size_t)i;
+        float t;
+        if (!ray_hits_plane(&r, pl, &t) || t >= dist)   /* :47-49 */
+            continue;
+        dist = t;
+        prim = PRIM_PLANE | i;
+        material = s->plane_material[i];
+        hit_pos = ray_at(r.o, r.d, t);
+        hit_normal = v3_make(pl[0], pl[1], pl[2]);      /* :58 */
+    }
+    /* hit_tests(scene.boxes), :62 -- a box leaves hit_normal as it was (:55-58 have no box branch) */
+    for (uint32_t i = 0; i < s->n_boxes; i++)
+    {
+        const float o[3] = { r.o.x, r.o.y, r.o.z }, d[3] = { r.d.x, r.d.y, r.d.z };
+        float t;
+        if (!rtref_ray_hits_box(o, d, s->boxes + 6 * (size_t)i, &t) || t >= dist)
+            continue;
+        dist = t;
+        prim = PRIM_BOX | i;
+        material = s->box_material[i];
+        hit_pos = ray_at(r.o, r.d, t);
+    }
+    /* hit_tests(scene.spheres), :63 */
+    for (uint32_t i = 0; i < s->n_spheres; i++)
+    {
+        const float* sp = s->spheres + 4 * (size_t)i;
+        float t;
+        if (!ray_hits_sphere(&r, sp, &t) || t >= dist)
+            continue;
+        dist = t;
+        prim = i;
+        material = s->sphere_material[i];
+        hit_pos = ray_at(r.o, r.d, t);
+        hit_normal = normalize3(v3_sub(hit_pos, v3_make(sp[0], sp[1], sp[2]))); /* :56 */
+    }
+    if (prim_out) *prim_out = prim;
+    if (depth_out) *depth_out = dist;
+
+    float c[3];
+    if (prim != PRIM_MISS)
+    {
+        /* :70-76: min(0.25 + lambert(n, direction(hit_pos, near), albedo).rgb * 0.75, 1); lambert (:14-20) =
+         * l.dot(n) * vec3{albedo} * intensity(1.0f) */
+        const v3 l = normalize3(v3_sub(near_p, hit_pos));
+        const float k = dot3(l, hit_normal);
+        const float* albedo = s->materials[material].albedo;
+        for (int i = 0; i < 3; i++)
+        {
+            const float lam = (k * albedo[i]) * 1.0f;
+            const float x = 0.25f + lam * 0.75f; /* rule R: separate multiply and add */
+            c[i] = (x < 1.0f) ? x : 1.0f;        /* vec3::min */
+        }
+    }
+    else
+    {
+        /* :65-66, :79-82: colour{238,245,255} / colour{208,228,255} are int-constructed, so every channel saturates to
+         * 1.0f (colour.hpp:64-83); the lerp (S8 form) of the two whites over y/(h-1) is kept as written */
+        const float a = (float)py / (float)(v->height - 1u);
+        const float w = 1.0f - a;
+        for (int i = 0; i < 3; i++)
+            c[i] = FMA(1.0f, a, 1.0f * w);
+    }
+    /* colour -> uint32_t (colour.hpp:100-106), no gamma on this path */
+    return (to_byte(c[0]) << 24) | (to_byte(c[1]) << 16) | (to_byte(c[2]) << 8) | to_byte(1.0f);
+}
+
+typedef struct {
+    const rtref_scene* s;
+    const rtref_view* v;
+    uint32_t* rgba8;
+    uint32_t* prim;
+    float* depth;
+    uint32_t row_step;
+    int tid, nthreads;
+} raster_job_t;
+
+static void* raster_rows(void* arg)
+{
+    raster_job_t* j = (raster_job_t*)arg;
+    const rtref_view* v = j->v;
+    uint32_t row = 0;
+    for (uint32_t y = v->tile_y0; y < v->tile_y1; y += j->row_step, row++)
+    {
+        if ((int)(row % (uint32_t)j->nthreads) != j->tid)
+            continue;
+        for (uint32_t x = v->tile_x0; x < v->tile_x1; x++)
+        {
+            const size_t pixel = (size_t)y * v->width + x;
+            uint32_t prim;
+            float depth;
+            const uint32_t c = raster_pixel(j->s, v, x, y, &prim, &depth);
+            if (j->rgba8) j->rgba8[pixel] = c;
+            if (j->prim) j->prim[pixel] = prim;
+            if (j->depth) j->depth[pixel] = depth;
+        }
+    }
+    return NULL;
+}
+
+int rtref_rasterize(const rtref_scene* s, const rtref_view* v, uint32_t* rgba8, uint32_t* prim, float* depth,
+                    int threads, uint32_t row_step)
+{
+    if (!s || !v || v->tile_x1 > v->width || v->tile_y1 > v->height)
+        return -1;
+    for (uint32_t i = 0; i < s->n_spheres; i++)
+        if (s->sphere_material[i] >= s->n_materials) return -2;
+    for (uint32_t i = 0; i < s->n_planes; i++)
+        if (s->plane_material[i] >= s->n_materials) return -2;
+    for (uint32_t i = 0; i < s->n_boxes; i++)
+        if (s->box_material[i] >= s->n_materials) return -2;
+    if (row_step == 0) row_step = 1;
+    if (threads <= 0) threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (threads < 1) threads = 1;
+    if (threads > 1024) threads = 1024;
+    raster_job_t* jobs = (raster_job_t*)calloc((size_t)threads, sizeof(raster_job_t));
+    pthread_t* tids = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; t++)
+    {
+        const raster_job_t j = { s, v, rgba8, prim, depth, row_step, t, threads };
+        jobs[t] = j;
+        if (t > 0) pthread_create(&tids[t], NULL, raster_rows, &jobs[t]);
+    }
+    raster_rows(&jobs[0]);
+    for (int t = 1; t < threads; t++)
+        pthread_join(tids[t], NULL);
+    free(jobs);
+    free(tids);
+    return 0;
+}
+
 const char* rtref_build_flavour(void)
 {
 #ifdef RTREF_FAST

@@ -48,6 +48,10 @@ typedef struct rtref_scene {
     uint32_t              n_planes;
     const rtref_material* materials;
     uint32_t              n_materials;
+    /* read by rtref_rasterize only; the path tracers never hit a box (mg_ray_tracer.cpp:89-93) */
+    const float*          boxes;            /* n_boxes x {cx,cy,cz,ex,ey,ez} == boxes.value()    */
+    const uint32_t*       box_material;
+    uint32_t              n_boxes;
 } rtref_scene;
 
 typedef struct rtref_view {
@@ -95,6 +99,15 @@ int rtref_render(const rtref_scene* s, const rtref_view* v, uint32_t* rgba8, flo
  * the number of segments of that path */
 uint32_t rtref_trace_sample(const rtref_scene* s, const rtref_view* v, uint32_t px, uint32_t py,
                             uint32_t sample, float out[3]);
+
+/* --- rasterizer.cpp:22-88: one ray per pixel through the pixel centre, nearest of planes, boxes, spheres (in that
+ * order, strict '<', no minimum distance), N.L shading against the eye, no gamma.  Uses inv_view_proj, width, height and
+ * the tile of the view; prim (nullable) receives per pixel the sphere index, 0x80000000|plane, 0x40000000|box or
+ * 0xFFFFFFFF, depth (nullable) the accepted distance (max_dist + 1 on a miss).                                      */
+int rtref_rasterize(const rtref_scene* s, const rtref_view* v, uint32_t* rgba8, uint32_t* prim, float* depth,
+                    int threads, uint32_t row_step);
+/* S13: ray against a centre/extents box; returns 1 and *t on a hit */
+int rtref_ray_hits_box(const float o[3], const float d[3], const float box[6], float* t);
 
 const char* rtref_build_flavour(void); /* "strict" or "fast" */
 

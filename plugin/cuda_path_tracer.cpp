@@ -2,8 +2,9 @@
 // src/renderers/meson.build next to mg_ray_tracer.cpp, and link librtcu.so.
 //
 // `rt --scene <toml> --renderer cuda_path_tracer` then renders through the B200 library instead of the CPU
-// loops of mg_ray_tracer.cpp:178-205 / sm_ray_tracer.cpp:263-289.  The plugin only flattens rt::scene into
-// the POD descriptor of include/rtcu.h and calls the C ABI; scene.hpp, image.cpp and the window stay untouched.
+// loops of mg_ray_tracer.cpp:178-205 / sm_ray_tracer.cpp:263-289, and `--renderer cuda_rasterizer` replaces the
+// preview of rasterizer.cpp:22-88.  The plugin only flattens rt::scene into the POD descriptor of include/rtcu.h and
+// calls the C ABI; scene.hpp, image.cpp and the window stay untouched.
 //
 // Behaviour at the boundary (reference src/renderer.hpp:9-14, src/main.cpp:315-321):
 //  * render() is noexcept and has no error channel: on failure it logs to stderr and leaves the image as the
@@ -37,27 +38,25 @@ using namespace rt;
 
 namespace
 {
-	struct cuda_path_tracer final : renderer_interface
+	// what both renderers share: the context, the scene upload and the view
+	struct cuda_renderer : renderer_interface
 	{
 		rtcu_ctx* ctx_ = nullptr;
-		uint32_t material_mode_ = RTCU_MODE_SM;
 
 		// last uploaded scene columns (content comparison, see header comment)
-		std::vector<float> spheres_, planes_;
-		std::vector<uint32_t> sphere_mat_, plane_mat_;
+		std::vector<float> spheres_, planes_, boxes_;
+		std::vector<uint32_t> sphere_mat_, plane_mat_, box_mat_;
 		std::vector<rtcu_material> materials_;
 		bool uploaded_ = false;
 
-		cuda_path_tracer()
+		explicit cuda_renderer(const char* name)
 		{
 			ctx_ = rtcu_create(0);
 			if (!ctx_)
-				throw std::runtime_error{ std::string{ "cuda_path_tracer: " } + rtcu_last_error() };
-			if (const char* mode = std::getenv("RT_CUDA_MATERIAL_MODE"); mode && std::strcmp(mode, "mg") == 0)
-				material_mode_ = RTCU_MODE_MG;
+				throw std::runtime_error{ std::string{ name } + ": " + rtcu_last_error() };
 		}
 
-		~cuda_path_tracer() noexcept override
+		~cuda_renderer() noexcept override
 		{
 			rtcu_destroy(ctx_);
 		}
@@ -82,6 +81,10 @@ namespace
 			changed |= assign_if_changed(sphere_mat_, scene.spheres.material(), scene.spheres.size());
 			changed |= assign_if_changed(planes_, reinterpret_cast<const float*>(scene.planes.value()), scene.planes.size() * 4);
 			changed |= assign_if_changed(plane_mat_, scene.planes.material(), scene.planes.size());
+			// boxes.value() is muu::bounding_box<float>[] = {center.xyz, extents.xyz}; only the rasterizer draws them
+			static_assert(sizeof(scene.boxes.value()[0]) == 6 * sizeof(float));
+			changed |= assign_if_changed(boxes_, reinterpret_cast<const float*>(scene.boxes.value()), scene.boxes.size() * 6);
+			changed |= assign_if_changed(box_mat_, scene.boxes.material(), scene.boxes.size());
 
 			std::vector<rtcu_material> mats(scene.materials.size());
 			for (size_t i = 0; i < mats.size(); i++)
@@ -104,18 +107,15 @@ namespace
 			desc.n_planes		 = static_cast<uint32_t>(plane_mat_.size());
 			desc.materials		 = materials_.data();
 			desc.n_materials	 = static_cast<uint32_t>(materials_.size());
+			desc.boxes			 = boxes_.data();
+			desc.box_material	 = box_mat_.data();
+			desc.n_boxes		 = static_cast<uint32_t>(box_mat_.size());
 			uploaded_			 = rtcu_upload_scene(ctx_, &desc) == RTCU_OK;
 			return uploaded_;
 		}
 
-		void render(const rt::scene& scene, image_view& pixels, muu::thread_pool& /*threads*/) noexcept override
+		static rtcu_view make_view(const rt::scene& scene, const image_view& pixels) noexcept
 		{
-			if (!sync_scene(scene))
-			{
-				std::fprintf(stderr, "cuda_path_tracer: %s\n", rtcu_last_error());
-				return;
-			}
-
 			const auto view = scene.camera.viewport(pixels.size());
 
 			rtcu_view v{};
@@ -133,8 +133,30 @@ namespace
 			v.tile_x1			= v.width;
 			v.tile_y1			= v.height;
 			v.seed				= 0x5EEDull;
-			v.material_mode		= material_mode_;
 			v.flags				= RTCU_ACCEL_AUTO | RTCU_PIPE_AUTO;
+			return v;
+		}
+	};
+
+	struct cuda_path_tracer final : cuda_renderer
+	{
+		uint32_t material_mode_ = RTCU_MODE_SM;
+
+		cuda_path_tracer() : cuda_renderer{ "cuda_path_tracer" }
+		{
+			if (const char* mode = std::getenv("RT_CUDA_MATERIAL_MODE"); mode && std::strcmp(mode, "mg") == 0)
+				material_mode_ = RTCU_MODE_MG;
+		}
+
+		void render(const rt::scene& scene, image_view& pixels, muu::thread_pool& /*threads*/) noexcept override
+		{
+			if (!sync_scene(scene))
+			{
+				std::fprintf(stderr, "cuda_path_tracer: %s\n", rtcu_last_error());
+				return;
+			}
+			rtcu_view v		= make_view(scene, pixels);
+			v.material_mode = material_mode_;
 
 			// image_view memory is pageable host memory (image.cpp:9-13); rtcu_render stages through pinned memory
 			if (rtcu_render(ctx_, &v, pixels.data(), nullptr) != RTCU_OK)
@@ -142,5 +164,24 @@ namespace
 		}
 	};
 
+	// the preview renderer (rasterizer.cpp:22-88): one ray per pixel, N.L shading; also draws scene.boxes
+	struct cuda_rasterizer final : cuda_renderer
+	{
+		cuda_rasterizer() : cuda_renderer{ "cuda_rasterizer" } {}
+
+		void render(const rt::scene& scene, image_view& pixels, muu::thread_pool& /*threads*/) noexcept override
+		{
+			if (!sync_scene(scene))
+			{
+				std::fprintf(stderr, "cuda_rasterizer: %s\n", rtcu_last_error());
+				return;
+			}
+			const rtcu_view v = make_view(scene, pixels);
+			if (rtcu_rasterize(ctx_, &v, pixels.data(), nullptr, nullptr) != RTCU_OK)
+				std::fprintf(stderr, "cuda_rasterizer: %s\n", rtcu_last_error());
+		}
+	};
+
 	REGISTER_RENDERER(cuda_path_tracer);
+	REGISTER_RENDERER(cuda_rasterizer);
 }

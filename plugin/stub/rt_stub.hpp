@@ -25,6 +25,7 @@ namespace rt
 	struct vec3 { float x, y, z; };
 	struct sphere { vec3 center; float radius; };
 	struct plane { vec3 normal; float d; };
+	struct box { vec3 center; vec3 extents; };
 	struct colour { float r, g, b, a; };
 	enum class material_type : unsigned { lambert, metal, dielectric, air, vacuum, water, ice, diamond };
 
@@ -69,6 +70,14 @@ namespace rt
 		const unsigned* material() const noexcept { return nullptr; }
 	};
 
+	class boxes
+	{
+	  public:
+		size_t size() const noexcept { return 0; }
+		const box* value() const noexcept { return nullptr; }
+		const unsigned* material() const noexcept { return nullptr; }
+	};
+
 	struct scene
 	{
 		unsigned samples_per_pixel = 30;
@@ -77,6 +86,7 @@ namespace rt
 		rt::materials materials;
 		rt::planes planes;
 		rt::spheres spheres;
+		rt::boxes boxes;
 	};
 
 	class image_view

@@ -18,13 +18,14 @@ RTCU_OK, RTCU_ERR_INVALID, RTCU_ERR_CUDA, RTCU_ERR_STATE = 0, -1, -2, -3
 MODE_MG, MODE_SM = 0, 1
 ACCEL_AUTO, ACCEL_LINEAR, ACCEL_BVH = 0, 1, 2
 PIPE_AUTO, PIPE_MEGAKERNEL, PIPE_WAVEFRONT = 0 << 4, 1 << 4, 2 << 4
-PRIM_MISS, PRIM_PLANE = 0xFFFFFFFF, 0x80000000
+PRIM_MISS, PRIM_PLANE, PRIM_BOX = 0xFFFFFFFF, 0x80000000, 0x40000000
 
 # every symbol include/rtcu.h declares (tests check the .so exports exactly these)
 EXPORTS = (
     "rtcu_abi_version", "rtcu_device_count", "rtcu_create", "rtcu_destroy", "rtcu_last_error", "rtcu_bvh_threshold",
     "rtcu_upload_scene", "rtcu_render", "rtcu_render_device", "rtcu_resolve_device", "rtcu_sync", "rtcu_render_multi",
     "rtcu_intersect_batch", "rtcu_primary_rays", "rtcu_scatter_batch", "rtcu_philox_batch", "rtcu_get_stats", "rtcu_measure_fp32_peak", "rtcu_bvh_build_host",
+    "rtcu_rasterize", "rtcu_rasterize_device",
 )
 
 
@@ -37,6 +38,7 @@ class SceneDesc(C.Structure):
         ("spheres", C.c_void_p), ("sphere_material", C.c_void_p), ("n_spheres", C.c_uint32),
         ("planes", C.c_void_p), ("plane_material", C.c_void_p), ("n_planes", C.c_uint32),
         ("materials", C.c_void_p), ("n_materials", C.c_uint32),
+        ("boxes", C.c_void_p), ("box_material", C.c_void_p), ("n_boxes", C.c_uint32),
     ]
 
 
@@ -102,6 +104,8 @@ def load_library() -> C.CDLL:
         "rtcu_get_stats": (i, [p, C.POINTER(Stats)]),
         "rtcu_measure_fp32_peak": (i, [p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "rtcu_bvh_build_host": (i, [p, u32, p, p, u32, C.POINTER(u32), C.POINTER(u32)]),
+        "rtcu_rasterize": (i, [p, C.POINTER(View), p, p, p]),
+        "rtcu_rasterize_device": (i, [p, C.POINTER(View), p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -56,8 +56,10 @@ struct RenderParams {
     unsigned int* straggler_count;
 };
 
+#ifndef RTCU_PRIM_MISS
 #define RTCU_PRIM_MISS 0xFFFFFFFFu
 #define RTCU_PRIM_PLANE 0x80000000u
+#endif
 
 struct Hit { float t; uint32_t prim; }; // prim: sphere index | PLANE|index | MISS
 

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "wavefront.cuh"
 #include "pool.cuh"
+#include "raster.cuh"
 #include "bvh.h"
 
 #include <cstdarg>
@@ -110,6 +111,14 @@ struct rtcu_ctx {
     DevBuf<float4> planes;
     DevBuf<uint32_t> plane_mat;
     DevBuf<MatRec> mats;
+    DevBuf<float4> boxes;      // rasterizer only: {lo.xyz,0},{hi.xyz,0} per box
+    DevBuf<uint32_t> box_mat;
+    DevBuf<float4> albedo;     // rasterizer only: materials.albedo()
+    RasterScene raster = {};
+    DevBuf<uint32_t> raster_prim;
+    DevBuf<float> raster_depth;
+    PinnedBuf<uint32_t> h_raster_prim;
+    PinnedBuf<float> h_raster_depth;
     DevBuf<float4> bvh_nodes, leaf_sph;
     DevBuf<uint32_t> leaf_idx;
     bool have_bvh = false;
@@ -445,6 +454,63 @@ struct Carver {
 size_t padded(size_t bytes) { return ((bytes + 255) & ~(size_t)255) + 256; }
 } // namespace
 
+namespace {
+
+// ---- rasterizer (rasterizer.cpp:22-88) ---------------------------------------------------------------------------------
+int launch_rasterize(rtcu_ctx* ctx, const rtcu_view* v, uint32_t* d_rgba8, uint32_t* d_prim, float* d_depth, cudaStream_t st)
+{
+    if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
+    if (v->width == 0 || v->height == 0) return fail(RTCU_ERR_INVALID, "empty image");
+    if ((uint64_t)v->width * v->height > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "image too large");
+    if (v->tile_x0 >= v->tile_x1 || v->tile_y0 >= v->tile_y1 || v->tile_x1 > v->width || v->tile_y1 > v->height)
+        return fail(RTCU_ERR_INVALID, "bad tile [%u,%u)x[%u,%u) for %ux%u", v->tile_x0, v->tile_x1, v->tile_y0, v->tile_y1, v->width, v->height);
+    rtcu_view pv = *v; // the preview ignores the sampling fields; give make_params values it accepts
+    pv.samples_per_pixel = pv.max_bounces = 1;
+    pv.sample_begin = 0;
+    pv.sample_end = 1;
+    pv.material_mode = RTCU_MODE_MG;
+    RenderParams rp;
+    const int rc = make_params(ctx, &pv, rp);
+    if (rc) return rc;
+    RasterParams p;
+    p.cam = rp.cam;
+    p.width = v->width; p.height = v->height;
+    p.tile_x0 = v->tile_x0; p.tile_y0 = v->tile_y0; p.tile_x1 = v->tile_x1; p.tile_y1 = v->tile_y1;
+    p.rgba8 = d_rgba8;
+    p.prim = d_prim;
+    p.depth = d_depth;
+    const dim3 grid((v->tile_x1 - v->tile_x0 + RASTER_TILE_W - 1) / RASTER_TILE_W, (v->tile_y1 - v->tile_y0 + RASTER_TILE_H - 1) / RASTER_TILE_H);
+    k_rasterize<<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, p);
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches = 1;
+    ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
+    ctx->stats.accel = RTCU_ACCEL_LINEAR;
+    ctx->stats.samples = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0);
+    ctx->stats.segments = ctx->stats.samples;
+    ctx->stats.sphere_tests = ctx->stats.samples * ctx->raster.n_spheres;
+    ctx->stats.node_visits = 0;
+    ctx->counters_pending = false;
+    return RTCU_OK;
+}
+
+// tile rows of a width*height device plane -> the caller's host plane (staged through `staging`)
+template <typename T>
+int copy_tile_out(rtcu_ctx* ctx, const rtcu_view* v, T* dst, const T* d_src, PinnedBuf<T>& staging)
+{
+    const size_t npix = (size_t)v->width * v->height;
+    const bool full = v->tile_x0 == 0 && v->tile_y0 == 0 && v->tile_x1 == v->width && v->tile_y1 == v->height;
+    if (full) return copy_out(ctx, dst, d_src, npix, staging);
+    const size_t off = (size_t)v->tile_y0 * v->width, cnt = (size_t)(v->tile_y1 - v->tile_y0) * v->width;
+    CU(staging.reserve(npix));
+    CU(cudaMemcpyAsync(staging.p + off, d_src + off, cnt * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t y = v->tile_y0; y < v->tile_y1; y++)
+        memcpy(dst + (size_t)y * v->width + v->tile_x0, staging.p + (size_t)y * v->width + v->tile_x0, (size_t)(v->tile_x1 - v->tile_x0) * sizeof(T));
+    return RTCU_OK;
+}
+
+} // namespace
+
 extern "C" {
 
 int rtcu_abi_version(void) { return RTCU_ABI_VERSION; }
@@ -529,6 +595,8 @@ void rtcu_destroy(rtcu_ctx* ctx)
     for (int i = 0; i < 2; i++) { ctx->wf_o[i].release(); ctx->wf_d[i].release(); ctx->wf_thr[i].release(); }
     for (auto& l : ctx->wf_list) l.release();
     ctx->wf_rad.release(); ctx->wf_sum.release(); ctx->wf_hit.release(); ctx->wf_counts.release(); ctx->h_wf_counts.release();
+    ctx->boxes.release(); ctx->box_mat.release(); ctx->albedo.release(); ctx->raster_prim.release(); ctx->raster_depth.release();
+    ctx->h_raster_prim.release(); ctx->h_raster_depth.release();
     ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -544,12 +612,15 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     if (s->n_materials == 0 || !s->materials) return fail(RTCU_ERR_INVALID, "scene has no materials (scene.cpp:565-566 always provides one)");
     if ((s->n_spheres && (!s->spheres || !s->sphere_material)) || (s->n_planes && (!s->planes || !s->plane_material)))
         return fail(RTCU_ERR_INVALID, "null primitive column");
-    if (s->n_spheres >= 0x80000000u || s->n_planes >= 0x7FFFFFFFu) return fail(RTCU_ERR_INVALID, "too many primitives");
+    if (s->n_boxes && (!s->boxes || !s->box_material)) return fail(RTCU_ERR_INVALID, "null primitive column");
+    if (s->n_spheres >= 0x40000000u || s->n_planes >= 0x40000000u || s->n_boxes >= 0x40000000u) return fail(RTCU_ERR_INVALID, "too many primitives");
     // scene.cpp:568-574 range-checks material indices at load; re-check at the boundary
     for (uint32_t i = 0; i < s->n_spheres; i++)
         if (s->sphere_material[i] >= s->n_materials) return fail(RTCU_ERR_INVALID, "sphere %u: material index %u out-of-range", i, s->sphere_material[i]);
     for (uint32_t i = 0; i < s->n_planes; i++)
         if (s->plane_material[i] >= s->n_materials) return fail(RTCU_ERR_INVALID, "plane %u: material index %u out-of-range", i, s->plane_material[i]);
+    for (uint32_t i = 0; i < s->n_boxes; i++)
+        if (s->box_material[i] >= s->n_materials) return fail(RTCU_ERR_INVALID, "box %u: material index %u out-of-range", i, s->box_material[i]);
     for (uint32_t i = 0; i < s->n_materials; i++)
         if (s->materials[i].type > RTCU_DIAMOND) return fail(RTCU_ERR_INVALID, "material %u: type %u is not a material_type", i, s->materials[i].type);
 
@@ -592,6 +663,21 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     CU(ctx->planes.reserve(s->n_planes ? s->n_planes : 1));
     CU(ctx->plane_mat.reserve(s->n_planes ? s->n_planes : 1));
     CU(ctx->mats.reserve(s->n_materials));
+    // rasterizer columns (rasterizer.cpp reads boxes.value() and materials.albedo(), which the path tracers never touch)
+    std::vector<float4> boxes(2 * (size_t)s->n_boxes), albedo(s->n_materials);
+    for (uint32_t i = 0; i < s->n_boxes; i++)
+    {
+        const float* b = s->boxes + 6 * (size_t)i;
+        const volatile float lx = b[0] - b[3], ly = b[1] - b[4], lz = b[2] - b[5]; // S13: lo = c - e, hi = c + e
+        const volatile float hx = b[0] + b[3], hy = b[1] + b[4], hz = b[2] + b[5];
+        boxes[2 * i] = make_float4(lx, ly, lz, 0.0f);
+        boxes[2 * i + 1] = make_float4(hx, hy, hz, 0.0f);
+    }
+    for (uint32_t i = 0; i < s->n_materials; i++)
+        albedo[i] = make_float4(s->materials[i].albedo[0], s->materials[i].albedo[1], s->materials[i].albedo[2], s->materials[i].albedo[3]);
+    CU(ctx->boxes.reserve(boxes.size() ? boxes.size() : 1));
+    CU(ctx->box_mat.reserve(s->n_boxes ? s->n_boxes : 1));
+    CU(ctx->albedo.reserve(s->n_materials));
     // make sure no kernel of a previous frame still reads the old scene
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), pairs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
@@ -606,6 +692,12 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         CU(cudaMemcpyAsync(ctx->plane_mat.p, s->plane_material, s->n_planes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     CU(cudaMemcpyAsync(ctx->mats.p, mats.data(), mats.size() * sizeof(MatRec), cudaMemcpyHostToDevice, ctx->stream));
+    if (s->n_boxes)
+    {
+        CU(cudaMemcpyAsync(ctx->boxes.p, boxes.data(), boxes.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->box_mat.p, s->box_material, s->n_boxes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->albedo.p, albedo.data(), albedo.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     // BVH: built whenever there are spheres (cheap for small scenes; lets ACCEL_BVH be requested explicitly for parity
     // tests); RTCU_ACCEL_AUTO uses it from rtcu_bvh_threshold() spheres up
     ctx->have_bvh = false;
@@ -688,7 +780,69 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     ctx->scene.n_planes = s->n_planes;
     ctx->scene.materials = ctx->mats.p;
     ctx->scene.n_materials = s->n_materials;
+    ctx->raster.spheres = ctx->sph.p;
+    ctx->raster.pairs = ctx->pairs.p;
+    ctx->raster.sphere_material = ctx->sph_mat.p;
+    ctx->raster.n_spheres = s->n_spheres;
+    ctx->raster.planes = ctx->planes.p;
+    ctx->raster.plane_material = ctx->plane_mat.p;
+    ctx->raster.n_planes = s->n_planes;
+    ctx->raster.boxes = ctx->boxes.p;
+    ctx->raster.box_material = ctx->box_mat.p;
+    ctx->raster.n_boxes = s->n_boxes;
+    ctx->raster.albedo = ctx->albedo.p;
     ctx->have_scene = true;
+    return RTCU_OK;
+}
+
+int rtcu_rasterize_device(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* d_rgba8, void* stream)
+{
+    if (!ctx || !view || !d_rgba8) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    return launch_rasterize(ctx, view, d_rgba8, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int rtcu_rasterize(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, uint32_t* prim_out, float* depth_out)
+{
+    if (!ctx || !view || !rgba8_out) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)view->width * view->height;
+    if (npix == 0) return fail(RTCU_ERR_INVALID, "empty image");
+    CU(ctx->rgba8.reserve(npix));
+    if (prim_out) CU(ctx->raster_prim.reserve(npix));
+    if (depth_out) CU(ctx->raster_depth.reserve(npix));
+    const bool full = view->tile_x0 == 0 && view->tile_y0 == 0 && view->tile_x1 == view->width && view->tile_y1 == view->height;
+    // zero-copy into a pinned / registered image, as rtcu_render does
+    uint32_t* d_out = ctx->rgba8.p;
+    bool zero_copy = false;
+    if (full && is_device_accessible_host(rgba8_out))
+    {
+        const char* e = getenv("RTCU_ZERO_COPY");
+        void* mapped = nullptr;
+        if (!(e && e[0] == '0') && cudaHostGetDevicePointer(&mapped, rgba8_out, 0) == cudaSuccess && mapped)
+        {
+            d_out = static_cast<uint32_t*>(mapped);
+            zero_copy = true;
+        }
+        else
+            cudaGetLastError();
+    }
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = launch_rasterize(ctx, view, d_out, prim_out ? ctx->raster_prim.p : nullptr, depth_out ? ctx->raster_depth.p : nullptr, ctx->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (zero_copy)
+        CU(cudaStreamSynchronize(ctx->stream));
+    else if ((rc = copy_tile_out(ctx, view, rgba8_out, ctx->rgba8.p, ctx->h_rgba8)))
+        return rc;
+    if (prim_out && (rc = copy_tile_out(ctx, view, prim_out, ctx->raster_prim.p, ctx->h_raster_prim))) return rc;
+    if (depth_out && (rc = copy_tile_out(ctx, view, depth_out, ctx->raster_depth.p, ctx->h_raster_depth))) return rc;
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev[2]));
+    CU(cudaEventElapsedTime(&ctx->stats.ms_render, ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(&ctx->stats.ms_d2h, ctx->ev[1], ctx->ev[2]));
+    ctx->stats.ms_resolve = 0.0f;
+    ctx->stats.ms_h2d = 0.0f;
     return RTCU_OK;
 }
 

@@ -16,7 +16,7 @@
 
 namespace {
 
-const char* const renderer_names[] = { "cuda_path_tracer" };
+const char* const renderer_names[] = { "cuda_path_tracer", "cuda_rasterizer" };
 
 // main.cpp:68-81: exact name, then prefix
 const char* find_renderer(const std::string& name)
@@ -144,12 +144,18 @@ int run(int argc, char** argv)
         if (rtcu_upload_scene(ctx, &desc) != RTCU_OK) throw std::runtime_error(std::string(found) + ": " + rtcu_last_error());
     }
     std::vector<uint32_t> pixels(static_cast<size_t>(width) * height, 0x000000FFu); // cleared to black like main.cpp:318
-    const int rc = gpus == 1 ? rtcu_render(ctxs[0], &v, pixels.data(), nullptr) : rtcu_render_multi(ctxs.data(), static_cast<uint32_t>(gpus), &v, pixels.data(), nullptr);
+    const bool raster = std::string(found) == "cuda_rasterizer"; // the preview is one ray per pixel: a single device
+    const int rc = raster      ? rtcu_rasterize(ctxs[0], &v, pixels.data(), nullptr, nullptr)
+                   : gpus == 1 ? rtcu_render(ctxs[0], &v, pixels.data(), nullptr)
+                               : rtcu_render_multi(ctxs.data(), static_cast<uint32_t>(gpus), &v, pixels.data(), nullptr);
     if (rc != RTCU_OK) throw std::runtime_error(std::string(found) + ": " + rtcu_last_error());
     rtcu_stats st{};
     rtcu_get_stats(ctxs[0], &st);
-    std::fprintf(stderr, "%s: %ux%u, %u spp, depth %u: %.3f ms on the device, %.1f Msamples/s, %llu segments\n", found, width, height, scene.samples_per_pixel,
-                 scene.max_bounces, st.ms_render, double(width) * height * scene.samples_per_pixel / (st.ms_render * 1e3), static_cast<unsigned long long>(st.segments));
+    if (raster)
+        std::fprintf(stderr, "%s: %ux%u: %.3f ms on the device, %.1f Mpixels/s\n", found, width, height, st.ms_render, double(width) * height / (st.ms_render * 1e3));
+    else
+        std::fprintf(stderr, "%s: %ux%u, %u spp, depth %u: %.3f ms on the device, %.1f Msamples/s, %llu segments\n", found, width, height, scene.samples_per_pixel,
+                     scene.max_bounces, st.ms_render, double(width) * height * scene.samples_per_pixel / (st.ms_render * 1e3), static_cast<unsigned long long>(st.segments));
     if (!out_path.empty())
     {
         FILE* f = std::fopen(out_path.c_str(), "wb");

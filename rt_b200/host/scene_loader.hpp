@@ -40,7 +40,7 @@ struct scene {
     std::vector<uint32_t> sphere_material;
     std::vector<std::array<float, 4>> planes;  // planes.value(): {nx,ny,nz,d}
     std::vector<uint32_t> plane_material;
-    std::vector<std::array<float, 6>> boxes;   // centre, extents (never hit by the ray tracers, mg_ray_tracer.cpp:89-93)
+    std::vector<std::array<float, 6>> boxes;   // centre, extents (drawn by the rasterizer only; never hit by the ray tracers, mg_ray_tracer.cpp:89-93)
     std::vector<uint32_t> box_material;
 
     rtcu_scene descriptor() const
@@ -54,6 +54,9 @@ struct scene {
         d.n_planes = static_cast<uint32_t>(planes.size());
         d.materials = materials.data();
         d.n_materials = static_cast<uint32_t>(materials.size());
+        d.boxes = boxes.empty() ? nullptr : boxes[0].data();
+        d.box_material = box_material.data();
+        d.n_boxes = static_cast<uint32_t>(boxes.size());
         return d;
     }
 };

@@ -176,9 +176,12 @@ class Context:
         pl = nat.contiguous(scene.planes, np.float32).reshape(-1, 4)
         pmat = nat.contiguous(scene.plane_material, np.uint32)
         mats = np.ascontiguousarray(scene.materials.astype(MATERIAL_DTYPE))
+        bx = nat.contiguous(getattr(scene, "boxes", np.zeros((0, 6))), np.float32).reshape(-1, 6)  # rasterizer only
+        bmat = nat.contiguous(getattr(scene, "box_material", np.zeros(0)), np.uint32)
         d = nat.SceneDesc(nat.ptr(sph) if len(sph) else None, nat.ptr(smat) if len(smat) else None, len(sph),
                           nat.ptr(pl) if len(pl) else None, nat.ptr(pmat) if len(pmat) else None, len(pl),
-                          nat.ptr(mats) if len(mats) else None, len(mats))
+                          nat.ptr(mats) if len(mats) else None, len(mats),
+                          nat.ptr(bx) if len(bx) else None, nat.ptr(bmat) if len(bmat) else None, len(bx))
         nat.check(self._lib.rtcu_upload_scene(self._h, C.byref(d)))
 
     # -- render ---------------------------------------------------------------------------------
@@ -192,6 +195,19 @@ class Context:
             accum = np.zeros((h, w, 4), np.float32)
         nat.check(self._lib.rtcu_render(self._h, C.byref(view), nat.ptr(rgba8), nat.ptr(accum)))
         return rgba8, accum
+
+    def rasterize(self, view: nat.View, rgba8: Optional[np.ndarray] = None, want_prim: bool = False, want_depth: bool = False):
+        """rtcu_rasterize (rasterizer.cpp:22-88) -> (rgba8 (H,W) u32, prim (H,W) u32 | None, depth (H,W) f32 | None)"""
+        h, w = view.height, view.width
+        if rgba8 is None:
+            rgba8 = np.zeros((h, w), np.uint32)
+        prim = np.full((h, w), nat.PRIM_MISS, np.uint32) if want_prim else None
+        depth = np.zeros((h, w), np.float32) if want_depth else None
+        nat.check(self._lib.rtcu_rasterize(self._h, C.byref(view), nat.ptr(rgba8), nat.ptr(prim), nat.ptr(depth)))
+        return rgba8, prim, depth
+
+    def rasterize_device(self, view: nat.View, d_rgba8_ptr: int, stream: int = 0) -> None:
+        nat.check(self._lib.rtcu_rasterize_device(self._h, C.byref(view), d_rgba8_ptr, stream or None))
 
     def render_device(self, view: nat.View, d_accum_ptr: int, accumulate: bool = False, stream: int = 0) -> None:
         nat.check(self._lib.rtcu_render_device(self._h, C.byref(view), d_accum_ptr, int(accumulate), stream or None))
@@ -321,7 +337,8 @@ class ProgressiveRenderer:
 def scene_fingerprint(scene: Scene) -> bytes:
     """The reference scene has no dirty flag: detect changes by content."""
     h = hashlib.blake2b(digest_size=16)
-    for a in (scene.spheres, scene.sphere_material, scene.planes, scene.plane_material, scene.materials):
+    for a in (scene.spheres, scene.sphere_material, scene.planes, scene.plane_material, scene.materials,
+              getattr(scene, "boxes", ()), getattr(scene, "box_material", ())):
         h.update(np.ascontiguousarray(a).tobytes())
         h.update(b"|")
     return h.digest()
@@ -359,4 +376,29 @@ class cuda_path_tracer(RendererInterface):  # noqa: N801 -- the CLI name is the 
             print(f"cuda_path_tracer: {e}", file=sys.stderr)
 
 
+@register_renderer
+class cuda_rasterizer(RendererInterface):  # noqa: N801
+    """Drop-in for `rasterizer` (reference src/renderers/rasterizer.cpp:22-88): the one-ray-per-pixel N.L preview.
+    Unlike the path tracers it also draws `scene.boxes`."""
+
+    def __init__(self, device: int = 0):
+        self.ctx = Context(device)
+        self._fingerprint: Optional[bytes] = None
+        self.last_error: Optional[str] = None
+
+    def render(self, scene: Scene, pixels: ImageView, threads=None) -> None:
+        try:
+            fp = scene_fingerprint(scene)
+            if fp != self._fingerprint:
+                self.ctx.upload_scene(scene)
+                self._fingerprint = fp
+            w, h = pixels.size()
+            self.ctx.rasterize(make_view(scene, w, h), rgba8=pixels.data)
+            self.last_error = None
+        except Exception as e:  # noexcept: log, leave the pre-cleared image alone
+            self.last_error = str(e)
+            print(f"cuda_rasterizer: {e}", file=sys.stderr)
+
+
 CudaPathTracer = cuda_path_tracer
+CudaRasterizer = cuda_rasterizer

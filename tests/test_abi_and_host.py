@@ -35,7 +35,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(nat.Material) == 28
     assert ctypes.sizeof(nat.View) == 64 + 4 * 10 + 8 + 8
     assert nat.View.seed.offset == 104 and nat.View.material_mode.offset == 112
-    assert ctypes.sizeof(nat.SceneDesc) == 64
+    assert ctypes.sizeof(nat.SceneDesc) == 88 and nat.SceneDesc.boxes.offset == 64  # ABI 2 appended the box columns
     assert ctypes.sizeof(nat.Stats) == 64
     assert S.MATERIAL_DTYPE.itemsize == ctypes.sizeof(nat.Material)
 
@@ -47,7 +47,7 @@ def test_library_is_sm100a_only():
 
 
 def test_abi_version_and_threshold(lib):
-    assert lib.rtcu_abi_version() == 1
+    assert lib.rtcu_abi_version() == 2
     assert lib.rtcu_bvh_threshold() > 0
 
 
@@ -55,6 +55,7 @@ def test_null_arguments_are_rejected_without_a_device(lib):
     # argument validation happens before any CUDA call
     assert lib.rtcu_upload_scene(None, None) == nat.RTCU_ERR_INVALID
     assert lib.rtcu_render(None, None, None, None) == nat.RTCU_ERR_INVALID
+    assert lib.rtcu_rasterize(None, None, None, None, None) == nat.RTCU_ERR_INVALID
     assert lib.rtcu_get_stats(None, None) == nat.RTCU_ERR_INVALID
     assert b"null" in lib.rtcu_last_error()
     lib.rtcu_destroy(None)  # no-op
@@ -86,7 +87,8 @@ def test_registry_semantics():
     assert reg.find("be").name == "beta"  # prefix match like main.cpp:68-81
     # the plugin registers under its type name
     assert R.renderers.find_by_name("cuda_path_tracer") is not None
-    assert R.renderers.find("cuda").create is R.cuda_path_tracer
+    assert R.renderers.find("cuda").create is R.cuda_path_tracer  # first registered wins a shared prefix
+    assert R.renderers.find("cuda_r").create is R.cuda_rasterizer
 
 
 def test_image_view():

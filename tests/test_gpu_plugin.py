@@ -20,13 +20,16 @@ def _plugin_build():
 
 def test_plugin_registers_under_its_type_name_and_fails_loudly_without_a_device():
     ref = _plugin_build()
-    assert ref.renderers() == ["mg_ray_tracer", "sm_ray_tracer", "cuda_path_tracer"]  # REGISTER_RENDERER(cuda_path_tracer)
+    # REGISTER_RENDERER(cuda_path_tracer) / REGISTER_RENDERER(cuda_rasterizer) next to the reference's own three
+    assert ref.renderers() == ["mg_ray_tracer", "sm_ray_tracer", "rasterizer", "cuda_path_tracer", "cuda_rasterizer"]
     from rt_b200 import _native as nat
 
     if nat.load_library().rtcu_device_count() > 0:
         pytest.skip("device present: covered by the gpu test below")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ref.render(S.load("scenes/basic.toml"), 32, 24, 1, 2, 0x5EED, "cuda_path_tracer")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ref.render(S.load("scenes/basic.toml"), 32, 24, 1, 2, 0x5EED, "cuda_rasterizer")
 
 
 @pytest.mark.gpu
@@ -46,3 +49,16 @@ def test_plugin_renders_like_the_reference_renderers(monkeypatch, scene_file, cp
     assert d.max() <= 1, int(d.max())
     assert (d > 0).mean() <= 0.005
     assert len(np.unique(gpu)) > 100  # a real image, not the cleared buffer
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene_file", ["scenes/basic.toml", "scenes/dielectric.toml", "scenes/boxes.toml"])
+def test_plugin_rasterizer_equals_the_reference_rasterizer(scene_file):
+    """cuda_rasterizer against rasterizer.cpp in the same binary, same rt::scene: no RNG on this path, so bit for bit"""
+    ref = _plugin_build()
+    sc = S.load(scene_file)
+    w, h = 400, 250
+    cpu, _ = ref.render(sc, w, h, 1, 1, 0, "rasterizer", threads=0)
+    gpu, _ = ref.render(sc, w, h, 1, 1, 0, "cuda_rasterizer")
+    np.testing.assert_array_equal(gpu, cpu)
+    assert len(np.unique(gpu)) > 50

@@ -44,13 +44,13 @@ def assert_same_scene(d: dict, s: S.Scene):
 
 
 def test_list_and_renderer_lookup(cli):
-    assert run(cli, "--list").stdout.split() == ["cuda_path_tracer"]
+    assert run(cli, "--list").stdout.split() == ["cuda_path_tracer", "cuda_rasterizer"]
     r = run(cli, "--scene", "scenes/basic.toml", "--renderer", "nope", check=False)
     assert r.returncode == 1 and "error: unknown renderer 'nope'" in r.stderr
     assert run(cli, "--scene", "scenes/basic.toml", "--renderer", "cuda", "--dump-view").returncode == 0  # prefix match (main.cpp:68-81)
 
 
-@pytest.mark.parametrize("name", ["basic.toml", "dielectric.toml"])
+@pytest.mark.parametrize("name", ["basic.toml", "dielectric.toml", "boxes.toml"])
 def test_shipped_scenes_load_like_the_python_loader(cli, name):
     assert_same_scene(dumped(cli, f"scenes/{name}"), S.load(f"scenes/{name}"))
 
@@ -169,6 +169,23 @@ def test_cli_render_equals_the_python_path_byte_for_byte(cli, ctx, tmp_path):
         run(cli, "--scene", "scenes/dielectric.toml", "--size", "320x180", "--spp", "8", "--bounces", "50", "--gpus", "2", "--out", str(out2))
         img2 = np.frombuffer(out2.read_bytes()[len(header):], np.uint8).reshape(180, 320, 3)
         assert np.abs(img2.astype(int) - img.astype(int)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_cli_rasterizer_equals_the_oracle(cli, oracle, tmp_path):
+    from rt_b200.renderer import make_view
+
+    out = tmp_path / "preview.ppm"
+    r = run(cli, "--scene", "scenes/boxes.toml", "--renderer", "cuda_rasterizer", "--size", "320x200", "--out", str(out))
+    assert "Mpixels/s" in r.stderr
+    header = b"P6\n320 200\n255\n"
+    img = np.frombuffer(out.read_bytes()[len(header):], np.uint8).reshape(200, 320, 3)
+    sc = S.load("scenes/boxes.toml")
+    v = make_view(sc, 320, 200)
+    v.inv_view_proj[:] = json.loads(run(cli, "--scene", "scenes/boxes.toml", "--size", "320x200", "--dump-view").stdout)
+    rgba8, _, _ = oracle.rasterize(sc, v)
+    ref = np.stack([(rgba8 >> 24) & 255, (rgba8 >> 16) & 255, (rgba8 >> 8) & 255], axis=-1).astype(np.uint8)
+    np.testing.assert_array_equal(img, ref)
 
 
 def nat_device_count() -> int:

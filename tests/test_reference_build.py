@@ -48,7 +48,7 @@ def refbuild():
 
 
 def test_reference_build_registers_both_ray_tracers(refbuild):
-    assert refbuild.renderers() == ["mg_ray_tracer", "sm_ray_tracer"]  # REGISTER_RENDERER ran at load time
+    assert refbuild.renderers() == ["mg_ray_tracer", "sm_ray_tracer", "rasterizer"]  # REGISTER_RENDERER ran at load time
 
 
 def _random_scene(seed: int) -> S.Scene:

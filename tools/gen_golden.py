@@ -66,8 +66,36 @@ def gen_reference_build_goldens():
         print("reference build", name, renderer, rgba8.shape)
 
 
+RASTER_SCENES = {**{k: v[0] for k, v in SCENES.items()}, "boxes": S.load(ROOT / "scenes" / "boxes.toml")}
+RASTER_CASES = [("c1", 160, 120), ("c2", 192, 108), ("planes", 128, 96), ("c3", 96, 54), ("boxes", 200, 125)]  # (scene, width, height)
+
+
+def gen_raster_goldens():
+    """rgba8 = the reference's OWN rasterizer.cpp (compiled against the muu stand-in); prim / depth = the oracle's per-pixel
+    record for the same matrix (the reference has no such output)."""
+    from oracle.binding import ReferenceBuild
+
+    if not ReferenceBuild.available():
+        print("reference build unavailable: raster_* fixtures not regenerated")
+        return
+    ref = ReferenceBuild()
+    for name, w, h in RASTER_CASES:
+        sc = RASTER_SCENES[name]
+        rgba8, ivp = ref.render(sc, w, h, 1, 1, 0, "rasterizer", threads=0)
+        v = make_view(sc, w, h)
+        v.inv_view_proj[:] = ivp.tolist()
+        o_rgba8, prim, depth = O.rasterize(sc, v, threads=0)
+        assert np.array_equal(o_rgba8, rgba8), (name, int((o_rgba8 != rgba8).sum()))
+        np.savez_compressed(OUT / f"raster_{name}.npz", rgba8=rgba8, prim=prim, depth=depth, inv_view_proj=ivp, width=w, height=h)
+        print("raster", name, rgba8.shape, "hit fraction", float((prim != 0xFFFFFFFF).mean()))
+
+
 if __name__ == "__main__":
+    if "--raster-only" in sys.argv:
+        gen_raster_goldens()
+        sys.exit(0)
     gen_reference_build_goldens()
+    gen_raster_goldens()
     for name, (sc, depth) in SCENES.items():
         o, d = synth.random_rays(sc, 4096, seed=7)
         hit, prim, t, nrm = O.intersect_batch(sc, o, d)
