@@ -140,7 +140,8 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
 
 /* ---- preview: replaces rasterizer::render (reference src/renderers/rasterizer.cpp:22-88): one ray per pixel through the
  * pixel centre, nearest of planes, boxes, spheres (strict '<' in that order, no minimum distance), N.L shading against
- * the eye, no gamma.  Uses inv_view_proj, width, height and the tile of the view; every other field is ignored.
+ * the eye, no gamma.  Uses inv_view_proj, width, height, the tile and the RTCU_ACCEL_* bits of flags; every other field is
+ * ignored.
  * rgba8_out as in rtcu_render.  prim_out / depth_out (nullable, width*height each): per pixel the sphere index,
  * RTCU_PRIM_PLANE|index, RTCU_PRIM_BOX|index or RTCU_PRIM_MISS, and the accepted distance -- the parity hooks. */
 int rtcu_rasterize(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, uint32_t* prim_out, float* depth_out);

@@ -1,7 +1,8 @@
 /*
  * rtref.c -- CPU ORACLE for the marzer/rt path-tracing hot path.  TEST INFRASTRUCTURE ONLY
- * (see rtref.h for who may load it).  PARITY UNPINNED against a reference binary: the
- * reference cannot be compiled here (muu absent) and has no tests; see rtref.h.
+ * (see rtref.h for who may load it).  Pinned bit for bit against the reference's own renderer
+ * sources compiled against a muu stand-in (oracle/Makefile `ref`); muu's arithmetic itself is
+ * restated (SPEC below) and UNPINNED -- see rtref.h.
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  *
@@ -47,6 +48,10 @@
  *                     (mg_ray_tracer.cpp:195-200, colour.hpp:100-106)
  *  S12 radiance       recursive, right-nested: att_1 * (att_2 * (... * sky))  (mg_ray_tracer.cpp:171)
  *                     per pixel: sum += radiance in ascending sample order      (:187-194)
+ *  S13 ray vs box     (rasterizer.cpp:47 only) lo = c - e, hi = c + e; per axis t1 = (lo-o)/d, t2 = (hi-o)/d;
+ *                     tmin = max_k fminf(t1,t2), tmax = min_k fmaxf(t1,t2) (a NaN operand is dropped);
+ *                     tmax < 0 or tmin > tmax -> miss; t = tmin < 0 ? tmax : tmin
+ *                     (muu ray::hits(bounding_box), UNVERIFIED; Game-Physics-Cookbook form like S4/S5)
  * ------------------------------------------------------------------------------------------
  */
 #define _GNU_SOURCE

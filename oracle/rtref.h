@@ -4,13 +4,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (rt_b200/, include/rtcu.h) never links, imports or calls it.
  *
- * PARITY STATUS: "parity unpinned" against a reference *binary*: marzer/rt cannot be built in
- * this environment (its math library muu @06dbcecb, toml++, SDL2, imgui, argparse, magic_enum
- * and meson are absent) and the reference ships no tests, golden vectors
- * or fixtures.  This file restates the reference *source* line by line; the muu primitives it
- * calls are restated from their published algorithms and written down as the numbered SPEC in
- * rtref.c.  The pins that exist are the ones this repo creates (tests/golden/, hand-derived
- * known-answer vectors, published Philox4x32-10 vectors).
+ * PARITY STATUS: pinned against the reference's OWN renderer sources, unpinned against muu.  marzer/rt as a
+ * whole cannot be built in this environment (its math library muu @06dbcecb, toml++, SDL2, imgui, argparse,
+ * magic_enum and meson are absent) and it ships no tests, golden vectors or fixtures.
+ * But oracle/Makefile `ref` compiles mg_ray_tracer.cpp, sm_ray_tracer.cpp, rasterizer.cpp and renderer.cpp
+ * where they lie against oracle/ref_shim (a stand-in for the muu headers); this file reproduces the packed
+ * images of that build bit for bit (tests/test_reference_build.py, tests/test_raster_oracle.py; fixtures
+ * tests/golden/refbuild_*.npz, raster_*.npz).  What stays unpinned is muu's own arithmetic, restated from
+ * its published algorithms as the numbered SPEC in rtref.c.  Further pins: hand-derived known-answer
+ * vectors and the published Philox4x32-10 vectors.
  *
  * The data structures deliberately mirror include/rtcu.h field by field so one harness can feed
  * both sides, but the two headers are independent files.

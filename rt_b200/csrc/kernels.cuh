@@ -137,18 +137,21 @@ struct BvhStats { uint32_t nodes, tests; };
 
 // two spheres of a leaf on the packed FP32 pipe (same arithmetic as sphere_pair_test, hence as the scan); candidates are
 // accepted by (t, index) lexicographic order because leaves are visited in traversal order, not index order
+// ANY_T (the rasterizer, rasterizer.cpp:48): no minimum distance, negative distances included.
+template <bool ANY_T = false>
 __device__ __forceinline__ void bvh_leaf_candidate(const float a, const float e2, const float r2, const float disc, const int index,
                                                    float& best_t, int& best_i)
 {
     const float f = __fsqrt_rn(disc);
     const float t = (e2 < r2) ? __fadd_rn(a, f) : __fsub_rn(a, f);
-    if (!(t < 0.001f) && (t < best_t || (t == best_t && index < best_i)))
+    if ((ANY_T || !(t < 0.001f)) && (t < best_t || (t == best_t && index < best_i)))
     {
         best_t = t;
         best_i = index;
     }
 }
 
+template <bool ANY_T = false>
 __device__ __forceinline__ void bvh_leaf_pair_test(const float4 A, const float4 B, const int i0, const int i1, const Ray& r, float& best_t, int& best_i)
 {
     const float2 ex = __fadd2_rn(make_float2(A.x, A.y), make_float2(-r.o.x, -r.o.x));
@@ -161,9 +164,9 @@ __device__ __forceinline__ void bvh_leaf_pair_test(const float4 A, const float4 
     if (!(disc.x < 0.0f) || !(disc.y < 0.0f))
     {
         if (!(disc.x < 0.0f))
-            bvh_leaf_candidate(a.x, e2.x, B.z, disc.x, i0, best_t, best_i);
+            bvh_leaf_candidate<ANY_T>(a.x, e2.x, B.z, disc.x, i0, best_t, best_i);
         if (!(disc.y < 0.0f))
-            bvh_leaf_candidate(a.y, e2.y, B.w, disc.y, i1, best_t, best_i);
+            bvh_leaf_candidate<ANY_T>(a.y, e2.y, B.w, disc.y, i1, best_t, best_i);
     }
 }
 
@@ -196,7 +199,9 @@ __device__ __forceinline__ bool trav_init(const Ray& r, Trav& tv)
 }
 
 // one node visit: slab-test both children, test leaf children immediately, descend near-first / push / pop.
-// Returns true when the traversal is complete.
+// Returns true when the traversal is complete.  ANY_T: the whole line counts, not only t >= 0 (the margin argument above
+// never uses the sign of t: a computed hit lies within the inflated ball, whose line interval lies within the inflated box).
+template <bool ANY_T = false>
 __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav& tv, uint32_t* __restrict__ stack_ref,
                                           float* __restrict__ stack_t, BvhStats& st)
 {
@@ -229,8 +234,8 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
         const float tmax_r = fminf(fminf(fmaxf(t1x.y, t2x.y), fmaxf(t1y.y, t2y.y)), fmaxf(t1z.y, t2z.y));
         tn[0] = tmin_l;
         tn[1] = tmin_r;
-        hit[0] = tmax_l >= fmaxf(tmin_l, 0.0f) && tmin_l <= tv.best_t; // empty boxes (lo > hi) fail the first test
-        hit[1] = tmax_r >= fmaxf(tmin_r, 0.0f) && tmin_r <= tv.best_t;
+        hit[0] = tmax_l >= (ANY_T ? tmin_l : fmaxf(tmin_l, 0.0f)) && tmin_l <= tv.best_t; // empty boxes (lo > hi) fail the first test
+        hit[1] = tmax_r >= (ANY_T ? tmin_r : fmaxf(tmin_r, 0.0f)) && tmin_r <= tv.best_t;
     }
     // leaves are tested immediately, inner children are descended near-first
     uint32_t next = 0xffffffffu;
@@ -245,8 +250,8 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
             const float4* lp = sc.leaf_sph + 4 * (size_t)leaf;
             const uint4 idx = __ldg(reinterpret_cast<const uint4*>(sc.leaf_idx) + leaf);
             st.tests += 4; // sphere test slots (a leaf holds 1-4 spheres)
-            bvh_leaf_pair_test(__ldg(lp), __ldg(lp + 1), (int)idx.x, (int)idx.y, r, tv.best_t, tv.best_i);
-            bvh_leaf_pair_test(__ldg(lp + 2), __ldg(lp + 3), (int)idx.z, (int)idx.w, r, tv.best_t, tv.best_i);
+            bvh_leaf_pair_test<ANY_T>(__ldg(lp), __ldg(lp + 1), (int)idx.x, (int)idx.y, r, tv.best_t, tv.best_i);
+            bvh_leaf_pair_test<ANY_T>(__ldg(lp + 2), __ldg(lp + 3), (int)idx.z, (int)idx.w, r, tv.best_t, tv.best_i);
         }
         else if (next == 0xffffffffu)
         {

@@ -91,7 +91,11 @@ __device__ __forceinline__ void raster_sphere_pair(const float4 A, const float4 
     }
 }
 
-__global__ void __launch_bounds__(RASTER_TILE_W* RASTER_TILE_H) k_rasterize(const RasterScene s, const RasterParams p)
+// BVH: the sphere loop becomes a traversal of the path tracer's tree (same exact-result construction, see kernels.cuh)
+// started with best = (distance accepted so far, index -1): ties with a plane or box keep the earlier category, ties
+// between spheres go to the lower index -- what the index-ordered loop with its strict '<' produces.
+template <bool BVH>
+__global__ void __launch_bounds__(RASTER_TILE_W* RASTER_TILE_H) k_rasterize(const RasterScene s, const SceneDev sc, const RasterParams p)
 {
     const uint32_t x = p.tile_x0 + blockIdx.x * RASTER_TILE_W + (threadIdx.x % RASTER_TILE_W);
     const uint32_t y = p.tile_y0 + blockIdx.y * RASTER_TILE_H + (threadIdx.x / RASTER_TILE_W);
@@ -138,8 +142,27 @@ __global__ void __launch_bounds__(RASTER_TILE_W* RASTER_TILE_H) k_rasterize(cons
             prim = RTCU_PRIM_BOX | i;
         }
     }
-    // hit_tests(scene.spheres), :63 -- packed pair sweep, the next pair in flight while this one is tested
+    // hit_tests(scene.spheres), :63
+    Trav tv;
+    if (BVH && trav_init(r, tv))
     {
+        tv.best_t = dist;
+        tv.best_i = -1;
+        uint32_t stack_ref[BVH_STACK];
+        float stack_t[BVH_STACK];
+        BvhStats st = { 0, 0 };
+        while (!trav_step<true>(sc, r, tv, stack_ref, stack_t, st))
+        {
+        }
+        if (tv.best_i >= 0)
+        {
+            dist = tv.best_t;
+            prim = (uint32_t)tv.best_i;
+        }
+    }
+    else
+    {
+        // packed pair sweep, the next pair in flight while this one is tested
         const uint32_t n_pairs = (s.n_spheres + 1u) >> 1;
         uint32_t sphere = RTCU_PRIM_MISS;
         float4 A = __ldg(s.pairs), B = __ldg(s.pairs + 1);

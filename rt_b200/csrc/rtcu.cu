@@ -480,11 +480,16 @@ int launch_rasterize(rtcu_ctx* ctx, const rtcu_view* v, uint32_t* d_rgba8, uint3
     p.prim = d_prim;
     p.depth = d_depth;
     const dim3 grid((v->tile_x1 - v->tile_x0 + RASTER_TILE_W - 1) / RASTER_TILE_W, (v->tile_y1 - v->tile_y0 + RASTER_TILE_H - 1) / RASTER_TILE_H);
-    k_rasterize<<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, p);
+    const uint32_t accel = v->flags & 0xFu;
+    if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
+    if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or tree deeper than %d)", BVH_STACK - 2);
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
+    if (use_bvh) k_rasterize<true><<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, ctx->scene, p);
+    else k_rasterize<false><<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, ctx->scene, p);
     CU(cudaGetLastError());
     ctx->stats.kernel_launches = 1;
     ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
-    ctx->stats.accel = RTCU_ACCEL_LINEAR;
+    ctx->stats.accel = use_bvh ? RTCU_ACCEL_BVH : RTCU_ACCEL_LINEAR;
     ctx->stats.samples = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0);
     ctx->stats.segments = ctx->stats.samples;
     ctx->stats.sphere_tests = ctx->stats.samples * ctx->raster.n_spheres;

@@ -68,6 +68,32 @@ def test_many_spheres_equal_the_oracle(ctx, oracle):
     _same(ctx.rasterize(v, want_prim=True, want_depth=True), oracle.rasterize(sc, v))
 
 
+def _cloud_scene(seed: int, n: int) -> S.Scene:
+    """spheres all around the camera (in front, behind, enclosing it), duplicates for ties, a wall and a box"""
+    rng = np.random.default_rng(seed)
+    mats = [(0, tuple(rng.uniform(0.1, 1.0, 3)), 0.0, 1.0) for _ in range(5)]
+    sph = np.concatenate([rng.uniform(-8, 8, (n, 3)), rng.uniform(0.05, 0.9, (n, 1))], axis=1).astype(np.float32)
+    sph[n // 2:n // 2 + 8] = sph[:8]                 # exact duplicates: the lower index must win
+    sph[5] = [0.1, 1.3, 9.0, 0.8]                    # behind the camera: accepted with a negative distance
+    if seed % 2:
+        sph[3] = [0.2, 1.0, 5.5, 3.0]                # the camera sits inside this one
+    spheres = [(*row, int(rng.integers(0, 5))) for row in sph.tolist()]
+    return _scene(mats, spheres=spheres, planes=[(0, 0, 1, 7.5, 1)], boxes=[(1.0, 0.5, 1.0, 0.7, 0.7, 0.7, 2)], cam=((0.0, 1.0, 5.0), (0.05, -0.1, -1.0)))
+
+
+@pytest.mark.parametrize("seed,n", [(0, 40), (1, 257), (2, 1500), (3, 6000)])
+def test_bvh_traversal_equals_the_index_ordered_loop(ctx, oracle, seed, n):
+    sc = _cloud_scene(seed, n)
+    ctx.upload_scene(sc)
+    v = make_view(sc, 200, 120)
+    expect = oracle.rasterize(sc, v)
+    assert (expect[2] < 0).any()  # negative distances are part of the case
+    for accel in (nat.ACCEL_LINEAR, nat.ACCEL_BVH, nat.ACCEL_AUTO):
+        v.flags = accel
+        _same(ctx.rasterize(v, want_prim=True, want_depth=True), expect)
+        assert ctx.stats()["accel"] == (nat.ACCEL_LINEAR if accel == nat.ACCEL_LINEAR else nat.ACCEL_BVH)
+
+
 def test_tile_writes_only_the_tile(ctx, oracle, scenes):
     sc = S.load("scenes/boxes.toml")
     ctx.upload_scene(sc)
