@@ -186,6 +186,12 @@ int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t k
 
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out);
 
+/* exhaustive device-side check of the kernels' cheaper-but-exact square root / reciprocal / constant-divisor division
+ * (rt_b200/csrc/spec.cuh) against the IEEE intrinsics: counts[0..1] = float patterns (of all 2^32) where sqrt / 1/sqrt
+ * differ, counts[2] = differing quotients over every float a in {0} u [2^-24, 2^24] and every b in divisors (each in
+ * [1, 2^24], at most 256), counts[3] = quotients tested.  All three must be 0. */
+int rtcu_selftest_math(rtcu_ctx* ctx, const float* divisors, uint32_t n_divisors, uint64_t counts[4]);
+
 /* ---- host-only: the BVH builder used by rtcu_upload_scene (binned SAH, two children per node), exposed so its
  * invariants can be checked without a device.  The reference has no acceleration structure (mg_ray_tracer.cpp:62-87
  * scans all spheres); traversal returns the scan's exact result.

@@ -25,7 +25,7 @@ EXPORTS = (
     "rtcu_abi_version", "rtcu_device_count", "rtcu_create", "rtcu_destroy", "rtcu_last_error", "rtcu_bvh_threshold",
     "rtcu_upload_scene", "rtcu_render", "rtcu_render_device", "rtcu_resolve_device", "rtcu_sync", "rtcu_render_multi",
     "rtcu_intersect_batch", "rtcu_primary_rays", "rtcu_scatter_batch", "rtcu_philox_batch", "rtcu_get_stats", "rtcu_measure_fp32_peak", "rtcu_bvh_build_host",
-    "rtcu_rasterize", "rtcu_rasterize_device",
+    "rtcu_rasterize", "rtcu_rasterize_device", "rtcu_selftest_math",
 )
 
 
@@ -106,6 +106,7 @@ def load_library() -> C.CDLL:
         "rtcu_bvh_build_host": (i, [p, u32, p, p, u32, C.POINTER(u32), C.POINTER(u32)]),
         "rtcu_rasterize": (i, [p, C.POINTER(View), p, p, p]),
         "rtcu_rasterize_device": (i, [p, C.POINTER(View), p, p]),
+        "rtcu_selftest_math": (i, [p, p, u32, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

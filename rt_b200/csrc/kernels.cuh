@@ -8,6 +8,7 @@
 //   k_resolve / k_reduce_resolve    sum / spp, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200), the latter + NVLink peer sums
 //   k_intersect_batch / k_primary_rays / k_scatter_batch / k_philox_batch   step-wise parity kernels
 //   k_fp32_peak                     FFMA / FFMA2 calibration stream for the roofline denominator
+//   k_selftest_math                 exhaustive comparison of spec.cuh's cheaper sqrt / rcp / div with the IEEE intrinsics
 // (wavefront.cuh: the queue-based pipeline; pool.cuh: the warp-local ray pool; both selectable, neither the default)
 #pragma once
 #include "spec.cuh"
@@ -142,6 +143,8 @@ template <bool ANY_T = false>
 __device__ __forceinline__ void bvh_leaf_candidate(const float a, const float e2, const float r2, const float disc, const int index,
                                                    float& best_t, int& best_i)
 {
+    if (!ANY_T && !(e2 < r2) && a < 0.0f)
+        return; // t = a - f <= a < 0 fails the 0.001 filter: no sqrt (see sphere_candidate)
     const float f = __fsqrt_rn(disc);
     const float t = (e2 < r2) ? __fadd_rn(a, f) : __fsub_rn(a, f);
     if ((ANY_T || !(t < 0.001f)) && (t < best_t || (t == best_t && index < best_i)))
@@ -362,7 +365,7 @@ __device__ __forceinline__ MatRec load_material(const SceneDev& sc, uint32_t m)
     const float4 a = __ldg(p), b = __ldg(p + 1);
     MatRec r;
     r.att_r = a.x; r.att_g = a.y; r.att_b = a.z; r.roughness = a.w;
-    r.ior = b.x; r.type = __float_as_uint(b.y); r.pad0 = 0; r.pad1 = 0;
+    r.ior = b.x; r.type = __float_as_uint(b.y); r.inv_ior = b.z; r.r0 = b.w;
     return r;
 }
 
@@ -764,6 +767,41 @@ __global__ void k_philox_batch(const uint4* __restrict__ ctr, uint32_t n, const 
         out[i] = philox4x32_10(ctr[i], rk);
 }
 
+
+// ---- exhaustive check of the cheaper exact special functions of spec.cuh against the IEEE intrinsics ---------------
+// counts[0], counts[1]: float patterns x (all 2^32) for which sqrt_then_rcp's s / inv differ from __fsqrt_rn(x) /
+// __frcp_rn(__fsqrt_rn(x)) (two NaNs count as equal); counts[2]: (a, b) pairs with a in {0} u [2^-24, 2^24] (every float)
+// and b from `divisors` for which div_by_const(a, b, RN(1/b)) differs from __fdiv_rn(a, b); counts[3]: pairs tested.
+__device__ __forceinline__ bool same_float(float a, float b)
+{
+    return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b);
+}
+__global__ void __launch_bounds__(256) k_selftest_math(const float* __restrict__ divisors, uint32_t n_divisors, unsigned long long* __restrict__ counts)
+{
+    unsigned long long bad_s = 0, bad_inv = 0, bad_div = 0, pairs = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < 0x100000000ull; i += stride)
+    {
+        const float x = __uint_as_float((uint32_t)i);
+        float s, inv;
+        sqrt_then_rcp(x, s, inv);
+        const float rs = __fsqrt_rn(x);
+        bad_s += !same_float(s, rs);
+        bad_inv += !same_float(inv, __frcp_rn(rs));
+        const bool in_domain = i == 0 || (i >= 0x33800000ull && i <= 0x4B800000ull); // 0, or 2^-24 .. 2^24
+        if (in_domain)
+            for (uint32_t k = 0; k < n_divisors; k++)
+            {
+                const float b = divisors[k];
+                bad_div += !same_float(div_by_const(x, b, __frcp_rn(b)), __fdiv_rn(x, b));
+                pairs++;
+            }
+    }
+    atomicAdd(counts + 0, bad_s);
+    atomicAdd(counts + 1, bad_inv);
+    atomicAdd(counts + 2, bad_div);
+    atomicAdd(counts + 3, pairs);
+}
 
 // ---- FP32 peak calibration: dependent-chain-free FFMA / FFMA2 streams, 16 independent accumulators per
 // thread, no memory traffic.  Used by bench.py to report the roofline denominator at the clocks actually seen.

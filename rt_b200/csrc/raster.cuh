@@ -106,11 +106,12 @@ __global__ void __launch_bounds__(RASTER_TILE_W* RASTER_TILE_H) k_rasterize(cons
     primary_points(p.cam, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f), near_p, far_p);
     const V3 span = v3_sub(far_p, near_p);
     const float len2 = dot3(span, span);
-    const float max_dist = __fsqrt_rn(len2);                 // vec3::distance
+    float max_dist, inv_len;
+    sqrt_then_rcp(len2, max_dist, inv_len);                  // vec3::distance, and S2 on the same dot product
     float dist = __fadd_rn(max_dist, 1.0f);
     Ray r;
     r.o = near_p;
-    r.d = v3_scale(span, __frcp_rn(max_dist));               // vec3::direction = S2 on the same dot product
+    r.d = v3_scale(span, inv_len);                           // vec3::direction
 
     uint32_t prim = RTCU_PRIM_MISS;
     int last_plane = -1;

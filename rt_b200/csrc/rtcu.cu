@@ -160,6 +160,7 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     if (!v) return fail(RTCU_ERR_INVALID, "view is null");
     if (v->width == 0 || v->height == 0) return fail(RTCU_ERR_INVALID, "empty image");
     if ((uint64_t)v->width * v->height > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "image too large");
+    if (v->width > (1u << 23) || v->height > (1u << 23)) return fail(RTCU_ERR_INVALID, "image side above 2^23 pixels"); // pixel coordinates stay exact floats
     if (v->tile_x0 >= v->tile_x1 || v->tile_y0 >= v->tile_y1 || v->tile_x1 > v->width || v->tile_y1 > v->height)
         return fail(RTCU_ERR_INVALID, "bad tile [%u,%u)x[%u,%u) for %ux%u", v->tile_x0, v->tile_x1, v->tile_y0, v->tile_y1, v->width, v->height);
     if (v->sample_end < v->sample_begin) return fail(RTCU_ERR_INVALID, "bad sample range");
@@ -170,6 +171,11 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     memcpy(p.cam.m, v->inv_view_proj, sizeof p.cam.m);
     p.cam.w = (float)v->width;
     p.cam.h = (float)v->height;
+    {
+        const volatile float rw = 1.0f / p.cam.w, rh = 1.0f / p.cam.h; // IEEE division: RN(1/W), RN(1/H) for div_by_const
+        p.cam.rw = rw;
+        p.cam.rh = rh;
+    }
     {
         // perspective-divide reciprocals as frame constants when h.w is pixel-independent (see CameraConst)
         const float* m = v->inv_view_proj;
@@ -659,7 +665,16 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         r.roughness = m.roughness;
         r.ior = m.reflectivity;
         r.type = m.type;
-        r.pad0 = r.pad1 = 0;
+        {
+            // the per-material constants of the dielectric branch, each a single IEEE operation as in the source
+            // (sm_ray_tracer.cpp:176-177, :205): 1/ior and r0 = ((1 - ior) / (1 + ior))^2
+            const volatile float inv = 1.0f / m.reflectivity;
+            const volatile float num = 1.0f - m.reflectivity, den = 1.0f + m.reflectivity;
+            const volatile float q = num / den;
+            const volatile float r0 = q * q;
+            r.inv_ior = inv;
+            r.r0 = r0;
+        }
         mats[i] = r;
     }
     CU(ctx->sph.reserve(s->n_spheres ? s->n_spheres : 1));
@@ -1202,6 +1217,27 @@ int rtcu_measure_fp32_peak(rtcu_ctx* ctx, float* tflops_ffma, float* tflops_ffma
         }
         *results[variant] = best;
     }
+    return RTCU_OK;
+}
+
+int rtcu_selftest_math(rtcu_ctx* ctx, const float* divisors, uint32_t n_divisors, uint64_t counts[4])
+{
+    if (!ctx || !counts || (n_divisors && !divisors)) return fail(RTCU_ERR_INVALID, "null argument");
+    if (n_divisors > 256) return fail(RTCU_ERR_INVALID, "at most 256 divisors");
+    for (uint32_t i = 0; i < n_divisors; i++)
+        if (!(divisors[i] >= 1.0f && divisors[i] <= 16777216.0f)) return fail(RTCU_ERR_INVALID, "divisor %u outside [1, 2^24]", i);
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->scratch.reserve(4 * sizeof(unsigned long long) + 256 * sizeof(float)));
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(ctx->scratch.p);
+    float* d_div = reinterpret_cast<float*>(ctx->scratch.p + 4 * sizeof(unsigned long long));
+    CU(cudaMemsetAsync(d_counts, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (n_divisors) CU(cudaMemcpyAsync(d_div, divisors, n_divisors * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_selftest_math<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(d_div, n_divisors, d_counts);
+    CU(cudaGetLastError());
+    unsigned long long h[4];
+    CU(cudaMemcpyAsync(h, d_counts, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; i++) counts[i] = h[i];
     return RTCU_OK;
 }
 

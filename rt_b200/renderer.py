@@ -223,6 +223,13 @@ class Context:
         nat.check(self._lib.rtcu_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def selftest_math(self, divisors=(800, 600, 1920, 1080, 3840, 2160)) -> dict:
+        """rtcu_selftest_math: mismatches of the kernels' cheaper exact sqrt / rcp / division against the IEEE intrinsics"""
+        d = nat.contiguous(divisors, np.float32)
+        out = np.zeros(4, np.uint64)
+        nat.check(self._lib.rtcu_selftest_math(self._h, nat.ptr(d), len(d), nat.ptr(out)))
+        return {"sqrt": int(out[0]), "rcp_of_sqrt": int(out[1]), "div": int(out[2]), "div_pairs": int(out[3])}
+
     def measure_fp32_peak(self) -> tuple[float, float]:
         """(FFMA TFLOP/s, FFMA2 TFLOP/s) achieved by a register-only stream on this device right now."""
         a, b = C.c_float(0), C.c_float(0)

@@ -445,3 +445,13 @@ def test_progressive_refinement_converges_to_the_single_render(ctx, scenes):
     assert np.abs(unpack_rgba(img) - unpack_rgba(rgba8)).max() <= 1
     prog.reset()
     assert prog.samples_done == 0 and (prog.refine() == first).all()
+
+
+def test_cheaper_exact_sqrt_rcp_div_equal_the_ieee_intrinsics_for_every_input(ctx):
+    """spec.cuh replaces nvcc's __fsqrt_rn/__frcp_rn/__fdiv_rn expansions by the same fast-path sequences behind fewer range
+    tests; rtcu_selftest_math compares them on the device over all 2^32 float patterns (sqrt, 1/sqrt) and over every float
+    in {0} u [2^-24, 2^24] divided by a set of image sides"""
+    sides = [1, 2, 3, 7, 33, 97, 131, 160, 200, 256, 320, 600, 800, 1080, 1920, 2160, 3840, 4096, 8191, 65535, 2 ** 23]
+    r = ctx.selftest_math(sides)
+    assert r["div_pairs"] == len(sides) * (0x4B800000 - 0x33800000 + 2)
+    assert (r["sqrt"], r["rcp_of_sqrt"], r["div"]) == (0, 0, 0), r
