@@ -25,9 +25,9 @@ struct SceneDev {
     uint32_t n_planes;
     const MatRec* materials;
     uint32_t n_materials;
-    // BVH over the spheres (built when the scene size calls for it, see bvh.h); nodes = 4 float4 per node:
-    // {l.lo.x,r.lo.x,l.hi.x,r.hi.x}, same for y and z (left/right interleaved for the packed FP32 slab test), then
-    // {ref_left, ref_right, -, -} as bit patterns.
+    // BVH over the spheres (built when the scene size calls for it, see bvh.h); nodes = 4 float4 per node: child boxes as
+    // centre / half-extent, {l.c.x, r.c.x, l.h.x, r.h.x}, same for y and z (left/right interleaved for the packed FP32 slab
+    // test; h rounded outward, -inf for an empty child), then {ref_left, ref_right, H_left, H_right} with H = h.x+h.y+h.z.
     // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | leaf number; leaf L owns leaf_sph[4L..4L+3] (two packed
     // pairs {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}, padded with never-hit spheres) and leaf_idx[4L..4L+3].
     const float4* bvh_nodes;
@@ -181,8 +181,9 @@ struct Trav {
     int sp;
     float best_t;
     int best_i;
-    float ix, iy, iz; // 1 / d
-    float kappa;      // margin factor, see above
+    float ix, iy, iz;    // 1 / d
+    float aix, aiy, aiz; // |1 / d|
+    float kappa;         // margin factor, see above
 };
 
 // returns false when the ray direction is too far from unit length for the conservative margins (caller falls back
@@ -198,6 +199,9 @@ __device__ __forceinline__ bool trav_init(const Ray& r, Trav& tv)
     tv.ix = __frcp_rn(r.d.x);
     tv.iy = __frcp_rn(r.d.y);
     tv.iz = __frcp_rn(r.d.z);
+    tv.aix = fabsf(tv.ix);
+    tv.aiy = fabsf(tv.iy);
+    tv.aiz = fabsf(tv.iz);
     return eps_d <= 1e-3f;
 }
 
@@ -215,29 +219,28 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
     float tn[2];
     bool hit[2];
     {
-        // Both children at once on the packed FP32 pipe: the device node stores {l.lo, r.lo, l.hi, r.hi} per axis, so the
-        // left and right slab tests are the two halves of FADD2 / FMUL2 instructions (the kernel is issue-bound; only the
-        // min / max / abs steps stay scalar).  Rounding is irrelevant here: the boxes are inflated by the margin m.
-        const float2 nox = make_float2(-r.o.x, -r.o.x), noy = make_float2(-r.o.y, -r.o.y), noz = make_float2(-r.o.z, -r.o.z);
-        const float2 lox = __fadd2_rn(make_float2(bx.x, bx.y), nox), hix = __fadd2_rn(make_float2(bx.z, bx.w), nox);
-        const float2 loy = __fadd2_rn(make_float2(by.x, by.y), noy), hiy = __fadd2_rn(make_float2(by.z, by.w), noy);
-        const float2 loz = __fadd2_rn(make_float2(bz.x, bz.y), noz), hiz = __fadd2_rn(make_float2(bz.z, bz.w), noz);
-        const float2 ax = make_float2(fmaxf(fabsf(lox.x), fabsf(hix.x)), fmaxf(fabsf(lox.y), fabsf(hix.y)));
-        const float2 ay = make_float2(fmaxf(fabsf(loy.x), fabsf(hiy.x)), fmaxf(fabsf(loy.y), fabsf(hiy.y)));
-        const float2 az = make_float2(fmaxf(fabsf(loz.x), fabsf(hiz.x)), fmaxf(fabsf(loz.y), fabsf(hiz.y)));
-        const float2 m = __fmul2_rn(__fadd2_rn(__fadd2_rn(ax, ay), az), make_float2(tv.kappa, tv.kappa));
-        const float2 nm = make_float2(-m.x, -m.y);
-        const float2 ix2 = make_float2(tv.ix, tv.ix), iy2 = make_float2(tv.iy, tv.iy), iz2 = make_float2(tv.iz, tv.iz);
-        const float2 t1x = __fmul2_rn(__fadd2_rn(lox, nm), ix2), t2x = __fmul2_rn(__fadd2_rn(hix, m), ix2);
-        const float2 t1y = __fmul2_rn(__fadd2_rn(loy, nm), iy2), t2y = __fmul2_rn(__fadd2_rn(hiy, m), iy2);
-        const float2 t1z = __fmul2_rn(__fadd2_rn(loz, nm), iz2), t2z = __fmul2_rn(__fadd2_rn(hiz, m), iz2);
-        const float tmin_l = fmaxf(fmaxf(fminf(t1x.x, t2x.x), fminf(t1y.x, t2y.x)), fminf(t1z.x, t2z.x));
-        const float tmax_l = fminf(fminf(fmaxf(t1x.x, t2x.x), fmaxf(t1y.x, t2y.x)), fmaxf(t1z.x, t2z.x));
-        const float tmin_r = fmaxf(fmaxf(fminf(t1x.y, t2x.y), fminf(t1y.y, t2y.y)), fminf(t1z.y, t2z.y));
-        const float tmax_r = fminf(fminf(fmaxf(t1x.y, t2x.y), fmaxf(t1y.y, t2y.y)), fmaxf(t1z.y, t2z.y));
+        // Both children at once on the packed FP32 pipe.  The device node stores each child box as centre c and half-extent
+        // h (rounded outward) per axis, {c_l, c_r, h_l, h_r}, plus H = h.x + h.y + h.z: then E = |c - o|_1 + H bounds the L1
+        // distance from the origin to the box's farthest corner, the inflated slab is tc -+ (h + m)|1/d| with tc = (c - o)/d,
+        // and near / far come out already ordered -- 3 FADD2 + 3 FMUL2 + 6 FFMA2 + 5 for the margin + 4 FMNMX3 per node
+        // instead of 27 + 16.  Rounding is irrelevant here: it is far below the 1 % slack in kappa.  A zero direction
+        // component gives inf - inf = NaN on that axis, which the min / max drop: the axis then does not cull (conservative).
+        const float2 dcx = __fadd2_rn(make_float2(bx.x, bx.y), make_float2(-r.o.x, -r.o.x));
+        const float2 dcy = __fadd2_rn(make_float2(by.x, by.y), make_float2(-r.o.y, -r.o.y));
+        const float2 dcz = __fadd2_rn(make_float2(bz.x, bz.y), make_float2(-r.o.z, -r.o.z));
+        const float2 e3 = make_float2(fabsf(dcx.x) + fabsf(dcy.x) + fabsf(dcz.x), fabsf(dcx.y) + fabsf(dcy.y) + fabsf(dcz.y));
+        const float2 m = __fmul2_rn(__fadd2_rn(e3, make_float2(meta.z, meta.w)), make_float2(tv.kappa, tv.kappa));
+        const float2 hx = __fadd2_rn(make_float2(bx.z, bx.w), m), hy = __fadd2_rn(make_float2(by.z, by.w), m), hz = __fadd2_rn(make_float2(bz.z, bz.w), m);
+        const float2 tcx = __fmul2_rn(dcx, make_float2(tv.ix, tv.ix)), tcy = __fmul2_rn(dcy, make_float2(tv.iy, tv.iy)), tcz = __fmul2_rn(dcz, make_float2(tv.iz, tv.iz));
+        const float2 ax = make_float2(tv.aix, tv.aix), ay = make_float2(tv.aiy, tv.aiy), az = make_float2(tv.aiz, tv.aiz);
+        const float2 n_x = __ffma2_rn(make_float2(-hx.x, -hx.y), ax, tcx), f_x = __ffma2_rn(hx, ax, tcx);
+        const float2 n_y = __ffma2_rn(make_float2(-hy.x, -hy.y), ay, tcy), f_y = __ffma2_rn(hy, ay, tcy);
+        const float2 n_z = __ffma2_rn(make_float2(-hz.x, -hz.y), az, tcz), f_z = __ffma2_rn(hz, az, tcz);
+        const float tmin_l = fmaxf(fmaxf(n_x.x, n_y.x), n_z.x), tmax_l = fminf(fminf(f_x.x, f_y.x), f_z.x);
+        const float tmin_r = fmaxf(fmaxf(n_x.y, n_y.y), n_z.y), tmax_r = fminf(fminf(f_x.y, f_y.y), f_z.y);
         tn[0] = tmin_l;
         tn[1] = tmin_r;
-        hit[0] = tmax_l >= (ANY_T ? tmin_l : fmaxf(tmin_l, 0.0f)) && tmin_l <= tv.best_t; // empty boxes (lo > hi) fail the first test
+        hit[0] = tmax_l >= (ANY_T ? tmin_l : fmaxf(tmin_l, 0.0f)) && tmin_l <= tv.best_t; // empty children (h = -inf) fail the first test
         hit[1] = tmax_r >= (ANY_T ? tmin_r : fmaxf(tmin_r, 0.0f)) && tmin_r <= tv.best_t;
     }
     // leaves are tested immediately, inner children are descended near-first

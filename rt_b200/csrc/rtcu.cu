@@ -739,10 +739,38 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
             for (size_t i = 0; i < bvh.nodes.size(); i++)
             {
                 const rtcu_bvh::Node& nd = bvh.nodes[i];
-                // host node: {l.lo, l.hi, r.lo, r.hi} per axis -> device: {l.lo, r.lo, l.hi, r.hi} (packed slab test)
-                nodes_dev[4 * i + 0] = make_float4(nd.x[0], nd.x[2], nd.x[1], nd.x[3]);
-                nodes_dev[4 * i + 1] = make_float4(nd.y[0], nd.y[2], nd.y[1], nd.y[3]);
-                nodes_dev[4 * i + 2] = make_float4(nd.z[0], nd.z[2], nd.z[1], nd.z[3]);
+                // host node: {l.lo, l.hi, r.lo, r.hi} per axis -> device: centre / half-extent {l.c, r.c, l.h, r.h} with h
+                // rounded outward so that [c - h, c + h] contains [lo, hi]; an empty child (lo > hi) gets h = -inf: never hit
+                float cen[2][3], half[2][3], hsum[2];
+                const float* axes[3] = { nd.x, nd.y, nd.z };
+                for (int c = 0; c < 2; c++)
+                {
+                    double hs = 0.0;
+                    for (int k = 0; k < 3; k++)
+                    {
+                        const float lo = axes[k][2 * c], hi = axes[k][2 * c + 1];
+                        if (!(lo <= hi))
+                        {
+                            cen[c][k] = 0.0f;
+                            half[c][k] = -__builtin_inff();
+                            hs = -__builtin_inf();
+                            continue;
+                        }
+                        const float ce = (float)(0.5 * ((double)lo + (double)hi));
+                        const double need = std::max((double)hi - (double)ce, (double)ce - (double)lo);
+                        float h = (float)need;
+                        if ((double)h < need) h = nextafterf(h, __builtin_inff());
+                        cen[c][k] = ce;
+                        half[c][k] = h;
+                        hs += (double)h;
+                    }
+                    float H = (float)hs;
+                    if ((double)H < hs) H = nextafterf(H, __builtin_inff());
+                    hsum[c] = H;
+                }
+                nodes_dev[4 * i + 0] = make_float4(cen[0][0], cen[1][0], half[0][0], half[1][0]);
+                nodes_dev[4 * i + 1] = make_float4(cen[0][1], cen[1][1], half[0][1], half[1][1]);
+                nodes_dev[4 * i + 2] = make_float4(cen[0][2], cen[1][2], half[0][2], half[1][2]);
                 // leaves become fixed 4-sphere blocks in the packed pair layout of the sweep (two pairs = 4 float4, padded with
                 // never-hit spheres) + their 4 original indices: a leaf visit is two straight-line FFMA2 pair tests
                 uint32_t ref[2];
@@ -773,7 +801,8 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
                 float4 meta;
                 memcpy(&meta.x, &ref[0], 4);
                 memcpy(&meta.y, &ref[1], 4);
-                meta.z = meta.w = 0.0f;
+                meta.z = hsum[0];
+                meta.w = hsum[1];
                 nodes_dev[4 * i + 3] = meta;
             }
             if (leaf_idx.empty()) { leaf_idx.assign(4, 0x7fffffffu); leaf_sph.assign(4, make_float4(0.0f, 0.0f, -__builtin_inff(), -__builtin_inff())); }
