@@ -28,11 +28,11 @@ struct SceneDev {
     // BVH over the spheres (built when the scene size calls for it, see bvh.h); nodes = 4 float4 per node: child boxes as
     // centre / half-extent, {l.c.x, r.c.x, l.h.x, r.h.x}, same for y and z (left/right interleaved for the packed FP32 slab
     // test; h rounded outward, -inf for an empty child), then {ref_left, ref_right, H_left, H_right} with H = h.x+h.y+h.z.
-    // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | leaf number; leaf L owns leaf_sph[4L..4L+3] (two packed
-    // pairs {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}, padded with never-hit spheres) and leaf_idx[4L..4L+3].
+    // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | leaf number; leaf L is the 80-byte block leaf_blk[5L..5L+4]:
+    // two packed pairs {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1} (padded with never-hit spheres) and, as bit patterns, the four
+    // original sphere indices (0x7fffffff = padding) -- one address computation, five 16-byte loads issued together.
     const float4* bvh_nodes;
-    const float4* leaf_sph;
-    const uint32_t* leaf_idx; // original sphere indices (0x7fffffff = padding)
+    const float4* leaf_blk;
     uint32_t n_bvh_nodes;
 };
 
@@ -253,11 +253,11 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
         if (ref[c] & 0x80000000u)
         {
             const uint32_t leaf = ref[c] & 0x7fffffffu;
-            const float4* lp = sc.leaf_sph + 4 * (size_t)leaf;
-            const uint4 idx = __ldg(reinterpret_cast<const uint4*>(sc.leaf_idx) + leaf);
+            const float4* lp = sc.leaf_blk + 5u * leaf; // leaf < 2^29 (checked at upload): 32-bit index arithmetic
+            const float4 a0 = __ldg(lp), b0 = __ldg(lp + 1), a1 = __ldg(lp + 2), b1 = __ldg(lp + 3), idx = __ldg(lp + 4);
             st.tests += 4; // sphere test slots (a leaf holds 1-4 spheres)
-            bvh_leaf_pair_test<ANY_T>(__ldg(lp), __ldg(lp + 1), (int)idx.x, (int)idx.y, r, tv.best_t, tv.best_i);
-            bvh_leaf_pair_test<ANY_T>(__ldg(lp + 2), __ldg(lp + 3), (int)idx.z, (int)idx.w, r, tv.best_t, tv.best_i);
+            bvh_leaf_pair_test<ANY_T>(a0, b0, __float_as_int(idx.x), __float_as_int(idx.y), r, tv.best_t, tv.best_i);
+            bvh_leaf_pair_test<ANY_T>(a1, b1, __float_as_int(idx.z), __float_as_int(idx.w), r, tv.best_t, tv.best_i);
         }
         else if (next == 0xffffffffu)
         {

@@ -119,8 +119,7 @@ struct rtcu_ctx {
     DevBuf<float> raster_depth;
     PinnedBuf<uint32_t> h_raster_prim;
     PinnedBuf<float> h_raster_depth;
-    DevBuf<float4> bvh_nodes, leaf_sph;
-    DevBuf<uint32_t> leaf_idx;
+    DevBuf<float4> bvh_nodes, leaf_blk;
     bool have_bvh = false;
     uint32_t bvh_depth = 0;
     float ms_bvh_build = 0.0f;
@@ -602,7 +601,7 @@ void rtcu_destroy(rtcu_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->sph.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
-    ctx->mats.release(); ctx->bvh_nodes.release(); ctx->leaf_sph.release(); ctx->leaf_idx.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
+    ctx->mats.release(); ctx->bvh_nodes.release(); ctx->leaf_blk.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
     for (int i = 0; i < 2; i++) { ctx->wf_o[i].release(); ctx->wf_d[i].release(); ctx->wf_thr[i].release(); }
     for (auto& l : ctx->wf_list) l.release();
     ctx->wf_rad.release(); ctx->wf_sum.release(); ctx->wf_hit.release(); ctx->wf_counts.release(); ctx->h_wf_counts.release();
@@ -722,8 +721,7 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     // tests); RTCU_ACCEL_AUTO uses it from rtcu_bvh_threshold() spheres up
     ctx->have_bvh = false;
     ctx->scene.bvh_nodes = nullptr;
-    ctx->scene.leaf_sph = nullptr;
-    ctx->scene.leaf_idx = nullptr;
+    ctx->scene.leaf_blk = nullptr;
     ctx->scene.n_bvh_nodes = 0;
     std::vector<float4> nodes_dev, leaf_sph;
     std::vector<uint32_t> leaf_idx;
@@ -806,15 +804,20 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
                 nodes_dev[4 * i + 3] = meta;
             }
             if (leaf_idx.empty()) { leaf_idx.assign(4, 0x7fffffffu); leaf_sph.assign(4, make_float4(0.0f, 0.0f, -__builtin_inff(), -__builtin_inff())); }
+            // one 80-byte block per leaf: its two packed pairs, then its four indices as bit patterns
+            std::vector<float4> leaf_blk(5 * (leaf_idx.size() / 4));
+            for (size_t l = 0; l < leaf_idx.size() / 4; l++)
+            {
+                for (int k = 0; k < 4; k++) leaf_blk[5 * l + k] = leaf_sph[4 * l + k];
+                memcpy(&leaf_blk[5 * l + 4], &leaf_idx[4 * l], sizeof(float4));
+            }
             CU(ctx->bvh_nodes.reserve(nodes_dev.size()));
-            CU(ctx->leaf_sph.reserve(leaf_sph.size()));
-            CU(ctx->leaf_idx.reserve(leaf_idx.size()));
+            CU(ctx->leaf_blk.reserve(leaf_blk.size()));
             CU(cudaMemcpyAsync(ctx->bvh_nodes.p, nodes_dev.data(), nodes_dev.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaMemcpyAsync(ctx->leaf_sph.p, leaf_sph.data(), leaf_sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaMemcpyAsync(ctx->leaf_idx.p, leaf_idx.data(), leaf_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->leaf_blk.p, leaf_blk.data(), leaf_blk.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream)); // leaf_blk dies with this scope
             ctx->scene.bvh_nodes = ctx->bvh_nodes.p;
-            ctx->scene.leaf_sph = ctx->leaf_sph.p;
-            ctx->scene.leaf_idx = ctx->leaf_idx.p;
+            ctx->scene.leaf_blk = ctx->leaf_blk.p;
             ctx->scene.n_bvh_nodes = (uint32_t)bvh.nodes.size();
             ctx->have_bvh = true;
         }
