@@ -25,9 +25,10 @@ struct SceneDev {
     uint32_t n_planes;
     const MatRec* materials;
     uint32_t n_materials;
-    // BVH over the spheres (built when the scene size calls for it, see bvh.h); nodes = 4 float4 per node: child boxes as
-    // centre / half-extent, {l.c.x, r.c.x, l.h.x, r.h.x}, same for y and z (left/right interleaved for the packed FP32 slab
-    // test; h rounded outward, -inf for an empty child), then {ref_left, ref_right, H_left, H_right} with H = h.x+h.y+h.z.
+    // BVH over the spheres (built when the scene size calls for it: bvh.h builds a binary SAH tree, rtcu.cu collapses it to
+    // 4-wide nodes).  8 float4 per node: children (0,1) as centre / half-extent {c0, c1, h0, h1} for x, y, z (interleaved
+    // for the packed FP32 slab test; h rounded outward, -inf for an empty slot), the same for children (2,3), the four child
+    // references as bit patterns, and the four H = h.x + h.y + h.z.
     // ref >= 0: inner node index; ref < 0: leaf = 0x80000000 | leaf number; leaf L is the 80-byte block leaf_blk[5L..5L+4]:
     // two packed pairs {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1} (padded with never-hit spheres) and, as bit patterns, the four
     // original sphere indices (0x7fffffff = padding) -- one address computation, five 16-byte loads issued together.
@@ -173,7 +174,7 @@ __device__ __forceinline__ void bvh_leaf_pair_test(const float4 A, const float4 
     }
 }
 
-constexpr int BVH_STACK = 64;
+constexpr int BVH_STACK = 64; // entries; a visit pushes at most 3, so trees up to 20 levels of 4-wide nodes (4^20 leaves)
 
 // traversal state of one ray; the node stack lives in (L1-cached) local memory of the calling kernel
 struct Trav {
@@ -181,9 +182,8 @@ struct Trav {
     int sp;
     float best_t;
     int best_i;
-    float ix, iy, iz;    // 1 / d
-    float aix, aiy, aiz; // |1 / d|
-    float kappa;         // margin factor, see above
+    float ix, iy, iz; // 1 / d
+    float kappa;      // margin factor, see above
 };
 
 // returns false when the ray direction is too far from unit length for the conservative margins (caller falls back
@@ -199,55 +199,58 @@ __device__ __forceinline__ bool trav_init(const Ray& r, Trav& tv)
     tv.ix = __frcp_rn(r.d.x);
     tv.iy = __frcp_rn(r.d.y);
     tv.iz = __frcp_rn(r.d.z);
-    tv.aix = fabsf(tv.ix);
-    tv.aiy = fabsf(tv.iy);
-    tv.aiz = fabsf(tv.iz);
     return eps_d <= 1e-3f;
 }
 
-// one node visit: slab-test both children, test leaf children immediately, descend near-first / push / pop.
-// Returns true when the traversal is complete.  ANY_T: the whole line counts, not only t >= 0 (the margin argument above
-// never uses the sign of t: a computed hit lies within the inflated ball, whose line interval lies within the inflated box).
+// slab test of two child boxes at once on the packed FP32 pipe.  cx/cy/cz = {c_a, c_b, h_a, h_b} per axis (centre and
+// outward-rounded half-extent), H = h.x + h.y + h.z per child: E = |c - o|_1 + H bounds the L1 distance from the origin to the
+// box's farthest corner, the inflated slab is tc -+ (h + m)|1/d| with tc = (c - o)/d and m = kappa E, and near / far come out
+// already ordered: 4 FADD2 + 3 FMUL2 + 9 FFMA2 + 4 FADD + 4 FMNMX3 for two boxes.  Rounding is irrelevant here (far below the
+// 1 % slack in kappa).  A zero direction component gives inf - inf = NaN on that axis, which min / max drop: the axis then
+// does not cull (conservative).  An empty slot has h = H = -inf: near = +inf, far = -inf, never hit.
+template <bool ANY_T>
+__device__ __forceinline__ void slab_pair(const float4 cx, const float4 cy, const float4 cz, const float Ha, const float Hb, const Ray& r,
+                                          const Trav& tv, float& tn_a, float& tn_b, bool& hit_a, bool& hit_b)
+{
+    const float2 dcx = __fadd2_rn(make_float2(cx.x, cx.y), make_float2(-r.o.x, -r.o.x));
+    const float2 dcy = __fadd2_rn(make_float2(cy.x, cy.y), make_float2(-r.o.y, -r.o.y));
+    const float2 dcz = __fadd2_rn(make_float2(cz.x, cz.y), make_float2(-r.o.z, -r.o.z));
+    const float2 e3 = make_float2(fabsf(dcx.x) + fabsf(dcy.x) + fabsf(dcz.x), fabsf(dcx.y) + fabsf(dcy.y) + fabsf(dcz.y));
+    const float2 m = __fmul2_rn(__fadd2_rn(e3, make_float2(Ha, Hb)), make_float2(tv.kappa, tv.kappa));
+    const float2 hx = __fadd2_rn(make_float2(cx.z, cx.w), m), hy = __fadd2_rn(make_float2(cy.z, cy.w), m), hz = __fadd2_rn(make_float2(cz.z, cz.w), m);
+    const float2 tcx = __fmul2_rn(dcx, make_float2(tv.ix, tv.ix)), tcy = __fmul2_rn(dcy, make_float2(tv.iy, tv.iy)), tcz = __fmul2_rn(dcz, make_float2(tv.iz, tv.iz));
+    const float2 ax = make_float2(fabsf(tv.ix), fabsf(tv.ix)), ay = make_float2(fabsf(tv.iy), fabsf(tv.iy)), az = make_float2(fabsf(tv.iz), fabsf(tv.iz));
+    const float2 n_x = __ffma2_rn(make_float2(-hx.x, -hx.y), ax, tcx), f_x = __ffma2_rn(hx, ax, tcx);
+    const float2 n_y = __ffma2_rn(make_float2(-hy.x, -hy.y), ay, tcy), f_y = __ffma2_rn(hy, ay, tcy);
+    const float2 n_z = __ffma2_rn(make_float2(-hz.x, -hz.y), az, tcz), f_z = __ffma2_rn(hz, az, tcz);
+    tn_a = fmaxf(fmaxf(n_x.x, n_y.x), n_z.x);
+    tn_b = fmaxf(fmaxf(n_x.y, n_y.y), n_z.y);
+    const float tf_a = fminf(fminf(f_x.x, f_y.x), f_z.x), tf_b = fminf(fminf(f_x.y, f_y.y), f_z.y);
+    hit_a = tf_a >= (ANY_T ? tn_a : fmaxf(tn_a, 0.0f)) && tn_a <= tv.best_t;
+    hit_b = tf_b >= (ANY_T ? tn_b : fmaxf(tn_b, 0.0f)) && tn_b <= tv.best_t;
+}
+
+// one visit of a 4-wide node: slab-test the four children, test leaf children immediately, continue with the nearest inner
+// child, push the others (in slot order) / pop.  Returns true when the traversal is complete.  ANY_T: the whole line counts,
+// not only t >= 0 (the margin argument above never uses the sign of t: a computed hit lies within the inflated ball, whose
+// line interval lies within the inflated box).
 template <bool ANY_T = false>
 __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav& tv, uint32_t* __restrict__ stack_ref,
                                           float* __restrict__ stack_t, BvhStats& st)
 {
     st.nodes++;
-    const float4* np = sc.bvh_nodes + 4 * (size_t)tv.node;
-    const float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2), meta = __ldg(np + 3);
-    const uint32_t ref[2] = { __float_as_uint(meta.x), __float_as_uint(meta.y) };
-    float tn[2];
-    bool hit[2];
-    {
-        // Both children at once on the packed FP32 pipe.  The device node stores each child box as centre c and half-extent
-        // h (rounded outward) per axis, {c_l, c_r, h_l, h_r}, plus H = h.x + h.y + h.z: then E = |c - o|_1 + H bounds the L1
-        // distance from the origin to the box's farthest corner, the inflated slab is tc -+ (h + m)|1/d| with tc = (c - o)/d,
-        // and near / far come out already ordered -- 3 FADD2 + 3 FMUL2 + 6 FFMA2 + 5 for the margin + 4 FMNMX3 per node
-        // instead of 27 + 16.  Rounding is irrelevant here: it is far below the 1 % slack in kappa.  A zero direction
-        // component gives inf - inf = NaN on that axis, which the min / max drop: the axis then does not cull (conservative).
-        const float2 dcx = __fadd2_rn(make_float2(bx.x, bx.y), make_float2(-r.o.x, -r.o.x));
-        const float2 dcy = __fadd2_rn(make_float2(by.x, by.y), make_float2(-r.o.y, -r.o.y));
-        const float2 dcz = __fadd2_rn(make_float2(bz.x, bz.y), make_float2(-r.o.z, -r.o.z));
-        const float2 e3 = make_float2(fabsf(dcx.x) + fabsf(dcy.x) + fabsf(dcz.x), fabsf(dcx.y) + fabsf(dcy.y) + fabsf(dcz.y));
-        const float2 m = __fmul2_rn(__fadd2_rn(e3, make_float2(meta.z, meta.w)), make_float2(tv.kappa, tv.kappa));
-        const float2 hx = __fadd2_rn(make_float2(bx.z, bx.w), m), hy = __fadd2_rn(make_float2(by.z, by.w), m), hz = __fadd2_rn(make_float2(bz.z, bz.w), m);
-        const float2 tcx = __fmul2_rn(dcx, make_float2(tv.ix, tv.ix)), tcy = __fmul2_rn(dcy, make_float2(tv.iy, tv.iy)), tcz = __fmul2_rn(dcz, make_float2(tv.iz, tv.iz));
-        const float2 ax = make_float2(tv.aix, tv.aix), ay = make_float2(tv.aiy, tv.aiy), az = make_float2(tv.aiz, tv.aiz);
-        const float2 n_x = __ffma2_rn(make_float2(-hx.x, -hx.y), ax, tcx), f_x = __ffma2_rn(hx, ax, tcx);
-        const float2 n_y = __ffma2_rn(make_float2(-hy.x, -hy.y), ay, tcy), f_y = __ffma2_rn(hy, ay, tcy);
-        const float2 n_z = __ffma2_rn(make_float2(-hz.x, -hz.y), az, tcz), f_z = __ffma2_rn(hz, az, tcz);
-        const float tmin_l = fmaxf(fmaxf(n_x.x, n_y.x), n_z.x), tmax_l = fminf(fminf(f_x.x, f_y.x), f_z.x);
-        const float tmin_r = fmaxf(fmaxf(n_x.y, n_y.y), n_z.y), tmax_r = fminf(fminf(f_x.y, f_y.y), f_z.y);
-        tn[0] = tmin_l;
-        tn[1] = tmin_r;
-        hit[0] = tmax_l >= (ANY_T ? tmin_l : fmaxf(tmin_l, 0.0f)) && tmin_l <= tv.best_t; // empty children (h = -inf) fail the first test
-        hit[1] = tmax_r >= (ANY_T ? tmin_r : fmaxf(tmin_r, 0.0f)) && tmin_r <= tv.best_t;
-    }
-    // leaves are tested immediately, inner children are descended near-first
+    const float4* np = sc.bvh_nodes + 8u * tv.node;
+    const float4 refs = __ldg(np + 6), hs = __ldg(np + 7);
+    const uint32_t ref[4] = { __float_as_uint(refs.x), __float_as_uint(refs.y), __float_as_uint(refs.z), __float_as_uint(refs.w) };
+    float tn[4];
+    bool hit[4];
+    slab_pair<ANY_T>(__ldg(np), __ldg(np + 1), __ldg(np + 2), hs.x, hs.y, r, tv, tn[0], tn[1], hit[0], hit[1]);
+    slab_pair<ANY_T>(__ldg(np + 3), __ldg(np + 4), __ldg(np + 5), hs.z, hs.w, r, tv, tn[2], tn[3], hit[2], hit[3]);
+    // leaves are tested immediately; of the inner children the nearest is descended, the others are pushed
     uint32_t next = 0xffffffffu;
     float next_t = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 2; c++)
+    for (int c = 0; c < 4; c++)
     {
         if (!hit[c]) continue;
         if (ref[c] & 0x80000000u)
@@ -266,7 +269,7 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
         }
         else
         {
-            // both children are inner nodes: continue with the nearer, push the farther
+            // another inner child: keep the nearer as the one to descend, push the farther
             const bool swap = tn[c] < next_t;
             stack_ref[tv.sp] = swap ? next : ref[c];
             stack_t[tv.sp] = swap ? next_t : tn[c];

@@ -322,7 +322,7 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     if (rc) return rc;
     const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
     if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
-    if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or tree deeper than %d)", BVH_STACK - 2);
+    if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or 4-wide tree deeper than %d)", (BVH_STACK - 2) / 3);
     if (pipe > RTCU_PIPE_WAVEFRONT) return fail(RTCU_ERR_INVALID, "bad pipeline selector %u", pipe);
     const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
     p.accum = d_accum;
@@ -461,6 +461,131 @@ size_t padded(size_t bytes) { return ((bytes + 255) & ~(size_t)255) + 256; }
 
 namespace {
 
+// ---- device BVH: the host builder's binary tree (bvh.h) collapsed to 4-wide nodes ---------------------------------------
+// A 4-wide node holds up to four child boxes: the two children of a binary node, the larger inner ones replaced by their own
+// children until four are reached (greedy by surface area).  Halving the depth halves the node visits of a traversal, and a
+// visit's fixed cost (loads, child ordering, stack) is paid once for four slab tests instead of twice for two each.
+// Layout (8 float4 = 128 B per node): children (0,1) as centre / half-extent {c0,c1,h0,h1} for x, y, z, the same for children
+// (2,3), then the four child references and the four H = h.x + h.y + h.z.  h is rounded outward so that [c - h, c + h]
+// contains the builder's box; an empty slot has h = -inf and can never be hit.  Leaves: see SceneDev::leaf_blk.
+struct Kid4 {
+    float lo[3], hi[3];
+    int32_t child;  // >= 0: binary inner node; < 0: leaf, first primitive = ~child
+    uint32_t count; // primitives of a leaf (0 = empty)
+};
+
+Kid4 kid_of(const rtcu_bvh::Node& nd, int c)
+{
+    Kid4 k;
+    k.lo[0] = nd.x[2 * c]; k.hi[0] = nd.x[2 * c + 1];
+    k.lo[1] = nd.y[2 * c]; k.hi[1] = nd.y[2 * c + 1];
+    k.lo[2] = nd.z[2 * c]; k.hi[2] = nd.z[2 * c + 1];
+    k.child = nd.child[c];
+    k.count = nd.count[c];
+    return k;
+}
+
+void pack_bvh4(const rtcu_bvh::Result& bvh, const std::vector<float4>& sph, std::vector<float4>& nodes_dev, std::vector<float4>& leaf_blk,
+               uint32_t& depth4)
+{
+    struct Work { int32_t binary; uint32_t depth; };
+    std::vector<Work> queue{ Work{ 0, 1 } }; // breadth-first: a node's index in the 4-wide array is its position in the queue
+    const float ninf = -__builtin_inff();
+    depth4 = 0;
+    for (size_t qi = 0; qi < queue.size(); qi++)
+    {
+        const Work w = queue[qi];
+        depth4 = std::max(depth4, w.depth);
+        Kid4 kids[4];
+        int nk = 2;
+        kids[0] = kid_of(bvh.nodes[(size_t)w.binary], 0);
+        kids[1] = kid_of(bvh.nodes[(size_t)w.binary], 1);
+        while (nk < 4)
+        {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int j = 0; j < nk; j++)
+            {
+                if (kids[j].child < 0) continue;
+                const float dx = kids[j].hi[0] - kids[j].lo[0], dy = kids[j].hi[1] - kids[j].lo[1], dz = kids[j].hi[2] - kids[j].lo[2];
+                const float area = dx * dy + dy * dz + dz * dx;
+                if (area > best_area) { best_area = area; best = j; }
+            }
+            if (best < 0) break;
+            const rtcu_bvh::Node& nd = bvh.nodes[(size_t)kids[best].child];
+            kids[best] = kid_of(nd, 0);
+            kids[nk++] = kid_of(nd, 1);
+        }
+        float cen[4][3], half[4][3], hsum[4];
+        uint32_t ref[4];
+        for (int c = 0; c < 4; c++)
+        {
+            const bool empty = c >= nk || (kids[c].child < 0 && kids[c].count == 0) || !(kids[c].lo[0] <= kids[c].hi[0]);
+            ref[c] = 0x80000000u; // an empty slot points at leaf 0 but is never hit
+            if (empty)
+            {
+                for (int k = 0; k < 3; k++) { cen[c][k] = 0.0f; half[c][k] = ninf; }
+                hsum[c] = ninf;
+                continue;
+            }
+            double hs = 0.0;
+            for (int k = 0; k < 3; k++)
+            {
+                const float lo = kids[c].lo[k], hi = kids[c].hi[k];
+                const float ce = (float)(0.5 * ((double)lo + (double)hi));
+                const double need = std::max((double)hi - (double)ce, (double)ce - (double)lo);
+                float h = (float)need;
+                if ((double)h < need) h = nextafterf(h, __builtin_inff());
+                cen[c][k] = ce;
+                half[c][k] = h;
+                hs += (double)h;
+            }
+            hsum[c] = (float)hs;
+            if ((double)hsum[c] < hs) hsum[c] = nextafterf(hsum[c], __builtin_inff());
+            if (kids[c].child >= 0)
+            {
+                ref[c] = (uint32_t)queue.size();
+                queue.push_back(Work{ kids[c].child, w.depth + 1 });
+                continue;
+            }
+            // a leaf becomes one 80-byte block: its 1-4 spheres as two packed pairs of the sweep's layout (padded with never-hit
+            // spheres), then their four original indices as bit patterns
+            const uint32_t leaf = (uint32_t)(leaf_blk.size() / 5);
+            ref[c] = 0x80000000u | leaf;
+            const float4 never = make_float4(0.0f, 0.0f, 0.0f, ninf);
+            float4 sp[4];
+            uint32_t idx[4];
+            for (uint32_t k = 0; k < 4; k++)
+            {
+                const bool real = k < kids[c].count;
+                idx[k] = real ? bvh.order[(size_t)(~kids[c].child) + k] : 0x7fffffffu;
+                sp[k] = real ? sph[idx[k]] : never;
+            }
+            for (int pr = 0; pr < 2; pr++)
+            {
+                leaf_blk.push_back(make_float4(sp[2 * pr].x, sp[2 * pr + 1].x, sp[2 * pr].y, sp[2 * pr + 1].y));
+                leaf_blk.push_back(make_float4(sp[2 * pr].z, sp[2 * pr + 1].z, sp[2 * pr].w, sp[2 * pr + 1].w));
+            }
+            float4 ib;
+            memcpy(&ib, idx, sizeof ib);
+            leaf_blk.push_back(ib);
+        }
+        for (int pr = 0; pr < 2; pr++)
+            for (int k = 0; k < 3; k++)
+                nodes_dev.push_back(make_float4(cen[2 * pr][k], cen[2 * pr + 1][k], half[2 * pr][k], half[2 * pr + 1][k]));
+        float4 refs;
+        memcpy(&refs, ref, sizeof refs);
+        nodes_dev.push_back(refs);
+        nodes_dev.push_back(make_float4(hsum[0], hsum[1], hsum[2], hsum[3]));
+    }
+    if (leaf_blk.empty()) // every reference needs a block to point at
+        for (int k = 0; k < 5; k++) leaf_blk.push_back(make_float4(0.0f, 0.0f, ninf, ninf));
+}
+
+} // namespace
+
+namespace {
+
 // ---- rasterizer (rasterizer.cpp:22-88) ---------------------------------------------------------------------------------
 int launch_rasterize(rtcu_ctx* ctx, const rtcu_view* v, uint32_t* d_rgba8, uint32_t* d_prim, float* d_depth, cudaStream_t st)
 {
@@ -487,7 +612,7 @@ int launch_rasterize(rtcu_ctx* ctx, const rtcu_view* v, uint32_t* d_rgba8, uint3
     const dim3 grid((v->tile_x1 - v->tile_x0 + RASTER_TILE_W - 1) / RASTER_TILE_W, (v->tile_y1 - v->tile_y0 + RASTER_TILE_H - 1) / RASTER_TILE_H);
     const uint32_t accel = v->flags & 0xFu;
     if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
-    if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or tree deeper than %d)", BVH_STACK - 2);
+    if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or 4-wide tree deeper than %d)", (BVH_STACK - 2) / 3);
     const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
     if (use_bvh) k_rasterize<true><<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, ctx->scene, p);
     else k_rasterize<false><<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, ctx->scene, p);
@@ -723,102 +848,27 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     ctx->scene.bvh_nodes = nullptr;
     ctx->scene.leaf_blk = nullptr;
     ctx->scene.n_bvh_nodes = 0;
-    std::vector<float4> nodes_dev, leaf_sph;
-    std::vector<uint32_t> leaf_idx;
+    std::vector<float4> nodes_dev, leaf_blk;
     if (s->n_spheres)
     {
         const auto t0 = std::chrono::steady_clock::now();
         const rtcu_bvh::Result bvh = rtcu_bvh::build(s->spheres, s->n_spheres);
         ctx->ms_bvh_build = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ctx->bvh_depth = bvh.max_depth;
-        if (bvh.max_depth + 2 <= (uint32_t)BVH_STACK && s->n_spheres < (1u << 29))
+        uint32_t depth4 = 0;
+        if (s->n_spheres < (1u << 29))
+            pack_bvh4(bvh, sph, nodes_dev, leaf_blk, depth4);
+        // a visit pushes at most three children: the traversal stack needs 3 entries per level
+        if (!nodes_dev.empty() && 3 * depth4 + 2 <= (uint32_t)BVH_STACK)
         {
-            nodes_dev.resize(4 * bvh.nodes.size());
-            for (size_t i = 0; i < bvh.nodes.size(); i++)
-            {
-                const rtcu_bvh::Node& nd = bvh.nodes[i];
-                // host node: {l.lo, l.hi, r.lo, r.hi} per axis -> device: centre / half-extent {l.c, r.c, l.h, r.h} with h
-                // rounded outward so that [c - h, c + h] contains [lo, hi]; an empty child (lo > hi) gets h = -inf: never hit
-                float cen[2][3], half[2][3], hsum[2];
-                const float* axes[3] = { nd.x, nd.y, nd.z };
-                for (int c = 0; c < 2; c++)
-                {
-                    double hs = 0.0;
-                    for (int k = 0; k < 3; k++)
-                    {
-                        const float lo = axes[k][2 * c], hi = axes[k][2 * c + 1];
-                        if (!(lo <= hi))
-                        {
-                            cen[c][k] = 0.0f;
-                            half[c][k] = -__builtin_inff();
-                            hs = -__builtin_inf();
-                            continue;
-                        }
-                        const float ce = (float)(0.5 * ((double)lo + (double)hi));
-                        const double need = std::max((double)hi - (double)ce, (double)ce - (double)lo);
-                        float h = (float)need;
-                        if ((double)h < need) h = nextafterf(h, __builtin_inff());
-                        cen[c][k] = ce;
-                        half[c][k] = h;
-                        hs += (double)h;
-                    }
-                    float H = (float)hs;
-                    if ((double)H < hs) H = nextafterf(H, __builtin_inff());
-                    hsum[c] = H;
-                }
-                nodes_dev[4 * i + 0] = make_float4(cen[0][0], cen[1][0], half[0][0], half[1][0]);
-                nodes_dev[4 * i + 1] = make_float4(cen[0][1], cen[1][1], half[0][1], half[1][1]);
-                nodes_dev[4 * i + 2] = make_float4(cen[0][2], cen[1][2], half[0][2], half[1][2]);
-                // leaves become fixed 4-sphere blocks in the packed pair layout of the sweep (two pairs = 4 float4, padded with
-                // never-hit spheres) + their 4 original indices: a leaf visit is two straight-line FFMA2 pair tests
-                uint32_t ref[2];
-                for (int c = 0; c < 2; c++)
-                {
-                    if (nd.child[c] >= 0)
-                    {
-                        ref[c] = (uint32_t)nd.child[c];
-                        continue;
-                    }
-                    const uint32_t leaf = (uint32_t)(leaf_idx.size() / 4);
-                    ref[c] = 0x80000000u | leaf;
-                    const float4 never = make_float4(0.0f, 0.0f, 0.0f, -__builtin_inff());
-                    float4 sp[4];
-                    for (uint32_t k = 0; k < 4; k++)
-                    {
-                        const bool real = k < nd.count[c];
-                        const uint32_t orig = real ? bvh.order[(size_t)(~nd.child[c]) + k] : 0x7fffffffu;
-                        sp[k] = real ? sph[orig] : never;
-                        leaf_idx.push_back(orig);
-                    }
-                    for (int pr = 0; pr < 2; pr++)
-                    {
-                        leaf_sph.push_back(make_float4(sp[2 * pr].x, sp[2 * pr + 1].x, sp[2 * pr].y, sp[2 * pr + 1].y));
-                        leaf_sph.push_back(make_float4(sp[2 * pr].z, sp[2 * pr + 1].z, sp[2 * pr].w, sp[2 * pr + 1].w));
-                    }
-                }
-                float4 meta;
-                memcpy(&meta.x, &ref[0], 4);
-                memcpy(&meta.y, &ref[1], 4);
-                meta.z = hsum[0];
-                meta.w = hsum[1];
-                nodes_dev[4 * i + 3] = meta;
-            }
-            if (leaf_idx.empty()) { leaf_idx.assign(4, 0x7fffffffu); leaf_sph.assign(4, make_float4(0.0f, 0.0f, -__builtin_inff(), -__builtin_inff())); }
-            // one 80-byte block per leaf: its two packed pairs, then its four indices as bit patterns
-            std::vector<float4> leaf_blk(5 * (leaf_idx.size() / 4));
-            for (size_t l = 0; l < leaf_idx.size() / 4; l++)
-            {
-                for (int k = 0; k < 4; k++) leaf_blk[5 * l + k] = leaf_sph[4 * l + k];
-                memcpy(&leaf_blk[5 * l + 4], &leaf_idx[4 * l], sizeof(float4));
-            }
+            ctx->bvh_depth = depth4;
             CU(ctx->bvh_nodes.reserve(nodes_dev.size()));
             CU(ctx->leaf_blk.reserve(leaf_blk.size()));
             CU(cudaMemcpyAsync(ctx->bvh_nodes.p, nodes_dev.data(), nodes_dev.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaMemcpyAsync(ctx->leaf_blk.p, leaf_blk.data(), leaf_blk.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream)); // leaf_blk dies with this scope
             ctx->scene.bvh_nodes = ctx->bvh_nodes.p;
             ctx->scene.leaf_blk = ctx->leaf_blk.p;
-            ctx->scene.n_bvh_nodes = (uint32_t)bvh.nodes.size();
+            ctx->scene.n_bvh_nodes = (uint32_t)(nodes_dev.size() / 8);
             ctx->have_bvh = true;
         }
     }
