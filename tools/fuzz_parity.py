@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Randomised parity campaign on a GPU box: N random scenes (1-300 spheres, 0-3 planes, all eight material types, random
 cameras, both scatter tables) rendered by the CUDA path (linear scan, BVH, wavefront pipeline, ray-pool kernel) and by the
-strict CPU oracle; closest hits of random + silhouette-grazing ray batches compared bit for bit.  Prints one JSON summary.
+strict CPU oracle; closest hits of random + silhouette-grazing ray batches compared bit for bit; the preview renderer
+(rtcu_rasterize, scan and BVH, with random boxes) compared bit for bit (pixels, primitive ids, depth).  Prints one JSON summary.
 usage: python tools/fuzz_parity.py [n_scenes] [seed]"""
 import json, os, pathlib, sys
 
@@ -16,7 +17,8 @@ from rt_b200.renderer import Context, make_view  # noqa: E402
 n_scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 oracle, ctx = Oracle("strict"), Context(0)
-stats = dict(scenes=0, renders=0, rays=0, seg_mismatch=0, accum_max_rel=0.0, rgba_max_lsb=0, hit_mismatch=0, bvh_vs_linear_mismatch=0, failures=[])
+stats = dict(scenes=0, renders=0, rays=0, seg_mismatch=0, accum_max_rel=0.0, rgba_max_lsb=0, hit_mismatch=0, bvh_vs_linear_mismatch=0,
+             raster_frames=0, raster_mismatch=0, failures=[])
 
 
 def random_scene(seed):
@@ -37,6 +39,9 @@ def random_scene(seed):
         nrm = rng.normal(size=(npl, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
         sc.planes = np.concatenate([nrm, rng.uniform(0.5, 8, (npl, 1))], axis=1).astype(np.float32)
         sc.plane_material = rng.integers(0, k, npl).astype(np.uint32)
+    nb = int(rng.integers(0, 5)) if rng.random() < 0.5 else 0  # drawn by the rasterizer only
+    sc.boxes = np.concatenate([rng.normal(0, spread, (nb, 3)), rng.uniform(0.05, 2.0, (nb, 3))], axis=1).astype(np.float32)
+    sc.box_material = rng.integers(0, k, nb).astype(np.uint32)
     d = rng.normal(size=3); d[1] *= 0.3
     sc.camera = S.Camera(position=tuple(float(x) for x in rng.normal(0, spread * 1.5, 3) + [0, 1, 0]), direction=tuple(float(x) for x in d))
     return sc, rng
@@ -76,6 +81,16 @@ for i in range(n_scenes):
             stats["rays"] += len(o)
             stats["hit_mismatch"] += int(sum((a != b).sum() for a, b in zip(lin, orc)))
             stats["bvh_vs_linear_mismatch"] += int(sum((a != b).sum() for a, b in zip(bvh, lin)))
+        pv = make_view(sc, w, h)
+        expect = oracle.rasterize(sc, pv)
+        for accel in (nat.ACCEL_LINEAR, nat.ACCEL_BVH):
+            pv.flags = accel
+            got = ctx.rasterize(pv, want_prim=True, want_depth=True)
+            stats["raster_frames"] += 1
+            bad = int((got[0] != expect[0]).sum() + (got[1] != expect[1]).sum() + (got[2].view(np.uint32) != expect[2].view(np.uint32)).sum())
+            if bad:
+                stats["raster_mismatch"] += bad
+                stats["failures"].append((i, "raster", accel, bad))
         stats["scenes"] += 1
     except Exception as e:  # keep going, report at the end
         stats["failures"].append((i, "exception", str(e)[:200]))
