@@ -144,8 +144,6 @@ template <bool ANY_T = false>
 __device__ __forceinline__ void bvh_leaf_candidate(const float a, const float e2, const float r2, const float disc, const int index,
                                                    float& best_t, int& best_i)
 {
-    if (!ANY_T && !(e2 < r2) && a < 0.0f)
-        return; // t = a - f <= a < 0 fails the 0.001 filter: no sqrt (see sphere_candidate)
     const float f = __fsqrt_rn(disc);
     const float t = (e2 < r2) ? __fadd_rn(a, f) : __fsub_rn(a, f);
     if ((ANY_T || !(t < 0.001f)) && (t < best_t || (t == best_t && index < best_i)))
