@@ -218,11 +218,18 @@ def run_gpu(args):
     view = make_view(scene, WIDTH, HEIGHT, samples_per_pixel=total_spp, max_bounces=MAX_BOUNCES, material_mode=nat.MODE_SM)
     mine = rdist.partition_view(view, rank, world, by="samples")
     gr = rdist.GpuRank(ctx, WIDTH, HEIGHT, dev, world=world)
+    peer = world > 1 and args.exchange == "peer"
+    if peer:
+        gr.enable_peer_exchange(rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
     def step_device():
-        if world > 1:
+        if peer:
+            # trace into an IPC-shared buffer -> barrier -> ONE kernel per rank: peer-load sum of its row band + resolve +
+            # store into rank 0's image over NVLink -> barrier
+            gr.render_peer_reduce_resolve(mine, total_spp)
+        elif world > 1:
             # trace -> reduce-scatter fp32 row bands (NCCL) -> resolve the band on every rank -> gather RGBA8 bands on rank 0
             gr.render_reduce_resolve(mine, rank, total_spp)
         else:
@@ -247,9 +254,17 @@ def run_gpu(args):
             tdist.barrier()
         ev[i][0].record(stream)
         kev[i][0].record(stream)
-        accum = gr.render_accum(mine)
+        if peer:
+            ctx.render_device(mine, gr.peer_accum, accumulate=False, stream=stream.cuda_stream)
+        else:
+            accum = gr.render_accum(mine)
         kev[i][1].record(stream)
-        if world > 1:
+        if peer:
+            tdist.all_reduce(gr._peer_sync)
+            row0, row1 = rdist.row_band_for_rank(0, HEIGHT, rank, world)
+            ctx.reduce_resolve_rows(gr.peer_accums, WIDTH, row0, row1 - row0, total_spp, gr.peer_img, stream=stream.cuda_stream)
+            tdist.all_reduce(gr._peer_sync)
+        elif world > 1:
             band = rdist.sum_row_bands(gr.accum_padded, rank, world)
             rdist.gather_bands(gr.resolve_band(band, total_spp), HEIGHT, rank, world)
         else:
@@ -284,7 +299,7 @@ def run_gpu(args):
         if world == 1:
             ctx.render(view, rgba8=host_np, want_accum=False)  # rtcu_render: launch + D2H into the pinned buffer + sync
         else:
-            img = gr.render_reduce_resolve(mine, rank, total_spp)
+            img = gr.render_peer_reduce_resolve(mine, total_spp) if peer else gr.render_reduce_resolve(mine, rank, total_spp)
             if rank == 0:
                 host_rgba.copy_(img, non_blocking=False)
             torch.cuda.synchronize(dev)
@@ -341,7 +356,9 @@ def run_gpu(args):
             "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_total": total_spp, "max_bounces": MAX_BOUNCES,
-                       "n_spheres": n_sph, "partition": "sample-range" if world > 1 else "single", "seed": view.seed,
+                       "n_spheres": n_sph, "partition": "sample-range" if world > 1 else "single",
+                       "exchange": ("fused peer-load reduce+resolve kernel over CUDA IPC / NVLink" if peer else "NCCL reduce-scatter + gather") if world > 1 else None,
+                       "seed": view.seed,
                        "l2": "flushed between steps (256 MiB fill, outside the per-step CUDA events)",
                        "pipeline": "megakernel", "accel": "linear"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
@@ -364,6 +381,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--exchange", choices=("peer", "nccl"), default="peer",
+                    help="N > 1: 'peer' = IPC-shared buffers + one fused NVLink reduce/resolve kernel per rank; 'nccl' = reduce-scatter + gather")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.steps < 1:

@@ -186,6 +186,19 @@ int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t k
 
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out);
 
+/* ---- one process per GPU (torch.distributed / MPI style launches): the exchange step without a collective library.
+ * rtcu_ipc_alloc allocates a zeroed device buffer and returns its 64-byte CUDA IPC handle; the other ranks of the node map
+ * it with rtcu_ipc_open (NVLink peer access).  rtcu_reduce_resolve_rows then sums the n_bufs accumulation buffers in the
+ * order given (use rank order for a deterministic result) over image rows [row0, row0 + rows) and writes the resolved
+ * RGBA8 pixels (mg_ray_tracer.cpp:195-200) into d_rgba8 -- the full-image buffer of the destination rank, own or mapped --
+ * in one kernel on `stream`.  The caller orders it after every rank's render (any barrier on the stream) and keeps the
+ * buffers unchanged until every rank's reduce has finished.  rtcu_ipc_release frees / unmaps; rtcu_destroy does so too. */
+int rtcu_ipc_alloc(rtcu_ctx* ctx, uint64_t bytes, void** d_ptr, unsigned char handle[64]);
+int rtcu_ipc_open(rtcu_ctx* ctx, const unsigned char handle[64], void** d_ptr);
+int rtcu_ipc_release(rtcu_ctx* ctx, void* d_ptr);
+int rtcu_reduce_resolve_rows(rtcu_ctx* ctx, const float* const* d_accums, uint32_t n_bufs, uint32_t width, uint32_t row0, uint32_t rows,
+                             uint32_t spp, uint32_t* d_rgba8, void* stream);
+
 /* exhaustive device-side check of the kernels' cheaper-but-exact square root / reciprocal / constant-divisor division
  * (rt_b200/csrc/spec.cuh) against the IEEE intrinsics: counts[0..1] = float patterns (of all 2^32) where sqrt / 1/sqrt
  * differ, counts[2] = differing quotients over every float a in {0} u [2^-24, 2^24] and every b in divisors (each in

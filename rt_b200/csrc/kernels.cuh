@@ -5,7 +5,8 @@
 //                     instead of recursed).  Linear scenes: primitives staged in shared memory as packed pairs, read as
 //                     warp-uniform LDS.128, two spheres per FFMA2.  BVH scenes: closest_hit_bvh (exact, conservative culls).
 //   k_render_stragglers<BVH>        second pass: one warp per pixel that exceeded its per-thread segment budget
-//   k_resolve / k_reduce_resolve    sum / spp, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200), the latter + NVLink peer sums
+//   k_resolve / k_reduce_resolve / k_reduce_resolve_rows   sum / spp, sqrt, clamp, pack (mg_ray_tracer.cpp:195-200); the
+//                                   latter two fused with the cross-GPU sum over NVLink peer loads (one process / one per GPU)
 //   k_intersect_batch / k_primary_rays / k_scatter_batch / k_philox_batch   step-wise parity kernels
 //   k_fp32_peak                     FFMA / FFMA2 calibration stream for the roofline denominator
 //   k_selftest_math                 exhaustive comparison of spec.cuh's cheaper sqrt / rcp / div with the IEEE intrinsics
@@ -676,6 +677,26 @@ __global__ void k_reduce_resolve(float4* __restrict__ accum, const PeerList peer
         accum[i] = a;
         if (rgba8)
             rgba8[i] = pack_pixel(a.x, a.y, a.z, spp);
+    }
+}
+
+// The same for one process per GPU: bufs[g] are all ranks' accumulation buffers (the rank's own plus the peers' buffers
+// opened through CUDA IPC and read over NVLink), summed in rank order 0, 1, 2, ... for the pixels [first, first + count) of
+// this rank's row band; the packed pixels go straight into the destination rank's image (a peer store when that is
+// another GPU).  One kernel is the whole exchange step: no staging copy, no collective library on the data path.
+__global__ void __launch_bounds__(256) k_reduce_resolve_rows(const PeerList bufs, uint32_t first, uint32_t count, float spp, uint32_t* __restrict__ rgba8)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count)
+    {
+        const uint32_t i = first + k;
+        float4 a = bufs.ptr[0][i];
+        for (int g = 1; g < bufs.n; g++)
+        {
+            const float4 b = bufs.ptr[g][i];
+            a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+        }
+        rgba8[i] = pack_pixel(a.x, a.y, a.z, spp);
     }
 }
 

@@ -147,6 +147,9 @@ struct rtcu_ctx {
     // scratch for the batch entry points
     DevBuf<unsigned char> scratch;
 
+    // buffers shared between the processes of a multi-GPU job through CUDA IPC: {pointer, owned (cudaMalloc here) or opened}
+    std::vector<std::pair<void*, bool>> ipc;
+
     rtcu_stats stats = {};
     cudaStream_t last_stream = nullptr; // stream of the last rtcu_render_device call
     bool counters_pending = false;      // its counters have not been read back yet
@@ -733,6 +736,11 @@ void rtcu_destroy(rtcu_ctx* ctx)
     ctx->boxes.release(); ctx->box_mat.release(); ctx->albedo.release(); ctx->raster_prim.release(); ctx->raster_depth.release();
     ctx->h_raster_prim.release(); ctx->h_raster_depth.release();
     ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
+    for (auto& b : ctx->ipc)
+    {
+        if (b.second) cudaFree(b.first);
+        else cudaIpcCloseMemHandle(b.first);
+    }
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->copy_events)
@@ -1125,6 +1133,81 @@ int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* vi
     root->stats.sphere_tests = segs * root->scene.n_spheres;
     root->stats.samples = (uint64_t)(view->tile_x1 - view->tile_x0) * (view->tile_y1 - view->tile_y0) * total;
     root->stats.kernel_launches = n_ctx + 1;
+    return RTCU_OK;
+}
+
+// ---- one process per GPU: buffers shared through CUDA IPC, exchange fused into the resolve kernel -------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "rtcu_ipc_* pass the handle as 64 opaque bytes");
+
+int rtcu_ipc_alloc(rtcu_ctx* ctx, uint64_t bytes, void** d_ptr, unsigned char handle[64])
+{
+    if (!ctx || !bytes || !d_ptr || !handle) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess)
+    {
+        cudaFree(p);
+        return fail(RTCU_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(handle, &h, 64);
+    ctx->ipc.emplace_back(p, true);
+    *d_ptr = p;
+    return RTCU_OK;
+}
+
+int rtcu_ipc_open(rtcu_ctx* ctx, const unsigned char handle[64], void** d_ptr)
+{
+    if (!ctx || !handle || !d_ptr) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc.emplace_back(p, false);
+    *d_ptr = p;
+    return RTCU_OK;
+}
+
+int rtcu_ipc_release(rtcu_ctx* ctx, void* d_ptr)
+{
+    if (!ctx || !d_ptr) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < ctx->ipc.size(); i++)
+        if (ctx->ipc[i].first == d_ptr)
+        {
+            const bool owned = ctx->ipc[i].second;
+            ctx->ipc.erase(ctx->ipc.begin() + (long)i);
+            CU(cudaDeviceSynchronize());
+            if (owned) CU(cudaFree(d_ptr));
+            else CU(cudaIpcCloseMemHandle(d_ptr));
+            return RTCU_OK;
+        }
+    return fail(RTCU_ERR_INVALID, "not a buffer of rtcu_ipc_alloc / rtcu_ipc_open");
+}
+
+int rtcu_reduce_resolve_rows(rtcu_ctx* ctx, const float* const* d_accums, uint32_t n_bufs, uint32_t width, uint32_t row0, uint32_t rows, uint32_t spp,
+                             uint32_t* d_rgba8, void* stream)
+{
+    if (!ctx || !d_accums || !d_rgba8 || !width || !spp) return fail(RTCU_ERR_INVALID, "bad argument");
+    if (n_bufs == 0 || n_bufs > 8) return fail(RTCU_ERR_INVALID, "1..8 buffers");
+    if ((uint64_t)width * ((uint64_t)row0 + rows) > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "image too large");
+    PeerList bufs;
+    bufs.n = (int)n_bufs;
+    for (uint32_t g = 0; g < n_bufs; g++)
+    {
+        if (!d_accums[g]) return fail(RTCU_ERR_INVALID, "buffer %u is null", g);
+        bufs.ptr[g] = reinterpret_cast<const float4*>(d_accums[g]);
+    }
+    if (rows == 0) return RTCU_OK;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t count = width * rows;
+    k_reduce_resolve_rows<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bufs, width * row0, count, (float)spp, d_rgba8);
+    CU(cudaGetLastError());
     return RTCU_OK;
 }
 

@@ -1,6 +1,12 @@
 """Multi-GPU composition: one process per GPU, sample-range (and optional row-band) partition, one
 reduce of the fp32 accumulation buffers.
 
+Two exchanges are implemented.  "peer" (default on NCCL/NVLink): every rank renders into a buffer shared through CUDA IPC,
+and after a stream-ordered barrier ONE kernel per rank (rtcu_reduce_resolve_rows) sums all ranks' buffers over its row
+band through NVLink peer loads, resolves, and stores the packed pixels straight into rank 0's image -- no staging, no
+collective on the data path, deterministic sum order.  "nccl": reduce-scatter of the fp32 row bands, resolve per rank,
+gather of the packed bands (also what the gloo CPU tests exercise through all-reduce).
+
 Every (pixel, sample) is independent under the counter-based RNG (key = seed, counter = pixel, sample,
 block), so rank g of G renders global sample indices [g*spp/G, (g+1)*spp/G) of the whole image and the
 only exchange is `torch.distributed.reduce(accum, dst=0, SUM)` over NCCL/NVLink; rank 0 then resolves
@@ -95,6 +101,13 @@ def gather_bands(band_rgba8, height: int, rank: int, world: int, dst: int = 0, g
     return torch.cat(parts, dim=0)[:height]
 
 
+class _DeviceArray:
+    """__cuda_array_interface__ over a raw device pointer, so torch can view library-owned memory without copying"""
+
+    def __init__(self, ptr: int, shape: tuple, typestr: str):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
 class GpuRank:
     """One rank's device state for bench.py / multi-GPU runs: a Context plus torch-owned frame buffers."""
 
@@ -132,6 +145,40 @@ class GpuRank:
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
         self.ctx.resolve_device(band_accum.data_ptr(), self.width, self.band, spp, self.band_rgba8.data_ptr(), stream=stream)
         return self.band_rgba8
+
+    # ---- "peer" exchange: IPC-shared buffers + the fused reduce/resolve kernel ---------------------------------
+    def enable_peer_exchange(self, rank: int, dst: int = 0, group=None) -> None:
+        """Allocates this rank's accumulation buffer (and, on `dst`, the packed image) as CUDA-IPC-exportable memory in
+        the library, swaps the handles between the ranks and maps the peers' buffers (NVLink peer access)."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        npix = self.width * self.height
+        self.peer_rank, self.peer_dst = rank, dst
+        self.peer_accum, h_accum = self.ctx.ipc_alloc(npix * 16)
+        h_img = None
+        if rank == dst:
+            self.peer_img, h_img = self.ctx.ipc_alloc(npix * 4)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (h_accum, h_img), group=group)
+        self.peer_accums = [self.peer_accum if g == rank else self.ctx.ipc_open(handles[g][0]) for g in range(self.world)]
+        if rank != dst:
+            self.peer_img = self.ctx.ipc_open(handles[dst][1])
+        self._peer_sync = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if rank == dst:  # the image as a torch tensor over the library's memory (for read-back through torch)
+            self.peer_rgba8 = torch.as_tensor(_DeviceArray(self.peer_img, (self.height, self.width), "<i4"), device=self.device)
+
+    def render_peer_reduce_resolve(self, view: nat.View, spp_total: int, group=None):
+        """One multi-GPU frame without a collective on the data path.  Returns the (H, W) packed image on dst, None elsewhere."""
+        import torch.distributed as dist
+
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.render_device(view, self.peer_accum, accumulate=False, stream=stream)
+        dist.all_reduce(self._peer_sync, group=group)  # stream-ordered barrier: every rank's buffer is complete
+        row0, row1 = row_band_for_rank(0, self.height, self.peer_rank, self.world)
+        self.ctx.reduce_resolve_rows(self.peer_accums, self.width, row0, row1 - row0, spp_total, self.peer_img, stream=stream)
+        dist.all_reduce(self._peer_sync, group=group)  # every band is stored; the buffers may be overwritten again
+        return self.peer_rgba8 if self.peer_rank == self.peer_dst else None
 
     def render_reduce_resolve(self, view: nat.View, rank: int, spp_total: int, dst: int = 0):
         """One multi-GPU frame: trace this rank's share, reduce-scatter the fp32 sums by row band, resolve the band here,

@@ -223,6 +223,25 @@ class Context:
         nat.check(self._lib.rtcu_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    # -- one process per GPU: IPC-shared buffers and the fused exchange ---------------------------------
+    def ipc_alloc(self, nbytes: int) -> tuple[int, bytes]:
+        """(device pointer, 64-byte CUDA IPC handle) of a zeroed buffer owned by this context"""
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        nat.check(self._lib.rtcu_ipc_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle.raw)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        nat.check(self._lib.rtcu_ipc_open(self._h, C.create_string_buffer(handle, 64), C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_release(self, ptr: int) -> None:
+        nat.check(self._lib.rtcu_ipc_release(self._h, ptr))
+
+    def reduce_resolve_rows(self, accum_ptrs: Sequence[int], width: int, row0: int, rows: int, spp: int, d_rgba8_ptr: int, stream: int = 0) -> None:
+        arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
+        nat.check(self._lib.rtcu_reduce_resolve_rows(self._h, arr, len(accum_ptrs), width, row0, rows, spp, d_rgba8_ptr, stream or None))
+
     def selftest_math(self, divisors=(800, 600, 1920, 1080, 3840, 2160)) -> dict:
         """rtcu_selftest_math: mismatches of the kernels' cheaper exact sqrt / rcp / division against the IEEE intrinsics"""
         d = nat.contiguous(divisors, np.float32)

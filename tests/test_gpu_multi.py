@@ -39,3 +39,66 @@ def test_render_multi_matches_single_device(ctx, scenes, ngpu):
     finally:
         for c in ctxs:
             c.close()
+
+
+def _peer_worker(rank: int, world: int, port: int, out_path: str):
+    """one process per GPU: the fused peer exchange of rt_b200.dist (IPC-shared buffers, rtcu_reduce_resolve_rows)"""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from rt_b200 import dist as rdist, scene as S
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        sc = S.load("scenes/dielectric.toml")
+        ctx = Context(rank)
+        ctx.upload_scene(sc)
+        w, h, spp = 640, 360, 64
+        view = make_view(sc, w, h, samples_per_pixel=spp, max_bounces=50, material_mode=nat.MODE_SM)
+        mine = rdist.partition_view(view, rank, world)
+        gr = rdist.GpuRank(ctx, w, h, dev, world=world)
+        gr.enable_peer_exchange(rank)
+        frames = []
+        for _ in range(3):  # buffers are reused frame after frame: the second barrier must protect them
+            img = gr.render_peer_reduce_resolve(mine, spp)
+            torch.cuda.synchronize(dev)
+            if rank == 0:
+                frames.append(img.cpu().numpy().view(np.uint32).copy())
+        nccl = gr.render_reduce_resolve(mine, rank, spp)  # the NCCL exchange on the same share
+        torch.cuda.synchronize(dev)
+        if rank == 0:
+            np.savez(out_path, peer=np.stack(frames), nccl=nccl.cpu().numpy().view(np.uint32))
+        dist.barrier()
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ngpu", [2, 4])
+def test_peer_exchange_one_process_per_gpu(ctx, scenes, tmp_path, ngpu):
+    if _device_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "peer.npz")
+    mp.spawn(_peer_worker, args=(ngpu, 29650 + ngpu, out), nprocs=ngpu, join=True)
+    got = np.load(out)
+    sc = scenes["c2"][0]
+    view = make_view(sc, 640, 360, samples_per_pixel=64, max_bounces=50, material_mode=nat.MODE_SM)
+    # the single-process peer reduce (rtcu_render_multi) sums in the same device order: bit-identical
+    ctxs = [Context(g) for g in range(ngpu)]
+    try:
+        for c in ctxs:
+            c.upload_scene(sc)
+        ref, _ = render_multi(ctxs, view)
+    finally:
+        for c in ctxs:
+            c.close()
+    for frame in got["peer"]:
+        np.testing.assert_array_equal(frame, ref)
+    assert np.abs(unpack_rgba(got["nccl"]) - unpack_rgba(ref)).max() <= 1  # NCCL's sum order is its own
