@@ -41,9 +41,9 @@ WORKLOAD = "C2: scenes/dielectric.toml 1920x1080 64spp depth50 sm-table (lambert
 METRIC, UNIT = "Msamples/sec (paths*spp/s)", "Msamples/s"
 FLOP_PER_TEST, FLOP_PER_SEGMENT, FLOP_PER_SAMPLE = 18, 60, 60  # SURVEY.md 8d algorithmic work unit
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_render_mega launch on this workload, from the committed
-# `ncu --set full` capture (profiles/r1_final_ncu_summary.txt: 0.039 MB read + 0.80 MB written; the 33 MB accumulation
-# buffer stays in the 126 MB L2 for the duration of the launch)
-NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 39_170 + 802_000
+# `ncu --set full` capture (profiles/r1_final_ncu_summary.txt, first two lines: 0.040 MB read, 1.0-1.7 MB written -- the mean
+# of the two launches; the 33 MB accumulation buffer stays in the 126 MB L2 for the duration of the launch)
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 40_700 + 1_350_000
 
 
 def load_scene():
