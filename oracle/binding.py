@@ -191,6 +191,7 @@ class ReferenceBuild:
 
     PATH = HERE / "_ref" / "librt_ref.so"
     FAST_PATH = HERE / "_ref" / "librt_ref_fast.so"  # -O3 -ffast-math flavour for CPU timing
+    FAST_MT_PATH = HERE / "_ref" / "librt_ref_fast_mt.so"  # the same with the reference's own src/random.cpp (mt19937): non-deterministic
     PLUGIN_PATH = HERE / "_ref" / "librt_ref_plugin.so"  # + plugin/cuda_path_tracer.cpp against the reference's headers, linked to librtcu.so
 
     @classmethod
@@ -204,7 +205,7 @@ class ReferenceBuild:
     def __init__(self, flavour: str = "strict"):
         if not self.available():
             raise RuntimeError(f"{self.PATH} is missing and /root/reference is not present to build it")
-        path = {"fast": self.FAST_PATH, "plugin": self.PLUGIN_PATH}.get(flavour, self.PATH)
+        path = {"fast": self.FAST_PATH, "fast_mt": self.FAST_MT_PATH, "plugin": self.PLUGIN_PATH}.get(flavour, self.PATH)
         if not path.exists():
             raise RuntimeError(f"{path} is missing")
         self.lib = C.CDLL(str(path))

@@ -75,6 +75,7 @@ namespace rt::detail
 {
 	// draw n of the current event: lane n % 3 of block (pixel, sample, block, retry = n / 3) -- a unit-vector redraw
 	// (random.hpp:57-66) consumes the next retry block; the jitter (2 draws) and the dielectric draw (1) use retry 0
+#ifndef REFBIN_REFERENCE_RNG // the `_mt` flavour links the reference's own src/random.cpp (thread_local mt19937) instead
 	float random_float() noexcept
 	{
 		const uint32_t n = g_rng.draws++;
@@ -87,6 +88,7 @@ namespace rt::detail
 		}
 		return rtref_u01(g_rng.cached_out[n % 3u]);
 	}
+#endif
 }
 
 extern "C"
