@@ -254,7 +254,7 @@ def run_gpu(args):
     # ---- value: device-resident, CUDA events per step, L2 flushed between steps ----
     for _ in range(max(3, args.warmup)):
         step_device()
-    torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)  # lets the library time the first frames of this view and settle its tile issue order
     sampler = ClockSampler(local_rank)
     if world > 1:
         tdist.barrier()
@@ -376,7 +376,9 @@ def run_gpu(args):
                        "exchange": ("fused peer-load reduce+resolve kernel over CUDA IPC / NVLink" if peer else "NCCL reduce-scatter + gather") if world > 1 else None,
                        "seed": view.seed,
                        "l2": "flushed between steps (256 MiB fill, outside the per-step CUDA events)",
-                       "pipeline": "megakernel", "accel": "linear"},
+                       "pipeline": "megakernel", "accel": "linear",
+                       "tile_order": "chosen by the library per view: row-major vs descending cost of the previous frame's tiles, whichever it timed faster "
+                                     "in the warm-up frames (scheduling only: every sample is traced every step, the image is bit-identical)"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
             "gpu_launches": args.steps * 3 * world,  # per step and rank: k_render_mega, k_render_stragglers, k_resolve (band)
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

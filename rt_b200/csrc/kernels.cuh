@@ -57,6 +57,10 @@ struct RenderParams {
     uint32_t segment_budget;
     uint2* stragglers;            // queue storage, width*height entries
     unsigned int* straggler_count;
+    // longest-tile-first scheduling (see launch_render): every frame records the segments of each tile in tile_cost; the next
+    // frame of the same view takes its tiles from tile_order (tile ids by descending cost of the previous frame)
+    uint32_t* tile_cost;          // += segments traced for the CTA's tile (nullable)
+    const uint32_t* tile_order;   // CTA b renders tile tile_order[b] (nullable: CTA b renders tile b)
 };
 
 #ifndef RTCU_PRIM_MISS
@@ -459,8 +463,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
 
     // a warp covers an 8x4 pixel patch; the block a 16 x MEGA_TILE_H tile
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t px = p.tile_x0 + blockIdx.x * MEGA_TILE_W + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t py = p.tile_y0 + blockIdx.y * MEGA_TILE_H + (warp >> 1) * 4u + (lane >> 3);
+    uint32_t tile_col = blockIdx.x, tile_row = blockIdx.y;
+    const uint32_t tile_id = p.tile_order ? __ldg(p.tile_order + blockIdx.y * gridDim.x + blockIdx.x) : blockIdx.y * gridDim.x + blockIdx.x;
+    if (p.tile_order)
+    {
+        tile_col = tile_id % gridDim.x;
+        tile_row = tile_id / gridDim.x;
+    }
+    const uint32_t px = p.tile_x0 + tile_col * MEGA_TILE_W + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t py = p.tile_y0 + tile_row * MEGA_TILE_H + (warp >> 1) * 4u + (lane >> 3);
     const bool in_tile = px < p.tile_x1 && py < p.tile_y1;
 
     // (measured on C3, 484 spheres: the plain loop keeps 23/32 lanes active in the sweep, the vote loop ~29/32;
@@ -572,12 +583,87 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
     }
     if (lane == 0 && segs)
     {
+        if (p.tile_cost)
+            atomicAdd(p.tile_cost + tile_id, (uint32_t)segs);
         atomicAdd(p.counters, segs);
         if (BVH)
         {
             atomicAdd(p.counters + 1, nodes);
             atomicAdd(p.counters + 2, tests);
         }
+    }
+}
+
+// Tile ids by descending cost: a stable counting sort over 64 linear cost classes (class 0 = the most expensive), the
+// row-major order kept inside a class so that neighbouring CTAs still work on neighbouring tiles (BVH nodes and leaves stay
+// warm in L1/L2).  One CTA of 32 warps; every warp owns a contiguous chunk of tiles, counts them per class, and after one
+// block-wide exclusive scan over (class, warp) places them with match_any ranks -- deterministic.
+constexpr int TILE_CLASSES = 64;
+__device__ __forceinline__ uint32_t tile_class(uint32_t cost, uint32_t mx)
+{
+    return (uint32_t)(TILE_CLASSES - 1) - (uint32_t)((unsigned long long)min(cost, mx) * (TILE_CLASSES - 1) / mx);
+}
+__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ order)
+{
+    __shared__ uint32_t s_max;
+    __shared__ uint32_t s_cnt[TILE_CLASSES * 32]; // [class][warp]
+    __shared__ uint32_t s_part[32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) s_max = 1u;
+    for (uint32_t i = t; i < TILE_CLASSES * 32; i += 1024u) s_cnt[i] = 0u;
+    __syncthreads();
+    uint32_t m = 0;
+    for (uint32_t i = t; i < n; i += 1024u) m = max(m, cost[i]);
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, off));
+    if (lane == 0) atomicMax(&s_max, m);
+    __syncthreads();
+    const uint32_t mx = s_max;
+    const uint32_t chunk = ((n + 31u) / 32u + 31u) & ~31u; // tiles per warp, a multiple of 32
+    const uint32_t lo = min(n, warp * chunk), hi = min(n, lo + chunk);
+    for (uint32_t i = lo + lane; i < hi; i += 32u)
+        atomicAdd(&s_cnt[tile_class(cost[i], mx) * 32u + warp], 1u);
+    __syncthreads();
+    // exclusive scan of the 2048 counters in (class, warp) order: two per thread
+    const uint32_t a = s_cnt[2 * t], b = s_cnt[2 * t + 1];
+    uint32_t v = a + b;
+    for (int off = 1; off < 32; off <<= 1)
+    {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= (uint32_t)off) v += u;
+    }
+    if (lane == 31) s_part[warp] = v;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const uint32_t w = s_part[lane];
+        uint32_t x = w;
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= (uint32_t)off) x += u;
+        }
+        s_part[lane] = x - w;
+    }
+    __syncthreads();
+    const uint32_t excl = s_part[warp] + v - (a + b);
+    s_cnt[2 * t] = excl;
+    s_cnt[2 * t + 1] = excl + a;
+    __syncthreads();
+    for (uint32_t base = lo; base < hi; base += 32u)
+    {
+        const uint32_t i = base + lane;
+        const bool on = i < hi;
+        const uint32_t c = on ? tile_class(cost[i], mx) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (on)
+        {
+            const uint32_t at = s_cnt[c * 32u + warp] + __popc(peers & ((1u << lane) - 1u)); // rank in descending cost
+            order[at] = i;
+        }
+        __syncwarp();
+        if (on && lane == (uint32_t)(__ffs(peers) - 1))
+            s_cnt[c * 32u + warp] += __popc(peers);
+        __syncwarp();
     }
 }
 

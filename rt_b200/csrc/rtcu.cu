@@ -132,6 +132,16 @@ struct rtcu_ctx {
     PinnedBuf<uint32_t> h_rgba8;
     PinnedBuf<float> h_accum;
     DevBuf<unsigned long long> counters;
+    DevBuf<uint32_t> tile_cost, tile_order; // longest-tile-first scheduling of the megakernel (launch_render)
+    bool tile_hist_valid = false;           // tile_cost holds the per-tile segments of a frame of tile_hist_view
+    rtcu_view tile_hist_view = {};
+    cudaStream_t tile_hist_stream = nullptr; // ... recorded on this stream (the sort must be ordered after that frame)
+    // which issue order is faster for this view is measured, not guessed: frame 1 row-major, frame 2 sorted, then the better
+    int tile_phase = 0;                      // 0: time row-major, 1: time sorted, 2: decided
+    int tile_pending = -1;                   // phase whose timing events are in flight
+    int tile_sorted_wins = 0;
+    float tile_ms[2] = { 0.0f, 0.0f };
+    cudaEvent_t tile_ev[2] = {};
     DevBuf<uint2> stragglers;            // straggler queue of the last render (width*height entries)
     DevBuf<unsigned int> straggler_count;
     PinnedBuf<unsigned long long> h_counters;
@@ -197,6 +207,8 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     p.accum = nullptr;
     p.rgba8 = nullptr;
     p.counters = nullptr;
+    p.tile_cost = nullptr;
+    p.tile_order = nullptr;
     return RTCU_OK;
 }
 
@@ -349,29 +361,87 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     const dim3 grid((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W, (v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
     const size_t sb = stage_bytes(ctx);
     const bool flat = flat_loop_for(ctx->scene.n_spheres + ctx->scene.n_planes);
-    if (use_bvh)
+    // RTCU_BVH_KERNEL=pool selects the warp-local ray pool (pool.cuh): correct and deterministic, but measured 20-30 % slower
+    // (DESIGN.md), so it is not the default.
+    const char* which = getenv("RTCU_BVH_KERNEL");
+    const bool pool = use_bvh && which && strcmp(which, "pool") == 0;
+    if (pool) p.segment_budget = 0; // work is shared by the 32 lanes of a warp: no per-thread stragglers
+    auto launch_mega = [&](const RenderParams& q) {
+        if (pool) k_render_pool<<<grid, 32 * POOL_WARPS, 0, st>>>(ctx->scene, q);
+        else if (use_bvh) k_render_mega<false, true, true><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q); // flat loop (nested measures the same on C3/C4)
+        else if (sb > MAX_STAGE_BYTES) k_render_mega<false, true, false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q);
+        else if (flat) k_render_mega<true, true, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, q);
+        else k_render_mega<true, false, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, q);
+    };
+    // Tile issue order.  CTAs are issued in index order and a tile's cost varies several-fold with what it shows, so the tiles
+    // that happen to be issued last decide how long the tail of the grid is.  Every frame records the path segments of each
+    // tile; later frames of the same view (same matrix, size, tile, sample count, depth and material table -- the interactive
+    // app's progressive refinement, or a benchmark loop) may take the tiles in descending order of that cost (k_tile_order).
+    // Measured, longest-first is worth -15 % on C1, -20 % on C2 with the mg table, -7 % on C3, but +2 % on C2 and +1..4 % on
+    // C4, and neither a coarser classification nor interleaving expensive and cheap tiles predicts which -- so the choice
+    // is measured too: the first frame of a view runs row-major, the second sorted, both timed with events on the caller's
+    // stream, and the faster order is kept until the view or the scene changes.  It is a scheduling decision only: every
+    // sample is traced every frame and the image is bit-identical whatever the order.  RTCU_TILE_ORDER=0: always
+    // row-major; =1: always sorted once a cost map exists.
+    const uint32_t n_tiles = grid.x * grid.y;
+    const char* lpt_env = getenv("RTCU_TILE_ORDER");
+    const bool lpt = !pool && n_tiles >= 2u * 8u * (uint32_t)ctx->sm_count && !(lpt_env && lpt_env[0] == '0');
+    ctx->stats.kernel_launches = 1;
+    bool time_this_frame = false;
+    if (lpt)
     {
-        // default: the one-segment-per-iteration loop (flat; the nested form measures the same on C3/C4).
-        // RTCU_BVH_KERNEL=pool selects the warp-local ray pool (pool.cuh): correct and deterministic, but measured 20-30 %
-        // slower, so it is not the default.
-        const char* which = getenv("RTCU_BVH_KERNEL");
-        if (which && strcmp(which, "pool") == 0)
+        const rtcu_view& h = ctx->tile_hist_view;
+        const bool same_view = ctx->tile_hist_valid && ctx->tile_hist_stream == st && memcmp(h.inv_view_proj, v->inv_view_proj, sizeof h.inv_view_proj) == 0 &&
+                               h.width == v->width && h.height == v->height && h.tile_x0 == v->tile_x0 && h.tile_y0 == v->tile_y0 &&
+                               h.tile_x1 == v->tile_x1 && h.tile_y1 == v->tile_y1 && h.sample_end - h.sample_begin == v->sample_end - v->sample_begin &&
+                               h.max_bounces == v->max_bounces && h.material_mode == v->material_mode;
+        if (!same_view)
         {
-            p.segment_budget = 0; // work is shared by the 32 lanes of a warp: no per-thread stragglers
-            k_render_pool<<<grid, 32 * POOL_WARPS, 0, st>>>(ctx->scene, p);
+            ctx->tile_phase = 0;
+            ctx->tile_pending = -1;
         }
-        else
-            k_render_mega<false, true, true><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
-    }
-    else if (sb <= MAX_STAGE_BYTES)
-    {
-        if (flat) k_render_mega<true, true, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, p);
-        else k_render_mega<true, false, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, p);
+        else if (ctx->tile_pending >= 0 && cudaEventQuery(ctx->tile_ev[1]) == cudaSuccess)
+        {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ctx->tile_ev[0], ctx->tile_ev[1]) == cudaSuccess)
+            {
+                ctx->tile_ms[ctx->tile_pending] = ms;
+                if (ctx->tile_pending == 1) ctx->tile_sorted_wins = ctx->tile_ms[1] < ctx->tile_ms[0];
+                ctx->tile_phase = ctx->tile_pending + 1;
+            }
+            ctx->tile_pending = -1;
+        }
+        cudaGetLastError(); // cudaEventQuery reports cudaErrorNotReady through the sticky-free error slot
+        // a frame is a test frame (timed) when its phase has no measurement in flight; while one is in flight -- the caller
+        // queues frames without synchronising -- frames run row-major, the order that is never a regression
+        const bool forced = lpt_env && lpt_env[0] == '1';
+        time_this_frame = !forced && ctx->tile_phase < 2 && ctx->tile_pending < 0 && (ctx->tile_phase == 0 || same_view);
+        const bool sorted = same_view && (forced || (time_this_frame && ctx->tile_phase == 1) || (ctx->tile_phase == 2 && ctx->tile_sorted_wins));
+        CU(ctx->tile_cost.reserve(n_tiles));
+        CU(ctx->tile_order.reserve(n_tiles));
+        if (time_this_frame)
+        {
+            for (auto& e : ctx->tile_ev)
+                if (!e) CU(cudaEventCreate(&e));
+            CU(cudaEventRecord(ctx->tile_ev[0], st));
+        }
+        if (sorted)
+        {
+            k_tile_order<<<1, 1024, 0, st>>>(ctx->tile_cost.p, n_tiles, ctx->tile_order.p);
+            CU(cudaGetLastError());
+            p.tile_order = ctx->tile_order.p;
+            ctx->stats.kernel_launches = 2;
+        }
+        CU(cudaMemsetAsync(ctx->tile_cost.p, 0, n_tiles * sizeof(uint32_t), st));
+        p.tile_cost = ctx->tile_cost.p;
+        ctx->tile_hist_view = *v;
+        ctx->tile_hist_stream = st;
+        ctx->tile_hist_valid = true;
     }
     else
-        k_render_mega<false, true, false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, p);
+        ctx->tile_hist_valid = false;
+    launch_mega(p);
     CU(cudaGetLastError());
-    ctx->stats.kernel_launches = 1;
     if (p.segment_budget)
     {
         // the accumulate flag only applies to the first pass: the second adds onto what the first wrote
@@ -379,7 +449,12 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
         if (use_bvh) k_render_stragglers<true><<<blocks, 128, 0, st>>>(ctx->scene, p);
         else k_render_stragglers<false><<<blocks, 128, 0, st>>>(ctx->scene, p);
         CU(cudaGetLastError());
-        ctx->stats.kernel_launches = 2;
+        ctx->stats.kernel_launches++;
+    }
+    if (time_this_frame)
+    {
+        CU(cudaEventRecord(ctx->tile_ev[1], st));
+        ctx->tile_pending = ctx->tile_phase;
     }
     ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
     ctx->stats.accel = use_bvh ? RTCU_ACCEL_BVH : RTCU_ACCEL_LINEAR;
@@ -735,7 +810,10 @@ void rtcu_destroy(rtcu_ctx* ctx)
     ctx->wf_rad.release(); ctx->wf_sum.release(); ctx->wf_hit.release(); ctx->wf_counts.release(); ctx->h_wf_counts.release();
     ctx->boxes.release(); ctx->box_mat.release(); ctx->albedo.release(); ctx->raster_prim.release(); ctx->raster_depth.release();
     ctx->h_raster_prim.release(); ctx->h_raster_depth.release();
+    ctx->tile_cost.release(); ctx->tile_order.release();
     ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
+    for (auto& e : ctx->tile_ev)
+        if (e) cudaEventDestroy(e);
     for (auto& b : ctx->ipc)
     {
         if (b.second) cudaFree(b.first);
@@ -852,6 +930,7 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     CU(cudaMemcpyAsync(ctx->albedo.p, albedo.data(), albedo.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     // BVH: built whenever there are spheres (cheap for small scenes; lets ACCEL_BVH be requested explicitly for parity
     // tests); RTCU_ACCEL_AUTO uses it from rtcu_bvh_threshold() spheres up
+    ctx->tile_hist_valid = false; // per-tile costs belong to the scene they were measured on
     ctx->have_bvh = false;
     ctx->scene.bvh_nodes = nullptr;
     ctx->scene.leaf_blk = nullptr;

@@ -455,3 +455,29 @@ def test_cheaper_exact_sqrt_rcp_div_equal_the_ieee_intrinsics_for_every_input(ct
     r = ctx.selftest_math(sides)
     assert r["div_pairs"] == len(sides) * (0x4B800000 - 0x33800000 + 2)
     assert (r["sqrt"], r["rcp_of_sqrt"], r["div"]) == (0, 0, 0), r
+
+
+def test_tile_issue_order_never_changes_the_image(ctx, scenes, monkeypatch):
+    """The library times row-major against cost-sorted tile order over the first frames of a view and keeps the faster
+    (rtcu.cu: launch_render).  Whatever it picks, and whichever phase a frame falls in, accum and pixels are bit-identical."""
+    for name, spp, flags in (("c2", 16, 0), ("c3", 8, 0), ("c3", 8, nat.ACCEL_LINEAR)):
+        sc, depth = scenes[name]
+        ctx.upload_scene(sc)  # resets the per-view history
+        v = make_view(sc, 1280, 720, samples_per_pixel=spp, max_bounces=depth, material_mode=nat.MODE_SM, flags=flags)
+        monkeypatch.setenv("RTCU_TILE_ORDER", "0")
+        ref_rgba8, ref_accum = ctx.render(v, want_accum=True)
+        segs = ctx.stats()["segments"]
+        monkeypatch.delenv("RTCU_TILE_ORDER")
+        launches = []
+        for _ in range(5):  # row-major (timed), sorted (timed), then the winner
+            rgba8, accum = ctx.render(v, want_accum=True)
+            np.testing.assert_array_equal(accum, ref_accum)
+            np.testing.assert_array_equal(rgba8, ref_rgba8)
+            assert ctx.stats()["segments"] == segs
+            launches.append(ctx.stats()["kernel_launches"])
+        assert launches[0] == 2 and launches[1] == 3  # second frame: k_tile_order + megakernel + stragglers
+        monkeypatch.setenv("RTCU_TILE_ORDER", "1")
+        rgba8, accum = ctx.render(v, want_accum=True)
+        np.testing.assert_array_equal(accum, ref_accum)
+        assert ctx.stats()["kernel_launches"] == 3
+        monkeypatch.delenv("RTCU_TILE_ORDER")
