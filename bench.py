@@ -236,7 +236,15 @@ def run_gpu(args):
     gr = rdist.GpuRank(ctx, WIDTH, HEIGHT, dev, world=world)
     peer = world > 1 and args.exchange == "peer"
     if peer:
-        gr.enable_peer_exchange(rank)
+        # every rank must agree: if CUDA IPC / peer access is unavailable anywhere, all ranks use the NCCL exchange
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            gr.enable_peer_exchange(rank)
+        except Exception as e:  # noqa: BLE001
+            print(f"[rank {rank}] peer exchange unavailable ({e}); using --exchange nccl", file=sys.stderr, flush=True)
+            ok.zero_()
+        tdist.all_reduce(ok, op=tdist.ReduceOp.MIN)
+        peer = bool(ok.item())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 

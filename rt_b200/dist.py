@@ -155,12 +155,19 @@ class GpuRank:
         torch = self.torch
         npix = self.width * self.height
         self.peer_rank, self.peer_dst = rank, dst
-        self.peer_accum, h_accum = self.ctx.ipc_alloc(npix * 16)
-        h_img = None
-        if rank == dst:
-            self.peer_img, h_img = self.ctx.ipc_alloc(npix * 4)
+        # every rank takes part in the handle swap even if its own allocation failed, so that nobody waits forever
+        h_accum = h_img = err = None
+        try:
+            self.peer_accum, h_accum = self.ctx.ipc_alloc(npix * 16)
+            if rank == dst:
+                self.peer_img, h_img = self.ctx.ipc_alloc(npix * 4)
+        except Exception as e:  # noqa: BLE001
+            err = str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, (h_accum, h_img), group=group)
+        dist.all_gather_object(handles, (h_accum, h_img, err), group=group)
+        failed = [(g, h[2]) for g, h in enumerate(handles) if h[2] is not None or h[0] is None]
+        if failed:
+            raise RuntimeError(f"CUDA IPC allocation failed on rank(s) {failed}")
         self.peer_accums = [self.peer_accum if g == rank else self.ctx.ipc_open(handles[g][0]) for g in range(self.world)]
         if rank != dst:
             self.peer_img = self.ctx.ipc_open(handles[dst][1])
