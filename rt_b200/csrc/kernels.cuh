@@ -669,35 +669,62 @@ __global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict_
 
 // Second pass of a render call: the few pixels whose paths are far longer than the frame average (a crevice between
 // two bright spheres can take 20x the mean) would otherwise each keep one lane -- and its whole CTA slot -- busy long
-// after the rest of the grid has drained.  Here one warp takes one queued pixel: lane l traces samples next+l, next+l+32,
-// ...; the 32 partial sums are combined in a fixed butterfly order (deterministic) and added to the pixel's partial
-// result from the first pass.  Primitives are read from global memory (L1-resident for the scenes that reach this path).
+// after the rest of the grid has drained.  Here one warp takes one queued pixel at a time (handed out dynamically) and its
+// 32 lanes share the pixel's remaining samples, each lane claiming the next unclaimed one as soon as its path ends; the 32
+// partial sums are combined in a fixed butterfly order and added to the pixel's partial result from the first pass --
+// deterministic, since which lane traces which sample depends only on the path lengths.  Primitives are read from global memory (L1-resident for the scenes that reach this path).
 template <bool BVH>
-__global__ void __launch_bounds__(128) k_render_stragglers(const SceneDev sc, const RenderParams p)
+__global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc, const RenderParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t count = *p.straggler_count;
     unsigned long long segs = 0;
     BvhStats bst;
     bst.nodes = 0;
     bst.tests = 0;
-    for (uint32_t item = warp_global; item < count; item += n_warps)
+    for (;;)
     {
+        // queued pixels are handed out dynamically (their remaining work differs by orders of magnitude); counters[3]
+        // doubles as the hand-out cursor
+        uint32_t item = 0;
+        if (lane == 0) item = (uint32_t)atomicAdd(p.counters + 3, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= count) break;
         const uint2 w = p.stragglers[item];
         const uint32_t px = w.x % p.width, py = w.x / p.width;
         RngKey key;
         key.ks = &p.rk;
         key.pixel = w.x;
+        key.sample = 0;
         V3 sum = v3(0.0f, 0.0f, 0.0f);
-        for (key.sample = w.y + lane; key.sample < p.sample_end; key.sample += 32u)
+        V3 thr = v3(1.0f, 1.0f, 1.0f);
+        uint32_t seg = 0;
+        Ray ray;
+        ray.o = v3(0.0f, 0.0f, 0.0f);
+        ray.d = v3(0.0f, 0.0f, 1.0f);
+        // the 32 lanes share the pixel's remaining samples: a lane whose path ended takes the next unclaimed sample at once
+        // (ballot rank in lane order -- deterministic), so lanes stay busy until the pixel runs out of samples
+        uint32_t next = w.y;
+        bool live = false;
+        for (;;)
         {
-            V3 thr = v3(1.0f, 1.0f, 1.0f);
-            uint32_t seg = 0;
-            Ray ray = generate(p.cam, key, px, py);
-            do
+            const unsigned idle = __ballot_sync(0xffffffffu, !live);
+            const uint32_t mine = next + __popc(idle & ((1u << lane) - 1u));
+            if (!live && mine < p.sample_end)
+            {
+                key.sample = mine;
+                seg = 0;
+                thr = v3(1.0f, 1.0f, 1.0f);
+                ray = generate(p.cam, key, px, py);
+                live = true;
+            }
+            next = min(p.sample_end, next + (uint32_t)__popc(idle));
+            if (!__any_sync(0xffffffffu, live)) break;
+            if (live)
+            {
                 segs++;
-            while (!segment_step<BVH>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst));
+                if (segment_step<BVH>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst)) live = false;
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
@@ -731,7 +758,6 @@ __global__ void __launch_bounds__(128) k_render_stragglers(const SceneDev sc, co
             atomicAdd(p.counters + 1, nodes);
             atomicAdd(p.counters + 2, tests);
         }
-        atomicAdd(p.counters + 3, 1ull); // warps that had straggler work (diagnostic)
     }
 }
 

@@ -445,7 +445,7 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     if (p.segment_budget)
     {
         // the accumulate flag only applies to the first pass: the second adds onto what the first wrote
-        const unsigned blocks = (unsigned)ctx->sm_count * 4;
+        const unsigned blocks = (unsigned)ctx->sm_count * 8;
         if (use_bvh) k_render_stragglers<true><<<blocks, 128, 0, st>>>(ctx->scene, p);
         else k_render_stragglers<false><<<blocks, 128, 0, st>>>(ctx->scene, p);
         CU(cudaGetLastError());
