@@ -61,6 +61,7 @@ struct RenderParams {
     // frame of the same view takes its tiles from tile_order (tile ids by descending cost of the previous frame)
     uint32_t* tile_cost;          // += segments traced for the CTA's tile (nullable)
     const uint32_t* tile_order;   // CTA b renders tile tile_order[b] (nullable: CTA b renders tile b)
+    int direct;                   // k_render_stragglers renders every pixel of the tile itself (no first pass, no queue)
 };
 
 #ifndef RTCU_PRIM_MISS
@@ -677,7 +678,8 @@ template <bool BVH>
 __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc, const RenderParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t count = *p.straggler_count;
+    const uint32_t tile_w = p.tile_x1 - p.tile_x0;
+    const uint32_t count = p.direct ? ((tile_w + 7u) >> 3) * ((p.tile_y1 - p.tile_y0 + 3u) >> 2) * 32u : *p.straggler_count;
     unsigned long long segs = 0;
     BvhStats bst;
     bst.nodes = 0;
@@ -690,7 +692,17 @@ __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc,
         if (lane == 0) item = (uint32_t)atomicAdd(p.counters + 3, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= count) break;
-        const uint2 w = p.stragglers[item];
+        uint2 w; // {pixel, first sample}
+        if (p.direct)
+        {
+            // pixels in 8x4 patches, patches row-major: consecutive warps work on neighbouring pixels (warm BVH nodes in L1)
+            const uint32_t patches_x = (tile_w + 7u) >> 3, patch = item >> 5, in_patch = item & 31u;
+            const uint32_t qx = (patch % patches_x) * 8u + (in_patch & 7u), qy = (patch / patches_x) * 4u + (in_patch >> 3);
+            if (qx >= tile_w || qy >= p.tile_y1 - p.tile_y0) continue; // ragged edge of the patch grid
+            w = make_uint2((p.tile_y0 + qy) * p.width + p.tile_x0 + qx, p.sample_begin);
+        }
+        else
+            w = p.stragglers[item];
         const uint32_t px = w.x % p.width, py = w.x / p.width;
         RngKey key;
         key.ks = &p.rk;
@@ -735,7 +747,8 @@ __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc,
         }
         if (lane == 0)
         {
-            float4 acc = p.accum[w.x];
+            // queue mode: add onto the first pass' partial result; direct mode: store (or add when the call accumulates)
+            float4 acc = (p.direct && !p.accumulate) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : p.accum[w.x];
             acc.x = __fadd_rn(acc.x, sum.x); acc.y = __fadd_rn(acc.y, sum.y); acc.z = __fadd_rn(acc.z, sum.z);
             acc.w = __fadd_rn(acc.w, (float)(p.sample_end - w.y));
             p.accum[w.x] = acc;

@@ -209,6 +209,7 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     p.counters = nullptr;
     p.tile_cost = nullptr;
     p.tile_order = nullptr;
+    p.direct = 0;
     return RTCU_OK;
 }
 
@@ -385,6 +386,28 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     // stream, and the faster order is kept until the view or the scene changes.  It is a scheduling decision only: every
     // sample is traced every frame and the image is bit-identical whatever the order.  RTCU_TILE_ORDER=0: always
     // row-major; =1: always sorted once a cost map exists.
+    // BVH scenes with enough samples per pixel skip the thread-per-pixel kernel altogether: k_render_stragglers in direct
+    // mode gives every pixel to a warp whose 32 lanes share its samples.  The samples of one pixel start from (almost) the same
+    // ray and their first bounces from (almost) the same point, so the warp traverses far more coherently than 32
+    // neighbouring pixels do, and pixel-sized work items leave no grid tail (C4 -18 %, C3 -6 %).  The
+    // per-pixel sum is then a fixed butterfly over 32 lane sums instead of the sequential sum (same paths, same segment
+    // count; fp32 summation order only).  Below 64 samples the lanes run dry.  RTCU_BVH_DIRECT=0 disables.
+    const char* direct_env = getenv("RTCU_BVH_DIRECT");
+    if (use_bvh && !pool && n_samples >= 64 && !(direct_env && direct_env[0] == '0'))
+    {
+        p.direct = 1;
+        p.segment_budget = 0;
+        const unsigned long long n_items = (unsigned long long)((v->tile_x1 - v->tile_x0 + 7) / 8) * ((v->tile_y1 - v->tile_y0 + 3) / 4) * 32ull;
+        if (n_items > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "tile too large");
+        RenderParams q = p; // the kernel derives the item count from the tile (8x4 patches, ragged edges skipped)
+        q.tile_cost = nullptr;
+        k_render_stragglers<true><<<(unsigned)ctx->sm_count * 8, 128, 0, st>>>(ctx->scene, q);
+        CU(cudaGetLastError());
+        ctx->tile_hist_valid = false;
+        ctx->stats.kernel_launches = 1;
+        ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
+        return RTCU_OK;
+    }
     const uint32_t n_tiles = grid.x * grid.y;
     const char* lpt_env = getenv("RTCU_TILE_ORDER");
     const bool lpt = !pool && n_tiles >= 2u * 8u * (uint32_t)ctx->sm_count && !(lpt_env && lpt_env[0] == '0');

@@ -54,7 +54,7 @@ def test_c3_full_size(ctx, oracle, c3):
     assert np.abs(unpack_rgba(rgba_a[rows]) - unpack_rgba(r_rgba8[rows])).max() <= 1
 
 
-def test_c4_full_size(ctx, c4):
+def test_c4_full_size(ctx, c4, monkeypatch):
     # configs[3]: 100 001 spheres, 3840x2160, 64 spp, depth 10 (530.8 M samples) -- BVH traversal + divergence
     assert len(c4.spheres) == 100001
     ctx.upload_scene(c4)
@@ -73,9 +73,17 @@ def test_c4_full_size(ctx, c4):
     _, acc_bvh = ctx.render(make_view(c4, 3840, 2160, tile=tile, flags=nat.ACCEL_BVH, **kw), want_accum=True)
     segs_bvh = ctx.stats()["segments"]
     rgba_lin, acc_lin = ctx.render(make_view(c4, 3840, 2160, tile=tile, flags=nat.ACCEL_LINEAR, **kw), want_accum=True)
-    assert ctx.stats()["segments"] == segs_bvh and ctx.stats()["sphere_tests"] == segs_bvh * 100001
-    np.testing.assert_array_equal(acc_bvh, acc_lin)
-    np.testing.assert_array_equal(rgba_lin[1200:1232, 1900:1964], rgba_a[1200:1232, 1900:1964])
+    assert ctx.stats()["segments"] == segs_bvh and ctx.stats()["sphere_tests"] == segs_bvh * 100001  # the very same paths
+    # at >= 64 spp the BVH path gives every pixel to a warp whose lanes share its samples (launch_render, direct mode): the
+    # per-pixel sum is a butterfly over 32 lane sums instead of the scan kernel's sequential sum -- fp32 order only
+    np.testing.assert_array_equal(acc_bvh[..., 3], acc_lin[..., 3])
+    np.testing.assert_allclose(acc_bvh[..., :3], acc_lin[..., :3], rtol=4e-6, atol=1e-6)
+    assert np.abs(unpack_rgba(rgba_lin[1200:1232, 1900:1964]) - unpack_rgba(rgba_a[1200:1232, 1900:1964])).max() <= 1
+    # with the thread-per-pixel kernel on both sides the buffers are bit-identical
+    monkeypatch.setenv("RTCU_BVH_DIRECT", "0")
+    _, acc_bvh_tpp = ctx.render(make_view(c4, 3840, 2160, tile=tile, flags=nat.ACCEL_BVH, **kw), want_accum=True)
+    monkeypatch.delenv("RTCU_BVH_DIRECT")
+    np.testing.assert_array_equal(acc_bvh_tpp, acc_lin)
     # closest hits of 2^16 random + 2^16 silhouette-grazing rays: BVH == scan
     for o, d in (synth.random_rays(c4, 1 << 16, seed=3, spread=60.0), synth.grazing_rays(c4, 1 << 16, seed=4)):
         lin = ctx.intersect_batch(o, d, accel=nat.ACCEL_LINEAR)

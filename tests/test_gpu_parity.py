@@ -481,3 +481,46 @@ def test_tile_issue_order_never_changes_the_image(ctx, scenes, monkeypatch):
         np.testing.assert_array_equal(accum, ref_accum)
         assert ctx.stats()["kernel_launches"] == 3
         monkeypatch.delenv("RTCU_TILE_ORDER")
+
+
+def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes, monkeypatch):
+    """From 64 samples per call a BVH scene is rendered warp-per-pixel (k_render_stragglers in direct mode): same paths as the
+    thread-per-pixel kernel (equal segment counts), per-pixel sums equal up to fp32 order, partial tiles / ragged 8x4 patches /
+    sample ranges / accumulate-onto-a-device-buffer all behave like the other kernels, and the oracle agrees."""
+    import torch
+
+    sc, depth = scenes["c3"]
+    ctx.upload_scene(sc)
+    w, h, spp = 203, 117, 96  # ragged against the 8x4 patches
+    kw = dict(samples_per_pixel=spp, max_bounces=depth, material_mode=nat.MODE_SM)
+    v = make_view(sc, w, h, **kw)
+    rgba8, accum = ctx.render(v, want_accum=True)
+    segs = ctx.stats()["segments"]
+    assert ctx.stats()["kernel_launches"] == 1 and (accum[..., 3] == spp).all()
+    monkeypatch.setenv("RTCU_BVH_DIRECT", "0")
+    rgba8_t, accum_t = ctx.render(v, want_accum=True)
+    assert ctx.stats()["segments"] == segs
+    monkeypatch.delenv("RTCU_BVH_DIRECT")
+    np.testing.assert_allclose(accum[..., :3], accum_t[..., :3], rtol=4e-6, atol=1e-6)
+    assert np.abs(unpack_rgba(rgba8) - unpack_rgba(rgba8_t)).max() <= 1
+    r_rgba8, r_accum, r_segs = oracle.render(sc, v, threads=0)
+    assert r_segs == segs
+    np.testing.assert_allclose(accum[..., :3], r_accum[..., :3], rtol=3e-5, atol=1e-5)
+    assert np.abs(unpack_rgba(rgba8) - unpack_rgba(r_rgba8)).max() <= 1
+    # a partial tile writes only the tile, and equals the same pixels of the frame bit for bit (per-pixel work is independent)
+    img = np.full((h, w), 0xDEADBEEF, np.uint32)
+    tv = make_view(sc, w, h, tile=(13, 9, 150, 100), **kw)
+    part, pacc = ctx.render(tv, rgba8=img, want_accum=True)
+    np.testing.assert_array_equal(pacc[9:100, 13:150], accum[9:100, 13:150])
+    assert (part[:9] == 0xDEADBEEF).all() and (part[:, 150:] == 0xDEADBEEF).all()
+    # rtcu_render_device with accumulate: two calls of 64 samples onto one device buffer = one call of 128 (fp32 order)
+    dev = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    for rng in ((0, 64), (64, 128)):
+        ctx.render_device(make_view(sc, w, h, samples_per_pixel=128, max_bounces=depth, material_mode=nat.MODE_SM, sample_range=rng),
+                          dev.data_ptr(), accumulate=rng[0] > 0, stream=st)
+    torch.cuda.synchronize()
+    _, whole = ctx.render(make_view(sc, w, h, samples_per_pixel=128, max_bounces=depth, material_mode=nat.MODE_SM), want_accum=True)
+    got = dev.cpu().numpy()
+    np.testing.assert_array_equal(got[..., 3], whole[..., 3])
+    np.testing.assert_allclose(got[..., :3], whole[..., :3], rtol=4e-6, atol=1e-6)
