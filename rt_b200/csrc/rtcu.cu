@@ -332,6 +332,17 @@ int launch_wavefront(rtcu_ctx* ctx, const rtcu_view* v, RenderParams p, bool use
 }
 
 // launches the trace kernels of one view on `st`; accum/rgba8 are device pointers
+// whether launch_render will take the warp-per-pixel path (k_render_stragglers in direct mode) for this view
+bool uses_direct_mode(const rtcu_ctx* ctx, const rtcu_view* v)
+{
+    const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
+    const char* which = getenv("RTCU_BVH_KERNEL");
+    const char* direct_env = getenv("RTCU_BVH_DIRECT");
+    return use_bvh && ctx->have_bvh && pipe != RTCU_PIPE_WAVEFRONT && !(which && strcmp(which, "pool") == 0) && v->sample_end - v->sample_begin >= 64 &&
+           !(direct_env && direct_env[0] == '0');
+}
+
 int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st)
 {
     if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
@@ -392,8 +403,7 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     // neighbouring pixels do, and pixel-sized work items leave no grid tail (C4 -18 %, C3 -6 %).  The
     // per-pixel sum is then a fixed butterfly over 32 lane sums instead of the sequential sum (same paths, same segment
     // count; fp32 summation order only).  Below 64 samples the lanes run dry.  RTCU_BVH_DIRECT=0 disables.
-    const char* direct_env = getenv("RTCU_BVH_DIRECT");
-    if (use_bvh && !pool && n_samples >= 64 && !(direct_env && direct_env[0] == '0'))
+    if (uses_direct_mode(ctx, v))
     {
         p.direct = 1;
         p.segment_budget = 0;
@@ -1104,7 +1114,8 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     // frame instead of following it (RTCU_ZERO_COPY=0 disables; pageable buffers -- the reference's image.cpp -- are staged).
     uint32_t* d_out = rgba8_out ? ctx->rgba8.p : nullptr;
     bool zero_copy = false;
-    if (rgba8_out && full && is_device_accessible_host(rgba8_out))
+    // (not in direct mode: there one lane per pixel stores 4 bytes at a time, which would cross PCIe as single-pixel writes)
+    if (rgba8_out && full && is_device_accessible_host(rgba8_out) && !uses_direct_mode(ctx, view))
     {
         const char* e = getenv("RTCU_ZERO_COPY");
         void* mapped = nullptr;
