@@ -61,7 +61,7 @@ struct RenderParams {
     // frame of the same view takes its tiles from tile_order (tile ids by descending cost of the previous frame)
     uint32_t* tile_cost;          // += segments traced for the CTA's tile (nullable)
     const uint32_t* tile_order;   // CTA b renders tile tile_order[b] (nullable: CTA b renders tile b)
-    int direct;                   // k_render_stragglers renders every pixel of the tile itself (no first pass, no queue)
+    int direct;                   // != 0: k_render_stragglers renders every pixel of the tile itself (no first pass, no queue)
 };
 
 #ifndef RTCU_PRIM_MISS
@@ -674,32 +674,35 @@ __global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict_
 // 32 lanes share the pixel's remaining samples, each lane claiming the next unclaimed one as soon as its path ends; the 32
 // partial sums are combined in a fixed butterfly order and added to the pixel's partial result from the first pass --
 // deterministic, since which lane traces which sample depends only on the path lengths.  Primitives are read from global memory (L1-resident for the scenes that reach this path).
-template <bool BVH>
+template <bool BVH, int G_LANES = 32>
 __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc, const RenderParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tile_w = p.tile_x1 - p.tile_x0;
-    const uint32_t count = p.direct ? ((tile_w + 7u) >> 3) * ((p.tile_y1 - p.tile_y0 + 3u) >> 2) * 32u : *p.straggler_count;
+    const uint32_t tile_w = p.tile_x1 - p.tile_x0, tile_h = p.tile_y1 - p.tile_y0;
+    // G lanes share one pixel (32 in queue mode; 16 or 8 in direct mode, so that every lane gets >= 2 samples): a warp works
+    // on 32 / G horizontally adjacent pixels at a time, lane group g on pixel g
+    constexpr uint32_t G = G_LANES, ppw = 32u / G;
+    const uint32_t grp = lane / G, gmask = (G == 32u ? 0xffffffffu : ((1u << G) - 1u) << (grp * G)), below = gmask & ((1u << lane) - 1u);
+    const uint32_t count = p.direct ? ((tile_w + 7u) >> 3) * ((tile_h + 3u) >> 2) * G : *p.straggler_count;
     unsigned long long segs = 0;
     BvhStats bst;
     bst.nodes = 0;
     bst.tests = 0;
     for (;;)
     {
-        // queued pixels are handed out dynamically (their remaining work differs by orders of magnitude); counters[3]
-        // doubles as the hand-out cursor
+        // work items are handed out dynamically (their cost differs by orders of magnitude); counters[3] doubles as the cursor
         uint32_t item = 0;
         if (lane == 0) item = (uint32_t)atomicAdd(p.counters + 3, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= count) break;
-        uint2 w; // {pixel, first sample}
+        uint2 w = make_uint2(0u, p.sample_end); // {pixel, first sample}; first sample = sample_end: nothing to do
         if (p.direct)
         {
             // pixels in 8x4 patches, patches row-major: consecutive warps work on neighbouring pixels (warm BVH nodes in L1)
-            const uint32_t patches_x = (tile_w + 7u) >> 3, patch = item >> 5, in_patch = item & 31u;
+            const uint32_t patches_x = (tile_w + 7u) >> 3, patch = item / G, in_patch = (item % G) * ppw + grp;
             const uint32_t qx = (patch % patches_x) * 8u + (in_patch & 7u), qy = (patch / patches_x) * 4u + (in_patch >> 3);
-            if (qx >= tile_w || qy >= p.tile_y1 - p.tile_y0) continue; // ragged edge of the patch grid
-            w = make_uint2((p.tile_y0 + qy) * p.width + p.tile_x0 + qx, p.sample_begin);
+            if (qx < tile_w && qy < tile_h) // else: ragged edge of the patch grid
+                w = make_uint2((p.tile_y0 + qy) * p.width + p.tile_x0 + qx, p.sample_begin);
         }
         else
             w = p.stragglers[item];
@@ -714,14 +717,14 @@ __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc,
         Ray ray;
         ray.o = v3(0.0f, 0.0f, 0.0f);
         ray.d = v3(0.0f, 0.0f, 1.0f);
-        // the 32 lanes share the pixel's remaining samples: a lane whose path ended takes the next unclaimed sample at once
-        // (ballot rank in lane order -- deterministic), so lanes stay busy until the pixel runs out of samples
+        // the lanes of a group share their pixel's remaining samples: a lane whose path ended takes the next unclaimed sample
+        // at once (ballot rank in lane order -- deterministic), so lanes stay busy until the pixel runs out of samples
         uint32_t next = w.y;
         bool live = false;
         for (;;)
         {
-            const unsigned idle = __ballot_sync(0xffffffffu, !live);
-            const uint32_t mine = next + __popc(idle & ((1u << lane) - 1u));
+            const unsigned idle = __ballot_sync(0xffffffffu, !live) & gmask;
+            const uint32_t mine = next + __popc(idle & below);
             if (!live && mine < p.sample_end)
             {
                 key.sample = mine;
@@ -738,14 +741,13 @@ __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc,
                 if (segment_step<BVH>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst)) live = false;
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
+        for (uint32_t off = G >> 1; off > 0; off >>= 1) // fixed butterfly inside the group
         {
             sum.x = __fadd_rn(sum.x, __shfl_xor_sync(0xffffffffu, sum.x, off));
             sum.y = __fadd_rn(sum.y, __shfl_xor_sync(0xffffffffu, sum.y, off));
             sum.z = __fadd_rn(sum.z, __shfl_xor_sync(0xffffffffu, sum.z, off));
         }
-        if (lane == 0)
+        if ((lane & (G - 1u)) == 0u && w.y < p.sample_end)
         {
             // queue mode: add onto the first pass' partial result; direct mode: store (or add when the call accumulates)
             float4 acc = (p.direct && !p.accumulate) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : p.accum[w.x];

@@ -339,7 +339,7 @@ bool uses_direct_mode(const rtcu_ctx* ctx, const rtcu_view* v)
     const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
     const char* which = getenv("RTCU_BVH_KERNEL");
     const char* direct_env = getenv("RTCU_BVH_DIRECT");
-    return use_bvh && ctx->have_bvh && pipe != RTCU_PIPE_WAVEFRONT && !(which && strcmp(which, "pool") == 0) && v->sample_end - v->sample_begin >= 64 &&
+    return use_bvh && ctx->have_bvh && pipe != RTCU_PIPE_WAVEFRONT && !(which && strcmp(which, "pool") == 0) && v->sample_end - v->sample_begin >= 16 &&
            !(direct_env && direct_env[0] == '0');
 }
 
@@ -397,21 +397,25 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     // stream, and the faster order is kept until the view or the scene changes.  It is a scheduling decision only: every
     // sample is traced every frame and the image is bit-identical whatever the order.  RTCU_TILE_ORDER=0: always
     // row-major; =1: always sorted once a cost map exists.
-    // BVH scenes with enough samples per pixel skip the thread-per-pixel kernel altogether: k_render_stragglers in direct
-    // mode gives every pixel to a warp whose 32 lanes share its samples.  The samples of one pixel start from (almost) the same
-    // ray and their first bounces from (almost) the same point, so the warp traverses far more coherently than 32
-    // neighbouring pixels do, and pixel-sized work items leave no grid tail (C4 -18 %, C3 -6 %).  The
-    // per-pixel sum is then a fixed butterfly over 32 lane sums instead of the sequential sum (same paths, same segment
-    // count; fp32 summation order only).  Below 64 samples the lanes run dry.  RTCU_BVH_DIRECT=0 disables.
+    // BVH scenes with at least 16 samples per call skip the thread-per-pixel kernel altogether: k_render_stragglers in direct
+    // mode lets 16 (or 8) lanes share ONE pixel's samples.  The samples of a pixel start from (almost) the same ray and their
+    // first bounces from (almost) the same point, so the warp traverses far more coherently than 32 neighbouring pixels do,
+    // and pixel-sized work items leave no grid tail (C4 -19 %, C3 -6 %; at 30 spp -18 % / -8 %).  The per-pixel sum is then a
+    // fixed butterfly over the lane sums instead of the sequential sum (same paths, same segment count; fp32 summation
+    // order only).  Below 16 samples the lanes would run dry.  RTCU_BVH_DIRECT=0 disables.
     if (uses_direct_mode(ctx, v))
     {
         p.direct = 1;
         p.segment_budget = 0;
-        const unsigned long long n_items = (unsigned long long)((v->tile_x1 - v->tile_x0 + 7) / 8) * ((v->tile_y1 - v->tile_y0 + 3) / 4) * 32ull;
+        const unsigned long long n_items = (unsigned long long)((v->tile_x1 - v->tile_x0 + 7) / 8) * ((v->tile_y1 - v->tile_y0 + 3) / 4) * 16ull;
         if (n_items > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "tile too large");
         RenderParams q = p; // the kernel derives the item count from the tile (8x4 patches, ragged edges skipped)
         q.tile_cost = nullptr;
-        k_render_stragglers<true><<<(unsigned)ctx->sm_count * 8, 128, 0, st>>>(ctx->scene, q);
+        // lanes per pixel: 16 (two pixels per warp) from 32 samples -- measured equal or better than 32 lanes on one pixel even
+        // at 256 samples -- and 8 (four pixels per warp) below, so that every lane gets at least two samples
+        const unsigned blocks = (unsigned)ctx->sm_count * 8;
+        if (n_samples >= 32) k_render_stragglers<true, 16><<<blocks, 128, 0, st>>>(ctx->scene, q);
+        else k_render_stragglers<true, 8><<<blocks, 128, 0, st>>>(ctx->scene, q);
         CU(cudaGetLastError());
         ctx->tile_hist_valid = false;
         ctx->stats.kernel_launches = 1;
