@@ -484,8 +484,8 @@ def test_tile_issue_order_never_changes_the_image(ctx, scenes, monkeypatch):
 
 
 def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes, monkeypatch):
-    """From 64 samples per call a BVH scene is rendered warp-per-pixel (k_render_stragglers in direct mode): same paths as the
-    thread-per-pixel kernel (equal segment counts), per-pixel sums equal up to fp32 order, partial tiles / ragged 8x4 patches /
+    """From 16 samples per call a BVH scene is rendered with 16 or 8 lanes sharing each pixel's samples (k_render_stragglers in
+    direct mode): same paths as the thread-per-pixel kernel (equal segment counts), per-pixel sums equal up to fp32 order, partial tiles / ragged 8x4 patches /
     sample ranges / accumulate-onto-a-device-buffer all behave like the other kernels, and the oracle agrees."""
     import torch
 
