@@ -135,7 +135,11 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* scene);
 /* ---- render: replaces mg_ray_tracer::render / sm_ray_tracer::render.
  * rgba8_out (nullable): width*height uint32 in image_view layout (row 0 = top, src/image.hpp:150-159),
  *   packed as colour::operator uint32_t (colour.hpp:100-106); only the tile is written.
- * accum_out (nullable): width*height*4 floats {sum_r,sum_g,sum_b,n_samples}; only the tile is written. */
+ * accum_out (nullable): width*height*4 floats {sum_r,sum_g,sum_b,n_samples}; only the tile is written.  The paths are the
+ *   reference's (same segments per sample for the same seed); the per-pixel sum runs in ascending sample order as in
+ *   mg_ray_tracer.cpp:187-194, except where several lanes share a pixel (BVH scenes from 16 samples per call, pixels handed
+ *   to the second pass, multi-GPU sample splits): there it is a fixed tree of partial sums -- deterministic, equal to the
+ *   sequential sum up to fp32 rounding. */
 int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out);
 
 /* ---- preview: replaces rasterizer::render (reference src/renderers/rasterizer.cpp:22-88): one ray per pixel through the
