@@ -2,7 +2,8 @@
 """Randomised parity campaign on a GPU box: N random scenes (1-300 spheres, 0-3 planes, all eight material types, random
 cameras, both scatter tables) rendered by the CUDA path (linear scan, BVH, wavefront pipeline, ray-pool kernel) and by the
 strict CPU oracle; closest hits of random + silhouette-grazing ray batches compared bit for bit; the preview renderer
-(rtcu_rasterize, scan and BVH, with random boxes) compared bit for bit (pixels, primitive ids, depth).  Prints one JSON summary.
+(rtcu_rasterize, scan and BVH, with random boxes) compared bit for bit (pixels, primitive ids, depth); every third scene also rendered through the lanes-share-a-pixel BVH path.
+Prints one JSON summary.
 usage: python tools/fuzz_parity.py [n_scenes] [seed]"""
 import json, os, pathlib, sys
 
@@ -81,6 +82,22 @@ for i in range(n_scenes):
             stats["rays"] += len(o)
             stats["hit_mismatch"] += int(sum((a != b).sum() for a, b in zip(lin, orc)))
             stats["bvh_vs_linear_mismatch"] += int(sum((a != b).sum() for a, b in zip(bvh, lin)))
+        # the lanes-share-a-pixel BVH path (>= 16 samples per call; 8 or 16 lanes per pixel), every third scene
+        if i % 3 == 0:
+            spp_d = int(rng.choice([16, 24, 33, 70]))
+            vd = make_view(sc, w, h, samples_per_pixel=spp_d, material_mode=mode, seed=2000 + i, flags=nat.ACCEL_BVH)
+            rgba8, accum = ctx.render(vd, want_accum=True)
+            segs = ctx.stats()["segments"]
+            r_rgba8, r_accum, r_segs = oracle.render(sc, vd)
+            stats["renders"] += 1
+            stats["direct_renders"] = stats.get("direct_renders", 0) + 1
+            if segs != r_segs or ctx.stats()["kernel_launches"] != 1:
+                stats["seg_mismatch"] += 1
+                stats["failures"].append((i, "bvh_direct", "segments", segs, r_segs))
+            denom = np.maximum(np.abs(r_accum[..., :3]), 1e-3)
+            stats["accum_max_rel"] = max(stats["accum_max_rel"], float((np.abs(accum[..., :3] - r_accum[..., :3]) / denom).max()))
+            lsb = int(np.abs(((rgba8[..., None] >> np.uint32([24, 16, 8])) & 255).astype(int) - ((r_rgba8[..., None] >> np.uint32([24, 16, 8])) & 255).astype(int)).max())
+            stats["rgba_max_lsb"] = max(stats["rgba_max_lsb"], lsb)
         pv = make_view(sc, w, h)
         expect = oracle.rasterize(sc, pv)
         for accel in (nat.ACCEL_LINEAR, nat.ACCEL_BVH):
