@@ -216,6 +216,13 @@ int rtcu_selftest_math(rtcu_ctx* ctx, const float* divisors, uint32_t n_divisors
  * node, < 0 leaf starting at ~child in order_out); uint32 count[2]}.  order_out (nullable): n original sphere indices. */
 int rtcu_bvh_build_host(const float* spheres, uint32_t n, float* nodes_out, uint32_t* order_out, uint32_t max_nodes,
                         uint32_t* n_nodes, uint32_t* depth);
+/* the same tree as the device sees it: collapsed to 4-wide nodes (8 x float4 each: children (0,1) as {c0,c1,h0,h1} for x, y,
+ * z -- centre and outward-rounded half-extent, -inf for an empty slot --, the same for children (2,3), the four child
+ * references as bit patterns (>= 0 inner node, 0x80000000 | leaf), the four H = h.x+h.y+h.z) and 80-byte leaf blocks
+ * (5 x float4: two packed sphere pairs {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}, then four original indices as bit patterns,
+ * 0x7fffffff = padding).  depth = levels of 4-wide nodes.  Pass NULL buffers first to learn the sizes. */
+int rtcu_bvh4_build_host(const float* spheres, uint32_t n, float* nodes_out, uint32_t max_nodes, float* leaves_out, uint32_t max_leaves,
+                         uint32_t* n_nodes, uint32_t* n_leaves, uint32_t* depth);
 
 /* ---- roofline calibration: achieved non-tensor FP32 TFLOP/s of an FFMA stream and of a packed FFMA2
  * (fma.rn.f32x2) stream on ctx's device at the clocks it currently runs (no memory traffic). */

@@ -26,7 +26,7 @@ EXPORTS = (
     "rtcu_upload_scene", "rtcu_render", "rtcu_render_device", "rtcu_resolve_device", "rtcu_sync", "rtcu_render_multi",
     "rtcu_intersect_batch", "rtcu_primary_rays", "rtcu_scatter_batch", "rtcu_philox_batch", "rtcu_get_stats", "rtcu_measure_fp32_peak", "rtcu_bvh_build_host",
     "rtcu_rasterize", "rtcu_rasterize_device", "rtcu_selftest_math",
-    "rtcu_ipc_alloc", "rtcu_ipc_open", "rtcu_ipc_release", "rtcu_reduce_resolve_rows",
+    "rtcu_ipc_alloc", "rtcu_ipc_open", "rtcu_ipc_release", "rtcu_reduce_resolve_rows", "rtcu_bvh4_build_host",
 )
 
 
@@ -108,6 +108,7 @@ def load_library() -> C.CDLL:
         "rtcu_rasterize": (i, [p, C.POINTER(View), p, p, p]),
         "rtcu_rasterize_device": (i, [p, C.POINTER(View), p, p]),
         "rtcu_selftest_math": (i, [p, p, u32, p]),
+        "rtcu_bvh4_build_host": (i, [p, u32, p, u32, p, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "rtcu_ipc_alloc": (i, [p, u64, C.POINTER(p), p]),
         "rtcu_ipc_open": (i, [p, p, C.POINTER(p)]),
         "rtcu_ipc_release": (i, [p, p]),

@@ -1541,6 +1541,38 @@ int rtcu_bvh_build_host(const float* spheres, uint32_t n, float* nodes_out, uint
     return RTCU_OK;
 }
 
+int rtcu_bvh4_build_host(const float* spheres, uint32_t n, float* nodes_out, uint32_t max_nodes, float* leaves_out, uint32_t max_leaves,
+                         uint32_t* n_nodes, uint32_t* n_leaves, uint32_t* depth)
+{
+    if ((n && !spheres) || !n_nodes || !n_leaves || !depth) return fail(RTCU_ERR_INVALID, "null argument");
+    if (n == 0 || n >= (1u << 29)) return fail(RTCU_ERR_INVALID, "1 .. 2^29 - 1 spheres");
+    std::vector<float4> sph(n);
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const float* p = spheres + 4 * (size_t)i;
+        const volatile float r2 = p[3] * p[3];
+        sph[i] = make_float4(p[0], p[1], p[2], r2);
+    }
+    const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n);
+    std::vector<float4> nodes, leaves;
+    uint32_t d4 = 0;
+    pack_bvh4(bvh, sph, nodes, leaves, d4);
+    *n_nodes = (uint32_t)(nodes.size() / 8);
+    *n_leaves = (uint32_t)(leaves.size() / 5);
+    *depth = d4;
+    if (nodes_out)
+    {
+        if (*n_nodes > max_nodes) return fail(RTCU_ERR_INVALID, "nodes_out too small: need %u", *n_nodes);
+        memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(float4));
+    }
+    if (leaves_out)
+    {
+        if (*n_leaves > max_leaves) return fail(RTCU_ERR_INVALID, "leaves_out too small: need %u", *n_leaves);
+        memcpy(leaves_out, leaves.data(), leaves.size() * sizeof(float4));
+    }
+    return RTCU_OK;
+}
+
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out)
 {
     if (!ctx || !out) return fail(RTCU_ERR_INVALID, "null argument");

@@ -310,6 +310,19 @@ def bvh_build_host(spheres: np.ndarray):
     return nodes, order, int(depth.value)
 
 
+def bvh4_build_host(spheres: np.ndarray):
+    """The 4-wide device tree built on the host (no device needed): (nodes (N, 8, 4) f32, leaves (L, 5, 4) f32, depth)."""
+    lib = nat.load_library()
+    sph = nat.contiguous(spheres, np.float32).reshape(-1, 4)
+    n_nodes, n_leaves, depth = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    nat.check(lib.rtcu_bvh4_build_host(nat.ptr(sph), len(sph), None, 0, None, 0, C.byref(n_nodes), C.byref(n_leaves), C.byref(depth)))
+    nodes = np.zeros((n_nodes.value, 8, 4), np.float32)
+    leaves = np.zeros((n_leaves.value, 5, 4), np.float32)
+    nat.check(lib.rtcu_bvh4_build_host(nat.ptr(sph), len(sph), nat.ptr(nodes), len(nodes), nat.ptr(leaves), len(leaves),
+                                       C.byref(n_nodes), C.byref(n_leaves), C.byref(depth)))
+    return nodes, leaves, int(depth.value)
+
+
 def render_multi(contexts: Sequence[Context], view: nat.View, want_accum: bool = False):
     """rtcu_render_multi: single-process sample-range split over several devices."""
     lib = nat.load_library()

@@ -190,3 +190,76 @@ def test_bvh_builder_invariants(lib, n):
     sys.setrecursionlimit(10000)
     check(0)
     assert seen.all()
+
+
+# ---- the 4-wide device tree (collapsed on upload), built on the host: same invariants in the device layout ---------
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 9, 33, 484, 5000, 100001])
+def test_bvh4_device_tree_invariants(lib, n):
+    from rt_b200 import synth
+
+    if n == 484:
+        sph = synth.rtiow_scene().spheres
+    elif n == 100001:
+        sph = synth.grid_scene().spheres
+    else:
+        rng = np.random.default_rng(100 + n)
+        sph = np.concatenate([rng.uniform(-20, 20, (n, 3)), rng.uniform(0.05, 2.0, (n, 1))], axis=1).astype(np.float32)
+        if n >= 5:
+            sph[0] = [0, -1000, 0, 1000]
+            sph[1] = sph[2]
+    n = len(sph)
+    nodes, leaves, depth = R.bvh4_build_host(sph)
+    assert len(nodes) >= 1 and 3 * depth + 2 <= 64  # the traversal stack (BVH_STACK) holds 3 entries per level
+    refs = nodes[:, 6, :].copy().view(np.uint32)    # four child references per node
+    H = nodes[:, 7, :]
+    lo_s = (sph[:, :3].astype(np.float64) - sph[:, 3:4]).astype(np.float64)
+    hi_s = (sph[:, :3].astype(np.float64) + sph[:, 3:4]).astype(np.float64)
+    seen = np.zeros(n, np.int64)
+    visited = np.zeros(len(nodes), bool)
+    max_depth = 0
+    stack = [(0, 1)]
+    # returns nothing: containment is checked child by child against the spheres below it, gathered iteratively
+    below = {}  # node -> (lo, hi) of everything below it, filled in post-order
+
+    order = []
+    while stack:
+        node, d = stack.pop()
+        assert not visited[node]
+        visited[node] = True
+        max_depth = max(max_depth, d)
+        order.append(node)
+        for c in range(4):
+            if not (refs[node, c] & 0x80000000) and np.isfinite(H[node, c]):
+                stack.append((int(refs[node, c]), d + 1))
+    assert visited.all() and max_depth == depth
+    for node in reversed(order):
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
+        for c in range(4):
+            pair, slot = c // 2, c % 2
+            cen = nodes[node, 3 * pair:3 * pair + 3, slot].astype(np.float64)
+            half = nodes[node, 3 * pair:3 * pair + 3, 2 + slot].astype(np.float64)
+            if not np.isfinite(H[node, c]):
+                assert (half == -np.inf).all() and H[node, c] == -np.inf  # empty slot: can never be hit
+                continue
+            assert H[node, c] >= half.sum() * (1 - 1e-7)
+            if refs[node, c] & 0x80000000:
+                blk = leaves[int(refs[node, c] & 0x7FFFFFFF)]
+                idx = blk[4].view(np.uint32)
+                real = idx[idx != 0x7FFFFFFF]
+                assert 1 <= len(real) <= 4 and list(real) == sorted(real)
+                # the packed pairs hold exactly those spheres: {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}, padding r2 = -inf
+                for k, i in enumerate(idx):
+                    a, b = blk[2 * (k // 2)], blk[2 * (k // 2) + 1]
+                    got = np.array([a[k % 2], a[2 + k % 2], b[k % 2], b[2 + k % 2]], np.float32)
+                    if i == 0x7FFFFFFF:
+                        assert got[3] == -np.inf
+                    else:
+                        assert (got[:3] == sph[i, :3]).all() and got[3] == np.float32(sph[i, 3]) * np.float32(sph[i, 3])
+                seen[real] += 1
+                sub_lo, sub_hi = lo_s[real].min(axis=0), hi_s[real].max(axis=0)
+            else:
+                sub_lo, sub_hi = below[int(refs[node, c])]
+            assert (cen - half <= sub_lo).all() and (cen + half >= sub_hi).all()  # [c - h, c + h] encloses the subtree
+            lo_all, hi_all = np.minimum(lo_all, sub_lo), np.maximum(hi_all, sub_hi)
+        below[node] = (lo_all, hi_all)
+    assert (seen == 1).all()  # every sphere in exactly one leaf
