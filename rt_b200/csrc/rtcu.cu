@@ -105,21 +105,13 @@ struct rtcu_ctx {
     int sm_count = 0;
 
     // scene (device)
-    DevBuf<float4> sph;        // {cx,cy,cz,r*r}
-    DevBuf<float4> pairs;      // packed-scan layout, see SceneDev::pairs
-    DevBuf<uint32_t> sph_mat;
-    DevBuf<float4> planes;
-    DevBuf<uint32_t> plane_mat;
-    DevBuf<MatRec> mats;
-    DevBuf<float4> boxes;      // rasterizer only: {lo.xyz,0},{hi.xyz,0} per box
-    DevBuf<uint32_t> box_mat;
-    DevBuf<float4> albedo;     // rasterizer only: materials.albedo()
+    DevBuf<unsigned char> scene_arena;       // every scene column and the BVH, each at a 256-byte aligned offset
+    PinnedBuf<unsigned char> h_scene_arena;  // its staging copy: one H2D transfer per upload
     RasterScene raster = {};
     DevBuf<uint32_t> raster_prim;
     DevBuf<float> raster_depth;
     PinnedBuf<uint32_t> h_raster_prim;
     PinnedBuf<float> h_raster_depth;
-    DevBuf<float4> bvh_nodes, leaf_blk;
     bool have_bvh = false;
     uint32_t bvh_depth = 0;
     float ms_bvh_build = 0.0f;
@@ -842,12 +834,12 @@ void rtcu_destroy(rtcu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    ctx->sph.release(); ctx->pairs.release(); ctx->sph_mat.release(); ctx->planes.release(); ctx->plane_mat.release();
-    ctx->mats.release(); ctx->bvh_nodes.release(); ctx->leaf_blk.release(); ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
+    ctx->scene_arena.release(); ctx->h_scene_arena.release();
+    ctx->accum.release(); ctx->rgba8.release(); ctx->h_rgba8.release(); ctx->h_accum.release();
     for (int i = 0; i < 2; i++) { ctx->wf_o[i].release(); ctx->wf_d[i].release(); ctx->wf_thr[i].release(); }
     for (auto& l : ctx->wf_list) l.release();
     ctx->wf_rad.release(); ctx->wf_sum.release(); ctx->wf_hit.release(); ctx->wf_counts.release(); ctx->h_wf_counts.release();
-    ctx->boxes.release(); ctx->box_mat.release(); ctx->albedo.release(); ctx->raster_prim.release(); ctx->raster_depth.release();
+    ctx->raster_prim.release(); ctx->raster_depth.release();
     ctx->h_raster_prim.release(); ctx->h_raster_depth.release();
     ctx->tile_cost.release(); ctx->tile_order.release();
     ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
@@ -926,12 +918,6 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         }
         mats[i] = r;
     }
-    CU(ctx->sph.reserve(s->n_spheres ? s->n_spheres : 1));
-    CU(ctx->pairs.reserve(pairs.size()));
-    CU(ctx->sph_mat.reserve(s->n_spheres ? s->n_spheres : 1));
-    CU(ctx->planes.reserve(s->n_planes ? s->n_planes : 1));
-    CU(ctx->plane_mat.reserve(s->n_planes ? s->n_planes : 1));
-    CU(ctx->mats.reserve(s->n_materials));
     // rasterizer columns (rasterizer.cpp reads boxes.value() and materials.albedo(), which the path tracers never touch)
     std::vector<float4> boxes(2 * (size_t)s->n_boxes), albedo(s->n_materials);
     for (uint32_t i = 0; i < s->n_boxes; i++)
@@ -944,36 +930,10 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     }
     for (uint32_t i = 0; i < s->n_materials; i++)
         albedo[i] = make_float4(s->materials[i].albedo[0], s->materials[i].albedo[1], s->materials[i].albedo[2], s->materials[i].albedo[3]);
-    CU(ctx->boxes.reserve(boxes.size() ? boxes.size() : 1));
-    CU(ctx->box_mat.reserve(s->n_boxes ? s->n_boxes : 1));
-    CU(ctx->albedo.reserve(s->n_materials));
-    // make sure no kernel of a previous frame still reads the old scene
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), pairs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    if (s->n_spheres)
-    {
-        CU(cudaMemcpyAsync(ctx->sph.p, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->sph_mat.p, s->sphere_material, s->n_spheres * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if (s->n_planes)
-    {
-        CU(cudaMemcpyAsync(ctx->planes.p, s->planes, s->n_planes * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->plane_mat.p, s->plane_material, s->n_planes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    CU(cudaMemcpyAsync(ctx->mats.p, mats.data(), mats.size() * sizeof(MatRec), cudaMemcpyHostToDevice, ctx->stream));
-    if (s->n_boxes)
-    {
-        CU(cudaMemcpyAsync(ctx->boxes.p, boxes.data(), boxes.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->box_mat.p, s->box_material, s->n_boxes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    CU(cudaMemcpyAsync(ctx->albedo.p, albedo.data(), albedo.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     // BVH: built whenever there are spheres (cheap for small scenes; lets ACCEL_BVH be requested explicitly for parity
     // tests); RTCU_ACCEL_AUTO uses it from rtcu_bvh_threshold() spheres up
     ctx->tile_hist_valid = false; // per-tile costs belong to the scene they were measured on
     ctx->have_bvh = false;
-    ctx->scene.bvh_nodes = nullptr;
-    ctx->scene.leaf_blk = nullptr;
-    ctx->scene.n_bvh_nodes = 0;
     std::vector<float4> nodes_dev, leaf_blk;
     if (s->n_spheres)
     {
@@ -988,37 +948,71 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         if (!nodes_dev.empty() && 3 * depth4 + 2 <= (uint32_t)BVH_STACK)
         {
             ctx->bvh_depth = depth4;
-            CU(ctx->bvh_nodes.reserve(nodes_dev.size()));
-            CU(ctx->leaf_blk.reserve(leaf_blk.size()));
-            CU(cudaMemcpyAsync(ctx->bvh_nodes.p, nodes_dev.data(), nodes_dev.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaMemcpyAsync(ctx->leaf_blk.p, leaf_blk.data(), leaf_blk.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-            ctx->scene.bvh_nodes = ctx->bvh_nodes.p;
-            ctx->scene.leaf_blk = ctx->leaf_blk.p;
-            ctx->scene.n_bvh_nodes = (uint32_t)(nodes_dev.size() / 8);
             ctx->have_bvh = true;
         }
+        else
+        {
+            nodes_dev.clear();
+            leaf_blk.clear();
+        }
     }
-    CU(cudaStreamSynchronize(ctx->stream)); // the staging vectors die here
-    ctx->scene.spheres = ctx->sph.p;
-    ctx->scene.pairs = ctx->pairs.p;
-    ctx->scene.sphere_material = ctx->sph_mat.p;
+    // One arena, one copy: every column is laid out at a 256-byte aligned offset of a pinned staging buffer and goes to the
+    // device in a single transfer (a dozen small copies from pageable memory cost ~5 us each -- most of the upload for the
+    // small scenes an interactive session re-sends).
+    struct Seg { size_t off, bytes; const void* src; };
+    std::vector<Seg> segs;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) {
+        const size_t off = (total + 255) & ~(size_t)255;
+        total = off + (bytes ? bytes : 16); // an empty column still gets a valid address
+        segs.push_back(Seg{ off, bytes, src });
+        return off;
+    };
+    const size_t o_pairs = add(pairs.data(), pairs.size() * sizeof(float4));
+    const size_t o_sph = add(sph.data(), sph.size() * sizeof(float4));
+    const size_t o_sph_mat = add(s->sphere_material, (size_t)s->n_spheres * sizeof(uint32_t));
+    const size_t o_planes = add(s->planes, (size_t)s->n_planes * sizeof(float4));
+    const size_t o_plane_mat = add(s->plane_material, (size_t)s->n_planes * sizeof(uint32_t));
+    const size_t o_mats = add(mats.data(), mats.size() * sizeof(MatRec));
+    const size_t o_boxes = add(boxes.data(), boxes.size() * sizeof(float4));
+    const size_t o_box_mat = add(s->box_material, (size_t)s->n_boxes * sizeof(uint32_t));
+    const size_t o_albedo = add(albedo.data(), albedo.size() * sizeof(float4));
+    const size_t o_nodes = add(nodes_dev.data(), nodes_dev.size() * sizeof(float4));
+    const size_t o_leaves = add(leaf_blk.data(), leaf_blk.size() * sizeof(float4));
+    // make sure no kernel of a previous frame still reads the old scene, nor a previous upload the staging buffer
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->last_stream && ctx->last_stream != ctx->stream && cudaStreamSynchronize(ctx->last_stream) != cudaSuccess)
+        cudaGetLastError(); // the caller's stream may be gone by now; nothing of ours can be running on it then
+    CU(ctx->scene_arena.reserve(total));
+    CU(ctx->h_scene_arena.reserve(total));
+    for (const Seg& g : segs)
+        if (g.bytes) memcpy(ctx->h_scene_arena.p + g.off, g.src, g.bytes);
+    CU(cudaMemcpyAsync(ctx->scene_arena.p, ctx->h_scene_arena.p, total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // renders on other streams (rtcu_render_device) must see the new scene
+    unsigned char* base = ctx->scene_arena.p;
+    ctx->scene.bvh_nodes = ctx->have_bvh ? reinterpret_cast<const float4*>(base + o_nodes) : nullptr;
+    ctx->scene.leaf_blk = ctx->have_bvh ? reinterpret_cast<const float4*>(base + o_leaves) : nullptr;
+    ctx->scene.n_bvh_nodes = (uint32_t)(nodes_dev.size() / 8);
+    ctx->scene.spheres = reinterpret_cast<const float4*>(base + o_sph);
+    ctx->scene.pairs = reinterpret_cast<const float4*>(base + o_pairs);
+    ctx->scene.sphere_material = reinterpret_cast<const uint32_t*>(base + o_sph_mat);
     ctx->scene.n_spheres = s->n_spheres;
-    ctx->scene.planes = ctx->planes.p;
-    ctx->scene.plane_material = ctx->plane_mat.p;
+    ctx->scene.planes = reinterpret_cast<const float4*>(base + o_planes);
+    ctx->scene.plane_material = reinterpret_cast<const uint32_t*>(base + o_plane_mat);
     ctx->scene.n_planes = s->n_planes;
-    ctx->scene.materials = ctx->mats.p;
+    ctx->scene.materials = reinterpret_cast<const MatRec*>(base + o_mats);
     ctx->scene.n_materials = s->n_materials;
-    ctx->raster.spheres = ctx->sph.p;
-    ctx->raster.pairs = ctx->pairs.p;
-    ctx->raster.sphere_material = ctx->sph_mat.p;
+    ctx->raster.spheres = ctx->scene.spheres;
+    ctx->raster.pairs = ctx->scene.pairs;
+    ctx->raster.sphere_material = ctx->scene.sphere_material;
     ctx->raster.n_spheres = s->n_spheres;
-    ctx->raster.planes = ctx->planes.p;
-    ctx->raster.plane_material = ctx->plane_mat.p;
+    ctx->raster.planes = ctx->scene.planes;
+    ctx->raster.plane_material = ctx->scene.plane_material;
     ctx->raster.n_planes = s->n_planes;
-    ctx->raster.boxes = ctx->boxes.p;
-    ctx->raster.box_material = ctx->box_mat.p;
+    ctx->raster.boxes = reinterpret_cast<const float4*>(base + o_boxes);
+    ctx->raster.box_material = reinterpret_cast<const uint32_t*>(base + o_box_mat);
     ctx->raster.n_boxes = s->n_boxes;
-    ctx->raster.albedo = ctx->albedo.p;
+    ctx->raster.albedo = reinterpret_cast<const float4*>(base + o_albedo);
     ctx->have_scene = true;
     return RTCU_OK;
 }
