@@ -510,6 +510,18 @@ def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes,
         assert np.abs(unpack_rgba(rgba8) - unpack_rgba(r_rgba8)).max() <= 1
         rgba8_b, accum_b = ctx.render(v, want_accum=True)  # deterministic
         np.testing.assert_array_equal(accum_b, accum)
+    # images and tiles smaller than one 8x4 patch
+    for tw, th, tile in ((3, 2, None), (40, 30, (17, 11, 18, 12))):
+        tkw = dict(samples_per_pixel=16, max_bounces=depth, material_mode=nat.MODE_SM)
+        tv = make_view(sc, tw, th, tile=tile, **tkw) if tile else make_view(sc, tw, th, **tkw)
+        _, small = ctx.render(tv, want_accum=True)
+        assert ctx.stats()["kernel_launches"] == 1
+        monkeypatch.setenv("RTCU_BVH_DIRECT", "0")
+        _, small_t = ctx.render(tv, want_accum=True)
+        monkeypatch.delenv("RTCU_BVH_DIRECT")
+        np.testing.assert_array_equal(small[..., 3], small_t[..., 3])
+        np.testing.assert_allclose(small[..., :3], small_t[..., :3], rtol=4e-6, atol=1e-6)
+        assert small[..., 3].sum() == 16 * (1 if tile else tw * th)
     # a partial tile writes only the tile, and equals the same pixels of the frame bit for bit (per-pixel work is independent)
     img = np.full((h, w), 0xDEADBEEF, np.uint32)
     tv = make_view(sc, w, h, tile=(13, 9, 150, 100), **kw)
