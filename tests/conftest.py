@@ -25,7 +25,7 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def scenes():
-    sys.path.insert(0, str(ROOT / "tools"))
+    sys.path.insert(0, str(ROOT / "tests" / "tools"))
     import gen_golden
 
     return {k: v for k, v in gen_golden.SCENES.items()}

@@ -373,7 +373,7 @@ def test_bvh_auto_threshold(ctx, scenes):
 # ---- the CUDA path against outputs of the reference's own renderer sources (oracle/_ref, see test_reference_build.py) --
 def test_render_matches_reference_build_fixtures(ctx, scenes):
     import sys
-    sys.path.insert(0, str(GOLDEN.parent.parent / "tools"))
+    sys.path.insert(0, str(GOLDEN.parent / "tools"))
     import gen_golden
 
     for name, renderer, mode, w, h, spp, depth in gen_golden.REFBUILD_CASES:

@@ -15,7 +15,7 @@ MISS, PLANE, BOX = nat.PRIM_MISS, nat.PRIM_PLANE, nat.PRIM_BOX
 
 def _raster_cases():
     import sys
-    sys.path.insert(0, str(GOLDEN.parent.parent / "tools"))
+    sys.path.insert(0, str(GOLDEN.parent / "tools"))
     import gen_golden
 
     return gen_golden

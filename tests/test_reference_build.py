@@ -8,7 +8,7 @@ Schlick, draw order, recursion and attenuation nesting, per-pixel accumulation, 
 the reference's code, not a restatement.  The oracle must reproduce its packed images bit for bit.  What stays unverified is
 muu itself (vector / matrix / ray primitives), which both sides take from the same numbered SPEC.
 
-tests/golden/refbuild_*.npz are outputs of that build (tools/gen_golden.py), committed so the pin holds where the reference
+tests/golden/refbuild_*.npz are outputs of that build (tests/tools/gen_golden.py), committed so the pin holds where the reference
 tree is absent; the live tests run wherever the prebuilt library (or the reference tree) is available."""
 import numpy as np
 import pytest
@@ -21,7 +21,7 @@ from conftest import GOLDEN
 
 def _cases():
     import sys
-    sys.path.insert(0, str(GOLDEN.parent.parent / "tools"))
+    sys.path.insert(0, str(GOLDEN.parent / "tools"))
     import gen_golden
 
     return gen_golden.REFBUILD_CASES

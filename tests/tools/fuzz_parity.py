@@ -4,10 +4,10 @@ cameras, both scatter tables) rendered by the CUDA path (linear scan, BVH, wavef
 strict CPU oracle; closest hits of random + silhouette-grazing ray batches compared bit for bit; the preview renderer
 (rtcu_rasterize, scan and BVH, with random boxes) compared bit for bit (pixels, primitive ids, depth); every third scene also rendered through the lanes-share-a-pixel BVH path.
 Prints one JSON summary.
-usage: python tools/fuzz_parity.py [n_scenes] [seed]"""
+usage: python tests/tests/tools/fuzz_parity.py [n_scenes] [seed]"""
 import json, os, pathlib, sys
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 

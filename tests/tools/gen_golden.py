@@ -3,13 +3,13 @@
 
 The reference ships no golden vectors, so these fixtures pin the oracle's own
 output: a change to either the oracle or the CUDA path that alters results shows up against them.
-Run from the repo root: `python tools/gen_golden.py`.
+Run from the repo root: `python tests/tests/tools/gen_golden.py`.
 """
 import pathlib, sys
 
 import numpy as np
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from oracle.binding import Oracle  # noqa: E402
 from rt_b200 import scene as S, synth  # noqa: E402

@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
 """Times the BASELINE.json configs on cuda:0 through the C ABI (device-resident kernel time from CUDA events
 inside rtcu_render, best of `--reps`) and prints one JSON line per config.  Optionally times the CPU oracle's
-fast build beside it (`--cpu`, bounded row subsets).  Usage: python tools/run_configs.py [c1 c2 c2mg c3 c4 c5slice] """
+fast build beside it (`--cpu`, bounded row subsets).  Usage: python tests/tests/tools/run_configs.py [c1 c2 c2mg c3 c4 c5slice] """
 import argparse, json, os, pathlib, sys, time
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 

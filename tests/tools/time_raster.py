@@ -6,7 +6,7 @@ import argparse, json, pathlib, sys, time
 
 import numpy as np
 
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from rt_b200 import scene as S, synth  # noqa: E402
 from rt_b200.renderer import Context, make_view  # noqa: E402
