@@ -4,7 +4,7 @@
 // visiting order with its acceptance rule (`!hit || *hit >= dist` rejects: strict '<', first index wins ties, no
 // minimum distance, so a sphere entirely behind the near plane is accepted with a negative distance exactly as the
 // reference does), then N.L shading against the eye.  Arithmetic follows the numbered SPEC of spec.cuh (S1-S5, S7, S11)
-// plus S13 (ray against box) below; results are bit-identical to oracle/rtref.c:rtref_rasterize and to the reference's own
+// plus S13 (ray against box) below; results are bit-identical to the CPU checker's restatement and to the reference's own
 // rasterizer.cpp compiled against the muu stand-in (tests/test_gpu_raster.py).
 //
 // The sphere sweep is the same packed-FP32 pair test as the path tracer's linear scan (FFMA2/FADD2/FMUL2, two spheres per

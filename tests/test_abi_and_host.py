@@ -263,3 +263,21 @@ def test_bvh4_device_tree_invariants(lib, n):
             lo_all, hi_all = np.minimum(lo_all, sub_lo), np.maximum(hi_all, sub_hi)
         below[node] = (lo_all, hi_all)
     assert (seen == 1).all()  # every sphere in exactly one leaf
+
+
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: the product (rt_b200/, include/, plugin/, tools/) never imports, links or names it;
+    only tests/ (incl. tests/tools), __graft_entry__.smoke() and bench.py's CPU legs load it.  rt_b200/build.py may *build* it."""
+    allowed_py = {ROOT / "bench.py", ROOT / "__graft_entry__.py"}
+    offenders = []
+    for p in ROOT.rglob("*"):
+        rel = p.relative_to(ROOT)
+        if not p.is_file() or rel.parts[0] in ("tests", "oracle", "gpurun_out", ".git", "profiles") or p.suffix not in (".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".c"):
+            continue
+        text = p.read_text(errors="replace")
+        uses = re.search(r"from oracle|import oracle|oracle\.binding|rtref_|librtref|librt_ref", text) is not None
+        if uses and p not in allowed_py and rel != pathlib.Path("rt_b200/build.py"):
+            offenders.append(str(rel))
+    assert offenders == [], offenders
+    build_py = (ROOT / "rt_b200" / "build.py").read_text()
+    assert "oracle.binding" not in build_py and "CDLL" not in build_py  # it only runs `make -C oracle`
