@@ -318,8 +318,10 @@ def run_gpu(args):
     host_np = host_rgba.numpy().view(np.uint32)
     scene_bytes = int(scene.spheres.nbytes + scene.sphere_material.nbytes + scene.planes.nbytes + scene.plane_material.nbytes + scene.materials.nbytes)
 
+    prepared = ctx.prepare_scene(scene)  # the descriptor over the host arrays; the upload itself happens every step
+
     def step_e2e():
-        ctx.upload_scene(scene)
+        ctx.upload_prepared(prepared)
         if world == 1:
             ctx.render(view, rgba8=host_np, want_accum=False)  # rtcu_render: launch + D2H into the pinned buffer + sync
         else:

@@ -1136,7 +1136,8 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     const size_t off = row0 * view->width, cnt = rows * view->width;
     if (rgba8_out && zero_copy)
     {
-        CU(cudaStreamSynchronize(ctx->stream)); // the pixels are already in the caller's buffer
+        // the kernels store the pixels straight into the caller's buffer: the one synchronisation in fetch_counters below
+        // completes them together with the counters
     }
     else if (rgba8_out)
     {

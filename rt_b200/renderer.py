@@ -170,7 +170,9 @@ class Context:
         return self._h
 
     # -- scene ----------------------------------------------------------------------------------
-    def upload_scene(self, scene: Scene) -> None:
+    def prepare_scene(self, scene: Scene):
+        """Flattens `scene` into the C descriptor once: (rtcu_scene, arrays that must outlive it).  A caller that re-sends an
+        unchanged scene every frame (bench.py's end-to-end loop) skips the numpy conversions, not the upload."""
         sph = nat.contiguous(scene.spheres, np.float32).reshape(-1, 4)
         smat = nat.contiguous(scene.sphere_material, np.uint32)
         pl = nat.contiguous(scene.planes, np.float32).reshape(-1, 4)
@@ -182,7 +184,14 @@ class Context:
                           nat.ptr(pl) if len(pl) else None, nat.ptr(pmat) if len(pmat) else None, len(pl),
                           nat.ptr(mats) if len(mats) else None, len(mats),
                           nat.ptr(bx) if len(bx) else None, nat.ptr(bmat) if len(bmat) else None, len(bx))
-        nat.check(self._lib.rtcu_upload_scene(self._h, C.byref(d)))
+        return d, (sph, smat, pl, pmat, mats, bx, bmat)
+
+    def upload_prepared(self, prepared) -> None:
+        """rtcu_upload_scene with a descriptor from prepare_scene: validation, BVH build and the H2D transfer all happen"""
+        nat.check(self._lib.rtcu_upload_scene(self._h, C.byref(prepared[0])))
+
+    def upload_scene(self, scene: Scene) -> None:
+        self.upload_prepared(self.prepare_scene(scene))
 
     # -- render ---------------------------------------------------------------------------------
     def render(self, view: nat.View, rgba8: Optional[np.ndarray] = None, accum: Optional[np.ndarray] = None,
