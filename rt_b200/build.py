@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",  # every fused multiply-add in the kernels is written explicitly (arithmetic SPEC)
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC,-pthread", "-shared",
 ]
 
 

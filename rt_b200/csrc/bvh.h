@@ -7,9 +7,14 @@
 // spheres with the same S4 arithmetic, breaks ties by (t, index) and culls boxes conservatively (BVH).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace rtcu_bvh {
@@ -55,31 +60,140 @@ struct Result {
 constexpr int MAX_LEAF = 4;
 constexpr int BINS = 16;
 
-// spheres: n x {cx,cy,cz,radius}.  Boxes are rounded outward by one ulp-scale step so that c +- r computed in
-// float still encloses the sphere.
-inline Result build(const float* spheres, uint32_t n)
-{
-    Result out;
-    std::vector<Box> boxes(n);
-    std::vector<float> cent(3 * (size_t)n);
-    for (uint32_t i = 0; i < n; i++)
+// Worker threads for one build.  They are started once and parked on a generation counter between parallel sections: a short
+// spin (sections follow each other within microseconds in the lower levels), then a condition variable, so an idle or
+// oversubscribed machine is not burnt.  `run(total, chunk, fn)` calls fn(i) for every i in [0, total), handing out `chunk`
+// indices at a time, and returns when all calls have returned.
+class Pool {
+public:
+    explicit Pool(unsigned workers)
     {
-        const float* s = spheres + 4 * (size_t)i;
-        const float r = std::fabs(s[3]);
-        for (int k = 0; k < 3; k++)
+        for (unsigned w = 0; w < workers; w++) threads_.emplace_back([this] { park(); });
+    }
+    ~Pool()
+    {
+        quit_.store(true);
+        publish();
+        for (auto& th : threads_) th.join();
+    }
+    Pool(const Pool&) = delete;
+    Pool& operator=(const Pool&) = delete;
+    unsigned width() const { return (unsigned)threads_.size() + 1; }
+    template <class F>
+    void run(size_t total, size_t chunk, const F& fn)
+    {
+        if (threads_.empty() || total <= chunk)
         {
-            const float pad = (std::fabs(s[k]) + r) * 2.4e-7f; // 4 ulp of the larger magnitude
-            boxes[i].lo[k] = s[k] - r - pad;
-            boxes[i].hi[k] = s[k] + r + pad;
-            cent[3 * (size_t)i + k] = s[k];
+            for (size_t i = 0; i < total; i++) fn(i);
+            return;
+        }
+        struct Thunk { static void call(const void* f, size_t i) { (*static_cast<const F*>(f))(i); } };
+        fn_ = &fn; call_ = &Thunk::call; total_ = total; chunk_ = chunk;
+        cursor_.store(0);
+        parked_.store(0);
+        publish();
+        drain();
+        // the workers are running (or about to): spin, and give the core away if it takes long
+        for (unsigned spins = 0; parked_.load(std::memory_order_acquire) != threads_.size();)
+        {
+            relax();
+            if (++spins > SPIN) { std::this_thread::yield(); spins = 0; }
         }
     }
+
+private:
+    static constexpr unsigned SPIN = 1u << 15; // ~1 ms of pause instructions: longer than any serial stretch of a build
+    static void relax()
+    {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    void publish()
+    {
+        generation_.fetch_add(1); // seq_cst with the sleepers_ read below: a worker either sees the new generation or is seen here
+        if (sleepers_.load() != 0)
+        {
+            { std::lock_guard<std::mutex> lock(mutex_); }
+            wake_.notify_all();
+        }
+    }
+    void drain()
+    {
+        for (size_t i = cursor_.fetch_add(chunk_); i < total_; i = cursor_.fetch_add(chunk_))
+            for (size_t j = i, e = std::min(total_, i + chunk_); j < e; j++) call_(fn_, j);
+    }
+    void park()
+    {
+        for (uint64_t seen = 0;;)
+        {
+            unsigned spins = 0;
+            while (generation_.load(std::memory_order_acquire) == seen && ++spins <= SPIN) relax();
+            if (generation_.load() == seen)
+            {
+                std::unique_lock<std::mutex> lock(mutex_);
+                sleepers_.fetch_add(1);
+                wake_.wait(lock, [&] { return generation_.load() != seen; });
+                sleepers_.fetch_sub(1);
+            }
+            seen++;
+            if (quit_.load()) return;
+            drain();
+            parked_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mutex_;
+    std::condition_variable wake_;
+    std::atomic<uint64_t> generation_{ 0 };
+    std::atomic<unsigned> sleepers_{ 0 };
+    std::atomic<size_t> cursor_{ 0 };
+    std::atomic<size_t> parked_{ 0 };
+    std::atomic<bool> quit_{ false };
+    const void* fn_ = nullptr;
+    void (*call_)(const void*, size_t) = nullptr;
+    size_t total_ = 0, chunk_ = 1;
+};
+
+// threads of a build: the machine's, at most 16 (the passes are memory-bound long before that); RTCU_BVH_THREADS overrides
+inline unsigned thread_count()
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("RTCU_BVH_THREADS")) hw = (unsigned)std::max(1, std::atoi(e));
+    return std::min(std::max(hw, 1u), 16u);
+}
+
+// spheres: n x {cx,cy,cz,radius}.  Boxes are rounded outward by one ulp-scale step so that c +- r computed in
+// float still encloses the sphere.
+//
+// The result -- node order, primitive order, every box -- does not depend on the number of threads: boxes and bin counts are
+// min / max / integer sums (exact in any order), a split decides set membership only, node indices are assigned serially in
+// task order, and a leaf's primitives are sorted by original index (tests compare against RTCU_BVH_THREADS=1).
+inline Result build(const float* spheres, uint32_t n, Pool& pool)
+{
+    Result out;
+    const unsigned width = n >= 8192 ? pool.width() : 1u; // small scenes: one thread, the pool is not touched
+
+    std::vector<Box> boxes(n);
+    std::vector<float> cent(3 * (size_t)n);
     out.order.resize(n);
-    for (uint32_t i = 0; i < n; i++) out.order[i] = i;
+    pool.run(((size_t)n + 4095) / 4096, width > 1 ? 1 : SIZE_MAX, [&](size_t blk) {
+        for (uint32_t i = (uint32_t)(blk * 4096), e = (uint32_t)std::min<size_t>(n, (blk + 1) * 4096); i < e; i++)
+        {
+            const float* s = spheres + 4 * (size_t)i;
+            const float r = std::fabs(s[3]);
+            for (int k = 0; k < 3; k++)
+            {
+                const float pad = (std::fabs(s[k]) + r) * 2.4e-7f; // 4 ulp of the larger magnitude
+                boxes[i].lo[k] = s[k] - r - pad;
+                boxes[i].hi[k] = s[k] + r + pad;
+                cent[3 * (size_t)i + k] = s[k];
+            }
+            out.order[i] = i;
+        }
+    });
 
     struct Task { uint32_t begin, end; int32_t parent; int side; uint32_t depth; };
-    // breadth-first construction: node indices of the top levels are contiguous (shared-memory cache on the device)
-    std::vector<Task> queue;
     auto range_box = [&](uint32_t b, uint32_t e) {
         Box bb; bb.reset();
         for (uint32_t k = b; k < e; k++) bb.grow(boxes[out.order[k]]);
@@ -104,89 +218,198 @@ inline Result build(const float* spheres, uint32_t n)
         out.max_depth = 1;
         return out;
     }
-    queue.push_back({ 0, n, -1, 0, 1 });
-    for (size_t qi = 0; qi < queue.size(); qi++)
-    {
-        const Task t = queue[qi];
-        out.max_depth = std::max(out.max_depth, t.depth);
-        const uint32_t count = t.end - t.begin;
-        // this task becomes an inner node (the root task reuses node 0)
-        int32_t self = 0;
-        if (t.parent >= 0)
+
+    // binned SAH over the centroid bounds: per axis BINS boxes and counts, then the cheapest of the 3 x (BINS - 1) planes
+    struct Bins {
+        Box box[3][BINS]; uint32_t n[3][BINS];
+        void reset()
         {
-            self = (int32_t)out.nodes.size();
-            out.nodes.push_back(Node{});
-            set_child(t.parent, t.side, range_box(t.begin, t.end), self, 0);
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < BINS; b++) { box[a][b].reset(); n[a][b] = 0; }
         }
-        // choose the split: binned SAH over the centroid bounds, best of the three axes
-        Box cb; cb.reset();
-        for (uint32_t k = t.begin; k < t.end; k++) cb.grow_point(&cent[3 * (size_t)out.order[k]]);
-        int best_axis = -1, best_bin = -1;
-        float best_cost = FLT_MAX;
+    };
+    auto bin_of = [](float c, float lo, float scale) { return std::min(std::max((int)((c - lo) * scale), 0), BINS - 1); };
+    auto fill_bins = [&](Bins& bins, const Box& cb, uint32_t b, uint32_t e) {
         for (int axis = 0; axis < 3; axis++)
         {
             const float ext = cb.hi[axis] - cb.lo[axis];
             if (!(ext > 0.0f)) continue;
-            Box bin_box[BINS]; uint32_t bin_n[BINS] = {};
-            for (auto& b : bin_box) b.reset();
             const float scale = BINS / ext;
-            for (uint32_t k = t.begin; k < t.end; k++)
+            for (uint32_t k = b; k < e; k++)
             {
                 const uint32_t p = out.order[k];
-                int b = (int)((cent[3 * (size_t)p + axis] - cb.lo[axis]) * scale);
-                b = std::min(std::max(b, 0), BINS - 1);
-                bin_box[b].grow(boxes[p]);
-                bin_n[b]++;
+                const int bin = bin_of(cent[3 * (size_t)p + axis], cb.lo[axis], scale);
+                bins.box[axis][bin].grow(boxes[p]);
+                bins.n[axis][bin]++;
             }
+        }
+    };
+    auto choose_split = [&](const Bins& bins, const Box& cb, int& best_axis, int& best_bin) {
+        best_axis = -1; best_bin = -1;
+        float best_cost = FLT_MAX;
+        for (int axis = 0; axis < 3; axis++)
+        {
+            if (!(cb.hi[axis] - cb.lo[axis] > 0.0f)) continue;
             float right_area[BINS]; uint32_t right_n[BINS];
             Box acc; acc.reset(); uint32_t cnt = 0;
             for (int b = BINS - 1; b > 0; b--)
             {
-                acc.grow(bin_box[b]); cnt += bin_n[b];
+                acc.grow(bins.box[axis][b]); cnt += bins.n[axis][b];
                 right_area[b] = cnt ? acc.half_area() : 0.0f; right_n[b] = cnt;
             }
             acc.reset(); cnt = 0;
             for (int b = 0; b < BINS - 1; b++)
             {
-                acc.grow(bin_box[b]); cnt += bin_n[b];
+                acc.grow(bins.box[axis][b]); cnt += bins.n[axis][b];
                 if (cnt == 0 || right_n[b + 1] == 0) continue;
                 const float cost = acc.half_area() * cnt + right_area[b + 1] * right_n[b + 1];
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
             }
         }
-        uint32_t mid;
-        if (best_axis >= 0)
-        {
-            const float lo = cb.lo[best_axis], scale = BINS / (cb.hi[best_axis] - cb.lo[best_axis]);
-            auto it = std::partition(out.order.begin() + t.begin, out.order.begin() + t.end, [&](uint32_t p) {
-                int b = (int)((cent[3 * (size_t)p + best_axis] - lo) * scale);
-                b = std::min(std::max(b, 0), BINS - 1);
-                return b <= best_bin;
-            });
-            mid = (uint32_t)(it - out.order.begin());
-        }
-        else
-            mid = t.begin; // all centroids coincide
+    };
+    struct Split { Task child[2]; bool has[2]; };
+    // after the split: a side of <= MAX_LEAF primitives becomes a leaf of this node, a larger one a task of the next level
+    auto finish = [&](const Task& t, const int32_t self, uint32_t mid, Split& sp) {
         if (mid == t.begin || mid == t.end)
         {
-            // degenerate: split by index order in the middle (keeps leaves <= MAX_LEAF)
-            mid = t.begin + count / 2;
+            // degenerate (all centroids coincide, or every primitive on one side): split by index order in the middle
+            mid = t.begin + (t.end - t.begin) / 2;
             std::sort(out.order.begin() + t.begin, out.order.begin() + t.end);
         }
         const uint32_t ranges[2][2] = { { t.begin, mid }, { mid, t.end } };
         for (int side = 0; side < 2; side++)
         {
             const uint32_t b = ranges[side][0], e = ranges[side][1];
-            if (e - b <= (uint32_t)MAX_LEAF)
+            sp.has[side] = e - b > (uint32_t)MAX_LEAF;
+            if (!sp.has[side])
             {
                 std::sort(out.order.begin() + b, out.order.begin() + e); // ascending original index inside a leaf
                 set_child(self, side, range_box(b, e), ~(int32_t)b, e - b);
             }
             else
-                queue.push_back({ b, e, self, side, t.depth + 1 });
+                sp.child[side] = Task{ b, e, self, side, t.depth + 1 };
         }
+    };
+
+    // one task on one thread (most of the tree: a level has many tasks, which run side by side)
+    auto process = [&](const Task& t, const int32_t self, Split& sp) {
+        if (t.parent >= 0)
+            set_child(t.parent, t.side, range_box(t.begin, t.end), self, 0);
+        Box cb; cb.reset();
+        for (uint32_t k = t.begin; k < t.end; k++) cb.grow_point(&cent[3 * (size_t)out.order[k]]);
+        Bins bins; bins.reset();
+        fill_bins(bins, cb, t.begin, t.end);
+        int best_axis, best_bin;
+        choose_split(bins, cb, best_axis, best_bin);
+        uint32_t mid = t.begin; // stays there when all centroids coincide
+        if (best_axis >= 0)
+        {
+            const float lo = cb.lo[best_axis], scale = BINS / (cb.hi[best_axis] - cb.lo[best_axis]);
+            auto it = std::partition(out.order.begin() + t.begin, out.order.begin() + t.end,
+                                     [&](uint32_t p) { return bin_of(cent[3 * (size_t)p + best_axis], lo, scale) <= best_bin; });
+            mid = (uint32_t)(it - out.order.begin());
+        }
+        finish(t, self, mid, sp);
+    };
+
+    // one task on all threads (the first levels, where there are fewer tasks than threads): the range is cut into slices, every
+    // pass runs slice-parallel and the per-slice boxes / bins / counts are merged in slice order
+    std::vector<uint32_t> scratch;
+    auto process_wide = [&](const Task& t, const int32_t self, Split& sp) {
+        const uint32_t count = t.end - t.begin;
+        const uint32_t slices = std::min<uint32_t>(4 * width, (count + 1023) / 1024);
+        auto slice = [&](size_t s) { return t.begin + (uint32_t)((uint64_t)count * s / slices); };
+        std::vector<Box> part_box(slices), part_cb(slices);
+        pool.run(slices, 1, [&](size_t s) {
+            Box bb, cb; bb.reset(); cb.reset();
+            for (uint32_t k = slice(s), e = slice(s + 1); k < e; k++)
+            {
+                const uint32_t p = out.order[k];
+                bb.grow(boxes[p]); cb.grow_point(&cent[3 * (size_t)p]);
+            }
+            part_box[s] = bb; part_cb[s] = cb;
+        });
+        Box bb, cb; bb.reset(); cb.reset();
+        for (uint32_t s = 0; s < slices; s++) { bb.grow(part_box[s]); cb.grow(part_cb[s]); }
+        if (t.parent >= 0)
+            set_child(t.parent, t.side, bb, self, 0);
+        std::vector<Bins> part_bins(slices);
+        pool.run(slices, 1, [&](size_t s) { part_bins[s].reset(); fill_bins(part_bins[s], cb, slice(s), slice(s + 1)); });
+        Bins& bins = part_bins[0];
+        for (uint32_t s = 1; s < slices; s++)
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < BINS; b++) { bins.box[a][b].grow(part_bins[s].box[a][b]); bins.n[a][b] += part_bins[s].n[a][b]; }
+        int best_axis, best_bin;
+        choose_split(bins, cb, best_axis, best_bin);
+        uint32_t mid = t.begin;
+        if (best_axis >= 0)
+        {
+            // stable partition through a scratch copy: count per slice, exclusive scan, scatter, copy back
+            const float lo = cb.lo[best_axis], scale = BINS / (cb.hi[best_axis] - cb.lo[best_axis]);
+            auto left = [&](uint32_t p) { return bin_of(cent[3 * (size_t)p + best_axis], lo, scale) <= best_bin; };
+            std::vector<uint32_t> n_left(slices + 1, 0);
+            pool.run(slices, 1, [&](size_t s) {
+                uint32_t c = 0;
+                for (uint32_t k = slice(s), e = slice(s + 1); k < e; k++) c += left(out.order[k]) ? 1u : 0u;
+                n_left[s + 1] = c;
+            });
+            for (uint32_t s = 0; s < slices; s++) n_left[s + 1] += n_left[s];
+            mid = t.begin + n_left[slices];
+            if (scratch.size() < n) scratch.resize(n);
+            pool.run(slices, 1, [&](size_t s) {
+                uint32_t l = t.begin + n_left[s], r = mid + (slice(s) - t.begin - n_left[s]);
+                for (uint32_t k = slice(s), e = slice(s + 1); k < e; k++)
+                {
+                    const uint32_t p = out.order[k];
+                    if (left(p)) scratch[l++] = p; else scratch[r++] = p;
+                }
+            });
+            pool.run(slices, 1, [&](size_t s) { std::copy(scratch.begin() + slice(s), scratch.begin() + slice(s + 1), out.order.begin() + slice(s)); });
+        }
+        finish(t, self, mid, sp);
+    };
+
+    // Level-synchronous construction: the tasks of one level own disjoint primitive ranges and write disjoint fields (their own
+    // node, one side of their parent).
+    std::vector<Task> level{ Task{ 0, n, -1, 0, 1 } }, next_level;
+    std::vector<Split> splits;
+    std::vector<int32_t> self_of;
+    while (!level.empty())
+    {
+        out.max_depth = std::max(out.max_depth, level[0].depth);
+        // node indices in task order (the root task reuses node 0)
+        self_of.assign(level.size(), 0);
+        for (size_t i = 0; i < level.size(); i++)
+            if (level[i].parent >= 0)
+            {
+                self_of[i] = (int32_t)out.nodes.size();
+                out.nodes.push_back(Node{});
+            }
+        splits.assign(level.size(), Split{});
+        uint32_t prims = 0;
+        for (const Task& t : level) prims += t.end - t.begin;
+        if (width == 1 || prims < 4096)
+            for (size_t i = 0; i < level.size(); i++) process(level[i], self_of[i], splits[i]);
+        else if (level.size() < 2 * (size_t)width)
+            for (size_t i = 0; i < level.size(); i++)
+                if (level[i].end - level[i].begin >= 8192) process_wide(level[i], self_of[i], splits[i]);
+                else process(level[i], self_of[i], splits[i]);
+        else
+            pool.run(level.size(), std::min<size_t>(64, std::max<size_t>(1, level.size() / (16 * (size_t)width))),
+                     [&](size_t i) { process(level[i], self_of[i], splits[i]); });
+        next_level.clear();
+        for (const Split& sp : splits)
+            for (int side = 0; side < 2; side++)
+                if (sp.has[side]) next_level.push_back(sp.child[side]);
+        level.swap(next_level);
     }
     return out;
+}
+
+inline Result build(const float* spheres, uint32_t n)
+{
+    Pool pool(n >= 8192 ? thread_count() - 1 : 0);
+    return build(spheres, n, pool);
 }
 
 } // namespace rtcu_bvh

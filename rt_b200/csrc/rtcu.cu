@@ -595,43 +595,78 @@ Kid4 kid_of(const rtcu_bvh::Node& nd, int c)
 }
 
 void pack_bvh4(const rtcu_bvh::Result& bvh, const std::vector<float4>& sph, std::vector<float4>& nodes_dev, std::vector<float4>& leaf_blk,
-               uint32_t& depth4)
+               uint32_t& depth4, rtcu_bvh::Pool& pool)
 {
-    struct Work { int32_t binary; uint32_t depth; };
-    std::vector<Work> queue{ Work{ 0, 1 } }; // breadth-first: a node's index in the 4-wide array is its position in the queue
-    const float ninf = -__builtin_inff();
-    depth4 = 0;
-    for (size_t qi = 0; qi < queue.size(); qi++)
-    {
-        const Work w = queue[qi];
-        depth4 = std::max(depth4, w.depth);
+    // Pass 1 (serial, structure only): breadth-first collapse.  A node's index in the 4-wide array is its position in the queue,
+    // a leaf's block index the order in which the leaves are met.
+    struct Wide {
         Kid4 kids[4];
+        uint32_t ref[4]; // inner: index of the 4-wide child; leaf: 0x80000000 | block; empty: 0x80000000 (never hit)
+        bool empty[4];
+        int32_t binary;
+        uint32_t depth;
+    };
+    std::vector<Wide> wide;
+    wide.reserve(bvh.nodes.size());
+    wide.push_back(Wide{});
+    wide[0].binary = 0;
+    wide[0].depth = 1;
+    uint32_t n_leaves = 0;
+    depth4 = 0;
+    for (size_t qi = 0; qi < wide.size(); qi++)
+    {
+        Wide w = wide[qi];
+        depth4 = std::max(depth4, w.depth);
         int nk = 2;
-        kids[0] = kid_of(bvh.nodes[(size_t)w.binary], 0);
-        kids[1] = kid_of(bvh.nodes[(size_t)w.binary], 1);
+        w.kids[0] = kid_of(bvh.nodes[(size_t)w.binary], 0);
+        w.kids[1] = kid_of(bvh.nodes[(size_t)w.binary], 1);
         while (nk < 4)
         {
             int best = -1;
             float best_area = -1.0f;
             for (int j = 0; j < nk; j++)
             {
-                if (kids[j].child < 0) continue;
-                const float dx = kids[j].hi[0] - kids[j].lo[0], dy = kids[j].hi[1] - kids[j].lo[1], dz = kids[j].hi[2] - kids[j].lo[2];
+                if (w.kids[j].child < 0) continue;
+                const float dx = w.kids[j].hi[0] - w.kids[j].lo[0], dy = w.kids[j].hi[1] - w.kids[j].lo[1], dz = w.kids[j].hi[2] - w.kids[j].lo[2];
                 const float area = dx * dy + dy * dz + dz * dx;
                 if (area > best_area) { best_area = area; best = j; }
             }
             if (best < 0) break;
-            const rtcu_bvh::Node& nd = bvh.nodes[(size_t)kids[best].child];
-            kids[best] = kid_of(nd, 0);
-            kids[nk++] = kid_of(nd, 1);
+            const rtcu_bvh::Node& nd = bvh.nodes[(size_t)w.kids[best].child];
+            w.kids[best] = kid_of(nd, 0);
+            w.kids[nk++] = kid_of(nd, 1);
         }
-        float cen[4][3], half[4][3], hsum[4];
-        uint32_t ref[4];
         for (int c = 0; c < 4; c++)
         {
-            const bool empty = c >= nk || (kids[c].child < 0 && kids[c].count == 0) || !(kids[c].lo[0] <= kids[c].hi[0]);
-            ref[c] = 0x80000000u; // an empty slot points at leaf 0 but is never hit
-            if (empty)
+            w.empty[c] = c >= nk || (w.kids[c].child < 0 && w.kids[c].count == 0) || !(w.kids[c].lo[0] <= w.kids[c].hi[0]);
+            w.ref[c] = 0x80000000u; // an empty slot points at leaf 0 but is never hit
+            if (w.empty[c]) continue;
+            if (w.kids[c].child >= 0)
+            {
+                w.ref[c] = (uint32_t)wide.size();
+                Wide child{};
+                child.binary = w.kids[c].child;
+                child.depth = w.depth + 1;
+                wide.push_back(child);
+            }
+            else
+                w.ref[c] = 0x80000000u | n_leaves++;
+        }
+        wide[qi] = w;
+    }
+
+    // Pass 2 (every node on its own, worker threads for large trees): boxes as centre / half-extent rounded outward, and a leaf as
+    // one 80-byte block -- its 1-4 spheres as two packed pairs of the sweep's layout (padded with never-hit spheres), then their
+    // four original indices as bit patterns
+    const float ninf = -__builtin_inff();
+    nodes_dev.assign(8 * wide.size(), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    leaf_blk.assign(5 * (size_t)n_leaves, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    auto fill = [&](size_t qi) {
+        const Wide& w = wide[qi];
+        float cen[4][3], half[4][3], hsum[4];
+        for (int c = 0; c < 4; c++)
+        {
+            if (w.empty[c])
             {
                 for (int k = 0; k < 3; k++) { cen[c][k] = 0.0f; half[c][k] = ninf; }
                 hsum[c] = ninf;
@@ -640,7 +675,7 @@ void pack_bvh4(const rtcu_bvh::Result& bvh, const std::vector<float4>& sph, std:
             double hs = 0.0;
             for (int k = 0; k < 3; k++)
             {
-                const float lo = kids[c].lo[k], hi = kids[c].hi[k];
+                const float lo = w.kids[c].lo[k], hi = w.kids[c].hi[k];
                 const float ce = (float)(0.5 * ((double)lo + (double)hi));
                 const double need = std::max((double)hi - (double)ce, (double)ce - (double)lo);
                 float h = (float)need;
@@ -651,42 +686,35 @@ void pack_bvh4(const rtcu_bvh::Result& bvh, const std::vector<float4>& sph, std:
             }
             hsum[c] = (float)hs;
             if ((double)hsum[c] < hs) hsum[c] = nextafterf(hsum[c], __builtin_inff());
-            if (kids[c].child >= 0)
-            {
-                ref[c] = (uint32_t)queue.size();
-                queue.push_back(Work{ kids[c].child, w.depth + 1 });
-                continue;
-            }
-            // a leaf becomes one 80-byte block: its 1-4 spheres as two packed pairs of the sweep's layout (padded with never-hit
-            // spheres), then their four original indices as bit patterns
-            const uint32_t leaf = (uint32_t)(leaf_blk.size() / 5);
-            ref[c] = 0x80000000u | leaf;
+            if (w.kids[c].child >= 0) continue;
             const float4 never = make_float4(0.0f, 0.0f, 0.0f, ninf);
             float4 sp[4];
             uint32_t idx[4];
             for (uint32_t k = 0; k < 4; k++)
             {
-                const bool real = k < kids[c].count;
-                idx[k] = real ? bvh.order[(size_t)(~kids[c].child) + k] : 0x7fffffffu;
+                const bool real = k < w.kids[c].count;
+                idx[k] = real ? bvh.order[(size_t)(~w.kids[c].child) + k] : 0x7fffffffu;
                 sp[k] = real ? sph[idx[k]] : never;
             }
+            float4* blk = &leaf_blk[5 * (size_t)(w.ref[c] & 0x7fffffffu)];
             for (int pr = 0; pr < 2; pr++)
             {
-                leaf_blk.push_back(make_float4(sp[2 * pr].x, sp[2 * pr + 1].x, sp[2 * pr].y, sp[2 * pr + 1].y));
-                leaf_blk.push_back(make_float4(sp[2 * pr].z, sp[2 * pr + 1].z, sp[2 * pr].w, sp[2 * pr + 1].w));
+                blk[2 * pr] = make_float4(sp[2 * pr].x, sp[2 * pr + 1].x, sp[2 * pr].y, sp[2 * pr + 1].y);
+                blk[2 * pr + 1] = make_float4(sp[2 * pr].z, sp[2 * pr + 1].z, sp[2 * pr].w, sp[2 * pr + 1].w);
             }
-            float4 ib;
-            memcpy(&ib, idx, sizeof ib);
-            leaf_blk.push_back(ib);
+            memcpy(&blk[4], idx, sizeof(float4));
         }
+        float4* out = &nodes_dev[8 * qi];
         for (int pr = 0; pr < 2; pr++)
             for (int k = 0; k < 3; k++)
-                nodes_dev.push_back(make_float4(cen[2 * pr][k], cen[2 * pr + 1][k], half[2 * pr][k], half[2 * pr + 1][k]));
-        float4 refs;
-        memcpy(&refs, ref, sizeof refs);
-        nodes_dev.push_back(refs);
-        nodes_dev.push_back(make_float4(hsum[0], hsum[1], hsum[2], hsum[3]));
-    }
+                out[3 * pr + k] = make_float4(cen[2 * pr][k], cen[2 * pr + 1][k], half[2 * pr][k], half[2 * pr + 1][k]);
+        memcpy(&out[6], w.ref, sizeof(float4));
+        out[7] = make_float4(hsum[0], hsum[1], hsum[2], hsum[3]);
+    };
+    constexpr size_t BLOCK = 256;
+    pool.run((wide.size() + BLOCK - 1) / BLOCK, wide.size() >= 4096 ? 1 : SIZE_MAX, [&](size_t blk) {
+        for (size_t qi = blk * BLOCK, e = std::min(wide.size(), (blk + 1) * BLOCK); qi < e; qi++) fill(qi);
+    });
     if (leaf_blk.empty()) // every reference needs a block to point at
         for (int k = 0; k < 5; k++) leaf_blk.push_back(make_float4(0.0f, 0.0f, ninf, ninf));
 }
@@ -938,12 +966,13 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     if (s->n_spheres)
     {
         const auto t0 = std::chrono::steady_clock::now();
-        const rtcu_bvh::Result bvh = rtcu_bvh::build(s->spheres, s->n_spheres);
+        rtcu_bvh::Pool pool(s->n_spheres >= 8192 ? rtcu_bvh::thread_count() - 1 : 0); // one set of workers for build and pack
+        const rtcu_bvh::Result bvh = rtcu_bvh::build(s->spheres, s->n_spheres, pool);
         ctx->ms_bvh_build = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ctx->bvh_depth = bvh.max_depth;
         uint32_t depth4 = 0;
         if (s->n_spheres < (1u << 29))
-            pack_bvh4(bvh, sph, nodes_dev, leaf_blk, depth4);
+            pack_bvh4(bvh, sph, nodes_dev, leaf_blk, depth4, pool);
         // a visit pushes at most three children: the traversal stack needs 3 entries per level
         if (!nodes_dev.empty() && 3 * depth4 + 2 <= (uint32_t)BVH_STACK)
         {
@@ -1548,10 +1577,11 @@ int rtcu_bvh4_build_host(const float* spheres, uint32_t n, float* nodes_out, uin
         const volatile float r2 = p[3] * p[3];
         sph[i] = make_float4(p[0], p[1], p[2], r2);
     }
-    const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n);
+    rtcu_bvh::Pool pool(n >= 8192 ? rtcu_bvh::thread_count() - 1 : 0);
+    const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n, pool);
     std::vector<float4> nodes, leaves;
     uint32_t d4 = 0;
-    pack_bvh4(bvh, sph, nodes, leaves, d4);
+    pack_bvh4(bvh, sph, nodes, leaves, d4, pool);
     *n_nodes = (uint32_t)(nodes.size() / 8);
     *n_leaves = (uint32_t)(leaves.size() / 5);
     *depth = d4;

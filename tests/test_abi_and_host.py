@@ -265,6 +265,39 @@ def test_bvh4_device_tree_invariants(lib, n):
     assert (seen == 1).all()  # every sphere in exactly one leaf
 
 
+# ---- the builder runs on worker threads: the tree must not depend on how many -------------------------------------------
+@pytest.mark.parametrize("case", ["grid100k", "rtiow", "random20k", "identical10k", "line9k", "clusters30k"])
+def test_bvh_build_is_independent_of_thread_count(lib, case, monkeypatch):
+    from rt_b200 import synth
+
+    rng = np.random.default_rng(7)
+    if case == "grid100k":
+        sph = synth.grid_scene().spheres
+    elif case == "rtiow":
+        sph = synth.rtiow_scene().spheres  # below the builder's threading threshold: the serial path under every setting
+    elif case == "random20k":
+        sph = np.concatenate([rng.uniform(-50, 50, (20000, 3)), rng.uniform(0.01, 3.0, (20000, 1))], axis=1).astype(np.float32)
+        sph[0] = [0, -1000, 0, 1000]
+    elif case == "identical10k":
+        sph = np.tile(np.array([[1.0, 2.0, 3.0, 0.5]], np.float32), (10000, 1))  # all centroids coincide: index-order splits
+    elif case == "line9k":
+        sph = np.zeros((9000, 4), np.float32)  # one axis only, many equal centroids
+        sph[:, 0] = rng.integers(0, 40, 9000)
+        sph[:, 3] = 0.25
+    else:
+        centres = rng.uniform(-200, 200, (30, 3))
+        sph = np.concatenate([centres[rng.integers(0, 30, 30000)] + rng.normal(0, 0.5, (30000, 3)), rng.uniform(0.01, 0.2, (30000, 1))],
+                             axis=1).astype(np.float32)
+    monkeypatch.setenv("RTCU_BVH_THREADS", "1")
+    ref_nodes, ref_leaves, ref_depth = R.bvh4_build_host(sph)
+    for threads in ("2", "3", "8", "16"):
+        monkeypatch.setenv("RTCU_BVH_THREADS", threads)
+        nodes, leaves, depth = R.bvh4_build_host(sph)
+        assert depth == ref_depth
+        assert np.array_equal(nodes.view(np.uint32), ref_nodes.view(np.uint32)), threads
+        assert np.array_equal(leaves.view(np.uint32), ref_leaves.view(np.uint32)), threads
+
+
 def test_only_tests_smoke_and_bench_touch_the_oracle():
     """oracle/ is test infrastructure: the product (rt_b200/, include/, plugin/, tools/) never imports, links or names it;
     only tests/ (incl. tests/tools), __graft_entry__.smoke() and bench.py's CPU legs load it.  rt_b200/build.py may *build* it."""
