@@ -133,7 +133,7 @@ namespace
 			v.tile_x1			= v.width;
 			v.tile_y1			= v.height;
 			v.seed				= 0x5EEDull;
-			v.flags				= RTCU_ACCEL_AUTO | RTCU_PIPE_AUTO;
+			v.flags				= static_cast<uint32_t>(RTCU_ACCEL_AUTO) | static_cast<uint32_t>(RTCU_PIPE_AUTO);
 			return v;
 		}
 	};

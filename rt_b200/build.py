@@ -32,7 +32,7 @@ def _nvcc() -> str:
 
 
 def sources() -> list[pathlib.Path]:
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "rtcu.h"]
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "rtcu.h"]
 
 
 def needs_build() -> bool:

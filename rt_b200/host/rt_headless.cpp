@@ -9,6 +9,7 @@
 // --dump-scene / --dump-view print the flattened scene / the inverse view-projection as JSON and need no GPU.
 #include "scene_loader.hpp"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -28,19 +29,29 @@ const char* find_renderer(const std::string& name)
     return nullptr;
 }
 
+// a float as a JSON number that round-trips (9 significant digits); non-finite values -- a zero-length plane normal normalises to
+// NaN in the reference as well -- use the tokens Python's json module reads
+std::string json_number(float v)
+{
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-Infinity" : "Infinity";
+    if (v == 0.0f) return std::signbit(v) ? "-0.0" : "0"; // "-0" would be read back as the integer 0
+    char b[48];
+    std::snprintf(b, sizeof b, "%.9g", v);
+    return b;
+}
+
 void dump_scene(const rtb::scene& s)
 {
-    auto arr = [](const float* v, size_t n) { std::string o = "["; for (size_t i = 0; i < n; i++) { char b[48]; std::snprintf(b, sizeof b, "%s%.9g", i ? ", " : "", v[i]); o += b; } return o + "]"; };
+    auto arr = [](const float* v, size_t n) { std::string o = "["; for (size_t i = 0; i < n; i++) { o += i ? ", " : ""; o += json_number(v[i]); } return o + "]"; };
     std::printf("{\"samples_per_pixel\": %u, \"max_bounces\": %u, \"camera\": {\"position\": %s, \"direction\": %s},\n", s.samples_per_pixel, s.max_bounces,
                 arr(s.camera.position.data(), 3).c_str(), arr(s.camera.direction.data(), 3).c_str());
     std::printf(" \"materials\": [");
     for (size_t i = 0; i < s.materials.size(); i++)
     {
         const auto& m = s.materials[i];
-        char rough[48], refl[48];
-        std::snprintf(rough, sizeof rough, "%.9g", m.roughness);
-        std::snprintf(refl, sizeof refl, "%.9g", m.reflectivity);
-        std::printf("%s{\"type\": %u, \"albedo\": %s, \"roughness\": %s, \"reflectivity\": %s}", i ? ", " : "", m.type, arr(m.albedo, 4).c_str(), rough, refl);
+        std::printf("%s{\"type\": %u, \"albedo\": %s, \"roughness\": %s, \"reflectivity\": %s}", i ? ", " : "", m.type, arr(m.albedo, 4).c_str(),
+                    json_number(m.roughness).c_str(), json_number(m.reflectivity).c_str());
     }
     std::printf("],\n \"spheres\": [");
     for (size_t i = 0; i < s.spheres.size(); i++) std::printf("%s%s", i ? ", " : "", arr(s.spheres[i].data(), 4).c_str());
@@ -130,7 +141,7 @@ int run(int argc, char** argv)
     v.tile_y1 = height;
     v.seed = seed;
     v.material_mode = mode == "mg" ? RTCU_MODE_MG : RTCU_MODE_SM;
-    v.flags = RTCU_ACCEL_AUTO | RTCU_PIPE_AUTO;
+    v.flags = static_cast<uint32_t>(RTCU_ACCEL_AUTO) | static_cast<uint32_t>(RTCU_PIPE_AUTO);
 
     if (gpus < 1 || gpus > 8) throw std::runtime_error("--gpus must be 1..8");
     std::vector<rtcu_ctx*> ctxs;

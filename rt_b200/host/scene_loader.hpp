@@ -252,9 +252,20 @@ inline scene load_scene_text(const std::string& text, const std::string& path = 
     {
         const auto pos = vector3(t->get("position"), { 0, 0, 0 }, "plane.position");
         auto n = vector3(t->get("normal"), { 0, 1, 0 }, "plane.normal");
-        const float inv = 1.0f / std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-        for (auto& c : n) c *= inv;
-        const float d = -(n[0] * pos[0] + n[1] * pos[1] + n[2] * pos[2]); // muu plane{position, normal}: dot(n,p) + d == 0
+        // DESIGN.md SPEC S1 / S2 (the arithmetic the muu stand-in, the oracle and the kernels share): dot3(a, b) = fma(a.z, b.z,
+        // fma(a.y, b.y, a.x * b.x)), normalize(v) = v * (1 / sqrt(dot3(v, v))); a zero normal becomes NaN, as in the reference
+        auto dot3 = [](const std::array<float, 3>& a, const std::array<float, 3>& b) {
+            const volatile float xx = a[0] * b[0]; // one IEEE multiply, never contracted into the fma below
+            return std::fmaf(a[2], b[2], std::fmaf(a[1], b[1], xx));
+        };
+        const volatile float len = std::sqrt(dot3(n, n));
+        const volatile float inv = 1.0f / len;
+        for (auto& c : n)
+        {
+            const volatile float scaled = c * inv;
+            c = scaled;
+        }
+        const float d = -dot3(n, pos); // muu plane{position, normal}: dot(n,p) + d == 0
         s.planes.push_back({ n[0], n[1], n[2], d });
         s.plane_material.push_back(material_of(*t));
     }

@@ -4,6 +4,7 @@
 // floats (exponent, inf, nan), booleans.  Dates and multi-line strings are rejected with a message.
 #pragma once
 #include <cctype>
+#include <cerrno>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -167,38 +168,82 @@ class parser {
             n->b = tok == "true";
             return n;
         }
+        // TOML's number grammar, checked on the token itself (strtod / strtoll alone would accept "1.", ".5", "007", "1__0", hex floats)
+        auto digits = [&](size_t& p, auto is_digit) { // digit ( '_'? digit )*
+            if (p >= tok.size() || !is_digit(tok[p])) return false;
+            for (p++; p < tok.size();)
+            {
+                if (is_digit(tok[p])) p++;
+                else if (tok[p] == '_' && p + 1 < tok.size() && is_digit(tok[p + 1])) p += 2;
+                else break;
+            }
+            return true;
+        };
+        auto dec = [](char c) { return c >= '0' && c <= '9'; };
         std::string t;
         for (char c : tok)
             if (c != '_') t += c;
-        const std::string body = (!t.empty() && (t[0] == '+' || t[0] == '-')) ? t.substr(1) : t;
+        const bool sign = !tok.empty() && (tok[0] == '+' || tok[0] == '-');
+        const std::string body = sign ? t.substr(1) : t;
         if (body == "inf" || body == "nan")
         {
+            if (t.size() != tok.size()) fail("malformed number '" + tok + "'");
             n->kind = node::floating;
             n->f = body == "inf" ? INFINITY : NAN;
             if (t[0] == '-') n->f = -n->f;
             return n;
         }
-        if (t.find(':') != std::string::npos || (t.size() > 4 && t[4] == '-' && std::isdigit(static_cast<unsigned char>(t[0])))) fail("dates and times are not supported");
-        if (t.empty()) fail("expected a value");
+        if (tok.empty()) fail("expected a value");
+        const bool date_like = tok.size() > 4 && dec(tok[0]) && dec(tok[1]) && dec(tok[2]) && dec(tok[3]) && tok[4] == '-';
+        const bool time_like = tok.size() > 2 && dec(tok[0]) && dec(tok[1]) && tok[2] == ':';
+        if (date_like || time_like) fail("dates and times are not supported");
         char* end = nullptr;
-        if (body.size() > 2 && body[0] == '0' && (body[1] == 'x' || body[1] == 'o' || body[1] == 'b'))
+        if (!sign && tok.size() > 2 && tok[0] == '0' && (tok[1] == 'x' || tok[1] == 'o' || tok[1] == 'b'))
         {
-            const int base = body[1] == 'x' ? 16 : (body[1] == 'o' ? 8 : 2);
+            const int base = tok[1] == 'x' ? 16 : (tok[1] == 'o' ? 8 : 2);
+            size_t p = 2;
+            const bool ok = base == 16 ? digits(p, [](char c) { return std::isxdigit(static_cast<unsigned char>(c)) != 0; })
+                          : base == 8 ? digits(p, [](char c) { return c >= '0' && c <= '7'; })
+                                      : digits(p, [](char c) { return c == '0' || c == '1'; });
+            if (!ok || p != tok.size()) fail("malformed integer '" + tok + "'");
+            errno = 0;
+            const unsigned long long u = std::strtoull(body.c_str() + 2, &end, base);
+            if (*end || errno == ERANGE || u > (unsigned long long)INT64_MAX) fail("integer '" + tok + "' is out of range");
             n->kind = node::integer;
-            n->i = std::strtoll(body.c_str() + 2, &end, base);
-            if (*end) fail("malformed integer '" + tok + "'");
+            n->i = (int64_t)u;
             return n;
         }
-        if (t.find_first_of(".eE") != std::string::npos)
+        // [+-] ( '0' | nonzero digits ) [ '.' digits ] [ (e|E) [+-] digits ]
+        size_t p = sign ? 1 : 0;
+        const size_t int_begin = p;
+        if (!digits(p, dec)) fail("malformed number '" + tok + "'");
+        if (tok[int_begin] == '0' && p - int_begin > 1) fail("malformed number '" + tok + "' (leading zero)");
+        bool is_float = false;
+        if (p < tok.size() && tok[p] == '.')
+        {
+            is_float = true;
+            if (!digits(++p, dec)) fail("malformed number '" + tok + "'");
+        }
+        if (p < tok.size() && (tok[p] == 'e' || tok[p] == 'E'))
+        {
+            is_float = true;
+            p++;
+            if (p < tok.size() && (tok[p] == '+' || tok[p] == '-')) p++;
+            if (!digits(p, dec)) fail("malformed number '" + tok + "'");
+        }
+        if (p != tok.size()) fail("malformed number '" + tok + "'");
+        if (is_float)
         {
             n->kind = node::floating;
             n->f = std::strtod(t.c_str(), &end);
             if (*end) fail("malformed number '" + tok + "'");
             return n;
         }
+        errno = 0;
         n->kind = node::integer;
         n->i = std::strtoll(t.c_str(), &end, 10);
         if (*end) fail("malformed number '" + tok + "'");
+        if (errno == ERANGE) fail("integer '" + tok + "' is out of range");
         return n;
     }
 

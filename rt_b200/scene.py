@@ -15,6 +15,7 @@ on purpose:
 from __future__ import annotations
 
 import dataclasses
+import fractions
 import math
 import pathlib
 import tomllib
@@ -144,6 +145,38 @@ def _f32(x: float) -> np.float32:
     return np.float32(x)
 
 
+def _round_f32(x: fractions.Fraction) -> np.float32:
+    """The binary32 nearest to the exact rational x (ties to even): one rounding, as a hardware fma performs it."""
+    f = np.float32(float(x))  # within one ulp; decide exactly between it and its neighbours
+    if not np.isfinite(f):
+        return f
+    best, best_err = f, abs(fractions.Fraction(float(f)) - x)
+    for g in (np.nextafter(f, np.float32(-np.inf)), np.nextafter(f, np.float32(np.inf))):
+        if not np.isfinite(g):
+            continue
+        err = abs(fractions.Fraction(float(g)) - x)
+        if err < best_err or (err == best_err and (int(g.view(np.uint32)) & 1) == 0 and (int(best.view(np.uint32)) & 1) == 1):
+            best, best_err = g, err
+    return best
+
+
+def _fma32(a, b, c) -> np.float32:
+    """fmaf(a, b, c): the product is not rounded (DESIGN.md SPEC, S1-S3)."""
+    a, b, c = np.float32(a), np.float32(b), np.float32(c)
+    if not (np.isfinite(a) and np.isfinite(b) and np.isfinite(c)):
+        with np.errstate(invalid="ignore"):
+            return np.float32(a * b + c)
+    exact = fractions.Fraction(float(a)) * fractions.Fraction(float(b)) + fractions.Fraction(float(c))
+    if exact == 0:  # the sign of an exact zero follows IEEE addition; the binary64 product of two binary32 values is exact
+        return np.float32(float(a) * float(b) + float(c))
+    return _round_f32(exact)
+
+
+def _dot3(a, b) -> np.float32:
+    """S1: dot3(a, b) = fma(a.z, b.z, fma(a.y, b.y, a.x * b.x))"""
+    return _fma32(a[2], b[2], _fma32(a[1], b[1], np.float32(a[0]) * np.float32(b[0])))
+
+
 @dataclasses.dataclass
 class Camera:
     """rt::camera (src/camera.hpp:51-138): vfov pi/4, near 0.01, far 1000 are fixed (private, no setter)."""
@@ -233,8 +266,9 @@ def loads(text: str, path: str = "") -> Scene:
     for tbl in _table_array(cfg, "planes"):
         pos = np.array(_vector(tbl.get("position"), (0, 0, 0), "plane.position"), np.float32)
         n = np.array(_vector(tbl.get("normal"), (0, 1, 0), "plane.normal"), np.float32)
-        n = (n * (_f32(1.0) / np.sqrt(np.dot(n, n), dtype=np.float32))).astype(np.float32)
-        d = -np.float32(np.dot(n, pos))  # muu plane{position, normal}: dot(n, p) + d == 0 (UNVERIFIED)
+        with np.errstate(divide="ignore", invalid="ignore"):  # a zero normal normalises to NaN, as in the reference
+            n = (n * (_f32(1.0) / np.sqrt(_dot3(n, n), dtype=np.float32))).astype(np.float32)  # S2: v * (1 / sqrt(dot3(v, v)))
+        d = -_dot3(n, pos)  # muu plane{position, normal}: dot(n, p) + d == 0 (UNVERIFIED), dot as S1
         planes.append((n[0], n[1], n[2], d))
         plane_mat.append(material_of(tbl))
 

@@ -129,6 +129,54 @@ def test_loader_errors_exit_1_with_the_reference_messages(cli, tmp_path, text, m
         S.loads(text)
 
 
+NUMBERS_OK = ["0", "+0", "-0", "7", "+7", "-17", "1_000", "1_2_3", "0x1F", "0xdead_beef", "0o17", "0b1_01", "1.5", "-0.25", "+1.0", "1e3", "1E-02", "1.2e-01",
+              "6.02e+23", "1_0.2_5e1_0", "9223372036854775807", "-9223372036854775808", "0e0", "0.0", "-0.0"]
+NUMBERS_BAD = ["007", "+007", "-01", "1.", ".5", "1._5", "1_.5", "_1", "1_", "1__0", "0x", "0x_1", "0xG", "+0x1", "-0b1", "0o8", "1e", "1e+", "1.5e", "1e1.5",
+               "0x1.8p3", "infinity", "in_f", "NaN", "Inf", "1-2", "1979-05-27", "07:32:00", "--1", "+-1", "1e_5"]
+
+
+NUMBERS_OUT_OF_RANGE = ["9223372036854775808", "-9223372036854775809", "0xFFFFFFFFFFFFFFFF"]  # TOML integers are int64 (tomllib keeps big ints)
+
+
+def test_number_grammar_is_tomls(cli, tmp_path):
+    """toml_lite accepts exactly TOML's integers and floats (found by tests/tools/fuzz_loader.py: `1.2e-01` was taken for a date;
+    strtod / strtoll alone would also take `1.`, `.5`, `007`, hex floats); tomllib is the yardstick."""
+    import tomllib
+
+    for tok in NUMBERS_OK + NUMBERS_BAD:
+        text = f"spheres = [ {{ radius = {tok} }} ]\n"
+        try:
+            v = tomllib.loads(text)["spheres"][0]["radius"]
+            expect_ok = isinstance(v, (int, float)) and not isinstance(v, bool)
+        except tomllib.TOMLDecodeError:
+            expect_ok = False
+        assert expect_ok == (tok in NUMBERS_OK), tok
+        p = tmp_path / "n.toml"
+        p.write_text(text)
+        r = run(cli, "--scene", str(p), "--dump-scene", check=False)
+        if expect_ok:
+            assert r.returncode == 0, (tok, r.stderr)
+            assert np.float32(json.loads(r.stdout)["spheres"][0][3]) == np.float32(v), tok
+        else:
+            assert r.returncode == 1 and "error: " in r.stderr, (tok, r.stdout, r.stderr)
+    for tok in NUMBERS_OUT_OF_RANGE:
+        p = tmp_path / "n.toml"
+        p.write_text(f"spheres = [ {{ radius = {tok} }} ]\n")
+        r = run(cli, "--scene", str(p), "--dump-scene", check=False)
+        assert r.returncode == 1 and "out of range" in r.stderr, (tok, r.stderr)
+
+
+def test_dump_keeps_signed_zeros_and_non_finite_values(cli, tmp_path):
+    p = tmp_path / "z.toml"
+    p.write_text("planes = [ {normal = -0.6}, {normal = [0, 0, 0]}, {position = [0, 2, 0]} ]\nspheres = [ {position = [-0.0, 0, 1e-46]} ]\n")
+    d = dumped(cli, p)
+    s = S.load(p)
+    for key in ("planes", "spheres"):
+        a, b = np.float32(d[key]).ravel(), getattr(s, key).ravel()
+        assert ((np.isnan(a) & np.isnan(b)) | (a.view(np.uint32) == b.view(np.uint32))).all(), key
+    assert np.signbit(np.float32(d["spheres"][0][0])) and np.isnan(np.float32(d["planes"][1])).all()
+
+
 def test_viewport_matrix_matches_the_python_camera(cli):
     for name, size in (("scenes/basic.toml", (800, 600)), ("scenes/dielectric.toml", (1920, 1080))):
         m = np.float32(json.loads(run(cli, "--scene", name, "--size", f"{size[0]}x{size[1]}", "--dump-view").stdout))

@@ -99,6 +99,37 @@ def test_planes_are_normalised_and_boxes_parse():
     np.testing.assert_array_equal(s.boxes[1], [0, 1, -3, 2, 2, 2])
 
 
+def test_plane_arithmetic_follows_the_spec_dot_and_normalize():
+    """S1 / S2 (DESIGN.md): dot3 = fma(z, z', fma(y, y', x * x')), normalize = v * (1 / sqrt(dot3(v, v))), d = -dot3(n, p) -- the
+    arithmetic of the muu stand-in the reference's sources are compiled against, so the loader's planes are the ones the
+    reference's scene::load would hand to the renderers."""
+    import math
+    from fractions import Fraction
+
+    # the fused multiply-add helper rounds once: against exact rational arithmetic on random operands, and on the classic
+    # double-rounding trap (a * b + c evaluated in binary64 and then rounded to binary32 gives the other neighbour)
+    rng = np.random.default_rng(5)
+    for a, b, c in rng.standard_normal((300, 3)).astype(np.float32) * np.float32(3):
+        exact = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+        got = S._fma32(a, b, c)
+        lo, hi = np.nextafter(got, np.float32(-np.inf)), np.nextafter(got, np.float32(np.inf))
+        assert abs(Fraction(float(got)) - exact) <= min(abs(Fraction(float(lo)) - exact), abs(Fraction(float(hi)) - exact))
+    a, b, c = np.float32(1 + 2.0**-12), np.float32(1 + 2.0**-12), np.float32(2.0**-60)  # exact: 1 + 2^-11 + 2^-24 + 2^-60
+    assert S._fma32(a, b, c) == np.float32(1 + 2.0**-11 + 2.0**-23)                       # above the tie: rounds up ...
+    assert np.float32(float(a) * float(b) + float(c)) == np.float32(1 + 2.0**-11)         # ... binary64 first: ties to even, down
+    assert math.copysign(1.0, float(S._fma32(-0.5, 0.0, -0.0))) == -1.0                   # (-0) + (-0) = -0
+    assert math.copysign(1.0, float(S._fma32(0.5, 0.5, -0.25))) == 1.0                    # exact cancellation = +0
+
+    s = S.loads("planes = [ {normal = [1.6840e-01, -0.46002, 0.6859540551275798], position = [2.5, -1, 0.75]}, {normal = -0.6}, {normal = [0, 0, 0]} ]")
+    n = np.float32([1.6840e-01, -0.46002, 0.6859540551275798])
+    inv = np.float32(1) / np.sqrt(S._dot3(n, n), dtype=np.float32)
+    unit = (n * inv).astype(np.float32)
+    np.testing.assert_array_equal(s.planes[0, :3], unit)
+    assert s.planes[0, 3] == -S._dot3(unit, np.float32([2.5, -1, 0.75]))
+    assert s.planes[1, 3] == 0 and not np.signbit(s.planes[1, 3])  # -((-0) + (-0) + (-0)) = +0
+    assert np.isnan(s.planes[2]).all()                              # a zero normal normalises to NaN (as muu's normalize would)
+
+
 def test_relative_path_search(tmp_path, monkeypatch):
     (tmp_path / "scenes").mkdir()
     (tmp_path / "scenes" / "x.toml").write_text("samples_per_pixel = 7")
