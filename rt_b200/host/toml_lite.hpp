@@ -1,7 +1,7 @@
 // toml_lite.hpp -- a small TOML reader for scene files (the reference uses toml++, which is not available here).
 // Covers what scene files use and a bit more: comments, bare / quoted / dotted keys, [tables], [[arrays of tables]],
 // inline tables, (multi-line) arrays with trailing commas, basic and literal strings, integers (dec/hex/oct/bin, '_'),
-// floats (exponent, inf, nan), booleans.  Dates and multi-line strings are rejected with a message.
+// floats (exponent, inf, nan), booleans, multi-line strings, every escape.  Dates and times are rejected with a message.
 #pragma once
 #include <cctype>
 #include <cerrno>
@@ -90,44 +90,120 @@ class parser {
         if (!eof()) next();
     }
 
+    void append_utf8(std::string& out, uint32_t cp)
+    {
+        if (cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) fail("escape is not a Unicode scalar value");
+        if (cp < 0x80) out += (char)cp;
+        else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+        else if (cp < 0x10000) { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+        else { out += (char)(0xF0 | (cp >> 18)); out += (char)(0x80 | ((cp >> 12) & 0x3F)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+    }
+    void parse_escape(std::string& out) // after the backslash
+    {
+        const char c = next();
+        switch (c)
+        {
+            case 'b': out += '\b'; break;
+            case 't': out += '\t'; break;
+            case 'n': out += '\n'; break;
+            case 'f': out += '\f'; break;
+            case 'r': out += '\r'; break;
+            case '\\': out += '\\'; break;
+            case '"': out += '"'; break;
+            case 'u':
+            case 'U':
+            {
+                uint32_t cp = 0;
+                for (int k = 0, n = c == 'u' ? 4 : 8; k < n; k++)
+                {
+                    const char h = next();
+                    if (!std::isxdigit(static_cast<unsigned char>(h))) fail("malformed unicode escape");
+                    cp = cp * 16 + (uint32_t)(std::isdigit(static_cast<unsigned char>(h)) ? h - '0' : (std::tolower(h) - 'a' + 10));
+                }
+                append_utf8(out, cp);
+                break;
+            }
+            default: fail("unsupported escape sequence");
+        }
+    }
+    static bool control(char c) { return (static_cast<unsigned char>(c) < 0x20 && c != '\t') || c == 0x7F; }
+    // the body of a multi-line string, after the opening delimiter: a newline right after it is dropped, up to two quotes may
+    // precede the closing delimiter, and (basic strings) a backslash at the end of a line swallows the whitespace that follows
+    std::string parse_multiline(char q)
+    {
+        const bool basic = q == '"';
+        if (peek() == '\r' && pos_ + 1 < src_.size() && src_[pos_ + 1] == '\n') next();
+        if (peek() == '\n') next();
+        std::string out;
+        for (;;)
+        {
+            if (eof()) fail("unterminated multi-line string");
+            const char c = next();
+            if (c == q)
+            {
+                size_t run = 1;
+                while (peek() == q && run < 5) { next(); run++; }
+                if (run >= 3)
+                {
+                    out.append(run - 3, q); // """"" ends a string that ends in two quotes
+                    return out;
+                }
+                out.append(run, q);
+            }
+            else if (basic && c == '\\')
+            {
+                size_t p = pos_;
+                while (p < src_.size() && (src_[p] == ' ' || src_[p] == '\t')) p++;
+                if (p < src_.size() && (src_[p] == '\n' || (src_[p] == '\r' && p + 1 < src_.size() && src_[p + 1] == '\n')))
+                    while (!eof() && (peek() == ' ' || peek() == '\t' || peek() == '\n' || peek() == '\r')) next(); // line-ending backslash
+                else
+                    parse_escape(out);
+            }
+            else if (c == '\r')
+            {
+                if (peek() != '\n') fail("bare carriage return in a string");
+            }
+            else if (c != '\n' && control(c))
+                fail("control character in a string");
+            else
+                out += c;
+        }
+    }
     std::string parse_basic_string()
     {
         next(); // "
-        if (src_.compare(pos_, 2, "\"\"") == 0) fail("multi-line strings are not supported");
+        if (src_.compare(pos_, 2, "\"\"") == 0)
+        {
+            next(); next();
+            return parse_multiline('"');
+        }
         std::string out;
         for (;;)
         {
             if (eof() || peek() == '\n') fail("unterminated string");
-            char c = next();
+            const char c = next();
             if (c == '"') break;
-            if (c == '\\')
-            {
-                c = next();
-                switch (c)
-                {
-                    case 'n': out += '\n'; break;
-                    case 't': out += '\t'; break;
-                    case 'r': out += '\r'; break;
-                    case '\\': out += '\\'; break;
-                    case '"': out += '"'; break;
-                    default: fail("unsupported escape sequence");
-                }
-            }
-            else
-                out += c;
+            if (c == '\\') parse_escape(out);
+            else if (control(c)) fail("control character in a string");
+            else out += c;
         }
         return out;
     }
     std::string parse_literal_string()
     {
         next(); // '
-        if (src_.compare(pos_, 2, "''") == 0) fail("multi-line strings are not supported");
+        if (src_.compare(pos_, 2, "''") == 0)
+        {
+            next(); next();
+            return parse_multiline('\'');
+        }
         std::string out;
         for (;;)
         {
             if (eof() || peek() == '\n') fail("unterminated string");
             const char c = next();
             if (c == '\'') break;
+            if (control(c)) fail("control character in a string");
             out += c;
         }
         return out;
@@ -135,6 +211,7 @@ class parser {
     std::string parse_key_part()
     {
         skip_ws();
+        if (src_.compare(pos_, 3, "\"\"\"") == 0 || src_.compare(pos_, 3, "'''") == 0) fail("a key cannot be a multi-line string");
         if (peek() == '"') return parse_basic_string();
         if (peek() == '\'') return parse_literal_string();
         std::string k;

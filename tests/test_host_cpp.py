@@ -1,6 +1,7 @@
 """The C++ host (rt_b200/host: TOML reader, scene loader restating scene.cpp, viewport, rt_headless CLI) against its Python
 twin (rt_b200/scene.py, camera.py) and, on a GPU, against the Python path through the same C ABI."""
 import json
+import pathlib
 import subprocess
 
 import numpy as np
@@ -164,6 +165,24 @@ def test_number_grammar_is_tomls(cli, tmp_path):
         p.write_text(f"spheres = [ {{ radius = {tok} }} ]\n")
         r = run(cli, "--scene", str(p), "--dump-scene", check=False)
         assert r.returncode == 1 and "out of range" in r.stderr, (tok, r.stderr)
+
+
+def test_string_forms_decode_like_tomllib(cli, tmp_path):
+    """multi-line basic / literal strings and every escape: the decoded text selects aliases, colours and material types, so
+    the loaded values tell whether both readers saw the same string"""
+    text = (pathlib.Path(__file__).parent / "golden" / "strings.toml").read_text()
+    p = tmp_path / "strings.toml"
+    p.write_text(text)
+    s = S.loads(text)
+    assert tuple(s.camera.position) == (0, 1, 0) and tuple(s.camera.direction) == (0, -1, 0) and int(s.materials[1]["type"]) == 1
+    assert_same_scene(dumped(cli, p), s)
+    for bad, message in [('name = "\\q"', "escape"), ('name = "\\u12"', "unicode escape"), ('name = "\\uD800"', "scalar value"),
+                         ('name = "a\x01b"', "control character"), ('name = """never closed', "unterminated"), ('"""k""" = 1', "key")]:
+        p.write_text(bad + "\n")
+        r = run(cli, "--scene", str(p), "--dump-scene", check=False)
+        assert r.returncode == 1 and "TOML parse error" in r.stderr and message in r.stderr, (bad, r.stderr)
+        with pytest.raises(S.SceneError):
+            S.loads(bad + "\n")
 
 
 def test_dump_keeps_signed_zeros_and_non_finite_values(cli, tmp_path):

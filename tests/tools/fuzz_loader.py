@@ -51,7 +51,36 @@ class Gen:
         return repr(v)
 
     def string(self, s: str) -> str:
-        return f"'{s}'" if self.r.random() < 0.5 else f'"{s}"'
+        """`s` in one of TOML's string forms; the loaders see the same text (aliases and colour names are looked up by it)"""
+        r = self.r
+        k = r.random()
+        if k < 0.4:
+            return f"'{s}'"
+        if k < 0.8 or not s:
+            return f'"{s}"'
+        if k < 0.88:  # one character as a unicode escape
+            i = r.randrange(len(s))
+            esc = f"\\u{ord(s[i]):04x}" if r.random() < 0.5 else f"\\U{ord(s[i]):08X}"
+            return '"' + s[:i] + esc + s[i + 1:] + '"'
+        if k < 0.94:  # multi-line basic: leading newline dropped, line-ending backslash joins
+            i = r.randrange(len(s) + 1)
+            return '"""' + r.choice(["", "\n"]) + s[:i] + r.choice(["", "\\\n   ", "\\  \n\n\t"]) + s[i:] + '"""'
+        return "'''" + r.choice(["", "\n"]) + s + "'''"
+
+    def name(self) -> str:
+        """a material name (loaded and dropped): every string form, escapes, quotes inside multi-line strings"""
+        r = self.r
+        word = "m" + str(r.randint(0, 99))
+        k = r.random()
+        if k < 0.5:
+            return self.string(word)
+        if k < 0.6:
+            return '"' + word + r.choice(["\\t", "\\n", "\\\\", '\\"', "\\u00e9", "\\U0001F600", "\\b\\f\\r"]) + '"'
+        if k < 0.7:
+            return '"' + word + r.choice(["\\q", "\\x41", "\\u12", "\\UD8000000", "\\uD800"]) + '"' if r.random() < self.p_error else self.string(word)
+        if k < 0.85:
+            return '"""' + r.choice(["", "\n"]) + word + r.choice(["", " \\\n    joined", "\nsecond line", ' "quoted" ', ' ""two'] ) + r.choice(['"""', '""""', '"""""'])
+        return "'''" + r.choice(["", "\n"]) + word + r.choice(["", "\nraw \\n line", " 'q' ", " ''two"]) + r.choice(["'''", "''''"])
 
     def bad_number(self) -> str:
         return self.r.choice(["nan", "inf", "-inf", "+nan"])
@@ -83,7 +112,7 @@ class Gen:
         r = self.r
         kv = []
         if r.random() < 0.3:
-            kv.append(("name", self.string("m" + str(r.randint(0, 99)))))
+            kv.append(("name", self.name()))
         if r.random() < 0.8:
             if r.random() < self.p_error:
                 kv.append(("type", r.choice(["8", "-1", self.string("glass"), "1.5", "[1]"])))
@@ -127,7 +156,7 @@ class Gen:
             return
         if r.random() < 0.5:
             sep = ",\n  " if r.random() < 0.5 else ", "
-            items = ["{ " + ", ".join(f"{k} = {v}" for k, v in row if "\n" not in v) + " }" for row in rows]
+            items = ["{ " + ", ".join(f"{k} = {v}" for k, v in row if "\n" not in v or k == "name") + " }" for row in rows]
             out_top.append(f"{key} = [{sep.join(items)}{',' if r.random() < 0.2 else ''}]")
         else:
             for row in rows:
