@@ -409,8 +409,33 @@ class parser {
   public:
     explicit parser(const std::string& src) : src_(src) {}
 
+    // a TOML document is UTF-8: reject overlong forms, surrogates, values past U+10FFFF and stray continuation bytes up front
+    void check_utf8() const
+    {
+        int line = 1;
+        for (size_t i = 0; i < src_.size();)
+        {
+            const unsigned char c = (unsigned char)src_[i];
+            if (c == '\n') line++;
+            size_t len = c < 0x80 ? 1 : (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 0;
+            bool ok = len != 0 && i + len <= src_.size();
+            uint32_t cp = len == 1 ? c : len == 2 ? c & 0x1Fu : len == 3 ? c & 0x0Fu : c & 0x07u;
+            for (size_t k = 1; ok && k < len; k++)
+            {
+                const unsigned char d = (unsigned char)src_[i + k];
+                ok = (d & 0xC0) == 0x80;
+                cp = (cp << 6) | (d & 0x3Fu);
+            }
+            static const uint32_t smallest[5] = { 0, 0, 0x80, 0x800, 0x10000 };
+            if (ok && len > 1) ok = cp >= smallest[len] && cp <= 0x10FFFF && !(cp >= 0xD800 && cp <= 0xDFFF);
+            if (!ok) throw parse_error("TOML parse error at line " + std::to_string(line) + ": the document is not valid UTF-8");
+            i += len;
+        }
+    }
+
     node_ptr parse()
     {
+        check_utf8();
         auto root = std::make_shared<node>();
         root->kind = node::table;
         node* current = root.get();

@@ -185,6 +185,18 @@ def test_string_forms_decode_like_tomllib(cli, tmp_path):
             S.loads(bad + "\n")
 
 
+def test_documents_must_be_utf8(cli, tmp_path):
+    p = tmp_path / "u.toml"
+    p.write_bytes('[[materials]]\nname = "caf\u00e9 \U0001F600"  # \u00e9 in a comment\n'.encode())
+    assert len(dumped(cli, p)["materials"]) == 1
+    for bad in (b'a = 1 # \x80 stray continuation\n', b'a = "\xc0\xaf"\n', b'a = "\xed\xa0\x80"\n', b'a = "\xf4\x90\x80\x80"\n', b'a = "\xe2\x82"\n'):
+        p.write_bytes(bad)
+        r = run(cli, "--scene", str(p), "--dump-scene", check=False)
+        assert r.returncode == 1 and "not valid UTF-8" in r.stderr, (bad, r.stderr)
+        with pytest.raises(UnicodeDecodeError):
+            bad.decode("utf-8")
+
+
 def test_dump_keeps_signed_zeros_and_non_finite_values(cli, tmp_path):
     p = tmp_path / "z.toml"
     p.write_text("planes = [ {normal = -0.6}, {normal = [0, 0, 0]}, {position = [0, 2, 0]} ]\nspheres = [ {position = [-0.0, 0, 1e-46]} ]\n")

@@ -288,7 +288,8 @@ def main():
                                env={"ASAN_OPTIONS": "detect_leaks=0", "PATH": "/usr/bin:/bin"})
             stats["cases"] += 1
             stats["mutated" if mutated else "generated"] += 1
-            ok_exit = r.returncode == 0 or (r.returncode == 1 and r.stderr.strip().splitlines()[-1:] and r.stderr.strip().splitlines()[-1].startswith("error: "))
+            ok_exit = r.returncode == 0 or (r.returncode == 1 and any(ln.startswith("error: ") for ln in r.stderr.splitlines()) and "Sanitizer" not in r.stderr
+                                            and "runtime error" not in r.stderr)
             if not ok_exit:
                 stats["crashes"] += 1
                 failures.append({"case": case, "kind": "crash", "rc": r.returncode, "stderr": r.stderr[-400:], "text": text})
