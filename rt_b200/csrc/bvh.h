@@ -219,6 +219,15 @@ inline Result build(const float* spheres, uint32_t n, Pool& pool)
         return out;
     }
 
+    // Builder experiments, both off by default ("Tree quality": measured with tools/bvh_visits.cpp, waiting
+    // for a device measurement): RTCU_BVH_SWEEP=N evaluates every split position exactly for ranges of <= N spheres instead of
+    // binning them; RTCU_BVH_LEAF_COST=1 counts a side in 4-sphere leaf blocks (ceil(n / 4)) instead of spheres.
+    uint32_t sweep_below = 0;
+    bool leaf_block_cost = false;
+    if (const char* e = std::getenv("RTCU_BVH_SWEEP")) sweep_below = (uint32_t)std::min(4096, std::max(0, std::atoi(e)));
+    if (const char* e = std::getenv("RTCU_BVH_LEAF_COST")) leaf_block_cost = std::atoi(e) != 0;
+    auto side_cost = [&](float half_area, uint32_t count) { return half_area * (float)(leaf_block_cost ? (count + MAX_LEAF - 1) / MAX_LEAF : count); };
+
     // binned SAH over the centroid bounds: per axis BINS boxes and counts, then the cheapest of the 3 x (BINS - 1) planes
     struct Bins {
         Box box[3][BINS]; uint32_t n[3][BINS];
@@ -262,7 +271,7 @@ inline Result build(const float* spheres, uint32_t n, Pool& pool)
             {
                 acc.grow(bins.box[axis][b]); cnt += bins.n[axis][b];
                 if (cnt == 0 || right_n[b + 1] == 0) continue;
-                const float cost = acc.half_area() * cnt + right_area[b + 1] * right_n[b + 1];
+                const float cost = side_cost(acc.half_area(), cnt) + side_cost(right_area[b + 1], right_n[b + 1]);
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
             }
         }
@@ -295,6 +304,35 @@ inline Result build(const float* spheres, uint32_t n, Pool& pool)
     auto process = [&](const Task& t, const int32_t self, Split& sp) {
         if (t.parent >= 0)
             set_child(t.parent, t.side, range_box(t.begin, t.end), self, 0);
+        if (t.end - t.begin <= sweep_below)
+        {
+            // exact sweep: per axis, order by (centroid, index) -- a total order, so the result does not depend on the order the
+            // range arrives in -- and evaluate all count - 1 split positions
+            const uint32_t count = t.end - t.begin;
+            std::vector<uint32_t> sorted(out.order.begin() + t.begin, out.order.begin() + t.end), best_order;
+            std::vector<float> right_area(count);
+            float best_cost = FLT_MAX;
+            uint32_t best_left = 0;
+            for (int axis = 0; axis < 3; axis++)
+            {
+                std::sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) {
+                    const float ca = cent[3 * (size_t)a + axis], cb = cent[3 * (size_t)b + axis];
+                    return ca < cb || (ca == cb && a < b);
+                });
+                Box acc; acc.reset();
+                for (uint32_t k = count - 1; k > 0; k--) { acc.grow(boxes[sorted[k]]); right_area[k] = acc.half_area(); }
+                acc.reset();
+                for (uint32_t k = 0; k + 1 < count; k++)
+                {
+                    acc.grow(boxes[sorted[k]]);
+                    const float cost = side_cost(acc.half_area(), k + 1) + side_cost(right_area[k + 1], count - k - 1);
+                    if (cost < best_cost) { best_cost = cost; best_left = k + 1; best_order = sorted; }
+                }
+            }
+            if (best_left) std::copy(best_order.begin(), best_order.end(), out.order.begin() + t.begin);
+            finish(t, self, t.begin + best_left, sp);
+            return;
+        }
         Box cb; cb.reset();
         for (uint32_t k = t.begin; k < t.end; k++) cb.grow_point(&cent[3 * (size_t)out.order[k]]);
         Bins bins; bins.reset();

@@ -193,9 +193,18 @@ def test_bvh_builder_invariants(lib, n):
 
 
 # ---- the 4-wide device tree (collapsed on upload), built on the host: same invariants in the device layout ---------
+@pytest.mark.parametrize("knobs", [{}, {"RTCU_BVH_SWEEP": "512"}, {"RTCU_BVH_LEAF_COST": "1"}, {"RTCU_BVH_SWEEP": "64", "RTCU_BVH_LEAF_COST": "1"}],
+                         ids=["default", "sweep", "leafcost", "sweep+leafcost"])
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 9, 33, 484, 5000, 100001])
-def test_bvh4_device_tree_invariants(lib, n):
+def test_bvh4_device_tree_invariants(lib, n, knobs, monkeypatch):
+    """every tree the builder can produce -- the default and the experimental split rules (bvh.h: RTCU_BVH_SWEEP,
+    RTCU_BVH_LEAF_COST) -- is a valid input for the traversal: coverage, containment, leaf packing, stack bound"""
     from rt_b200 import synth
+
+    if knobs and n in (1, 3, 4, 9, 5000):
+        pytest.skip("knob variants: a subset of sizes")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
 
     if n == 484:
         sph = synth.rtiow_scene().spheres
@@ -288,9 +297,19 @@ def test_bvh_build_is_independent_of_thread_count(lib, case, monkeypatch):
         centres = rng.uniform(-200, 200, (30, 3))
         sph = np.concatenate([centres[rng.integers(0, 30, 30000)] + rng.normal(0, 0.5, (30000, 3)), rng.uniform(0.01, 0.2, (30000, 1))],
                              axis=1).astype(np.float32)
+    if case in ("grid100k", "clusters30k"):  # the experimental split rules are order-independent as well
+        monkeypatch.setenv("RTCU_BVH_SWEEP", "64" if case == "grid100k" else "0")
+        monkeypatch.setenv("RTCU_BVH_LEAF_COST", "1")
+        check_threads(sph, monkeypatch, ("8",))
+        monkeypatch.delenv("RTCU_BVH_SWEEP")
+        monkeypatch.delenv("RTCU_BVH_LEAF_COST")
+    check_threads(sph, monkeypatch, ("2", "3", "8", "16"))
+
+
+def check_threads(sph, monkeypatch, counts):
     monkeypatch.setenv("RTCU_BVH_THREADS", "1")
     ref_nodes, ref_leaves, ref_depth = R.bvh4_build_host(sph)
-    for threads in ("2", "3", "8", "16"):
+    for threads in counts:
         monkeypatch.setenv("RTCU_BVH_THREADS", threads)
         nodes, leaves, depth = R.bvh4_build_host(sph)
         assert depth == ref_depth
