@@ -390,7 +390,9 @@ def run_gpu(args):
                        "tile_order": "chosen by the library per view: row-major vs descending cost of the previous frame's tiles, whichever it timed faster "
                                      "in the warm-up frames (scheduling only: every sample is traced every step, the image is bit-identical)"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
-            "gpu_launches": args.steps * 3 * world,  # per step and rank: k_render_mega, k_render_stragglers, k_resolve (band)
+            # per step and rank: the trace kernels the library counted for the last frame (k_render_mega, k_render_stragglers, and
+            # k_tile_order when the cost-sorted tile order won) + the resolve / fused reduce-resolve kernel
+            "gpu_launches": args.steps * (int(stats.get("kernel_launches") or 2) + 1) * world,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "wall_ms_per_step_incl_flush": round(wall * 1e3 / args.steps, 3),
             "segments_per_sample": round(segments_all / samples_per_step, 4),
