@@ -16,6 +16,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 namespace rtcu_bvh {
 
@@ -159,6 +162,10 @@ private:
 inline unsigned thread_count()
 {
     unsigned hw = std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t allowed; // a process pinned to fewer cores (taskset, a container's cpuset) gets that many
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0 && CPU_COUNT(&allowed) > 0) hw = std::min(hw ? hw : 1u, (unsigned)CPU_COUNT(&allowed));
+#endif
     if (const char* e = std::getenv("RTCU_BVH_THREADS")) hw = (unsigned)std::max(1, std::atoi(e));
     return std::min(std::max(hw, 1u), 16u);
 }
