@@ -28,7 +28,8 @@ enum {
     RTCU_OK = 0,
     RTCU_ERR_INVALID = -1, /* bad argument (null pointer, empty tile, material index out of range) */
     RTCU_ERR_CUDA = -2,    /* CUDA runtime error, or no usable device                              */
-    RTCU_ERR_STATE = -3    /* call order (render before upload_scene)                              */
+    RTCU_ERR_STATE = -3,   /* call order (render before upload_scene)                              */
+    RTCU_ERR_NOMEM = -4    /* a host allocation failed (C++ exceptions never cross this ABI)       */
 };
 
 /* rt::material_type values, reference src/common.hpp:105-115 (ABI of the materials table) */

@@ -14,7 +14,7 @@ import os
 # RTCU_LIB overrides the library path (kernel-variant experiments only; the default is the in-tree build)
 LIB_PATH = pathlib.Path(os.environ.get("RTCU_LIB") or (pathlib.Path(__file__).resolve().parent / "lib" / "librtcu.so"))
 
-RTCU_OK, RTCU_ERR_INVALID, RTCU_ERR_CUDA, RTCU_ERR_STATE = 0, -1, -2, -3
+RTCU_OK, RTCU_ERR_INVALID, RTCU_ERR_CUDA, RTCU_ERR_STATE, RTCU_ERR_NOMEM = 0, -1, -2, -3, -4
 MODE_MG, MODE_SM = 0, 1
 ACCEL_AUTO, ACCEL_LINEAR, ACCEL_BVH = 0, 1, 2
 PIPE_AUTO, PIPE_MEGAKERNEL, PIPE_WAVEFRONT = 0 << 4, 1 << 4, 2 << 4

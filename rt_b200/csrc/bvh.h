@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 #ifdef __linux__
@@ -71,7 +72,15 @@ class Pool {
 public:
     explicit Pool(unsigned workers)
     {
-        for (unsigned w = 0; w < workers; w++) threads_.emplace_back([this] { park(); });
+        try
+        {
+            threads_.reserve(workers);
+            for (unsigned w = 0; w < workers; w++) threads_.emplace_back([this] { park(); });
+        }
+        catch (...)
+        {
+            // no more threads to be had (a process limit, no memory for a stack): work with the ones that started
+        }
     }
     ~Pool()
     {
@@ -102,6 +111,7 @@ public:
             relax();
             if (++spins > SPIN) { std::this_thread::yield(); spins = 0; }
         }
+        if (failed_.exchange(false)) throw std::bad_alloc(); // an fn(i) threw on some thread (they only ever allocate)
     }
 
 private:
@@ -121,10 +131,17 @@ private:
             wake_.notify_all();
         }
     }
-    void drain()
+    void drain() noexcept
     {
         for (size_t i = cursor_.fetch_add(chunk_); i < total_; i = cursor_.fetch_add(chunk_))
-            for (size_t j = i, e = std::min(total_, i + chunk_); j < e; j++) call_(fn_, j);
+            try
+            {
+                for (size_t j = i, e = std::min(total_, i + chunk_); j < e && !failed_.load(std::memory_order_relaxed); j++) call_(fn_, j);
+            }
+            catch (...)
+            {
+                failed_.store(true); // the section is abandoned (remaining indices are skipped); run() reports it on the caller's thread
+            }
     }
     void park()
     {
@@ -153,6 +170,7 @@ private:
     std::atomic<size_t> cursor_{ 0 };
     std::atomic<size_t> parked_{ 0 };
     std::atomic<bool> quit_{ false };
+    std::atomic<bool> failed_{ false };
     const void* fn_ = nullptr;
     void (*call_)(const void*, size_t) = nullptr;
     size_t total_ = 0, chunk_ = 1;

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <vector>
 
@@ -29,6 +30,25 @@ int fail(int code, const char* fmt, ...)
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
     return code;
+}
+
+// C++ exceptions must not cross the C ABI: the entry points that allocate host memory (scene upload, the host BVH hooks) run
+// their body under this guard and report a failed allocation / a failed thread start as an error code
+template <class F>
+int guarded(const char* what, F&& body) noexcept
+{
+    try
+    {
+        return body();
+    }
+    catch (const std::bad_alloc&)
+    {
+        return fail(RTCU_ERR_NOMEM, "%s: out of host memory", what);
+    }
+    catch (const std::exception& e)
+    {
+        return fail(RTCU_ERR_STATE, "%s: %s", what, e.what());
+    }
 }
 
 #define CU(call)                                                                                                       \
@@ -886,7 +906,17 @@ void rtcu_destroy(rtcu_ctx* ctx)
     delete ctx;
 }
 
+namespace {
+int upload_scene(rtcu_ctx* ctx, const rtcu_scene* s);
+}
+
 int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
+{
+    return guarded("rtcu_upload_scene", [&] { return upload_scene(ctx, s); });
+}
+
+namespace {
+int upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
 {
     if (!ctx || !s) return fail(RTCU_ERR_INVALID, "null argument");
     if (s->n_materials == 0 || !s->materials) return fail(RTCU_ERR_INVALID, "scene has no materials (scene.cpp:565-566 always provides one)");
@@ -1045,6 +1075,7 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     ctx->have_scene = true;
     return RTCU_OK;
 }
+} // namespace
 
 int rtcu_rasterize_device(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* d_rgba8, void* stream)
 {
@@ -1553,16 +1584,18 @@ int rtcu_bvh_build_host(const float* spheres, uint32_t n, float* nodes_out, uint
                         uint32_t* depth)
 {
     if ((n && !spheres) || !n_nodes || !depth) return fail(RTCU_ERR_INVALID, "null argument");
-    const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n);
-    *n_nodes = (uint32_t)bvh.nodes.size();
-    *depth = bvh.max_depth;
-    if (nodes_out)
-    {
-        if (bvh.nodes.size() > max_nodes) return fail(RTCU_ERR_INVALID, "nodes_out too small: need %zu", bvh.nodes.size());
-        memcpy(nodes_out, bvh.nodes.data(), bvh.nodes.size() * sizeof(rtcu_bvh::Node));
-    }
-    if (order_out && n) memcpy(order_out, bvh.order.data(), n * sizeof(uint32_t));
-    return RTCU_OK;
+    return guarded("rtcu_bvh_build_host", [&]() -> int {
+        const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n);
+        *n_nodes = (uint32_t)bvh.nodes.size();
+        *depth = bvh.max_depth;
+        if (nodes_out)
+        {
+            if (bvh.nodes.size() > max_nodes) return fail(RTCU_ERR_INVALID, "nodes_out too small: need %zu", bvh.nodes.size());
+            memcpy(nodes_out, bvh.nodes.data(), bvh.nodes.size() * sizeof(rtcu_bvh::Node));
+        }
+        if (order_out && n) memcpy(order_out, bvh.order.data(), n * sizeof(uint32_t));
+        return RTCU_OK;
+    });
 }
 
 int rtcu_bvh4_build_host(const float* spheres, uint32_t n, float* nodes_out, uint32_t max_nodes, float* leaves_out, uint32_t max_leaves,
@@ -1570,32 +1603,34 @@ int rtcu_bvh4_build_host(const float* spheres, uint32_t n, float* nodes_out, uin
 {
     if ((n && !spheres) || !n_nodes || !n_leaves || !depth) return fail(RTCU_ERR_INVALID, "null argument");
     if (n == 0 || n >= (1u << 29)) return fail(RTCU_ERR_INVALID, "1 .. 2^29 - 1 spheres");
-    std::vector<float4> sph(n);
-    for (uint32_t i = 0; i < n; i++)
-    {
-        const float* p = spheres + 4 * (size_t)i;
-        const volatile float r2 = p[3] * p[3];
-        sph[i] = make_float4(p[0], p[1], p[2], r2);
-    }
-    rtcu_bvh::Pool pool(n >= 8192 ? rtcu_bvh::thread_count() - 1 : 0);
-    const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n, pool);
-    std::vector<float4> nodes, leaves;
-    uint32_t d4 = 0;
-    pack_bvh4(bvh, sph, nodes, leaves, d4, pool);
-    *n_nodes = (uint32_t)(nodes.size() / 8);
-    *n_leaves = (uint32_t)(leaves.size() / 5);
-    *depth = d4;
-    if (nodes_out)
-    {
-        if (*n_nodes > max_nodes) return fail(RTCU_ERR_INVALID, "nodes_out too small: need %u", *n_nodes);
-        memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(float4));
-    }
-    if (leaves_out)
-    {
-        if (*n_leaves > max_leaves) return fail(RTCU_ERR_INVALID, "leaves_out too small: need %u", *n_leaves);
-        memcpy(leaves_out, leaves.data(), leaves.size() * sizeof(float4));
-    }
-    return RTCU_OK;
+    return guarded("rtcu_bvh4_build_host", [&]() -> int {
+        std::vector<float4> sph(n);
+        for (uint32_t i = 0; i < n; i++)
+        {
+            const float* p = spheres + 4 * (size_t)i;
+            const volatile float r2 = p[3] * p[3];
+            sph[i] = make_float4(p[0], p[1], p[2], r2);
+        }
+        rtcu_bvh::Pool pool(n >= 8192 ? rtcu_bvh::thread_count() - 1 : 0);
+        const rtcu_bvh::Result bvh = rtcu_bvh::build(spheres, n, pool);
+        std::vector<float4> nodes, leaves;
+        uint32_t d4 = 0;
+        pack_bvh4(bvh, sph, nodes, leaves, d4, pool);
+        *n_nodes = (uint32_t)(nodes.size() / 8);
+        *n_leaves = (uint32_t)(leaves.size() / 5);
+        *depth = d4;
+        if (nodes_out)
+        {
+            if (*n_nodes > max_nodes) return fail(RTCU_ERR_INVALID, "nodes_out too small: need %u", *n_nodes);
+            memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(float4));
+        }
+        if (leaves_out)
+        {
+            if (*n_leaves > max_leaves) return fail(RTCU_ERR_INVALID, "leaves_out too small: need %u", *n_leaves);
+            memcpy(leaves_out, leaves.data(), leaves.size() * sizeof(float4));
+        }
+        return RTCU_OK;
+    });
 }
 
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out)

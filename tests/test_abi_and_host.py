@@ -5,6 +5,7 @@ import ctypes
 import pathlib
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -315,6 +316,31 @@ def check_threads(sph, monkeypatch, counts):
         assert depth == ref_depth
         assert np.array_equal(nodes.view(np.uint32), ref_nodes.view(np.uint32)), threads
         assert np.array_equal(leaves.view(np.uint32), ref_leaves.view(np.uint32)), threads
+
+
+NOMEM_SCRIPT = r"""
+import ctypes as C, resource, sys
+import numpy as np
+from rt_b200 import _native as nat
+lib = nat.load_library()
+n = 3_000_000
+rng = np.random.default_rng(1)
+sph = np.concatenate([rng.uniform(-50, 50, (n, 3)), rng.uniform(0.01, 0.2, (n, 1))], axis=1).astype(np.float32)
+vm = int([l for l in open('/proc/self/status') if l.startswith('VmSize')][0].split()[1]) * 1024
+resource.setrlimit(resource.RLIMIT_AS, (vm + (48 << 20), vm + (48 << 20)))  # the build needs ~250 MB more
+a, b, d = C.c_uint32(), C.c_uint32(), C.c_uint32()
+print(lib.rtcu_bvh4_build_host(nat.ptr(sph), n, None, 0, None, 0, C.byref(a), C.byref(b), C.byref(d)), nat.last_error())
+print(lib.rtcu_bvh_build_host(nat.ptr(sph), n, None, None, 0, C.byref(a), C.byref(d)), nat.last_error())
+"""
+
+
+def test_a_failed_host_allocation_is_an_error_code_not_an_exception(lib):
+    """C++ exceptions never cross the C ABI: under an address-space limit the builder (its vectors, its worker threads' stacks)
+    runs out of memory and the entry point returns RTCU_ERR_NOMEM"""
+    r = subprocess.run([sys.executable, "-c", NOMEM_SCRIPT], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = r.stdout.strip().splitlines()
+    assert lines == [f"{nat.RTCU_ERR_NOMEM} rtcu_bvh4_build_host: out of host memory", f"{nat.RTCU_ERR_NOMEM} rtcu_bvh_build_host: out of host memory"]
 
 
 def test_only_tests_smoke_and_bench_touch_the_oracle():
