@@ -11,6 +11,7 @@
 #include <rtcu.h>
 
 #include <array>
+#include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -88,14 +89,22 @@ inline std::array<float, 4> colour_by_name(const std::string& name)
     throw scene_error("unknown colour alias '" + name + "'");
 }
 
+// `node.value<float>()` + the infinity / NaN check of scene.cpp:89-102.  toml++ (un-vendored: subprojects/tomlplusplus.wrap @
+// f1a38d23) converts permissively; its rules as recalled, UNVERIFIED like the muu arithmetic: an integer converts when it lies in
+// [-2^24, 2^24] (the whole numbers a float holds exactly), a finite float when it lies inside float's range, inf / nan pass through
+// (and are then refused by the reference's own check); booleans, strings ... have no mapping.
 inline float finite_float(const node& n, const char* what)
 {
-    double v;
-    if (n.kind == node::integer) v = static_cast<double>(n.i);
-    else if (n.kind == node::floating) v = n.f;
-    else throw scene_error(std::string("No mapping from TOML ") + n.type_name() + " to float (" + what + ")");
-    if (std::isnan(v) || std::isinf(v)) throw scene_error("Infinities and NaNs are not allowed.");
-    return static_cast<float>(v);
+    auto no_mapping = [&]() { return scene_error(std::string("No mapping from TOML ") + n.type_name() + " to float (" + what + ")"); };
+    if (n.kind == node::integer)
+    {
+        if (n.i < -(int64_t{ 1 } << 24) || n.i > (int64_t{ 1 } << 24)) throw no_mapping();
+        return static_cast<float>(n.i);
+    }
+    if (n.kind != node::floating) throw no_mapping();
+    if (std::isnan(n.f) || std::isinf(n.f)) throw scene_error("Infinities and NaNs are not allowed.");
+    if (n.f < -static_cast<double>(FLT_MAX) || n.f > static_cast<double>(FLT_MAX)) throw no_mapping();
+    return static_cast<float>(n.f);
 }
 
 struct alias { const char* name; float v[3]; };
@@ -138,11 +147,23 @@ inline std::array<float, 4> colour(const node* n, std::array<float, 4> def)
     return out;
 }
 
+// `node.value<unsigned>()` (toml++, rules as recalled, UNVERIFIED): an integer inside [0, UINT_MAX] (out-of-range values have no
+// mapping -- they do not wrap), a float holding a whole number inside that range, a boolean as 0 / 1
 inline unsigned unsigned_value(const node* n, unsigned def, const char* what)
 {
     if (!n) return def;
-    if (n->kind != node::integer) throw scene_error(std::string("No mapping from TOML ") + n->type_name() + " to unsigned (" + what + ")");
-    return static_cast<unsigned>(n->i);
+    auto no_mapping = [&]() { return scene_error(std::string("No mapping from TOML ") + n->type_name() + " to unsigned (" + what + ")"); };
+    int64_t v;
+    if (n->kind == node::integer) v = n->i;
+    else if (n->kind == node::boolean) v = n->b ? 1 : 0;
+    else if (n->kind == node::floating)
+    {
+        if (!std::isfinite(n->f) || n->f < -9.2e18 || n->f > 9.2e18 || static_cast<double>(static_cast<int64_t>(n->f)) != n->f) throw no_mapping();
+        v = static_cast<int64_t>(n->f);
+    }
+    else throw no_mapping();
+    if (v < 0 || v > static_cast<int64_t>(UINT32_MAX)) throw no_mapping();
+    return static_cast<unsigned>(v);
 }
 
 // scene.cpp:381-404 (magic_enum by integer or by name)
@@ -169,8 +190,9 @@ inline const std::vector<toml_lite::node_ptr>& table_array(const node& cfg, cons
     const node* n = cfg.get(key);
     if (!n) return empty;
     if (n->kind != node::array) throw scene_error(std::string("expected array at key '") + key + "', got " + n->type_name());
-    for (auto& it : n->items)
-        if (it->kind != node::table) throw scene_error(std::string("expected table elements in '") + key + "'");
+    // an element that is not a table reads as an empty one, as in the reference: its lookups go through toml::node_view's
+    // operator[] (scene.cpp:420-430), which yields an empty view for a non-table parent, so every field takes its default
+    // (node::get finds nothing in a non-table node either)
     return n->items;
 }
 

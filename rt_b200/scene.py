@@ -63,13 +63,34 @@ def named_colour(name: str) -> tuple[float, float, float, float]:
     return tuple(min(max(float(c), 0.0), 1.0) for c in comps)  # type: ignore[return-value]
 
 
+_FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def _toml_type(node: Any) -> str:
+    """the node type as toml++ prints it (mismatch_error, src/scene.cpp:68-87)"""
+    for t, name in ((bool, "boolean"), (int, "integer"), (float, "floating-point"), (str, "string"), (list, "array"), (dict, "table")):
+        if isinstance(node, t):
+            return name
+    return type(node).__name__
+
+
 def _finite_float(node: Any, what: str) -> float:
+    """`node.value<float>()` + the infinity / NaN check of src/scene.cpp:89-102.  toml++ (un-vendored dependency,
+    subprojects/tomlplusplus.wrap @ f1a38d23) converts permissively; its rules as recalled, UNVERIFIED like the muu arithmetic:
+    an integer converts when it lies in [-2^24, 2^24], a finite float when it lies inside float's range, inf / nan pass through
+    (and are then refused by the reference's own check); booleans, strings ... have no mapping."""
+    no_mapping = SceneError(f"No mapping from TOML {_toml_type(node)} to float ({what})")
     if isinstance(node, bool) or not isinstance(node, (int, float)):
-        raise SceneError(f"No mapping from TOML {type(node).__name__} to float ({what})")
-    v = float(node)
-    if math.isnan(v) or math.isinf(v):
+        raise no_mapping
+    if isinstance(node, int):
+        if not -(1 << 24) <= node <= (1 << 24):
+            raise no_mapping
+        return float(node)
+    if math.isnan(node) or math.isinf(node):
         raise SceneError("Infinities and NaNs are not allowed.")
-    return float(np.float32(v))
+    if not -_FLT_MAX <= node <= _FLT_MAX:
+        raise no_mapping
+    return float(np.float32(node))
 
 
 def _vector(node: Any, default: Sequence[float], what: str) -> tuple[float, ...]:
@@ -84,7 +105,7 @@ def _vector(node: Any, default: Sequence[float], what: str) -> tuple[float, ...]
     if isinstance(node, (int, float)) and not isinstance(node, bool):
         return tuple(float(np.float32(node)) for _ in range(n))  # scalar broadcast (no NaN check, :146-157)
     if not isinstance(node, list) or len(node) > n:
-        raise SceneError(f"No mapping from TOML {type(node).__name__} to vector<float, {n}> ({what})")
+        raise SceneError(f"No mapping from TOML {_toml_type(node)} to vector<float, {n}> ({what})")
     out = [float(x) for x in default]
     for i, c in enumerate(node):
         out[i] = _finite_float(c, what)
@@ -98,7 +119,7 @@ def _colour(node: Any, default: tuple[float, float, float, float]) -> tuple[floa
     if isinstance(node, str):
         return named_colour(node)
     if not isinstance(node, list) or len(node) > 4:
-        raise SceneError(f"No mapping from TOML {type(node).__name__} to colour")
+        raise SceneError(f"No mapping from TOML {_toml_type(node)} to colour")
     out = [0.0, 0.0, 0.0, 0.0]
     for i, c in enumerate(node):
         out[i] = _finite_float(c, "colour")
@@ -108,11 +129,24 @@ def _colour(node: Any, default: tuple[float, float, float, float]) -> tuple[floa
 
 
 def _unsigned(node: Any, default: int, what: str) -> int:
+    """`node.value<unsigned>()` (toml++, rules as recalled, UNVERIFIED): an integer inside [0, UINT_MAX] -- out-of-range values
+    have no mapping, they do not wrap --, a float holding a whole number inside that range, a boolean as 0 / 1"""
     if node is None:
         return default
-    if isinstance(node, bool) or not isinstance(node, int):
-        raise SceneError(f"No mapping from TOML {type(node).__name__} to unsigned ({what})")
-    return int(node) & 0xFFFFFFFF  # toml++ value<unsigned>() narrows
+    no_mapping = SceneError(f"No mapping from TOML {_toml_type(node)} to unsigned ({what})")
+    if isinstance(node, bool):
+        v = int(node)
+    elif isinstance(node, int):
+        v = node
+    elif isinstance(node, float):
+        if not math.isfinite(node) or not -9.2e18 <= node <= 9.2e18 or float(int(node)) != node:
+            raise no_mapping
+        v = int(node)
+    else:
+        raise no_mapping
+    if not 0 <= v <= 0xFFFFFFFF:
+        raise no_mapping
+    return v
 
 
 def _material_type(node: Any) -> int:
@@ -129,7 +163,7 @@ def _material_type(node: Any) -> int:
         if node not in MATERIAL_TYPES:
             raise SceneError(f"string value '{node}' was not a member of enum material_type")
         return MATERIAL_TYPES.index(node)
-    raise SceneError(f"No mapping from TOML {type(node).__name__} to material_type")
+    raise SceneError(f"No mapping from TOML {_toml_type(node)} to material_type")
 
 
 def _table_array(cfg: dict, key: str) -> list:
@@ -137,8 +171,10 @@ def _table_array(cfg: dict, key: str) -> list:
     if node is None:
         return []
     if not isinstance(node, list):
-        raise SceneError(f"expected array at key '{key}', got {type(node).__name__}")
-    return node
+        raise SceneError(f"expected array at key '{key}', got {_toml_type(node)}")
+    # an element that is not a table reads as an empty one, as in the reference: its lookups go through toml::node_view's
+    # operator[] (src/scene.cpp:420-430), which yields an empty view for a non-table parent, so every field takes its default
+    return [t if isinstance(t, dict) else {} for t in node]
 
 
 def _f32(x: float) -> np.float32:
@@ -234,7 +270,7 @@ def loads(text: str, path: str = "") -> Scene:
     cam = cfg.get("camera")
     if cam is not None:
         if not isinstance(cam, dict):
-            raise SceneError(f"expected table at key 'camera', got {type(cam).__name__}")
+            raise SceneError(f"expected table at key 'camera', got {_toml_type(cam)}")
         s.camera = Camera(position=_vector(cam.get("position"), (0, 1, 0), "camera.position"),
                           direction=_vector(cam.get("direction"), (0, 0, -1), "camera.direction"))
 

@@ -82,6 +82,16 @@ class Gen:
             return '"""' + r.choice(["", "\n"]) + word + r.choice(["", " \\\n    joined", "\nsecond line", ' "quoted" ', ' ""two'] ) + r.choice(['"""', '""""', '"""""'])
         return "'''" + r.choice(["", "\n"]) + word + r.choice(["", "\nraw \\n line", " 'q' ", " ''two"]) + r.choice(["'''", "''''"])
 
+    def unsigned(self, lo: int, hi: int) -> str:
+        """a value for an unsigned field: mostly integers, sometimes the other number-like forms toml++'s value<unsigned>() is asked to
+        convert (whole / fractional floats, booleans, negative and > 32-bit integers)"""
+        r = self.r
+        k = r.random()
+        if k < 0.7:
+            return str(r.randint(lo, hi))
+        return r.choice([f"{r.randint(lo, hi)}.0", f"{r.randint(lo, hi)}e0", f"{r.randint(lo, hi)}.5", "true", "false", str(-r.randint(1, 9)), "4294967295", "4294967296",
+                         "9223372036854775807", "1e19", "-0.0", "inf"])
+
     def bad_number(self) -> str:
         return self.r.choice(["nan", "inf", "-inf", "+nan"])
 
@@ -134,7 +144,8 @@ class Gen:
         if r.random() < 0.85:
             kv.append(("position", self.vec()))
         if kind == "spheres" and r.random() < 0.8:
-            kv.append(("radius", self.num(0.05, 3) if r.random() > self.p_error else r.choice([self.bad_number(), "[1]", self.string("big")])))
+            kv.append(("radius", self.num(0.05, 3) if r.random() > self.p_error else r.choice([self.bad_number(), "[1]", self.string("big"), "16777216", "16777217",
+                                                                                                "-16777217", "1e39", "3.4028234e38", "3.4028236e38", "true"])))
         if kind == "planes" and r.random() < 0.7:
             kv.append(("normal", self.vec(lo=-1, hi=1)))
         if kind == "boxes" and r.random() < 0.7:
@@ -143,7 +154,7 @@ class Gen:
             m = r.randrange(max(n_mats, 1))
             if r.random() < self.p_error:
                 m = r.choice([n_mats + r.randint(0, 3) if n_mats else 1 + r.randint(0, 3), -1])
-            kv.append(("material", str(m)))
+            kv.append(("material", str(m) if r.random() < 0.9 else r.choice([f"{m}.0", "false", f"{m}.25"])))
         r.shuffle(kv)
         return kv
 
@@ -157,6 +168,8 @@ class Gen:
         if r.random() < 0.5:
             sep = ",\n  " if r.random() < 0.5 else ", "
             items = ["{ " + ", ".join(f"{k} = {v}" for k, v in row if "\n" not in v or k == "name") + " }" for row in rows]
+            if r.random() < 0.05:  # an element that is not a table reads as all defaults
+                items.insert(r.randrange(len(items) + 1), r.choice(["1", "'x'", "[1, 2]", "true", "0.5"]))
             out_top.append(f"{key} = [{sep.join(items)}{',' if r.random() < 0.2 else ''}]")
         else:
             for row in rows:
@@ -171,10 +184,10 @@ class Gen:
         if r.random() < 0.2:
             top.append("# generated by tests/tools/fuzz_loader.py")
         if r.random() < 0.6:
-            v = r.choice([r.randint(-3, 2000), r.randint(1, 64)])
+            v = self.unsigned(0, 2000) if r.random() < 0.5 else str(r.randint(1, 64))
             top.append(f"samples_per_pixel = {v if r.random() > self.p_error else self.r.choice(['1.5', self.string('many'), '[4]'])}")
         if r.random() < 0.6:
-            top.append(f"max_bounces = {r.randint(-3, 2000) if r.random() > 0.2 else f'{r.randint(1, 9)}_000'}")
+            top.append(f"max_bounces = {self.unsigned(0, 2000) if r.random() > 0.2 else f'{r.randint(1, 9)}_000'}")
         cam = []
         if r.random() < 0.7:
             cam.append(("position", self.vec()))
