@@ -110,7 +110,7 @@ int run(int argc, char** argv)
     if (!found) throw std::runtime_error("unknown renderer '" + renderer + "'");
     if (mode != "sm" && mode != "mg") throw std::runtime_error("bad --mode '" + mode + "' (sm or mg)");
 
-    rtb::scene scene = rtb::load_scene(scene_path);
+    rtb::scene scene = scene_path.empty() ? rtb::load_first_available() : rtb::load_scene(scene_path); // main.cpp:121-125
     // samples_per_pixel / max_bounces are public fields of rt::scene (scene.hpp:10-11): a harness may set them past the
     // loader's clamp (BASELINE config 5 uses 4096 spp)
     if (spp > 0) scene.samples_per_pixel = static_cast<unsigned>(spp);

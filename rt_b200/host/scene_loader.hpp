@@ -14,7 +14,9 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
+#include <iostream>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -309,23 +311,56 @@ inline scene load_scene_text(const std::string& text, const std::string& path = 
 }
 
 // scene::load(file) with the relative-path search of scene.cpp:479-525
+// scene::load (scene.cpp:483-525): "-" reads standard input; a relative path is searched under the six prefixes; only regular
+// files count
 inline scene load_scene(const std::string& path)
 {
+    namespace fs = std::filesystem;
     if (path.empty()) throw scene_error("no scene file path provided");
+    if (path == "-")
+    {
+        std::ostringstream ss;
+        ss << std::cin.rdbuf();
+        return load_scene_text(ss.str(), "");
+    }
     static const char* const prefixes[] = { "scenes/", "../scenes/", "../../scenes/", "", "../", "../../" };
-    std::vector<std::string> candidates;
-    if (path[0] == '/') candidates.push_back(path);
+    std::vector<fs::path> candidates;
+    if (fs::path(path).is_absolute()) candidates.emplace_back(path);
     else
-        for (const char* p : prefixes) candidates.push_back(std::string(p) + path);
+        for (const char* p : prefixes) candidates.push_back(*p ? fs::path(p) / path : fs::path(path));
     for (const auto& c : candidates)
     {
+        std::error_code ec;
+        if (!fs::is_regular_file(c, ec)) continue;
         std::ifstream f(c, std::ios::binary);
         if (!f) continue;
         std::ostringstream ss;
         ss << f.rdbuf();
-        return load_scene_text(ss.str(), c);
+        return load_scene_text(ss.str(), c.string());
     }
     throw scene_error("scene path '" + path + "' did not exist or was not a file");
+}
+
+// scene::load_first_available (scene.cpp:620-643; what the app loads when --scene is not given, main.cpp:121-125): the first
+// regular *.toml file of the first search directory that has one, in the directory's own iteration order
+inline scene load_first_available()
+{
+    namespace fs = std::filesystem;
+    static const char* const prefixes[] = { "scenes/", "../scenes/", "../../scenes/", "", "../", "../../" };
+    for (const char* p : prefixes)
+    {
+        std::error_code ec;
+        const fs::path dir(p); // the empty prefix is not a directory (fs::status("") is not_found): the working directory is not searched
+        if (!fs::is_directory(dir, ec)) continue;
+        for (fs::directory_iterator it(dir, ec), end; !ec && it != end; it.increment(ec))
+        {
+            const fs::path& file = it->path();
+            if (!file.has_stem() || !file.has_extension() || file.extension() != ".toml") continue;
+            if (!fs::is_regular_file(file, ec)) continue;
+            return load_scene(file.string());
+        }
+    }
+    throw scene_error("no scene files found");
 }
 
 // ---- camera::viewport -> inverse_view_projection, column-major (camera.hpp:122-137); same construction as rt_b200/camera.py:

@@ -17,7 +17,9 @@ from __future__ import annotations
 import dataclasses
 import fractions
 import math
+import os
 import pathlib
+import sys
 import tomllib
 from typing import Any, Sequence
 
@@ -335,9 +337,11 @@ _SEARCH_PREFIXES = ("scenes/", "../scenes/", "../../scenes/", "", "../", "../../
 
 
 def load(path: str | pathlib.Path) -> Scene:
-    """scene::load(file) including the relative-path search (src/scene.cpp:483-525)."""
+    """scene::load(file) including the relative-path search (src/scene.cpp:483-525); "-" reads standard input."""
     if not str(path):
         raise SceneError("no scene file path provided")
+    if str(path) == "-":
+        return loads(sys.stdin.read(), "")
     p = pathlib.Path(path)
     found = None
     if not p.is_absolute():
@@ -351,6 +355,22 @@ def load(path: str | pathlib.Path) -> Scene:
     if found is None:
         raise SceneError(f"scene path '{p}' did not exist or was not a file")
     return loads(found.read_text(), str(found))
+
+
+def load_first_available() -> Scene:
+    """scene::load_first_available (src/scene.cpp:620-643; what the app loads when --scene is not given, main.cpp:121-125): the
+    first regular *.toml file of the first search directory that has one, in the directory's own iteration order."""
+    for root in _SEARCH_PREFIXES:
+        d = pathlib.Path(root)
+        if not root or not d.is_dir():  # the empty prefix is not a directory (fs::status("") is not_found): the cwd is not searched
+            continue
+        with os.scandir(d) as it:  # the same (unsorted) order as std::filesystem::directory_iterator
+            for entry in it:
+                f = pathlib.Path(entry.path)
+                if not f.stem or f.suffix != ".toml" or not f.is_file():
+                    continue
+                return load(f)
+    raise SceneError("no scene files found")
 
 
 def dumps(s: Scene) -> str:

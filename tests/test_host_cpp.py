@@ -226,6 +226,34 @@ def test_non_table_elements_read_as_defaults(cli, tmp_path):
     np.testing.assert_array_equal(s.planes[0], [0, 1, 0, 0])
 
 
+def test_stdin_and_first_available_scene(cli, tmp_path, monkeypatch):
+    """scene::load("-") reads standard input (scene.cpp:490-493); without --scene the app loads the first *.toml of the first
+    search directory that has one (scene.cpp:620-643, main.cpp:121-125)"""
+    text = "samples_per_pixel = 7\nspheres = [ {radius = 2} ]\n"
+    r = subprocess.run([cli, "--scene", "-", "--dump-scene"], input=text, capture_output=True, text=True)
+    assert r.returncode == 0 and json.loads(r.stdout)["samples_per_pixel"] == 7
+    (tmp_path / "work").mkdir()
+    (tmp_path / "scenes").mkdir()
+    (tmp_path / "scenes" / "notes.txt").write_text("not a scene")
+    (tmp_path / "scenes" / "only.toml").write_text("samples_per_pixel = 11\n")
+    (tmp_path / "work" / "here.toml").write_text("samples_per_pixel = 13\n")  # the working directory itself is not searched
+    r = subprocess.run([cli, "--dump-scene"], capture_output=True, text=True, cwd=tmp_path / "work")
+    assert r.returncode == 0 and json.loads(r.stdout)["samples_per_pixel"] == 11, r.stderr
+    monkeypatch.chdir(tmp_path / "work")
+    assert S.load_first_available().samples_per_pixel == 11
+    (tmp_path / "scenes" / "only.toml").unlink()
+    r = subprocess.run([cli, "--dump-scene"], capture_output=True, text=True, cwd=tmp_path / "work")
+    assert r.returncode == 1 and "error: no scene files found" in r.stderr
+    with pytest.raises(S.SceneError, match="no scene files found"):
+        S.load_first_available()
+    d = tmp_path / "work" / "dir.toml"
+    d.mkdir()  # a directory is not a scene file
+    r = subprocess.run([cli, "--scene", "dir.toml", "--dump-scene"], capture_output=True, text=True, cwd=tmp_path / "work")
+    assert r.returncode == 1 and "did not exist or was not a file" in r.stderr
+    with pytest.raises(S.SceneError, match="did not exist or was not a file"):
+        S.load("dir.toml")
+
+
 def test_documents_must_be_utf8(cli, tmp_path):
     p = tmp_path / "u.toml"
     p.write_bytes('[[materials]]\nname = "caf\u00e9 \U0001F600"  # \u00e9 in a comment\n'.encode())
