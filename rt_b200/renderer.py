@@ -373,6 +373,47 @@ class ProgressiveRenderer:
         self.samples_done = end
         return self.resolve()
 
+    # -- checkpoint / resume (the reference is stateless per frame; a long render here is a sum over global
+    #    sample indices, so the accumulation buffer and the number of samples done are all there is to save) -------------------
+    def _identity(self) -> dict:
+        cam = self.scene.camera
+        return {"width": self.width, "height": self.height, "seed": int(self.seed), "material_mode": int(self.material_mode),
+                "max_bounces": int(self.scene.max_bounces if self.max_bounces is None else self.max_bounces),
+                "camera": [float(x) for x in (*cam.position, *cam.direction)], "scene": scene_fingerprint(self.scene).hex()}
+
+    def save(self, path) -> None:
+        """Writes the state of the render to `path` (.npz): fp32 sums, samples done, and what they are sums *of* (scene content,
+        camera, size, seed, scatter table, depth).  Written to a temporary file and renamed, so an interrupted save leaves the
+        previous checkpoint intact."""
+        import json, os, tempfile
+        path = os.fspath(path)
+        fd, tmp = tempfile.mkstemp(dir=os.path.dirname(os.path.abspath(path)), suffix=".tmp")
+        try:
+            with os.fdopen(fd, "wb") as f:
+                np.savez(f, accum=self.accum, samples_done=np.int64(self.samples_done), identity=np.frombuffer(json.dumps(self._identity()).encode(), np.uint8))
+            os.replace(tmp, path)
+        except BaseException:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise
+
+    def restore(self, path) -> int:
+        """Continues from a checkpoint written by `save`; returns the samples already done.  Refuses a checkpoint of a different
+        scene, camera, size, seed, scatter table or depth: its sums would not be sums of this render's samples."""
+        import json
+        with np.load(path) as z:
+            identity = json.loads(bytes(z["identity"]).decode())
+            accum, done = z["accum"], int(z["samples_done"])
+        mine = self._identity()
+        differs = sorted(k for k in mine if identity.get(k) != mine[k])
+        if differs:
+            raise ValueError(f"checkpoint {path} belongs to a different render ({', '.join(differs)} differ)")
+        if accum.shape != self.accum.shape or accum.dtype != np.float32 or done < 0:
+            raise ValueError(f"checkpoint {path} is malformed")
+        self.accum[...] = accum
+        self.samples_done = done
+        return done
+
     def resolve(self) -> np.ndarray:
         """divide / sqrt / pack over the samples so far (mg_ray_tracer.cpp:195-200), on the host copy"""
         n = np.float32(max(self.samples_done, 1))

@@ -359,3 +359,59 @@ def test_only_tests_smoke_and_bench_touch_the_oracle():
     assert offenders == [], offenders
     build_py = (ROOT / "rt_b200" / "build.py").read_text()
     assert "oracle.binding" not in build_py and "CDLL" not in build_py  # it only runs `make -C oracle`
+
+
+# ---- checkpoint / resume of a progressive render (host logic; the oracle stands in for the device) ------------------------
+class _OracleContext:
+    """what ProgressiveRenderer needs from a Context, answered by the CPU oracle: the same (pixel, sample)-indexed sums"""
+
+    def __init__(self, oracle):
+        self.oracle, self.scene = oracle, None
+
+    def upload_scene(self, scene):
+        self.scene = scene
+
+    def render(self, view, want_rgba8=True, want_accum=False, **_):
+        rgba8, accum, _ = self.oracle.render(self.scene, view, want_rgba8=want_rgba8, want_accum=want_accum)
+        return rgba8, accum
+
+
+def test_progressive_render_checkpoint_and_resume(oracle, tmp_path):
+    from rt_b200.renderer import ProgressiveRenderer
+
+    sc = S.load("scenes/dielectric.toml")
+    whole = ProgressiveRenderer(_OracleContext(oracle), sc, 48, 27, samples_per_step=3, max_bounces=12)
+    for _ in range(4):
+        final = whole.refine()
+
+    first = ProgressiveRenderer(_OracleContext(oracle), sc, 48, 27, samples_per_step=3, max_bounces=12)
+    first.refine()
+    first.refine()
+    ckpt = tmp_path / "render.npz"
+    first.save(ckpt)
+    first.refine()           # work after the checkpoint is lost with the process ...
+    del first
+
+    second = ProgressiveRenderer(_OracleContext(oracle), sc, 48, 27, samples_per_step=3, max_bounces=12)
+    assert second.restore(ckpt) == 6
+    second.refine()
+    resumed = second.refine()  # ... and redone: the samples are global indices, so the sums come out the same, bit for bit
+    assert second.samples_done == whole.samples_done == 12
+    assert np.array_equal(second.accum.view(np.uint32), whole.accum.view(np.uint32)) and np.array_equal(resumed, final)
+    assert [p.name for p in tmp_path.iterdir()] == ["render.npz"]  # no temporary file left behind
+
+    # a checkpoint is only good for the render it came from
+    for kwargs, what in (({"seed": 7}, "seed"), ({"material_mode": nat.MODE_MG}, "material_mode"), ({"max_bounces": 13}, "max_bounces")):
+        other = ProgressiveRenderer(_OracleContext(oracle), sc, 48, 27, samples_per_step=3, **{"max_bounces": 12, **kwargs})
+        with pytest.raises(ValueError, match=what):
+            other.restore(ckpt)
+    moved = S.load("scenes/dielectric.toml")
+    moved.camera.position = (0.0, 2.0, 5.0)
+    with pytest.raises(ValueError, match="camera"):
+        ProgressiveRenderer(_OracleContext(oracle), moved, 48, 27, samples_per_step=3, max_bounces=12).restore(ckpt)
+    edited = S.load("scenes/dielectric.toml")
+    edited.spheres[0, 3] *= 2
+    with pytest.raises(ValueError, match="scene"):
+        ProgressiveRenderer(_OracleContext(oracle), edited, 48, 27, samples_per_step=3, max_bounces=12).restore(ckpt)
+    with pytest.raises(ValueError, match="width"):
+        ProgressiveRenderer(_OracleContext(oracle), sc, 64, 27, samples_per_step=3, max_bounces=12).restore(ckpt)
