@@ -130,7 +130,9 @@ uint32_t    rtcu_bvh_threshold(void);
 
 /* ---- scene upload: replaces the implicit `const scene&` argument of render (renderer.hpp:11).
  * Copies the columns to the device (and builds the BVH when the sphere count calls for it).  The
- * caller may free its buffers afterwards. */
+ * caller may free its buffers afterwards.  The build runs on worker threads that live for this call (the cores the process
+ * may use, at most 16; RTCU_BVH_THREADS=n overrides); the tree does not depend on their number.  RTCU_ERR_NOMEM when a host
+ * allocation fails. */
 int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* scene);
 
 /* ---- render: replaces mg_ray_tracer::render / sm_ray_tracer::render.
