@@ -633,14 +633,88 @@ void pack_bvh4(const rtcu_bvh::Result& bvh, const std::vector<float4>& sph, std:
     wide[0].depth = 1;
     uint32_t n_leaves = 0;
     depth4 = 0;
+    // Which binary nodes fold into a 4-wide node.  Default: greedy -- replace the inner child of largest area by its two children
+    // until four slots are filled.  RTCU_BVH_COLLAPSE=sah (experiment, off by default; DESIGN.md section 8, "Tree quality"): the
+    // collapse of least SAH cost by dynamic programming (after Ylitie et al. 2017) -- C(e, i) = cheapest way to cover the subtree
+    // of child entry e with at most i slots of its parent's wide node: as one wide node of its own (i = 1: area x node cost + the
+    // best distribution of ITS four slots over its two children), or dissolved into the parent (its children share the i slots).
+    const char* collapse_env = getenv("RTCU_BVH_COLLAPSE");
+    const bool sah_collapse = collapse_env && strcmp(collapse_env, "sah") == 0;
+    const size_t n_binary = bvh.nodes.size();
+    std::vector<float> cost_entry, cost_split; // C[(2 * node + side) * 5 + i], D[node * 5 + j]
+    std::vector<uint8_t> split_left;           // slots given to the left child by the best distribution D[node][j]
+    if (sah_collapse)
+    {
+        constexpr float NODE_COST = 1.0f, LEAF_COST = 0.45f; // issue slots of a leaf visit relative to a node visit (~40 : 93)
+        cost_entry.assign(n_binary * 10, 0.0f);
+        cost_split.assign(n_binary * 5, 0.0f);
+        split_left.assign(n_binary * 5, 1);
+        for (size_t m = n_binary; m-- > 0;) // children have larger indices than their parent (level-order construction)
+        {
+            for (int side = 0; side < 2; side++)
+            {
+                const Kid4 e = kid_of(bvh.nodes[m], side);
+                float* c = &cost_entry[(2 * m + side) * 5];
+                const float dx = e.hi[0] - e.lo[0], dy = e.hi[1] - e.lo[1], dz = e.hi[2] - e.lo[2];
+                const float area = (e.child < 0 && e.count == 0) ? 0.0f : dx * dy + dy * dz + dz * dx;
+                if (e.child < 0)
+                {
+                    for (int i = 1; i <= 4; i++) c[i] = area * LEAF_COST;
+                    continue;
+                }
+                c[1] = area * NODE_COST + cost_split[(size_t)e.child * 5 + 4];
+                for (int i = 2; i <= 4; i++) c[i] = std::min(c[i - 1], cost_split[(size_t)e.child * 5 + i]);
+            }
+            for (int j = 2; j <= 4; j++)
+            {
+                float best = __builtin_inff();
+                for (int k = 1; k < j; k++)
+                {
+                    const float v = cost_entry[(2 * m) * 5 + k] + cost_entry[(2 * m + 1) * 5 + (j - k)];
+                    if (v < best) { best = v; split_left[m * 5 + j] = (uint8_t)k; }
+                }
+                cost_split[m * 5 + j] = best;
+            }
+        }
+    }
     for (size_t qi = 0; qi < wide.size(); qi++)
     {
         Wide w = wide[qi];
         depth4 = std::max(depth4, w.depth);
         int nk = 2;
-        w.kids[0] = kid_of(bvh.nodes[(size_t)w.binary], 0);
-        w.kids[1] = kid_of(bvh.nodes[(size_t)w.binary], 1);
-        while (nk < 4)
+        if (sah_collapse)
+        {
+            // unfold the recorded decisions: (binary node, slots) pairs, left before right
+            nk = 0;
+            struct Todo { int32_t node; int slots; };
+            Todo todo[8];
+            int nt = 0;
+            todo[nt++] = Todo{ w.binary, 4 };
+            while (nt > 0)
+            {
+                const Todo t = todo[--nt];
+                const int left = split_left[(size_t)t.node * 5 + t.slots];
+                const int budget[2] = { left, t.slots - left };
+                Todo defer[2];
+                int nd = 0;
+                for (int side = 0; side < 2; side++)
+                {
+                    const Kid4 e = kid_of(bvh.nodes[(size_t)t.node], side);
+                    const float* c = &cost_entry[(2 * (size_t)t.node + side) * 5];
+                    int i = budget[side];
+                    while (i > 1 && c[i] == c[i - 1]) i--; // the smallest budget that reaches the optimum
+                    if (e.child >= 0 && i >= 2) defer[nd++] = Todo{ e.child, i }; // dissolved: its children take the i slots
+                    else w.kids[nk++] = e;
+                }
+                for (int k = nd - 1; k >= 0; k--) todo[nt++] = defer[k];
+            }
+        }
+        else
+        {
+            w.kids[0] = kid_of(bvh.nodes[(size_t)w.binary], 0);
+            w.kids[1] = kid_of(bvh.nodes[(size_t)w.binary], 1);
+        }
+        while (!sah_collapse && nk < 4)
         {
             int best = -1;
             float best_area = -1.0f;

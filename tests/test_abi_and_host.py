@@ -194,12 +194,14 @@ def test_bvh_builder_invariants(lib, n):
 
 
 # ---- the 4-wide device tree (collapsed on upload), built on the host: same invariants in the device layout ---------
-@pytest.mark.parametrize("knobs", [{}, {"RTCU_BVH_SWEEP": "512"}, {"RTCU_BVH_LEAF_COST": "1"}, {"RTCU_BVH_SWEEP": "64", "RTCU_BVH_LEAF_COST": "1"}],
-                         ids=["default", "sweep", "leafcost", "sweep+leafcost"])
+@pytest.mark.parametrize("knobs", [{}, {"RTCU_BVH_SWEEP": "512"}, {"RTCU_BVH_LEAF_COST": "1"}, {"RTCU_BVH_SWEEP": "64", "RTCU_BVH_LEAF_COST": "1"},
+                                   {"RTCU_BVH_COLLAPSE": "sah"}, {"RTCU_BVH_COLLAPSE": "sah", "RTCU_BVH_LEAF_COST": "1"}],
+                         ids=["default", "sweep", "leafcost", "sweep+leafcost", "sah-collapse", "sah-collapse+leafcost"])
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 9, 33, 484, 5000, 100001])
 def test_bvh4_device_tree_invariants(lib, n, knobs, monkeypatch):
-    """every tree the builder can produce -- the default and the experimental split rules (bvh.h: RTCU_BVH_SWEEP,
-    RTCU_BVH_LEAF_COST) -- is a valid input for the traversal: coverage, containment, leaf packing, stack bound"""
+    """every tree the builder can produce -- the default and the experimental split / collapse rules (bvh.h: RTCU_BVH_SWEEP,
+    RTCU_BVH_LEAF_COST; rtcu.cu pack_bvh4: RTCU_BVH_COLLAPSE=sah) -- is a valid input for the traversal: coverage, containment,
+    leaf packing, stack bound"""
     from rt_b200 import synth
 
     if knobs and n in (1, 3, 4, 9, 5000):
@@ -301,9 +303,11 @@ def test_bvh_build_is_independent_of_thread_count(lib, case, monkeypatch):
     if case in ("grid100k", "clusters30k"):  # the experimental split rules are order-independent as well
         monkeypatch.setenv("RTCU_BVH_SWEEP", "64" if case == "grid100k" else "0")
         monkeypatch.setenv("RTCU_BVH_LEAF_COST", "1")
+        monkeypatch.setenv("RTCU_BVH_COLLAPSE", "sah")
         check_threads(sph, monkeypatch, ("8",))
         monkeypatch.delenv("RTCU_BVH_SWEEP")
         monkeypatch.delenv("RTCU_BVH_LEAF_COST")
+        monkeypatch.delenv("RTCU_BVH_COLLAPSE")
     check_threads(sph, monkeypatch, ("2", "3", "8", "16"))
 
 
