@@ -395,7 +395,13 @@ def dumps(s: Scene) -> str:
         out.append("planes = [")
         for pl, mat in zip(s.planes, s.plane_material):
             n = pl[:3].astype(np.float64)
-            pos = -float(pl[3]) * n  # a point on the plane
+            pos = -float(pl[3]) * n  # a point on the plane: the reloaded offset -dot3(n, pos) equals d up to rounding (exact for axis-aligned planes)
             out.append(f"    {{ material = {int(mat)}, position = {vec(pos)}, normal = {vec(pl[:3])} }},")
+        out += ["]", ""]
+    boxes, box_material = getattr(s, "boxes", ()), getattr(s, "box_material", ())
+    if len(boxes):
+        out.append("boxes = [")
+        for bx, mat in zip(boxes, box_material):
+            out.append(f"    {{ material = {int(mat)}, position = {vec(bx[:3])}, extents = {vec(bx[3:6])} }},")
         out += ["]", ""]
     return "\n".join(out)

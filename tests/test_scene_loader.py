@@ -130,6 +130,19 @@ def test_plane_arithmetic_follows_the_spec_dot_and_normalize():
     assert np.isnan(s.planes[2]).all()                              # a zero normal normalises to NaN (as muu's normalize would)
 
 
+def test_dumps_round_trips_every_primitive_table():
+    s = S.load("scenes/boxes.toml")
+    assert len(s.boxes) and len(s.planes) and len(s.spheres)
+    t = S.loads(S.dumps(s))
+    np.testing.assert_array_equal(t.boxes, s.boxes)
+    np.testing.assert_array_equal(t.box_material, s.box_material)
+    np.testing.assert_array_equal(t.spheres, s.spheres)
+    np.testing.assert_array_equal(t.materials, s.materials)
+    np.testing.assert_array_equal(t.planes[:, :3], s.planes[:, :3])
+    np.testing.assert_allclose(t.planes[:, 3], s.planes[:, 3], rtol=1e-6)
+    assert (t.samples_per_pixel, t.max_bounces, t.camera.position, t.camera.direction) == (s.samples_per_pixel, s.max_bounces, s.camera.position, s.camera.direction)
+
+
 def test_relative_path_search(tmp_path, monkeypatch):
     (tmp_path / "scenes").mkdir()
     (tmp_path / "scenes" / "x.toml").write_text("samples_per_pixel = 7")
