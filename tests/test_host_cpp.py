@@ -277,11 +277,24 @@ def test_dump_keeps_signed_zeros_and_non_finite_values(cli, tmp_path):
     assert np.signbit(np.float32(d["spheres"][0][0])) and np.isnan(np.float32(d["planes"][1])).all()
 
 
-def test_viewport_matrix_matches_the_python_camera(cli):
-    for name, size in (("scenes/basic.toml", (800, 600)), ("scenes/dielectric.toml", (1920, 1080))):
-        m = np.float32(json.loads(run(cli, "--scene", name, "--size", f"{size[0]}x{size[1]}", "--dump-view").stdout))
-        ref = inverse_view_projection(S.load(name).camera, *size)
-        np.testing.assert_allclose(m, ref, rtol=2e-6, atol=2e-6)
+def test_viewport_matrix_matches_the_python_camera(cli, tmp_path):
+    """both hosts build inverse(P * view) as world * inverse(P) with the same float64 sums: bit-identical matrices, exact
+    structural zeros (the w row is (0, 0, m11, m15), which lets the kernels take the cheaper perspective divide)"""
+    def check(path, size):
+        m = np.float32(json.loads(run(cli, "--scene", str(path), "--size", f"{size[0]}x{size[1]}", "--dump-view").stdout))
+        ref = inverse_view_projection(S.load(path).camera, *size)
+        assert np.array_equal(m.view(np.uint32), ref.view(np.uint32)), (path, m, ref)
+        assert m[3] == 0 and m[7] == 0 and np.isfinite(m).all()
+
+    for name, size in (("scenes/basic.toml", (800, 600)), ("scenes/dielectric.toml", (1920, 1080)), ("scenes/boxes.toml", (320, 200))):
+        check(name, size)
+    rng = np.random.default_rng(3)
+    directions = [(0, 1, 0), (0, -1, 0), (0, -1, 1e-5), (1e-3, 5, 2e-3), (3, 0, 0), (0, -0.35, -1), (-13, -2, -3)] + [tuple(rng.normal(size=3)) for _ in range(12)]
+    for i, d in enumerate(directions):
+        p = tmp_path / f"cam{i}.toml"
+        pos = rng.uniform(-20, 20, 3)
+        p.write_text(f"camera = {{ position = [{float(pos[0])!r}, {float(pos[1])!r}, {float(pos[2])!r}], direction = [{float(d[0])!r}, {float(d[1])!r}, {float(d[2])!r}] }}\n")
+        check(p, [(640, 360), (800, 600), (97, 131)][i % 3])
 
 
 def test_no_device_fails_loudly(cli):
