@@ -3,6 +3,7 @@ twin (rt_b200/scene.py, camera.py) and, on a GPU, against the Python path throug
 import json
 import pathlib
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -353,3 +354,14 @@ def nat_device_count() -> int:
     from rt_b200 import _native as nat
 
     return nat.load_library().rtcu_device_count()
+
+
+def test_loader_twins_agree_on_generated_and_mutated_files(cli):
+    """a short run of the differential fuzz (tests/tools/fuzz_loader.py; the campaigns of record are in profiles/): the Python and
+    the C++ loader accept and reject the same files and load the same values, and the C++ host never crashes"""
+    tool = pathlib.Path(__file__).parent / "tools" / "fuzz_loader.py"
+    r = subprocess.run([sys.executable, "-W", "ignore", str(tool), "--cases", "240", "--seed", "314"], capture_output=True, text=True)
+    stats = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert stats["cases"] == 240 and stats["crashes"] == stats["value_mismatch"] == stats["accept_mismatch_generated"] == 0
+    assert stats["both_accept"] >= 60 and stats["both_reject"] >= 60  # the generator exercises both outcomes
