@@ -1,0 +1,141 @@
+/* bvh_replay.c -- the device's BVH traversal (rt_b200/csrc/kernels.cuh: trav_init, slab_pair, trav_step, bvh_leaf_pair_test),
+ * restated in C over the arrays rtcu_bvh4_build_host returns, so that the claim "traversal returns the linear scan's result bit
+ * for bit" can be checked on the CPU against the oracle's scan -- for the default tree and for every experimental builder variant,
+ * on far more rays than a GPU test has time for.  What is replayed: the conservative margins (kappa, E = |c - o|_1 + H), the
+ * `tf >= max(tn, 0) && tn <= best_t` cull, leaves tested at once, nearest inner child first, the others pushed in slot order, the
+ * pop-time cull, the (t, index) acceptance rule, S4 with explicit fmaf (compile with -ffp-contract=off).  What is not: the packed
+ * FFMA2 instruction selection (the box arithmetic only has to be conservative; the leaf arithmetic is S4's, rounding for rounding).
+ * Test infrastructure only (tests/test_bvh_replay.py builds it into a temporary directory). */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define STACK 64
+
+static inline float dot3(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
+
+/* returns 0 when the direction is too far from unit length (the kernel then scans), else 1 with (t, index) of the closest hit
+ * (index -1 = miss); visits / leaf_visits are added to the counters */
+int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], const float d[3], float* t_out, int32_t* i_out,
+                   uint64_t* visits, uint64_t* leaf_visits, uint32_t* max_sp)
+{
+    const float eps_d = fabsf(dot3(d, d) - 1.0f);
+    if (!(eps_d <= 1e-3f)) return 0;
+    const float kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
+    const float inv[3] = { 1.0f / d[0], 1.0f / d[1], 1.0f / d[2] };
+    float best_t = INFINITY;
+    int32_t best_i = 0x7fffffff;
+    uint32_t stack_ref[STACK];
+    float stack_t[STACK];
+    uint32_t sp = 0, node = 0;
+    for (;;)
+    {
+        const float* np = nodes + 32u * (size_t)node;
+        uint32_t ref[4];
+        memcpy(ref, np + 24, sizeof ref);
+        const float* H = np + 28;
+        float tn[4];
+        int hit[4];
+        (*visits)++;
+        for (int c = 0; c < 4; c++)
+        {
+            const int pair = c >> 1, slot = c & 1;
+            const float* ax = np + 12 * pair; /* x: {c0,c1,h0,h1}, y, z */
+            float dc[3], tc[3];
+            for (int k = 0; k < 3; k++) dc[k] = ax[4 * k + slot] - o[k];
+            const float e3 = fabsf(dc[0]) + fabsf(dc[1]) + fabsf(dc[2]);
+#ifdef BVH_REPLAY_NO_MARGIN /* what the rays of the test are for: without the margins the traversal misses grazing hits */
+            const float m = 0.0f * (e3 + H[c]) * kappa;
+#else
+            const float m = (e3 + H[c]) * kappa;
+#endif
+            float near = -INFINITY, far = INFINITY;
+            for (int k = 0; k < 3; k++)
+            {
+                const float h = ax[4 * k + 2 + slot] + m, a = fabsf(inv[k]);
+                tc[k] = dc[k] * inv[k];
+                near = fmaxf(near, fmaf(-h, a, tc[k])); /* fmaxf / fminf drop a NaN operand, as the device's do */
+                far = fminf(far, fmaf(h, a, tc[k]));
+            }
+            tn[c] = near;
+            hit[c] = far >= fmaxf(near, 0.0f) && near <= best_t;
+        }
+        uint32_t next = 0xffffffffu;
+        float next_t = 0.0f;
+        for (int c = 0; c < 4; c++)
+        {
+            if (!hit[c]) continue;
+            if (ref[c] & 0x80000000u)
+            {
+                const float* lp = leaves + 20u * (size_t)(ref[c] & 0x7fffffffu);
+                int32_t idx[4];
+                memcpy(idx, lp + 16, sizeof idx);
+                (*leaf_visits)++;
+                for (int k = 0; k < 4; k++)
+                {
+                    const float* A = lp + 8 * (k >> 1);
+                    const float* B = A + 4;
+                    const int s = k & 1;
+                    const float e[3] = { A[s] - o[0], A[2 + s] - o[1], B[s] - o[2] };
+                    const float r2 = B[2 + s];
+                    const float e2 = dot3(e, e), a = dot3(e, d);
+                    const float disc = r2 - fmaf(-a, a, e2);
+                    if (disc < 0.0f) continue;
+                    const float f = sqrtf(disc);
+                    const float t = (e2 < r2) ? a + f : a - f;
+                    if (!(t < 0.001f) && (t < best_t || (t == best_t && idx[k] < best_i)))
+                    {
+                        best_t = t;
+                        best_i = idx[k];
+                    }
+                }
+            }
+            else if (next == 0xffffffffu)
+            {
+                next = ref[c];
+                next_t = tn[c];
+            }
+            else
+            {
+                const int swap = tn[c] < next_t;
+                if (sp >= STACK) return -1;
+                stack_ref[sp] = swap ? next : ref[c];
+                stack_t[sp] = swap ? next_t : tn[c];
+                sp++;
+                if (sp > *max_sp) *max_sp = sp;
+                if (swap) { next = ref[c]; next_t = tn[c]; }
+            }
+        }
+        if (next != 0xffffffffu && next_t <= best_t) { node = next; continue; }
+        int found = 0;
+        while (sp > 0)
+        {
+            sp--;
+            if (stack_t[sp] <= best_t) { node = stack_ref[sp]; found = 1; break; }
+        }
+        if (!found) break;
+    }
+    *t_out = best_t;
+    *i_out = best_i == 0x7fffffff ? -1 : best_i;
+    return 1;
+}
+
+/* n rays; hit[i] = 1 / 0, prim, t as the scan reports them (t = -1 on a miss), skipped[i] = 1 where the kernel would scan instead.
+ * Returns the deepest stack use, or -1 on overflow. */
+int bvh_replay_batch(const float* nodes, const float* leaves, const float* o, const float* d, uint32_t n, uint8_t* hit, uint32_t* prim, float* t,
+                     uint8_t* skipped, uint64_t counters[2])
+{
+    uint32_t max_sp = 0;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        float tt = 0.0f;
+        int32_t ii = -1;
+        const int rc = bvh_replay_ray(nodes, leaves, o + 3 * (size_t)i, d + 3 * (size_t)i, &tt, &ii, &counters[0], &counters[1], &max_sp);
+        if (rc < 0) return -1;
+        skipped[i] = rc == 0;
+        hit[i] = rc == 1 && ii >= 0;
+        prim[i] = hit[i] ? (uint32_t)ii : 0xffffffffu;
+        t[i] = hit[i] ? tt : -1.0f;
+    }
+    return (int)max_sp;
+}
