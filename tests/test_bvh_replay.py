@@ -20,14 +20,14 @@ def build_replay(tmp_path_factory, *defines):
                     str(ROOT / "tests" / "tools" / "bvh_replay.c"), "-lm"], check=True)
     lib = C.CDLL(str(so))
     lib.bvh_replay_batch.restype = C.c_int
-    lib.bvh_replay_batch.argtypes = [C.c_void_p] * 4 + [C.c_uint32] + [C.c_void_p] * 5
+    lib.bvh_replay_batch.argtypes = [C.c_void_p] * 4 + [C.c_uint32] + [C.c_void_p] * 5 + [C.c_int]
 
-    def run(nodes, leaves, o, d):
+    def run(nodes, leaves, o, d, any_t=False):
         n = len(o)
         hit, prim, t, skipped = np.zeros(n, np.uint8), np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
         counters = np.zeros(2, np.uint64)
         depth = lib.bvh_replay_batch(nodes.ctypes.data, leaves.ctypes.data, o.ctypes.data, d.ctypes.data, n, hit.ctypes.data, prim.ctypes.data,
-                                     t.ctypes.data, skipped.ctypes.data, counters.ctypes.data)
+                                     t.ctypes.data, skipped.ctypes.data, counters.ctypes.data, int(any_t))
         assert depth >= 0, "traversal stack overflow"
         return hit, prim, t, skipped.astype(bool), counters, depth
     return run
@@ -120,6 +120,34 @@ def test_replay_declines_non_unit_directions(replay):
     d = np.float32([[0, 0, -1], [0, 0, -1.01], [0, 0.5, -0.5]])
     _, _, _, skipped, _, _ = replay(nodes, leaves, o, d)
     assert skipped.tolist() == [False, True, True]  # |d.d - 1| > 1e-3: the kernel falls back to the scan
+
+
+def test_replayed_preview_traversal_equals_the_oracle_rasterizer(replay, oracle):
+    """the preview renderer's variant of the traversal (ANY_T: no minimum distance, negative distances count -- a sphere behind the
+    camera hides what is in front, rasterizer.cpp:41-52) against the oracle's rasterizer.cpp restatement: spheres in front of,
+    behind and around the camera, one ray per pixel"""
+    from rt_b200.renderer import make_view
+
+    rng = np.random.default_rng(8)
+    sph = np.concatenate([rng.uniform(-12, 12, (600, 3)), rng.uniform(0.1, 1.2, (600, 1))], axis=1).astype(np.float32)
+    sph[0] = [0, 0, 0, 3.0]        # the camera sits inside this one
+    sph[1] = [0.2, 0.1, 6.0, 1.0]  # behind the camera: negative distance
+    sph[2] = sph[3]                # identical spheres: the lower index wins
+    sc = scene_of(sph)
+    sc.camera.position, sc.camera.direction = (0.0, 0.0, 1.0), (0.1, -0.05, -1.0)
+    view = make_view(sc, 160, 100)
+    _, ref_prim, ref_depth = oracle.rasterize(sc, view)
+    px, py = np.meshgrid(np.arange(160), np.arange(100))
+    o, d = oracle.primary_rays(view, px.ravel(), py.ravel(), np.zeros(160 * 100, np.uint32))  # sample 0 = the pixel centre
+    nodes, leaves, _ = R.bvh4_build_host(sph)
+    hit, prim, t, skipped, _, _ = replay(nodes, leaves, np.ascontiguousarray(o), np.ascontiguousarray(d), any_t=True)
+    assert not skipped.any()
+    ref_prim, ref_depth = ref_prim.ravel(), ref_depth.ravel()
+    ref_hit = ref_prim != 0xFFFFFFFF
+    assert np.array_equal(hit.astype(bool), ref_hit) and ref_hit.mean() > 0.9
+    assert np.array_equal(prim[ref_hit], ref_prim[ref_hit])
+    assert np.array_equal(t[ref_hit].view(np.uint32), ref_depth[ref_hit].view(np.uint32))
+    assert (t[ref_hit] < 0).any() and len(np.unique(prim[ref_hit])) > 20  # negative distances do occur, and many spheres are seen
 
 
 def test_the_rays_need_the_margins(tmp_path_factory, oracle):

@@ -16,15 +16,17 @@ static inline float dot3(const float a[3], const float b[3]) { return fmaf(a[2],
 
 /* returns 0 when the direction is too far from unit length (the kernel then scans), else 1 with (t, index) of the closest hit
  * (index -1 = miss); visits / leaf_visits are added to the counters */
-int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], const float d[3], float* t_out, int32_t* i_out,
-                   uint64_t* visits, uint64_t* leaf_visits, uint32_t* max_sp)
+/* any_t: the preview renderer's variant (raster.cuh, rasterizer.cpp:41-52) -- the whole line counts, no minimum distance, and the
+ * search starts from (start_t, start_i) = (distance of the closest plane / box so far, -1) */
+int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], const float d[3], int any_t, float start_t, int32_t start_i,
+                   float* t_out, int32_t* i_out, uint64_t* visits, uint64_t* leaf_visits, uint32_t* max_sp)
 {
     const float eps_d = fabsf(dot3(d, d) - 1.0f);
     if (!(eps_d <= 1e-3f)) return 0;
     const float kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
     const float inv[3] = { 1.0f / d[0], 1.0f / d[1], 1.0f / d[2] };
-    float best_t = INFINITY;
-    int32_t best_i = 0x7fffffff;
+    float best_t = start_t;
+    int32_t best_i = start_i;
     uint32_t stack_ref[STACK];
     float stack_t[STACK];
     uint32_t sp = 0, node = 0;
@@ -58,7 +60,7 @@ int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], co
                 far = fminf(far, fmaf(h, a, tc[k]));
             }
             tn[c] = near;
-            hit[c] = far >= fmaxf(near, 0.0f) && near <= best_t;
+            hit[c] = far >= (any_t ? near : fmaxf(near, 0.0f)) && near <= best_t;
         }
         uint32_t next = 0xffffffffu;
         float next_t = 0.0f;
@@ -83,7 +85,7 @@ int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], co
                     if (disc < 0.0f) continue;
                     const float f = sqrtf(disc);
                     const float t = (e2 < r2) ? a + f : a - f;
-                    if (!(t < 0.001f) && (t < best_t || (t == best_t && idx[k] < best_i)))
+                    if ((any_t || !(t < 0.001f)) && (t < best_t || (t == best_t && idx[k] < best_i)))
                     {
                         best_t = t;
                         best_i = idx[k];
@@ -123,14 +125,15 @@ int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], co
 /* n rays; hit[i] = 1 / 0, prim, t as the scan reports them (t = -1 on a miss), skipped[i] = 1 where the kernel would scan instead.
  * Returns the deepest stack use, or -1 on overflow. */
 int bvh_replay_batch(const float* nodes, const float* leaves, const float* o, const float* d, uint32_t n, uint8_t* hit, uint32_t* prim, float* t,
-                     uint8_t* skipped, uint64_t counters[2])
+                     uint8_t* skipped, uint64_t counters[2], int any_t)
 {
     uint32_t max_sp = 0;
     for (uint32_t i = 0; i < n; i++)
     {
         float tt = 0.0f;
         int32_t ii = -1;
-        const int rc = bvh_replay_ray(nodes, leaves, o + 3 * (size_t)i, d + 3 * (size_t)i, &tt, &ii, &counters[0], &counters[1], &max_sp);
+        const int rc = bvh_replay_ray(nodes, leaves, o + 3 * (size_t)i, d + 3 * (size_t)i, any_t, INFINITY, any_t ? -1 : 0x7fffffff, &tt, &ii,
+                                      &counters[0], &counters[1], &max_sp);
         if (rc < 0) return -1;
         skipped[i] = rc == 0;
         hit[i] = rc == 1 && ii >= 0;
