@@ -115,7 +115,10 @@ public:
     }
 
 private:
-    static constexpr unsigned SPIN = 1u << 15; // ~1 ms of pause instructions: longer than any serial stretch of a build
+#ifndef RTCU_BVH_POOL_SPIN
+#define RTCU_BVH_POOL_SPIN (1u << 15) // ~1 ms of pause instructions: longer than any serial stretch of a build (a stress test shortens it)
+#endif
+    static constexpr unsigned SPIN = RTCU_BVH_POOL_SPIN;
     static void relax()
     {
 #if defined(__x86_64__) || defined(__i386__)

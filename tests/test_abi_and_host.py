@@ -419,3 +419,12 @@ def test_progressive_render_checkpoint_and_resume(oracle, tmp_path):
         ProgressiveRenderer(_OracleContext(oracle), edited, 48, 27, samples_per_step=3, max_bounces=12).restore(ckpt)
     with pytest.raises(ValueError, match="width"):
         ProgressiveRenderer(_OracleContext(oracle), sc, 64, 27, samples_per_step=3, max_bounces=12).restore(ckpt)
+
+
+def test_worker_pool_sleep_and_wake_protocol_under_stress(tmp_path):
+    """bvh.h's pool with its spin shortened to a few iterations, so nearly every hand-over goes through the condition variable:
+    160 builds at 1 - 11 workers must terminate (a lost wake-up would hang) and equal the one-thread tree"""
+    exe = tmp_path / "pool_stress"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-DRTCU_BVH_POOL_SPIN=4", "-o", str(exe), str(ROOT / "tests" / "tools" / "pool_stress.cpp")], check=True)
+    r = subprocess.run([str(exe), "20"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "ok 160 builds", r.stdout + r.stderr
