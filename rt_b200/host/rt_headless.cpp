@@ -9,6 +9,7 @@
 // --dump-scene / --dump-view print the flattened scene / the inverse view-projection as JSON and need no GPU.
 #include "scene_loader.hpp"
 
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -82,6 +83,19 @@ int run(int argc, char** argv)
             if (i + 1 >= argc) throw std::runtime_error("option '" + a + "' needs a value");
             return argv[++i];
         };
+        // a whole-string number in [lo, hi], or an error that names the option (std::stol alone says "stol")
+        auto number = [&](long long lo, unsigned long long hi) -> unsigned long long
+        {
+            const std::string v = value();
+            char* end = nullptr;
+            errno = 0;
+            const bool negative = !v.empty() && v[0] == '-';
+            const unsigned long long u = negative ? 0 : std::strtoull(v.c_str(), &end, 0);
+            const long long sgn = negative ? std::strtoll(v.c_str(), &end, 0) : 0;
+            if (v.empty() || *end || errno == ERANGE || (negative ? sgn < lo : u > hi) || (!negative && lo > 0 && u < (unsigned long long)lo))
+                throw std::runtime_error("bad " + a + " '" + v + "' (expected a whole number in [" + std::to_string(lo) + ", " + std::to_string(hi) + "])");
+            return negative ? (unsigned long long)sgn : u;
+        };
         if (a == "-l" || a == "--list") list = true;
         else if (a == "-s" || a == "--scene") scene_path = value();
         else if (a == "-r" || a == "--renderer") renderer = value();
@@ -90,13 +104,13 @@ int run(int argc, char** argv)
             const std::string v = value();
             if (std::sscanf(v.c_str(), "%ux%u", &width, &height) != 2 || !width || !height) throw std::runtime_error("bad --size '" + v + "' (expected WxH)");
         }
-        else if (a == "--spp") spp = std::stol(value());
-        else if (a == "--bounces") bounces = std::stol(value());
+        else if (a == "--spp") spp = (long)number(1, 1u << 30);
+        else if (a == "--bounces") bounces = (long)number(1, 1u << 30);
         else if (a == "--mode") mode = value();
-        else if (a == "--seed") seed = std::stoull(value(), nullptr, 0);
+        else if (a == "--seed") seed = number(0, ~0ull);
         else if (a == "--out") out_path = value();
-        else if (a == "--device") device = std::stoi(value());
-        else if (a == "--gpus") gpus = std::stoi(value());
+        else if (a == "--device") device = (int)number(0, 1023);
+        else if (a == "--gpus") gpus = (int)number(1, 8);
         else if (a == "--dump-scene") want_dump_scene = true;
         else if (a == "--dump-view") want_dump_view = true;
         else throw std::runtime_error("unknown option '" + a + "'");

@@ -255,6 +255,17 @@ def test_stdin_and_first_available_scene(cli, tmp_path, monkeypatch):
         S.load("dir.toml")
 
 
+@pytest.mark.parametrize("args,message", [
+    (["--spp", "abc"], "bad --spp 'abc'"), (["--spp", "0"], "bad --spp '0'"), (["--spp", "-5"], "bad --spp '-5'"), (["--bounces", "3x"], "bad --bounces '3x'"),
+    (["--gpus", "9"], "bad --gpus '9' (expected a whole number in [1, 8])"), (["--device", "x"], "bad --device 'x'"), (["--seed", "zz"], "bad --seed 'zz'"),
+    (["--size", "0x0"], "bad --size '0x0' (expected WxH)"), (["--size"], "option '--size' needs a value"), (["--bogus"], "unknown option '--bogus'"),
+    (["--mode", "xx"], "bad --mode 'xx'"),
+])
+def test_cli_argument_errors_name_the_option(cli, args, message):
+    r = run(cli, "--scene", "scenes/basic.toml", *args, check=False)
+    assert r.returncode == 1 and r.stderr.strip().splitlines()[-1].startswith("error: ") and message in r.stderr, r.stderr
+
+
 def test_documents_must_be_utf8(cli, tmp_path):
     p = tmp_path / "u.toml"
     p.write_bytes('[[materials]]\nname = "caf\u00e9 \U0001F600"  # \u00e9 in a comment\n'.encode())
