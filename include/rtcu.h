@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTCU_ABI_VERSION 2
+#define RTCU_ABI_VERSION 3
 
 enum {
     RTCU_OK = 0,
@@ -127,6 +127,15 @@ rtcu_ctx*   rtcu_create(int device);   /* NULL on failure, see rtcu_last_error()
 void        rtcu_destroy(rtcu_ctx* ctx);
 const char* rtcu_last_error(void);
 uint32_t    rtcu_bvh_threshold(void);
+/* The RTCU_* environment variables (experiment knobs) are read once in rtcu_create, never on the launch path;
+ * this re-reads them for a context that is already alive (A/B tests). */
+int         rtcu_reload_env(rtcu_ctx* ctx);
+
+/* Threading and ordering.  A context serves ONE frame at a time: the render kernels of a context share its counters, its
+ * straggler queue and its tile-cost map.  Calls on one context must come from one thread at a time (render() is called from the
+ * UI thread only, window.cpp:213-217).  Launches may go to different streams (rtcu_render_device): the library orders each
+ * launch after the previous one of the same context with an event, so two frames of one context never overlap on the device;
+ * use one context per concurrently rendered frame. */
 
 /* ---- scene upload: replaces the implicit `const scene&` argument of render (renderer.hpp:11).
  * Copies the columns to the device (and builds the BVH when the sphere count calls for it).  The
@@ -134,6 +143,9 @@ uint32_t    rtcu_bvh_threshold(void);
  * may use, at most 16; RTCU_BVH_THREADS=n overrides); the tree does not depend on their number.  RTCU_ERR_NOMEM when a host
  * allocation fails. */
 int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* scene);
+/* the same for the contexts of a single-process multi-GPU renderer (rtcu_render_multi): validated and built once, then copied to
+ * every context's device */
+int rtcu_upload_scene_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_scene* scene);
 
 /* ---- render: replaces mg_ray_tracer::render / sm_ray_tracer::render.
  * rgba8_out (nullable): width*height uint32 in image_view layout (row 0 = top, src/image.hpp:150-159),
@@ -142,7 +154,11 @@ int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* scene);
  *   reference's (same segments per sample for the same seed); the per-pixel sum runs in ascending sample order as in
  *   mg_ray_tracer.cpp:187-194, except where several lanes share a pixel (BVH scenes from 16 samples per call, pixels handed
  *   to the second pass, multi-GPU sample splits): there it is a fixed tree of partial sums -- deterministic, equal to the
- *   sequential sum up to fp32 rounding. */
+ *   sequential sum up to fp32 rounding.
+ * rgba8_out may be pageable (the reference's image, image.cpp:9-13): a full-frame destination is page-locked once per
+ *   (pointer, size) -- cudaHostRegister, undone when another image arrives or in rtcu_destroy; RTCU_REGISTER_OUTPUT=0 disables --
+ *   and then written by the kernels (zero-copy) or by one DMA; each frame is verified to have landed in the caller's pages, so a
+ *   buffer that was freed and re-allocated at the same address costs one staged frame, never a wrong image. */
 int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out);
 
 /* ---- preview: replaces rasterizer::render (reference src/renderers/rasterizer.cpp:22-88): one ray per pixel through the
@@ -205,6 +221,19 @@ int rtcu_ipc_open(rtcu_ctx* ctx, const unsigned char handle[64], void** d_ptr);
 int rtcu_ipc_release(rtcu_ctx* ctx, void* d_ptr);
 int rtcu_reduce_resolve_rows(rtcu_ctx* ctx, const float* const* d_accums, uint32_t n_bufs, uint32_t width, uint32_t row0, uint32_t rows,
                              uint32_t spp, uint32_t* d_rgba8, void* stream);
+/* The whole exchange step as ONE launch per rank, with no barrier from a collective library around it.  d_flags[g] is rank g's
+ * 128-byte flag block (rtcu_ipc_alloc(128), mapped by the peers like the buffers; zero = fresh).  Frame `epoch` (1, 2, 3, ... the
+ * same sequence on every rank): the kernel publishes "rank's buffer complete" to every rank (st.release.sys over NVLink), waits
+ * until all ranks have published (ld.acquire.sys on its own block), sums the n_ranks buffers over rows [row0, row0 + rows) in rank
+ * order, resolves and stores into d_rgba8 (the destination rank's image, own or mapped), then publishes "band stored" to the
+ * destination; the destination's kernel returns only when every band is stored.  The call must follow the rank's render on
+ * `stream`.  Alternate between TWO accumulation buffers per rank from frame to frame: a buffer is then never overwritten while a
+ * peer still reads it (kernels.cuh, k_exchange_reduce_resolve).  A rank that waits longer than ~20 s gives up and raises the
+ * block's error word: rtcu_exchange_check synchronises `stream` and returns RTCU_ERR_STATE if that happened. */
+int rtcu_exchange_reduce_resolve(rtcu_ctx* ctx, const float* const* d_accums, void* const* d_flags, uint32_t n_ranks, uint32_t rank,
+                                 uint32_t dst_rank, uint32_t epoch, uint32_t width, uint32_t row0, uint32_t rows, uint32_t spp,
+                                 uint32_t* d_rgba8, void* stream);
+int rtcu_exchange_check(rtcu_ctx* ctx, const void* d_flags, void* stream);
 
 /* exhaustive device-side check of the kernels' cheaper-but-exact square root / reciprocal / constant-divisor division
  * (rt_b200/csrc/spec.cuh) against the IEEE intrinsics: counts[0..1] = float patterns (of all 2^32) where sqrt / 1/sqrt

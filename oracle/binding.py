@@ -213,7 +213,38 @@ class ReferenceBuild:
         self.lib.refbin_list.argtypes = [C.c_char_p, u32]
         self.lib.refbin_last_error.restype = C.c_char_p
         self.lib.refbin_render.argtypes = [C.POINTER(SceneDesc), p, p, u32, u32, u32, u32, C.c_uint64, C.c_char_p, p, C.c_int, u32, p]
+        self.lib.refbin_open.restype = p
+        self.lib.refbin_open.argtypes = [C.c_char_p]
+        self.lib.refbin_close.argtypes = [p]
+        self.lib.refbin_render_with.argtypes = [p, C.POINTER(SceneDesc), p, p, u32, u32, u32, u32, C.c_uint64, p, C.c_int]
         self._keep = None
+
+    # a renderer that lives across frames, as in the application (main.cpp:49-53)
+    def open(self, renderer: str) -> int:
+        h = self.lib.refbin_open(renderer.encode())
+        if not h:
+            raise RuntimeError("renderer construction failed: " + self.lib.refbin_last_error().decode(errors="replace"))
+        return h
+
+    def close(self, handle: int) -> None:
+        self.lib.refbin_close(handle)
+
+    def render_with(self, handle: int, scene, rgba8: np.ndarray, spp: int, max_bounces: int, seed: int, threads: int = 0) -> np.ndarray:
+        """one frame of the open renderer into `rgba8` ((H, W) uint32, any host memory)"""
+        sd = self._desc(scene)
+        pos = np.array(scene.camera.position, np.float32); d = np.array(scene.camera.direction, np.float32)
+        h, w = rgba8.shape
+        rc = self.lib.refbin_render_with(handle, C.byref(sd), pos.ctypes.data, d.ctypes.data, w, h, spp, max_bounces, seed, rgba8.ctypes.data, threads)
+        assert rc == 0
+        return rgba8
+
+    def plugin_last_stats(self) -> dict:
+        """rt_cuda_last_stats of plugin/cuda_path_tracer.cpp (plugin flavour only): the library's statistics of the last frame"""
+        from rt_b200._native import Stats  # the struct layout of include/rtcu.h
+
+        st = Stats()
+        self.lib.rt_cuda_last_stats(C.byref(st))
+        return st.as_dict()
 
     def renderers(self) -> list:
         buf = C.create_string_buffer(1024)

@@ -137,6 +137,47 @@ extern "C"
 	// Renders with the reference's renderer `name` ("mg_ray_tracer" / "sm_ray_tracer").  Returns 0, or -1 when the
 	// renderer is unknown.  inv_view_proj_out receives the matrix the reference's camera produced (column-major) so the
 	// oracle and the CUDA path can be driven with exactly the same input.
+	static void fill_scene(rt::scene& scene, const refbin_scene* sc, const float cam_pos[3], const float cam_dir[3], uint32_t spp, uint32_t max_bounces);
+
+	// A renderer that lives across frames, as in the application (main.cpp:49-53: one instance per --renderer choice): what a
+	// plugin caches between calls (device buffers, the page-locked image, the uploaded scene) is only visible this way.
+	void* refbin_open(const char* name)
+	{
+		const auto* desc = rt::renderers::find_by_name(name);
+		if (!desc)
+		{
+			std::snprintf(g_last_error, sizeof g_last_error, "no renderer named %s", name);
+			return nullptr;
+		}
+		try
+		{
+			return desc->create();
+		}
+		catch (const std::exception& e)
+		{
+			std::snprintf(g_last_error, sizeof g_last_error, "%s", e.what());
+			return nullptr;
+		}
+	}
+	void refbin_close(void* renderer) { delete static_cast<rt::renderer_interface*>(renderer); }
+	// one frame into the caller's buffer (as back_buffer's image would be: any host memory, 64-byte aligned or not)
+	int refbin_render_with(void* renderer, const refbin_scene* sc, const float cam_pos[3], const float cam_dir[3], uint32_t width, uint32_t height,
+						   uint32_t spp, uint32_t max_bounces, uint64_t seed, uint32_t* rgba8, int threads)
+	{
+		if (!renderer || !rgba8)
+			return -1;
+		rt::scene scene;
+		fill_scene(scene, sc, cam_pos, cam_dir, spp, max_bounces);
+		g_seed				 = seed;
+		g_sample_begin		 = 0;
+		muu::shim::row_step	 = 1;
+		muu::shim::row_width = width;
+		rt::image_view pixels{ rgba8, rt::vec2u{ width, height } };
+		muu::thread_pool pool{ threads > 0 ? static_cast<unsigned>(threads) : 0u };
+		static_cast<rt::renderer_interface*>(renderer)->render(scene, pixels, pool);
+		return 0;
+	}
+
 	int refbin_render(const refbin_scene* sc, const float cam_pos[3], const float cam_dir[3], uint32_t width, uint32_t height, uint32_t spp,
 					  uint32_t max_bounces, uint64_t seed, const char* name, uint32_t* rgba8, int threads, uint32_t row_step,
 					  float inv_view_proj_out[16])
@@ -145,6 +186,38 @@ extern "C"
 		if (!desc)
 			return -1;
 		rt::scene scene;
+		fill_scene(scene, sc, cam_pos, cam_dir, spp, max_bounces);
+		if (inv_view_proj_out)
+		{
+			const auto view = scene.camera.viewport(rt::vec2u{ width, height });
+			for (int c = 0; c < 4; c++)
+				for (int r = 0; r < 4; r++)
+					inv_view_proj_out[c * 4 + r] = view.inverse_view_projection(static_cast<size_t>(r), static_cast<size_t>(c));
+		}
+		if (!rgba8)
+			return 0;
+		g_seed					= seed;
+		g_sample_begin			= 0;
+		muu::shim::row_step		= row_step ? row_step : 1;
+		muu::shim::row_width	= width;
+		std::unique_ptr<rt::renderer_interface> renderer;
+		try
+		{
+			renderer.reset(desc->create()); // a plugin constructor may throw (main.cpp:329-379 catches it in the real app)
+		}
+		catch (const std::exception& e)
+		{
+			std::snprintf(g_last_error, sizeof g_last_error, "%s", e.what());
+			return -2;
+		}
+		rt::image_view pixels{ rgba8, rt::vec2u{ width, height } };
+		muu::thread_pool pool{ threads > 0 ? static_cast<unsigned>(threads) : 0u };
+		renderer->render(scene, pixels, pool);
+		return 0;
+	}
+
+	static void fill_scene(rt::scene& scene, const refbin_scene* sc, const float cam_pos[3], const float cam_dir[3], uint32_t spp, uint32_t max_bounces)
+	{
 		scene.samples_per_pixel = spp;
 		scene.max_bounces		= max_bounces;
 		scene.camera.pose(rt::vec3{ cam_pos[0], cam_pos[1], cam_pos[2] }, rt::vec3{ cam_dir[0], cam_dir[1], cam_dir[2] });
@@ -173,32 +246,5 @@ extern "C"
 			const rt::box bx{ rt::vec3{ b[0], b[1], b[2] }, rt::vec3{ b[3], b[4], b[5] } };
 			scene.boxes.push_back(bx, sc->box_material[i], b[0], b[1], b[2], b[3], b[4], b[5]);
 		}
-		if (inv_view_proj_out)
-		{
-			const auto view = scene.camera.viewport(rt::vec2u{ width, height });
-			for (int c = 0; c < 4; c++)
-				for (int r = 0; r < 4; r++)
-					inv_view_proj_out[c * 4 + r] = view.inverse_view_projection(static_cast<size_t>(r), static_cast<size_t>(c));
-		}
-		if (!rgba8)
-			return 0;
-		g_seed					= seed;
-		g_sample_begin			= 0;
-		muu::shim::row_step		= row_step ? row_step : 1;
-		muu::shim::row_width	= width;
-		std::unique_ptr<rt::renderer_interface> renderer;
-		try
-		{
-			renderer.reset(desc->create()); // a plugin constructor may throw (main.cpp:329-379 catches it in the real app)
-		}
-		catch (const std::exception& e)
-		{
-			std::snprintf(g_last_error, sizeof g_last_error, "%s", e.what());
-			return -2;
-		}
-		rt::image_view pixels{ rgba8, rt::vec2u{ width, height } };
-		muu::thread_pool pool{ threads > 0 ? static_cast<unsigned>(threads) : 0u };
-		renderer->render(scene, pixels, pool);
-		return 0;
 	}
 }

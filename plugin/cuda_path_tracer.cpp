@@ -13,6 +13,11 @@
 //  * rt::scene has no dirty flag and is replaced wholesale on reload (main.cpp:123-125): the scene columns are
 //    compared by content against the last upload and re-uploaded when they differ.
 //  * RT_CUDA_MATERIAL_MODE=mg selects mg_ray_tracer's scatter table (no dielectric); default is sm_ray_tracer's.
+//  * every B200 of the box is used (RT_CUDA_DEVICES=n caps it): a frame with at least 16 samples per pixel and device is split
+//    by sample range over the devices (rtcu_render_multi: one context per device, the fp32 sums added over NVLink inside the
+//    resolve kernel of device 0); smaller frames, and boxes without peer access, render on device 0.
+//  * image_view memory is pageable (image.cpp:9-13): the library page-locks it once per (pointer, size) and writes later
+//    frames into it directly (rtcu.h, rtcu_render), so no staging copy follows the kernels.
 #ifdef RTCU_PLUGIN_STUB_CHECK
 	#include "rt_stub.hpp" // minimal stand-ins for the accessors used below (compile check without muu)
 #else
@@ -27,6 +32,7 @@ MUU_ENABLE_WARNINGS;
 
 #include <rtcu.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,9 +45,13 @@ using namespace rt;
 namespace
 {
 	// what both renderers share: the context, the scene upload and the view
+	rtcu_stats g_last_stats{}; // of the most recent frame drawn by any renderer of this file (rt_cuda_last_stats)
+
 	struct cuda_renderer : renderer_interface
 	{
-		rtcu_ctx* ctx_ = nullptr;
+		rtcu_ctx* ctx_ = nullptr;	  // device 0: every frame's destination
+		std::vector<rtcu_ctx*> ctxs_; // all devices in use, ctxs_[0] == ctx_
+		bool multi_ok_ = true;		  // cleared when rtcu_render_multi fails (no peer access): device 0 alone from then on
 
 		// last uploaded scene columns (content comparison, see header comment)
 		std::vector<float> spheres_, planes_, boxes_;
@@ -49,16 +59,31 @@ namespace
 		std::vector<rtcu_material> materials_;
 		bool uploaded_ = false;
 
-		explicit cuda_renderer(const char* name)
+		explicit cuda_renderer(const char* name, bool all_devices = false)
 		{
 			ctx_ = rtcu_create(0);
 			if (!ctx_)
 				throw std::runtime_error{ std::string{ name } + ": " + rtcu_last_error() };
+			ctxs_.push_back(ctx_);
+			int devices = all_devices ? rtcu_device_count() : 1;
+			if (const char* cap = std::getenv("RT_CUDA_DEVICES"); cap && std::atoi(cap) >= 1)
+				devices = std::min(devices, std::atoi(cap));
+			for (int d = 1; d < std::min(devices, 8); d++)
+			{
+				rtcu_ctx* c = rtcu_create(d);
+				if (!c) // a device that cannot be used is not an error: render on the ones before it
+				{
+					std::fprintf(stderr, "%s: device %d not used: %s\n", name, d, rtcu_last_error());
+					break;
+				}
+				ctxs_.push_back(c);
+			}
 		}
 
 		~cuda_renderer() noexcept override
 		{
-			rtcu_destroy(ctx_);
+			for (rtcu_ctx* c : ctxs_)
+				rtcu_destroy(c);
 		}
 
 		template <typename T>
@@ -110,7 +135,8 @@ namespace
 			desc.boxes			 = boxes_.data();
 			desc.box_material	 = box_mat_.data();
 			desc.n_boxes		 = static_cast<uint32_t>(box_mat_.size());
-			uploaded_			 = rtcu_upload_scene(ctx_, &desc) == RTCU_OK;
+			// validated and built (BVH) once, copied to every device in use
+			uploaded_ = rtcu_upload_scene_multi(ctxs_.data(), static_cast<uint32_t>(ctxs_.size()), &desc) == RTCU_OK;
 			return uploaded_;
 		}
 
@@ -142,7 +168,7 @@ namespace
 	{
 		uint32_t material_mode_ = RTCU_MODE_SM;
 
-		cuda_path_tracer() : cuda_renderer{ "cuda_path_tracer" }
+		cuda_path_tracer() : cuda_renderer{ "cuda_path_tracer", true }
 		{
 			if (const char* mode = std::getenv("RT_CUDA_MATERIAL_MODE"); mode && std::strcmp(mode, "mg") == 0)
 				material_mode_ = RTCU_MODE_MG;
@@ -158,9 +184,25 @@ namespace
 			rtcu_view v		= make_view(scene, pixels);
 			v.material_mode = material_mode_;
 
-			// image_view memory is pageable host memory (image.cpp:9-13); rtcu_render stages through pinned memory
+			// sample-range split over the devices while every device keeps at least 16 samples per pixel (below that the
+			// per-device kernels are too short to pay for the exchange)
+			uint32_t devices = multi_ok_ ? static_cast<uint32_t>(ctxs_.size()) : 1u;
+			while (devices > 1 && scene.samples_per_pixel < 16u * devices)
+				devices--;
+			if (devices > 1)
+			{
+				if (rtcu_render_multi(ctxs_.data(), devices, &v, pixels.data(), nullptr) == RTCU_OK)
+				{
+					rtcu_get_stats(ctx_, &g_last_stats);
+					return;
+				}
+				std::fprintf(stderr, "cuda_path_tracer: %s; rendering on device 0 from now on\n", rtcu_last_error());
+				multi_ok_ = false;
+			}
 			if (rtcu_render(ctx_, &v, pixels.data(), nullptr) != RTCU_OK)
 				std::fprintf(stderr, "cuda_path_tracer: %s\n", rtcu_last_error());
+			else
+				rtcu_get_stats(ctx_, &g_last_stats);
 		}
 	};
 
@@ -179,9 +221,19 @@ namespace
 			const rtcu_view v = make_view(scene, pixels);
 			if (rtcu_rasterize(ctx_, &v, pixels.data(), nullptr, nullptr) != RTCU_OK)
 				std::fprintf(stderr, "cuda_rasterizer: %s\n", rtcu_last_error());
+			else
+				rtcu_get_stats(ctx_, &g_last_stats);
 		}
 	};
 
 	REGISTER_RENDERER(cuda_path_tracer);
 	REGISTER_RENDERER(cuda_rasterizer);
+}
+
+// statistics of the most recent frame (device time, copy time, devices' kernel launches): a diagnostics hook for an imgui
+// overlay or a test; not part of the renderer interface
+extern "C" void rt_cuda_last_stats(rtcu_stats* out)
+{
+	if (out)
+		*out = g_last_stats;
 }

@@ -27,6 +27,7 @@ EXPORTS = (
     "rtcu_intersect_batch", "rtcu_primary_rays", "rtcu_scatter_batch", "rtcu_philox_batch", "rtcu_get_stats", "rtcu_measure_fp32_peak", "rtcu_bvh_build_host",
     "rtcu_rasterize", "rtcu_rasterize_device", "rtcu_selftest_math",
     "rtcu_ipc_alloc", "rtcu_ipc_open", "rtcu_ipc_release", "rtcu_reduce_resolve_rows", "rtcu_bvh4_build_host",
+    "rtcu_reload_env", "rtcu_upload_scene_multi", "rtcu_exchange_reduce_resolve", "rtcu_exchange_check",
 )
 
 
@@ -113,6 +114,10 @@ def load_library() -> C.CDLL:
         "rtcu_ipc_open": (i, [p, p, C.POINTER(p)]),
         "rtcu_ipc_release": (i, [p, p]),
         "rtcu_reduce_resolve_rows": (i, [p, C.POINTER(p), u32, u32, u32, u32, u32, p, p]),
+        "rtcu_reload_env": (i, [p]),
+        "rtcu_upload_scene_multi": (i, [C.POINTER(p), u32, C.POINTER(SceneDesc)]),
+        "rtcu_exchange_reduce_resolve": (i, [p, C.POINTER(p), C.POINTER(p), u32, u32, u32, u32, u32, u32, u32, u32, p, p]),
+        "rtcu_exchange_check": (i, [p, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -190,8 +190,8 @@ struct Trav {
     float kappa;      // margin factor, see above
 };
 
-// returns false when the ray direction is too far from unit length for the conservative margins (caller falls back
-// to the linear scan)
+// returns false when the ray direction is too far from unit length for the conservative margins, or the origin so far out
+// (beyond 2^62; NaN included) that S4 could overflow (caller falls back to the linear scan)
 __device__ __forceinline__ bool trav_init(const Ray& r, Trav& tv)
 {
     tv.node = 0;
@@ -203,7 +203,7 @@ __device__ __forceinline__ bool trav_init(const Ray& r, Trav& tv)
     tv.ix = __frcp_rn(r.d.x);
     tv.iy = __frcp_rn(r.d.y);
     tv.iz = __frcp_rn(r.d.z);
-    return eps_d <= 1e-3f;
+    return eps_d <= 1e-3f && fabsf(r.o.x) <= 0x1p62f && fabsf(r.o.y) <= 0x1p62f && fabsf(r.o.z) <= 0x1p62f; // (false for a NaN)
 }
 
 // slab test of two child boxes at once on the packed FP32 pipe.  cx/cy/cz = {c_a, c_b, h_a, h_b} per axis (centre and
@@ -824,6 +824,87 @@ __global__ void __launch_bounds__(256) k_reduce_resolve_rows(const PeerList bufs
             a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
         }
         rgba8[i] = pack_pixel(a.x, a.y, a.z, spp);
+    }
+}
+
+// ---- the exchange step of a one-process-per-GPU frame as ONE launch per rank and no collective library --------------------
+// Every rank owns one ExchangeFlags block in CUDA-IPC-shared device memory (zeroed at allocation).  Frame e (1, 2, 3, ...):
+//   ready[g] == e   rank g's accumulation buffer of frame e is complete        (rank g stores it into EVERY rank's block)
+//   done[g]  == e   rank g has stored its row band of frame e into the image   (rank g stores it into the DESTINATION's block)
+// The kernel is stream-ordered after the rank's own trace kernels, so its first CTA to arrive publishes ready[rank] with
+// st.release.sys over NVLink; all CTAs then poll their LOCAL block (ld.acquire.sys) until every rank has published, sum the
+// buffers of their pixels through peer loads in rank order, resolve and store the packed pixels into the destination's image.
+// The last CTA to finish publishes done[rank]; on the destination it also waits for the other ranks' done flags, so the end of
+// the destination's kernel is the end of the frame.  The callers alternate between two accumulation buffers: rank r overwrites
+// a buffer two frames after its peers read it, and a peer cannot publish ready[e+1] before its frame-e kernel has finished
+// reading -- so no flag is needed to release the buffers.  Every wait gives up after `timeout` clock cycles and sets `error`
+// (a rank that died must not hang the others' GPUs).
+struct ExchangeFlags {
+    unsigned int ready[8];
+    unsigned int done[8];
+    unsigned int ticket, finished; // arrival / completion counters of the local kernel (re-armed by its last CTA)
+    unsigned int error;
+    unsigned int pad[13];
+};
+static_assert(sizeof(ExchangeFlags) == 128, "ExchangeFlags is the 128-byte block rtcu_exchange_reduce_resolve documents");
+struct FlagList { ExchangeFlags* ptr[8]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spins until *p has reached `epoch` (wrap-safe); false after `timeout` cycles
+__device__ __forceinline__ bool wait_epoch(const unsigned int* p, unsigned int epoch, long long timeout)
+{
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(p) - epoch) < 0)
+    {
+        if (clock64() - t0 > timeout) return false;
+        __nanosleep(100);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_exchange_reduce_resolve(const PeerList bufs, const FlagList flags, int rank, int dst, unsigned int epoch,
+                                                                 uint32_t first, uint32_t count, float spp, uint32_t* __restrict__ rgba8, long long timeout)
+{
+    ExchangeFlags* mine = flags.ptr[rank];
+    if (threadIdx.x == 0 && atomicAdd(&mine->ticket, 1u) == 0u)
+    {
+        __threadfence_system();
+        for (int g = 0; g < bufs.n; g++) st_release_sys(&flags.ptr[g]->ready[rank], epoch);
+    }
+    if (threadIdx.x < (unsigned)bufs.n && !wait_epoch(&mine->ready[threadIdx.x], epoch, timeout)) atomicExch(&mine->error, 1u);
+    __syncthreads();
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count)
+    {
+        const uint32_t i = first + k;
+        float4 a = bufs.ptr[0][i];
+        for (int g = 1; g < bufs.n; g++)
+        {
+            const float4 b = bufs.ptr[g][i];
+            a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+        }
+        rgba8[i] = pack_pixel(a.x, a.y, a.z, spp);
+    }
+    __threadfence_system(); // the pixel stores (peer stores when the image lives on another GPU) before the completion count
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&mine->finished, 1u) == gridDim.x - 1u)
+    {
+        __threadfence_system();
+        mine->ticket = 0u;
+        mine->finished = 0u;
+        st_release_sys(&flags.ptr[dst]->done[rank], epoch);
+        if (rank == dst)
+            for (int g = 0; g < bufs.n; g++)
+                if (!wait_epoch(&mine->done[g], epoch, timeout)) atomicExch(&mine->error, 1u);
     }
 }
 

@@ -118,8 +118,56 @@ bool is_device_accessible_host(const void* ptr)
 
 } // namespace
 
+// Experiment knobs (environment variables, DESIGN.md "Knobs"): read ONCE when the context is created and again only when the
+// caller asks (rtcu_reload_env), never on the launch path.
+struct Knobs {
+    int regen_threshold = 0;   // RTCU_REGEN_THRESHOLD: 1..32, 0 = default
+    int straggler_budget = -1; // RTCU_STRAGGLER_BUDGET: multiple of the call's samples, -1 = default
+    int flat_loop = -1;        // RTCU_FLAT_LOOP: 0 / 1, -1 = by primitive count
+    size_t wf_rays = 8u << 20; // RTCU_WF_RAYS: rays per wave of the wavefront pipeline
+    bool pool = false;         // RTCU_BVH_KERNEL=pool
+    bool direct = true;        // RTCU_BVH_DIRECT=0 disables the lanes-share-a-pixel BVH path
+    int tile_order = -1;       // RTCU_TILE_ORDER: 0 row-major, 1 sorted, -1 measured per view
+    bool zero_copy = true;     // RTCU_ZERO_COPY=0: always stage the image
+    bool register_output = true; // RTCU_REGISTER_OUTPUT=0: never page-lock the caller's image
+    uint32_t bvh_threshold = 32; // RTCU_BVH_THRESHOLD
+    int bvh_trav = -1;         // RTCU_BVH_TRAV: traversal variant of the BVH kernels (-1 = default), see kernels.cuh
+    int bvh_lanes = 0;         // RTCU_BVH_LANES: lanes per pixel in direct mode (8 / 16 / 32), 0 = by sample count
+    void load()
+    {
+        *this = Knobs{};
+        if (const char* e = getenv("RTCU_REGEN_THRESHOLD")) { const int v = atoi(e); if (v >= 1 && v <= 32) regen_threshold = v; }
+        if (const char* e = getenv("RTCU_STRAGGLER_BUDGET")) straggler_budget = atoi(e) < 0 ? 0 : atoi(e);
+        if (const char* e = getenv("RTCU_FLAT_LOOP")) flat_loop = atoi(e) != 0;
+        if (const char* e = getenv("RTCU_WF_RAYS")) wf_rays = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("RTCU_BVH_KERNEL")) pool = strcmp(e, "pool") == 0;
+        if (const char* e = getenv("RTCU_BVH_DIRECT")) direct = e[0] != '0';
+        if (const char* e = getenv("RTCU_TILE_ORDER")) tile_order = e[0] == '0' ? 0 : e[0] == '1' ? 1 : -1;
+        if (const char* e = getenv("RTCU_ZERO_COPY")) zero_copy = e[0] != '0';
+        if (const char* e = getenv("RTCU_REGISTER_OUTPUT")) register_output = e[0] != '0';
+        if (const char* e = getenv("RTCU_BVH_THRESHOLD")) bvh_threshold = (uint32_t)strtoul(e, nullptr, 10);
+        if (const char* e = getenv("RTCU_BVH_TRAV")) bvh_trav = atoi(e);
+        if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) bvh_lanes = v; }
+    }
+};
+
+// the caller's pageable image, page-locked and mapped once per (pointer, size): see ensure_registered
+struct HostReg {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    void* dev = nullptr; // device-side alias of ptr
+    bool ok = false;     // false: registration failed for (ptr, bytes) -- do not retry every frame
+};
+
 struct rtcu_ctx {
     int device = 0;
+    Knobs knobs;
+    HostReg out_reg;
+    // one render in flight per context: launches share the counters, the straggler queue and the tile-cost map, so a launch on
+    // another stream first waits for the previous one (ev_launch is recorded after every launch)
+    cudaEvent_t ev_launch = nullptr;
+    cudaStream_t launch_stream = nullptr;
+    bool launch_pending = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     int sm_count = 0;
@@ -226,33 +274,24 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
 }
 
 // lanes idle before ended paths are regenerated (see k_render_mega); RTCU_REGEN_THRESHOLD overrides for tuning runs
-uint32_t regen_threshold_for(uint32_t n_prims)
-{
-    if (const char* e = getenv("RTCU_REGEN_THRESHOLD"))
-    {
-        const int v = atoi(e);
-        if (v >= 1 && v <= 32) return (uint32_t)v;
-    }
-    (void)n_prims;
-    return 1u;
-}
+uint32_t regen_threshold_for(const rtcu_ctx* ctx) { return ctx->knobs.regen_threshold ? (uint32_t)ctx->knobs.regen_threshold : 1u; }
 
 // per-thread segment budget before a pixel is handed to k_render_stragglers (0 disables; RTCU_STRAGGLER_BUDGET overrides
 // with a multiple of the call's samples per pixel).  BVH scenes with many samples per pixel hand over early: a warp that
 // shares ONE pixel's samples traverses more coherently than 32 neighbouring pixels do, and with >= 128 samples the 32 lanes
 // stay busy (C3 scene, budget 1 vs 3: -4 % at 128 spp, -9 % at 512 spp; at 64 spp it is +4 %)
-uint32_t straggler_budget_for(uint32_t n_samples, bool bvh)
+uint32_t straggler_budget_for(const rtcu_ctx* ctx, uint32_t n_samples, bool bvh)
 {
     int mult = bvh && n_samples >= 128 ? 1 : 3;
-    if (const char* e = getenv("RTCU_STRAGGLER_BUDGET")) mult = atoi(e);
+    if (ctx->knobs.straggler_budget >= 0) mult = ctx->knobs.straggler_budget;
     if (mult <= 0 || n_samples < 2) return 0;
     return (uint32_t)mult * n_samples + 64u;
 }
 
 // loop structure of k_render_mega: the warp-vote (flat) loop pays off once the O(N) sweep dominates a segment
-bool flat_loop_for(uint32_t n_prims)
+bool flat_loop_for(const rtcu_ctx* ctx, uint32_t n_prims)
 {
-    if (const char* e = getenv("RTCU_FLAT_LOOP")) return atoi(e) != 0;
+    if (ctx->knobs.flat_loop >= 0) return ctx->knobs.flat_loop != 0;
     return n_prims >= 32;
 }
 
@@ -264,8 +303,7 @@ size_t stage_bytes(const rtcu_ctx* ctx) { return ((size_t)pair_float4_count(ctx-
 int launch_wavefront(rtcu_ctx* ctx, const rtcu_view* v, RenderParams p, bool use_bvh, cudaStream_t st)
 {
     const uint32_t tw = v->tile_x1 - v->tile_x0, th = v->tile_y1 - v->tile_y0, npix = tw * th;
-    size_t target = 8u << 20; // rays per wave
-    if (const char* e = getenv("RTCU_WF_RAYS")) target = strtoull(e, nullptr, 10);
+    const size_t target = ctx->knobs.wf_rays; // rays per wave
     uint32_t slots = (uint32_t)(target / npix);
     if (slots < 1) slots = 1;
     if (slots > 4096) slots = 4096;
@@ -348,14 +386,25 @@ int launch_wavefront(rtcu_ctx* ctx, const rtcu_view* v, RenderParams p, bool use
 bool uses_direct_mode(const rtcu_ctx* ctx, const rtcu_view* v)
 {
     const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
-    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
-    const char* which = getenv("RTCU_BVH_KERNEL");
-    const char* direct_env = getenv("RTCU_BVH_DIRECT");
-    return use_bvh && ctx->have_bvh && pipe != RTCU_PIPE_WAVEFRONT && !(which && strcmp(which, "pool") == 0) && v->sample_end - v->sample_begin >= 16 &&
-           !(direct_env && direct_env[0] == '0');
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= ctx->knobs.bvh_threshold);
+    return use_bvh && ctx->have_bvh && pipe != RTCU_PIPE_WAVEFRONT && !ctx->knobs.pool && v->sample_end - v->sample_begin >= 16 && ctx->knobs.direct;
 }
 
+int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st);
+
+// launches the trace kernels of one view on `st` and marks the launch, so that the next one -- on whatever stream -- is ordered
+// after it (the kernels share the context's counters, straggler queue and tile-cost map)
 int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st)
+{
+    const int rc = launch_render_on(ctx, v, d_accum, d_rgba8, accumulate, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_launch, st));
+    ctx->launch_stream = st;
+    ctx->launch_pending = true;
+    return RTCU_OK;
+}
+
+int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st)
 {
     if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
     RenderParams p;
@@ -365,15 +414,17 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
     if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
     if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or 4-wide tree deeper than %d)", (BVH_STACK - 2) / 3);
     if (pipe > RTCU_PIPE_WAVEFRONT) return fail(RTCU_ERR_INVALID, "bad pipeline selector %u", pipe);
-    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= ctx->knobs.bvh_threshold);
+    // one render in flight per context (rtcu.h): a launch on another stream than the previous one waits for it first
+    if (ctx->launch_pending && ctx->launch_stream != st) CU(cudaStreamWaitEvent(st, ctx->ev_launch, 0));
     p.accum = d_accum;
     p.rgba8 = d_rgba8;
     p.accumulate = accumulate;
     p.counters = ctx->counters.p;
-    p.regen_threshold = regen_threshold_for(ctx->scene.n_spheres + ctx->scene.n_planes);
+    p.regen_threshold = regen_threshold_for(ctx);
     // straggler hand-off (see k_render_stragglers): budget = 3x the samples of this call + 64 segments per pixel
     const uint32_t n_samples = v->sample_end - v->sample_begin;
-    p.segment_budget = straggler_budget_for(n_samples, use_bvh);
+    p.segment_budget = straggler_budget_for(ctx, n_samples, use_bvh);
     CU(ctx->stragglers.reserve((size_t)v->width * v->height));
     p.stragglers = ctx->stragglers.p;
     p.straggler_count = ctx->straggler_count.p;
@@ -386,11 +437,10 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
         return launch_wavefront(ctx, v, p, use_bvh, st); // PIPE_AUTO = megakernel: measured faster on every config
     const dim3 grid((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W, (v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
     const size_t sb = stage_bytes(ctx);
-    const bool flat = flat_loop_for(ctx->scene.n_spheres + ctx->scene.n_planes);
+    const bool flat = flat_loop_for(ctx, ctx->scene.n_spheres + ctx->scene.n_planes);
     // RTCU_BVH_KERNEL=pool selects the warp-local ray pool (pool.cuh): correct and deterministic, but measured 20-30 % slower
     // (DESIGN.md), so it is not the default.
-    const char* which = getenv("RTCU_BVH_KERNEL");
-    const bool pool = use_bvh && which && strcmp(which, "pool") == 0;
+    const bool pool = use_bvh && ctx->knobs.pool;
     if (pool) p.segment_budget = 0; // work is shared by the 32 lanes of a warp: no per-thread stragglers
     auto launch_mega = [&](const RenderParams& q) {
         if (pool) k_render_pool<<<grid, 32 * POOL_WARPS, 0, st>>>(ctx->scene, q);
@@ -435,8 +485,7 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
         return RTCU_OK;
     }
     const uint32_t n_tiles = grid.x * grid.y;
-    const char* lpt_env = getenv("RTCU_TILE_ORDER");
-    const bool lpt = !pool && n_tiles >= 2u * 8u * (uint32_t)ctx->sm_count && !(lpt_env && lpt_env[0] == '0');
+    const bool lpt = !pool && n_tiles >= 2u * 8u * (uint32_t)ctx->sm_count && ctx->knobs.tile_order != 0;
     ctx->stats.kernel_launches = 1;
     bool time_this_frame = false;
     if (lpt)
@@ -465,7 +514,7 @@ int launch_render(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* 
         cudaGetLastError(); // cudaEventQuery reports cudaErrorNotReady through the sticky-free error slot
         // a frame is a test frame (timed) when its phase has no measurement in flight; while one is in flight -- the caller
         // queues frames without synchronising -- frames run row-major, the order that is never a regression
-        const bool forced = lpt_env && lpt_env[0] == '1';
+        const bool forced = ctx->knobs.tile_order == 1;
         time_this_frame = !forced && ctx->tile_phase < 2 && ctx->tile_pending < 0 && (ctx->tile_phase == 0 || same_view);
         const bool sorted = same_view && (forced || (time_this_frame && ctx->tile_phase == 1) || (ctx->tile_phase == 2 && ctx->tile_sorted_wins));
         CU(ctx->tile_cost.reserve(n_tiles));
@@ -567,6 +616,91 @@ int copy_out(rtcu_ctx* ctx, T* dst, const T* d_src, size_t n, PinnedBuf<T>& stag
         }
     }
     return RTCU_OK;
+}
+
+// ---- the caller's image as the device can reach it ---------------------------------------------------------------------
+// The reference's image is pageable (image.cpp:9-13, muu::aligned_alloc) and lives as long as its back buffer: the same
+// pointer arrives frame after frame.  It is page-locked and mapped ONCE per (pointer, size) -- cudaHostRegister costs about
+// a frame, then every later frame is written by DMA (or by the kernels themselves, zero-copy) instead of being staged through
+// a bounce buffer and a host memcpy.  A registration goes stale if the application frees the buffer and the allocator maps
+// new pages at the same address; nothing tells the library, so every frame is verified: two sentinel pixels with alpha 0 (no
+// packed pixel has that, colour.hpp:100-106) are written through the host pointer before the launch and must have been
+// overwritten when the frame is complete.  If not, the registration is dropped and the frame is delivered by the staged copy.
+uint32_t* output_alias(rtcu_ctx* ctx, uint32_t* out, size_t npix, bool* ours)
+{
+    *ours = false;
+    HostReg& r = ctx->out_reg;
+    const size_t bytes = npix * sizeof(uint32_t);
+    if (r.ptr == out && r.bytes == bytes)
+    {
+        *ours = r.ok;
+        return r.ok ? static_cast<uint32_t*>(r.dev) : nullptr;
+    }
+    // another image than the one registered here (a resize, another back buffer): drop that registration FIRST -- the new image
+    // may overlap the old range, and a pointer inside a range this context registered must not be mistaken for caller-pinned
+    // memory of the new size
+    if (r.ptr && r.ok && cudaHostUnregister(r.ptr) != cudaSuccess) cudaGetLastError();
+    r = HostReg{};
+    if (is_device_accessible_host(out)) // pinned / registered / managed by the caller: the caller vouches for its extent
+    {
+        void* mapped = nullptr;
+        if (cudaHostGetDevicePointer(&mapped, out, 0) == cudaSuccess && mapped) return static_cast<uint32_t*>(mapped);
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (!ctx->knobs.register_output) return nullptr;
+    r.ptr = out;
+    r.bytes = bytes;
+    if (cudaHostRegister(out, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr; // remembered: not retried for this (pointer, size)
+    }
+    void* mapped = nullptr;
+    if (cudaHostGetDevicePointer(&mapped, out, 0) != cudaSuccess || !mapped)
+    {
+        cudaGetLastError();
+        cudaHostUnregister(out);
+        return nullptr;
+    }
+    r.dev = mapped;
+    r.ok = true;
+    *ours = true;
+    return static_cast<uint32_t*>(mapped);
+}
+void arm_sentinels(uint32_t* out, size_t npix)
+{
+    reinterpret_cast<volatile uint32_t*>(out)[0] = 0u;
+    reinterpret_cast<volatile uint32_t*>(out)[npix - 1] = 0u;
+}
+bool sentinels_overwritten(const uint32_t* out, size_t npix)
+{
+    const volatile uint32_t* v = out;
+    return (v[0] & 255u) == 255u && (v[npix - 1] & 255u) == 255u;
+}
+void drop_registration(rtcu_ctx* ctx)
+{
+    HostReg& r = ctx->out_reg;
+    if (r.ptr && r.ok && cudaHostUnregister(r.ptr) != cudaSuccess) cudaGetLastError();
+    r.ok = false; // (pointer, size) stay: not retried until the application hands over another buffer
+    r.dev = nullptr;
+}
+
+// full frame, device -> the caller's image: one DMA when the image is page-locked (verified when the registration is ours),
+// the staged copy otherwise
+int deliver_image(rtcu_ctx* ctx, uint32_t* out, const uint32_t* d_src, size_t npix)
+{
+    bool ours = false;
+    uint32_t* alias = output_alias(ctx, out, npix, &ours);
+    if (alias)
+    {
+        if (ours) arm_sentinels(out, npix);
+        CU(cudaMemcpyAsync(out, d_src, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (!ours || sentinels_overwritten(out, npix)) return RTCU_OK;
+        drop_registration(ctx);
+    }
+    return copy_out(ctx, out, d_src, npix, ctx->h_rgba8);
 }
 
 } // namespace
@@ -844,7 +978,7 @@ int launch_rasterize(rtcu_ctx* ctx, const rtcu_view* v, uint32_t* d_rgba8, uint3
     const uint32_t accel = v->flags & 0xFu;
     if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
     if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene (no spheres, or 4-wide tree deeper than %d)", (BVH_STACK - 2) / 3);
-    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= ctx->knobs.bvh_threshold);
     if (use_bvh) k_rasterize<true><<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, ctx->scene, p);
     else k_rasterize<false><<<grid, RASTER_TILE_W * RASTER_TILE_H, 0, st>>>(ctx->raster, ctx->scene, p);
     CU(cudaGetLastError());
@@ -885,8 +1019,16 @@ const char* rtcu_last_error(void) { return g_err; }
 
 uint32_t rtcu_bvh_threshold(void)
 {
-    if (const char* e = getenv("RTCU_BVH_THRESHOLD")) return (uint32_t)strtoul(e, nullptr, 10);
-    return 32u; // measured crossover (profiles/bvh_crossover_r1.jsonl): BVH is ahead from ~24 spheres, 20 % at 32, 2x at 64
+    Knobs k;
+    k.load();
+    return k.bvh_threshold; // 32: measured crossover (profiles/bvh_crossover_r1.jsonl): BVH is ahead from ~24 spheres, 20 % at 32, 2x at 64
+}
+
+int rtcu_reload_env(rtcu_ctx* ctx)
+{
+    if (!ctx) return fail(RTCU_ERR_INVALID, "null context");
+    ctx->knobs.load();
+    return RTCU_OK;
 }
 
 int rtcu_device_count(void)
@@ -937,6 +1079,8 @@ rtcu_ctx* rtcu_create(int device)
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 6; i++)
         ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_launch, cudaEventDisableTiming) == cudaSuccess;
+    ctx->knobs.load();
     ok = ok && ctx->counters.reserve(4) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess && ctx->straggler_count.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_render_mega<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess
          && cudaFuncSetAttribute(k_render_mega<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
@@ -974,6 +1118,8 @@ void rtcu_destroy(rtcu_ctx* ctx)
     }
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->ev_launch) cudaEventDestroy(ctx->ev_launch);
+    if (ctx->out_reg.ptr && ctx->out_reg.ok && cudaHostUnregister(ctx->out_reg.ptr) != cudaSuccess) cudaGetLastError();
     for (auto& e : ctx->copy_events)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -981,17 +1127,27 @@ void rtcu_destroy(rtcu_ctx* ctx)
 }
 
 namespace {
-int upload_scene(rtcu_ctx* ctx, const rtcu_scene* s);
+int upload_scene(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_scene* s);
 }
 
 int rtcu_upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
 {
-    return guarded("rtcu_upload_scene", [&] { return upload_scene(ctx, s); });
+    return guarded("rtcu_upload_scene", [&] { return upload_scene(&ctx, 1, s); });
+}
+
+int rtcu_upload_scene_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_scene* s)
+{
+    if (!ctxs || n_ctx == 0 || n_ctx > 8) return fail(RTCU_ERR_INVALID, "1..8 contexts");
+    return guarded("rtcu_upload_scene_multi", [&] { return upload_scene(ctxs, n_ctx, s); });
 }
 
 namespace {
-int upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
+// validation, device columns and the BVH are made once; every context then receives the same arena from one pinned staging copy
+int upload_scene(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_scene* s)
 {
+    for (uint32_t g = 0; g < n_ctx; g++)
+        if (!ctxs[g]) return fail(RTCU_ERR_INVALID, "null context");
+    rtcu_ctx* ctx = ctxs[0];
     if (!ctx || !s) return fail(RTCU_ERR_INVALID, "null argument");
     if (s->n_materials == 0 || !s->materials) return fail(RTCU_ERR_INVALID, "scene has no materials (scene.cpp:565-566 always provides one)");
     if ((s->n_spheres && (!s->spheres || !s->sphere_material)) || (s->n_planes && (!s->planes || !s->plane_material)))
@@ -1064,24 +1220,33 @@ int upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
         albedo[i] = make_float4(s->materials[i].albedo[0], s->materials[i].albedo[1], s->materials[i].albedo[2], s->materials[i].albedo[3]);
     // BVH: built whenever there are spheres (cheap for small scenes; lets ACCEL_BVH be requested explicitly for parity
     // tests); RTCU_ACCEL_AUTO uses it from rtcu_bvh_threshold() spheres up
-    ctx->tile_hist_valid = false; // per-tile costs belong to the scene they were measured on
-    ctx->have_bvh = false;
+    bool have_bvh = false;
+    uint32_t bvh_depth = 0;
+    float ms_bvh_build = 0.0f;
     std::vector<float4> nodes_dev, leaf_blk;
-    if (s->n_spheres)
+    // The traversal returns the scan's result only while S4 cannot overflow: with every centre coordinate, radius and ray origin
+    // within 2^62, |e|^2, a^2 and r^2 stay finite, so no inf - inf = NaN can reach a comparison (the scan accepts a NaN distance where
+    // the leaves' (t, index) rule rejects it).  A scene beyond that range -- the loader only rejects NaN / Inf, scene.cpp:95-99 --
+    // keeps the reference's O(N) scan; rays whose origin leaves the range fall back to it one by one (trav_init).
+    bool bvh_safe = true;
+    for (uint32_t i = 0; i < s->n_spheres && bvh_safe; i++)
+        for (int k = 0; k < 4; k++)
+            bvh_safe = bvh_safe && std::fabs(s->spheres[4 * (size_t)i + k]) <= 0x1p62f; // false for NaN too
+    if (s->n_spheres && bvh_safe)
     {
         const auto t0 = std::chrono::steady_clock::now();
         rtcu_bvh::Pool pool(s->n_spheres >= 8192 ? rtcu_bvh::thread_count() - 1 : 0); // one set of workers for build and pack
         const rtcu_bvh::Result bvh = rtcu_bvh::build(s->spheres, s->n_spheres, pool);
-        ctx->ms_bvh_build = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        ctx->bvh_depth = bvh.max_depth;
+        ms_bvh_build = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        bvh_depth = bvh.max_depth;
         uint32_t depth4 = 0;
         if (s->n_spheres < (1u << 29))
             pack_bvh4(bvh, sph, nodes_dev, leaf_blk, depth4, pool);
         // a visit pushes at most three children: the traversal stack needs 3 entries per level
         if (!nodes_dev.empty() && 3 * depth4 + 2 <= (uint32_t)BVH_STACK)
         {
-            ctx->bvh_depth = depth4;
-            ctx->have_bvh = true;
+            bvh_depth = depth4;
+            have_bvh = true;
         }
         else
         {
@@ -1113,40 +1278,59 @@ int upload_scene(rtcu_ctx* ctx, const rtcu_scene* s)
     const size_t o_nodes = add(nodes_dev.data(), nodes_dev.size() * sizeof(float4));
     const size_t o_leaves = add(leaf_blk.data(), leaf_blk.size() * sizeof(float4));
     // make sure no kernel of a previous frame still reads the old scene, nor a previous upload the staging buffer
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->last_stream && ctx->last_stream != ctx->stream && cudaStreamSynchronize(ctx->last_stream) != cudaSuccess)
-        cudaGetLastError(); // the caller's stream may be gone by now; nothing of ours can be running on it then
-    CU(ctx->scene_arena.reserve(total));
-    CU(ctx->h_scene_arena.reserve(total));
+    for (uint32_t g = 0; g < n_ctx; g++)
+    {
+        rtcu_ctx* c = ctxs[g];
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->last_stream && c->last_stream != c->stream && cudaStreamSynchronize(c->last_stream) != cudaSuccess)
+            cudaGetLastError(); // the caller's stream may be gone by now; nothing of ours can be running on it then
+        CU(c->scene_arena.reserve(total));
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->h_scene_arena.reserve(total)); // (pinned memory is portable: every device copies from the first context's staging)
     for (const Seg& g : segs)
         if (g.bytes) memcpy(ctx->h_scene_arena.p + g.off, g.src, g.bytes);
-    CU(cudaMemcpyAsync(ctx->scene_arena.p, ctx->h_scene_arena.p, total, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream)); // renders on other streams (rtcu_render_device) must see the new scene
-    unsigned char* base = ctx->scene_arena.p;
-    ctx->scene.bvh_nodes = ctx->have_bvh ? reinterpret_cast<const float4*>(base + o_nodes) : nullptr;
-    ctx->scene.leaf_blk = ctx->have_bvh ? reinterpret_cast<const float4*>(base + o_leaves) : nullptr;
-    ctx->scene.n_bvh_nodes = (uint32_t)(nodes_dev.size() / 8);
-    ctx->scene.spheres = reinterpret_cast<const float4*>(base + o_sph);
-    ctx->scene.pairs = reinterpret_cast<const float4*>(base + o_pairs);
-    ctx->scene.sphere_material = reinterpret_cast<const uint32_t*>(base + o_sph_mat);
-    ctx->scene.n_spheres = s->n_spheres;
-    ctx->scene.planes = reinterpret_cast<const float4*>(base + o_planes);
-    ctx->scene.plane_material = reinterpret_cast<const uint32_t*>(base + o_plane_mat);
-    ctx->scene.n_planes = s->n_planes;
-    ctx->scene.materials = reinterpret_cast<const MatRec*>(base + o_mats);
-    ctx->scene.n_materials = s->n_materials;
-    ctx->raster.spheres = ctx->scene.spheres;
-    ctx->raster.pairs = ctx->scene.pairs;
-    ctx->raster.sphere_material = ctx->scene.sphere_material;
-    ctx->raster.n_spheres = s->n_spheres;
-    ctx->raster.planes = ctx->scene.planes;
-    ctx->raster.plane_material = ctx->scene.plane_material;
-    ctx->raster.n_planes = s->n_planes;
-    ctx->raster.boxes = reinterpret_cast<const float4*>(base + o_boxes);
-    ctx->raster.box_material = reinterpret_cast<const uint32_t*>(base + o_box_mat);
-    ctx->raster.n_boxes = s->n_boxes;
-    ctx->raster.albedo = reinterpret_cast<const float4*>(base + o_albedo);
-    ctx->have_scene = true;
+    for (uint32_t g = 0; g < n_ctx; g++)
+    {
+        CU(cudaSetDevice(ctxs[g]->device));
+        CU(cudaMemcpyAsync(ctxs[g]->scene_arena.p, ctx->h_scene_arena.p, total, cudaMemcpyHostToDevice, ctxs[g]->stream));
+    }
+    for (uint32_t g = 0; g < n_ctx; g++)
+    {
+        rtcu_ctx* c = ctxs[g];
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamSynchronize(c->stream)); // renders on other streams (rtcu_render_device) must see the new scene
+        c->tile_hist_valid = false; // per-tile costs belong to the scene they were measured on
+        c->have_bvh = have_bvh;
+        c->bvh_depth = bvh_depth;
+        c->ms_bvh_build = ms_bvh_build;
+        unsigned char* base = c->scene_arena.p;
+        c->scene.bvh_nodes = c->have_bvh ? reinterpret_cast<const float4*>(base + o_nodes) : nullptr;
+        c->scene.leaf_blk = c->have_bvh ? reinterpret_cast<const float4*>(base + o_leaves) : nullptr;
+        c->scene.n_bvh_nodes = (uint32_t)(nodes_dev.size() / 8);
+        c->scene.spheres = reinterpret_cast<const float4*>(base + o_sph);
+        c->scene.pairs = reinterpret_cast<const float4*>(base + o_pairs);
+        c->scene.sphere_material = reinterpret_cast<const uint32_t*>(base + o_sph_mat);
+        c->scene.n_spheres = s->n_spheres;
+        c->scene.planes = reinterpret_cast<const float4*>(base + o_planes);
+        c->scene.plane_material = reinterpret_cast<const uint32_t*>(base + o_plane_mat);
+        c->scene.n_planes = s->n_planes;
+        c->scene.materials = reinterpret_cast<const MatRec*>(base + o_mats);
+        c->scene.n_materials = s->n_materials;
+        c->raster.spheres = c->scene.spheres;
+        c->raster.pairs = c->scene.pairs;
+        c->raster.sphere_material = c->scene.sphere_material;
+        c->raster.n_spheres = s->n_spheres;
+        c->raster.planes = c->scene.planes;
+        c->raster.plane_material = c->scene.plane_material;
+        c->raster.n_planes = s->n_planes;
+        c->raster.boxes = reinterpret_cast<const float4*>(base + o_boxes);
+        c->raster.box_material = reinterpret_cast<const uint32_t*>(base + o_box_mat);
+        c->raster.n_boxes = s->n_boxes;
+        c->raster.albedo = reinterpret_cast<const float4*>(base + o_albedo);
+        c->have_scene = true;
+    }
     return RTCU_OK;
 }
 } // namespace
@@ -1171,24 +1355,31 @@ int rtcu_rasterize(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, ui
     // zero-copy into a pinned / registered image, as rtcu_render does
     uint32_t* d_out = ctx->rgba8.p;
     bool zero_copy = false;
-    if (full && is_device_accessible_host(rgba8_out))
+    bool verify = false;
+    if (full && ctx->knobs.zero_copy)
     {
-        const char* e = getenv("RTCU_ZERO_COPY");
-        void* mapped = nullptr;
-        if (!(e && e[0] == '0') && cudaHostGetDevicePointer(&mapped, rgba8_out, 0) == cudaSuccess && mapped)
+        if (uint32_t* alias = output_alias(ctx, rgba8_out, npix, &verify))
         {
-            d_out = static_cast<uint32_t*>(mapped);
+            d_out = alias;
             zero_copy = true;
+            if (verify) arm_sentinels(rgba8_out, npix);
         }
-        else
-            cudaGetLastError();
     }
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = launch_rasterize(ctx, view, d_out, prim_out ? ctx->raster_prim.p : nullptr, depth_out ? ctx->raster_depth.p : nullptr, ctx->stream);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (zero_copy)
+    {
         CU(cudaStreamSynchronize(ctx->stream));
+        if (verify && !sentinels_overwritten(rgba8_out, npix))
+        {
+            // stale registration (see output_alias): drop it, draw the frame again into device memory and stage it out
+            drop_registration(ctx);
+            if ((rc = launch_rasterize(ctx, view, ctx->rgba8.p, nullptr, nullptr, ctx->stream))) return rc;
+            if ((rc = copy_tile_out(ctx, view, rgba8_out, ctx->rgba8.p, ctx->h_rgba8))) return rc;
+        }
+    }
     else if ((rc = copy_tile_out(ctx, view, rgba8_out, ctx->rgba8.p, ctx->h_rgba8)))
         return rc;
     if (prim_out && (rc = copy_tile_out(ctx, view, prim_out, ctx->raster_prim.p, ctx->h_raster_prim))) return rc;
@@ -1244,20 +1435,19 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     // Zero-copy output: when the caller's image is pinned / registered host memory and the whole frame is rendered, the
     // kernels store the packed pixels straight into it over PCIe as each pixel finishes, so the read-back overlaps the
     // frame instead of following it (RTCU_ZERO_COPY=0 disables; pageable buffers -- the reference's image.cpp -- are staged).
+    // A pageable image (the reference's) is page-locked once per (pointer, size) and then treated the same way, with every frame
+    // verified (see output_alias).
     uint32_t* d_out = rgba8_out ? ctx->rgba8.p : nullptr;
-    bool zero_copy = false;
+    bool zero_copy = false, verify = false;
     // (not in direct mode: there one lane per pixel stores 4 bytes at a time, which would cross PCIe as single-pixel writes)
-    if (rgba8_out && full && is_device_accessible_host(rgba8_out) && !uses_direct_mode(ctx, view))
+    if (rgba8_out && full && ctx->knobs.zero_copy && !uses_direct_mode(ctx, view))
     {
-        const char* e = getenv("RTCU_ZERO_COPY");
-        void* mapped = nullptr;
-        if (!(e && e[0] == '0') && cudaHostGetDevicePointer(&mapped, rgba8_out, 0) == cudaSuccess && mapped)
+        if (uint32_t* alias = output_alias(ctx, rgba8_out, npix, &verify))
         {
-            d_out = static_cast<uint32_t*>(mapped);
+            d_out = alias;
             zero_copy = true;
+            if (verify) arm_sentinels(rgba8_out, npix);
         }
-        else
-            cudaGetLastError();
     }
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1276,7 +1466,7 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     else if (rgba8_out)
     {
         if (full)
-            rc = copy_out(ctx, rgba8_out, ctx->rgba8.p, npix, ctx->h_rgba8);
+            rc = deliver_image(ctx, rgba8_out, ctx->rgba8.p, npix);
         else
         {
             CU(ctx->h_rgba8.reserve(npix));
@@ -1311,6 +1501,16 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     CU(cudaEventElapsedTime(&ctx->stats.ms_d2h, ctx->ev[1], ctx->ev[2]));
     ctx->stats.ms_resolve = 0.0f;
     ctx->stats.ms_h2d = 0.0f;
+    if (zero_copy && verify && !sentinels_overwritten(rgba8_out, npix))
+    {
+        // the registration was stale (the application re-allocated its image at the same address): the kernels wrote into pages
+        // the application no longer sees.  Drop it and deliver this frame from the fp32 sums through the staged copy.
+        drop_registration(ctx);
+        k_resolve<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(ctx->accum.p, (uint32_t)npix, (float)view->samples_per_pixel, ctx->rgba8.p);
+        CU(cudaGetLastError());
+        rc = copy_out(ctx, rgba8_out, ctx->rgba8.p, npix, ctx->h_rgba8);
+        if (rc) return rc;
+    }
     return RTCU_OK;
 }
 
@@ -1332,11 +1532,15 @@ int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* vi
         v.sample_begin = s0 + (uint32_t)((uint64_t)total * g / n_ctx);
         v.sample_end = s0 + (uint32_t)((uint64_t)total * (g + 1) / n_ctx);
         if (g == 0) CU(cudaEventRecord(c->ev[0], c->stream));
+        c->stats.segments = c->stats.node_visits = c->stats.sphere_tests = 0; // a context with an empty share reports nothing
+        c->stats.kernel_launches = 0;
         if (v.sample_end > v.sample_begin)
         {
             const int rc = launch_render(c, &v, c->accum.p, nullptr, 0, c->stream);
             if (rc) return rc;
         }
+        else
+            CU(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream)); // not the counters of an earlier frame
         CU(cudaEventRecord(c->ev[3], c->stream));
     }
     // root waits for every peer, then sums their buffers through peer loads inside the resolve kernel
@@ -1362,25 +1566,32 @@ int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* vi
     CU(cudaGetLastError());
     CU(cudaEventRecord(root->ev[2], root->stream));
     int rc = RTCU_OK;
-    if (rgba8_out) rc = copy_out(root, rgba8_out, root->rgba8.p, npix, root->h_rgba8);
+    if (rgba8_out) rc = deliver_image(root, rgba8_out, root->rgba8.p, npix);
     if (!rc && accum_out) rc = copy_out(root, accum_out, reinterpret_cast<const float*>(root->accum.p), npix * 4, root->h_accum);
     if (rc) return rc;
-    uint64_t segs = 0;
+    uint64_t segs = 0, nodes = 0, tests = 0;
+    uint32_t launches = 1; // the fused reduce + resolve
+    const uint32_t accel = root->stats.accel;
     for (uint32_t g = 0; g < n_ctx; g++)
     {
         CU(cudaSetDevice(ctxs[g]->device));
+        ctxs[g]->stats.accel = accel; // (an empty share launched nothing: count its zeroed counters the same way)
         rc = fetch_counters(ctxs[g], ctxs[g]->stream);
         if (rc) return rc;
         segs += ctxs[g]->stats.segments;
+        nodes += ctxs[g]->stats.node_visits;
+        tests += ctxs[g]->stats.sphere_tests;
+        launches += ctxs[g]->stats.kernel_launches;
     }
     CU(cudaSetDevice(root->device));
     CU(cudaStreamSynchronize(root->stream));
     CU(cudaEventElapsedTime(&root->stats.ms_render, root->ev[0], root->ev[1]));
     CU(cudaEventElapsedTime(&root->stats.ms_resolve, root->ev[1], root->ev[2]));
     root->stats.segments = segs;
-    root->stats.sphere_tests = segs * root->scene.n_spheres;
+    root->stats.node_visits = nodes;   // counted per device (BVH); segments x spheres for the scan
+    root->stats.sphere_tests = tests;
     root->stats.samples = (uint64_t)(view->tile_x1 - view->tile_x0) * (view->tile_y1 - view->tile_y0) * total;
-    root->stats.kernel_launches = n_ctx + 1;
+    root->stats.kernel_launches = launches;
     return RTCU_OK;
 }
 
@@ -1459,6 +1670,43 @@ int rtcu_reduce_resolve_rows(rtcu_ctx* ctx, const float* const* d_accums, uint32
     return RTCU_OK;
 }
 
+int rtcu_exchange_reduce_resolve(rtcu_ctx* ctx, const float* const* d_accums, void* const* d_flags, uint32_t n_ranks, uint32_t rank, uint32_t dst_rank,
+                                 uint32_t epoch, uint32_t width, uint32_t row0, uint32_t rows, uint32_t spp, uint32_t* d_rgba8, void* stream)
+{
+    if (!ctx || !d_accums || !d_flags || !d_rgba8 || !width || !spp) return fail(RTCU_ERR_INVALID, "bad argument");
+    if (n_ranks == 0 || n_ranks > 8 || rank >= n_ranks || dst_rank >= n_ranks) return fail(RTCU_ERR_INVALID, "1..8 ranks, rank and destination among them");
+    if (epoch == 0) return fail(RTCU_ERR_INVALID, "frames are numbered from 1 (0 is the state of a fresh flag block)");
+    if ((uint64_t)width * ((uint64_t)row0 + rows) > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "image too large");
+    PeerList bufs;
+    FlagList flags;
+    bufs.n = (int)n_ranks;
+    for (uint32_t g = 0; g < n_ranks; g++)
+    {
+        if (!d_accums[g] || !d_flags[g]) return fail(RTCU_ERR_INVALID, "buffer %u is null", g);
+        bufs.ptr[g] = reinterpret_cast<const float4*>(d_accums[g]);
+        flags.ptr[g] = reinterpret_cast<ExchangeFlags*>(d_flags[g]);
+    }
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t count = width * rows;
+    const unsigned blocks = count ? (count + 255) / 256 : 1u; // a rank without rows still takes part in the handshake
+    const long long timeout = 20ll * 2000000000ll;            // ~20 s of SM clock cycles
+    k_exchange_reduce_resolve<<<blocks, 256, 0, (cudaStream_t)stream>>>(bufs, flags, (int)rank, (int)dst_rank, epoch, width * row0, count, (float)spp, d_rgba8, timeout);
+    CU(cudaGetLastError());
+    return RTCU_OK;
+}
+
+int rtcu_exchange_check(rtcu_ctx* ctx, const void* d_flags, void* stream)
+{
+    if (!ctx || !d_flags) return fail(RTCU_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    ExchangeFlags h;
+    CU(cudaMemcpyAsync(&h, d_flags, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h.error) return fail(RTCU_ERR_STATE, "exchange: a rank did not arrive within the time limit (ready %u %u %u %u %u %u %u %u)", h.ready[0], h.ready[1],
+                             h.ready[2], h.ready[3], h.ready[4], h.ready[5], h.ready[6], h.ready[7]);
+    return RTCU_OK;
+}
+
 int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t n, uint8_t* hit, uint32_t* prim, float* t, float* normal,
                          uint32_t accel)
 {
@@ -1466,7 +1714,7 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
     if (!ctx->have_scene) return fail(RTCU_ERR_STATE, "rtcu_upload_scene has not been called");
     if (accel > RTCU_ACCEL_BVH) return fail(RTCU_ERR_INVALID, "bad accel selector %u", accel);
     if (accel == RTCU_ACCEL_BVH && !ctx->have_bvh) return fail(RTCU_ERR_STATE, "no BVH for this scene");
-    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= rtcu_bvh_threshold());
+    const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= ctx->knobs.bvh_threshold);
     if (n == 0) return RTCU_OK;
     CU(cudaSetDevice(ctx->device));
     const size_t need = 2 * padded((size_t)n * 12) + padded(n) + 2 * padded((size_t)n * 4) + padded((size_t)n * 12);
@@ -1479,6 +1727,7 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
     float* d_t = c.take<float>(n);
     float* d_n = c.take<float>((size_t)n * 3);
     cudaStream_t st = ctx->stream;
+    if (ctx->launch_pending && ctx->launch_stream != st) CU(cudaStreamWaitEvent(st, ctx->ev_launch, 0)); // shares the counters with the render kernels
     CU(cudaMemcpyAsync(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     const unsigned blocks = (unsigned)((n + 255) / 256 < (uint32_t)ctx->sm_count * 8 ? (n + 255) / 256 : ctx->sm_count * 8);

@@ -1,10 +1,10 @@
 """Multi-GPU composition: one process per GPU, sample-range (and optional row-band) partition, one
 reduce of the fp32 accumulation buffers.
 
-Two exchanges are implemented.  "peer" (default on NCCL/NVLink): every rank renders into a buffer shared through CUDA IPC,
-and after a stream-ordered barrier ONE kernel per rank (rtcu_reduce_resolve_rows) sums all ranks' buffers over its row
-band through NVLink peer loads, resolves, and stores the packed pixels straight into rank 0's image -- no staging, no
-collective on the data path, deterministic sum order.  "nccl": reduce-scatter of the fp32 row bands, resolve per rank,
+Two exchanges are implemented.  "peer" (default on NVLink): every rank renders into a buffer shared through CUDA IPC, then
+ONE kernel per rank (rtcu_exchange_reduce_resolve) hand-shakes with the peers through release / acquire flags in device memory,
+sums all ranks' buffers over its row band through NVLink peer loads, resolves, and stores the packed pixels straight into
+rank 0's image -- no staging, no collective and no barrier on the frame path, deterministic sum order.  "nccl": reduce-scatter of the fp32 row bands, resolve per rank,
 gather of the packed bands (also what the gloo CPU tests exercise through all-reduce).
 
 Every (pixel, sample) is independent under the counter-based RNG (key = seed, counter = pixel, sample,
@@ -146,44 +146,81 @@ class GpuRank:
         self.ctx.resolve_device(band_accum.data_ptr(), self.width, self.band, spp, self.band_rgba8.data_ptr(), stream=stream)
         return self.band_rgba8
 
-    # ---- "peer" exchange: IPC-shared buffers + the fused reduce/resolve kernel ---------------------------------
+    # ---- "peer" exchange: IPC-shared buffers + the fused handshake / reduce / resolve kernel ---------------------
     def enable_peer_exchange(self, rank: int, dst: int = 0, group=None) -> None:
-        """Allocates this rank's accumulation buffer (and, on `dst`, the packed image) as CUDA-IPC-exportable memory in
-        the library, swaps the handles between the ranks and maps the peers' buffers (NVLink peer access)."""
+        """Allocates this rank's TWO accumulation buffers (frames alternate between them, see k_exchange_reduce_resolve), its
+        128-byte flag block and, on `dst`, the packed image as CUDA-IPC-exportable memory in the library, swaps the handles
+        between the ranks once (all_gather_object -- plumbing, not on the frame path) and maps the peers' memory (NVLink peer
+        access)."""
         import torch.distributed as dist
 
         torch = self.torch
         npix = self.width * self.height
         self.peer_rank, self.peer_dst = rank, dst
         # every rank takes part in the handle swap even if its own allocation failed, so that nobody waits forever
-        h_accum = h_img = err = None
+        mine = {"accum": [None, None], "flags": None, "img": None, "err": None}
         try:
-            self.peer_accum, h_accum = self.ctx.ipc_alloc(npix * 16)
+            own_accum = [self.ctx.ipc_alloc(npix * 16) for _ in range(2)]
+            own_flags = self.ctx.ipc_alloc(128)
+            mine["accum"] = [h for _, h in own_accum]
+            mine["flags"] = own_flags[1]
             if rank == dst:
-                self.peer_img, h_img = self.ctx.ipc_alloc(npix * 4)
+                self.peer_img, mine["img"] = self.ctx.ipc_alloc(npix * 4)
         except Exception as e:  # noqa: BLE001
-            err = str(e)
+            mine["err"] = str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, (h_accum, h_img, err), group=group)
-        failed = [(g, h[2]) for g, h in enumerate(handles) if h[2] is not None or h[0] is None]
+        dist.all_gather_object(handles, mine, group=group)
+        failed = [(g, h["err"]) for g, h in enumerate(handles) if h["err"] is not None or h["flags"] is None]
         if failed:
             raise RuntimeError(f"CUDA IPC allocation failed on rank(s) {failed}")
-        self.peer_accums = [self.peer_accum if g == rank else self.ctx.ipc_open(handles[g][0]) for g in range(self.world)]
+        # peer_accums[b][g]: buffer b of rank g, as this rank's device can address it
+        self.peer_accums = [[own_accum[b][0] if g == rank else self.ctx.ipc_open(handles[g]["accum"][b]) for g in range(self.world)] for b in range(2)]
+        self.peer_flags = [own_flags[0] if g == rank else self.ctx.ipc_open(handles[g]["flags"]) for g in range(self.world)]
+        self.peer_accum = self.peer_accums[0][rank]  # (first buffer; kept for callers that render into it directly)
         if rank != dst:
-            self.peer_img = self.ctx.ipc_open(handles[dst][1])
+            self.peer_img = self.ctx.ipc_open(handles[dst]["img"])
+        self._epoch = 0
         self._peer_sync = torch.zeros(1, dtype=torch.int32, device=self.device)
         if rank == dst:  # the image as a torch tensor over the library's memory (for read-back through torch)
             self.peer_rgba8 = torch.as_tensor(_DeviceArray(self.peer_img, (self.height, self.width), "<i4"), device=self.device)
 
+    def next_frame(self) -> tuple[int, int]:
+        """(epoch, buffer index) of the next multi-GPU frame -- the same sequence on every rank"""
+        self._epoch += 1
+        return self._epoch, self._epoch & 1
+
+    def exchange(self, epoch: int, buf: int, spp_total: int, stream: int) -> None:
+        """the exchange step of frame `epoch` whose share this rank has just rendered into buffer `buf`: ONE launch"""
+        row0, row1 = row_band_for_rank(0, self.height, self.peer_rank, self.world)
+        self.ctx.exchange_reduce_resolve(self.peer_accums[buf], self.peer_flags, self.peer_rank, self.peer_dst, epoch, self.width, row0, row1 - row0,
+                                         spp_total, self.peer_img, stream=stream)
+
     def render_peer_reduce_resolve(self, view: nat.View, spp_total: int, group=None):
-        """One multi-GPU frame without a collective on the data path.  Returns the (H, W) packed image on dst, None elsewhere."""
+        """One multi-GPU frame with neither a collective nor a barrier on the frame path: trace into this frame's IPC-shared
+        buffer, then one kernel that hand-shakes with the peers through flags in device memory, sums their buffers over this
+        rank's row band through NVLink peer loads, resolves and stores into dst's image.  Returns the (H, W) packed image on
+        dst (complete when the stream reaches this point), None elsewhere."""
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        epoch, buf = self.next_frame()
+        self.ctx.render_device(view, self.peer_accums[buf][self.peer_rank], accumulate=False, stream=stream)
+        self.exchange(epoch, buf, spp_total, stream)
+        return self.peer_rgba8 if self.peer_rank == self.peer_dst else None
+
+    def check_exchange(self) -> None:
+        """raises if a rank failed to arrive at an exchange (synchronises the stream)"""
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.exchange_check(self.peer_flags[self.peer_rank], stream=stream)
+
+    def render_peer_barrier_reduce_resolve(self, view: nat.View, spp_total: int, group=None):
+        """The round-1 form of the same exchange (kept for A/B timing): two stream-ordered one-element all-reduces as barriers
+        around rtcu_reduce_resolve_rows."""
         import torch.distributed as dist
 
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
-        self.ctx.render_device(view, self.peer_accum, accumulate=False, stream=stream)
+        self.ctx.render_device(view, self.peer_accums[0][self.peer_rank], accumulate=False, stream=stream)
         dist.all_reduce(self._peer_sync, group=group)  # stream-ordered barrier: every rank's buffer is complete
         row0, row1 = row_band_for_rank(0, self.height, self.peer_rank, self.world)
-        self.ctx.reduce_resolve_rows(self.peer_accums, self.width, row0, row1 - row0, spp_total, self.peer_img, stream=stream)
+        self.ctx.reduce_resolve_rows(self.peer_accums[0], self.width, row0, row1 - row0, spp_total, self.peer_img, stream=stream)
         dist.all_reduce(self._peer_sync, group=group)  # every band is stored; the buffers may be overwritten again
         return self.peer_rgba8 if self.peer_rank == self.peer_dst else None
 

@@ -227,6 +227,10 @@ class Context:
     def sync(self) -> None:
         nat.check(self._lib.rtcu_sync(self._h))
 
+    def reload_env(self) -> None:
+        """the RTCU_* knobs are read at rtcu_create; re-read them for this context (A/B tests that change os.environ)"""
+        nat.check(self._lib.rtcu_reload_env(self._h))
+
     def stats(self) -> dict:
         s = nat.Stats()
         nat.check(self._lib.rtcu_get_stats(self._h, C.byref(s)))
@@ -250,6 +254,16 @@ class Context:
     def reduce_resolve_rows(self, accum_ptrs: Sequence[int], width: int, row0: int, rows: int, spp: int, d_rgba8_ptr: int, stream: int = 0) -> None:
         arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
         nat.check(self._lib.rtcu_reduce_resolve_rows(self._h, arr, len(accum_ptrs), width, row0, rows, spp, d_rgba8_ptr, stream or None))
+
+    def exchange_reduce_resolve(self, accum_ptrs: Sequence[int], flag_ptrs: Sequence[int], rank: int, dst: int, epoch: int, width: int,
+                                row0: int, rows: int, spp: int, d_rgba8_ptr: int, stream: int = 0) -> None:
+        """rtcu_exchange_reduce_resolve: handshake + peer-load sum + resolve + store, one launch"""
+        a = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
+        f = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        nat.check(self._lib.rtcu_exchange_reduce_resolve(self._h, a, f, len(accum_ptrs), rank, dst, epoch, width, row0, rows, spp, d_rgba8_ptr, stream or None))
+
+    def exchange_check(self, flags_ptr: int, stream: int = 0) -> None:
+        nat.check(self._lib.rtcu_exchange_check(self._h, flags_ptr, stream or None))
 
     def selftest_math(self, divisors=(800, 600, 1920, 1080, 3840, 2160)) -> dict:
         """rtcu_selftest_math: mismatches of the kernels' cheaper exact sqrt / rcp / division against the IEEE intrinsics"""
@@ -332,11 +346,20 @@ def bvh4_build_host(spheres: np.ndarray):
     return nodes, leaves, int(depth.value)
 
 
-def render_multi(contexts: Sequence[Context], view: nat.View, want_accum: bool = False):
+def upload_scene_multi(contexts: Sequence[Context], scene: Scene) -> None:
+    """rtcu_upload_scene_multi: one validation / BVH build, one copy per device"""
+    lib = nat.load_library()
+    arr = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    prepared = contexts[0].prepare_scene(scene)
+    nat.check(lib.rtcu_upload_scene_multi(arr, len(contexts), C.byref(prepared[0])))
+
+
+def render_multi(contexts: Sequence[Context], view: nat.View, want_accum: bool = False, rgba8: Optional[np.ndarray] = None):
     """rtcu_render_multi: single-process sample-range split over several devices."""
     lib = nat.load_library()
     arr = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
-    rgba8 = np.zeros((view.height, view.width), np.uint32)
+    if rgba8 is None:
+        rgba8 = np.zeros((view.height, view.width), np.uint32)
     accum = np.zeros((view.height, view.width, 4), np.float32) if want_accum else None
     nat.check(lib.rtcu_render_multi(arr, len(contexts), C.byref(view), nat.ptr(rgba8), nat.ptr(accum)))
     return rgba8, accum

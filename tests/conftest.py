@@ -43,6 +43,24 @@ def ctx():
     c.close()
 
 
+@pytest.fixture
+def knobs(ctx, monkeypatch):
+    """Sets / clears RTCU_* experiment knobs for the session context: knobs(RTCU_BVH_DIRECT="0"), knobs(RTCU_BVH_DIRECT=None).
+    The library reads its environment once in rtcu_create (never on the launch path), so every change is followed by
+    rtcu_reload_env; the defaults are back when the test ends."""
+    def set_knobs(**kv):
+        for k, v in kv.items():
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, str(v))
+        ctx.reload_env()
+
+    yield set_knobs
+    monkeypatch.undo()
+    ctx.reload_env()
+
+
 def ulp_diff(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """distance in units of last place between two float32 arrays (same sign assumed where it matters)"""
     ia = a.astype(np.float32).view(np.int32).astype(np.int64)

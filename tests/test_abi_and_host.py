@@ -48,7 +48,7 @@ def test_library_is_sm100a_only():
 
 
 def test_abi_version_and_threshold(lib):
-    assert lib.rtcu_abi_version() == 2
+    assert lib.rtcu_abi_version() == 3
     assert lib.rtcu_bvh_threshold() > 0
 
 

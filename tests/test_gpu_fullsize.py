@@ -54,7 +54,7 @@ def test_c3_full_size(ctx, oracle, c3):
     assert np.abs(unpack_rgba(rgba_a[rows]) - unpack_rgba(r_rgba8[rows])).max() <= 1
 
 
-def test_c4_full_size(ctx, c4, monkeypatch):
+def test_c4_full_size(ctx, c4, knobs):
     # configs[3]: 100 001 spheres, 3840x2160, 64 spp, depth 10 (530.8 M samples) -- BVH traversal + divergence
     assert len(c4.spheres) == 100001
     ctx.upload_scene(c4)
@@ -80,9 +80,9 @@ def test_c4_full_size(ctx, c4, monkeypatch):
     np.testing.assert_allclose(acc_bvh[..., :3], acc_lin[..., :3], rtol=4e-6, atol=1e-6)
     assert np.abs(unpack_rgba(rgba_lin[1200:1232, 1900:1964]) - unpack_rgba(rgba_a[1200:1232, 1900:1964])).max() <= 1
     # with the thread-per-pixel kernel on both sides the buffers are bit-identical
-    monkeypatch.setenv("RTCU_BVH_DIRECT", "0")
+    knobs(RTCU_BVH_DIRECT="0")
     _, acc_bvh_tpp = ctx.render(make_view(c4, 3840, 2160, tile=tile, flags=nat.ACCEL_BVH, **kw), want_accum=True)
-    monkeypatch.delenv("RTCU_BVH_DIRECT")
+    knobs(RTCU_BVH_DIRECT=None)
     np.testing.assert_array_equal(acc_bvh_tpp, acc_lin)
     # closest hits of 2^16 random + 2^16 silhouette-grazing rays: BVH == scan
     for o, d in (synth.random_rays(c4, 1 << 16, seed=3, spread=60.0), synth.grazing_rays(c4, 1 << 16, seed=4)):

@@ -18,7 +18,7 @@ def _device_count():
 @pytest.mark.parametrize("ngpu", [2, 4, 8])
 def test_render_multi_matches_single_device(ctx, scenes, ngpu):
     if _device_count() < ngpu:
-        pytest.skip(f"needs {ngpu} GPUs")
+        pytest.skip(f"needs {ngpu} GPUs, this box has {_device_count()}")
     sc = scenes["c2"][0]
     view = make_view(sc, 640, 360, samples_per_pixel=64, max_bounces=50, material_mode=nat.MODE_SM)
     ctx.upload_scene(sc)
@@ -64,25 +64,30 @@ def _peer_worker(rank: int, world: int, port: int, out_path: str):
         gr = rdist.GpuRank(ctx, w, h, dev, world=world)
         gr.enable_peer_exchange(rank)
         frames = []
-        for _ in range(3):  # buffers are reused frame after frame: the second barrier must protect them
-            img = gr.render_peer_reduce_resolve(mine, spp)
-            torch.cuda.synchronize(dev)
+        for i in range(5):  # the two buffers per rank alternate frame after frame; frames 3 and 4 are queued back to back
+            img = gr.render_peer_reduce_resolve(mine, spp)  # one launch: flag handshake + peer-load sum + resolve + store
+            if i != 3:
+                torch.cuda.synchronize(dev)
             if rank == 0:
-                frames.append(img.cpu().numpy().view(np.uint32).copy())
+                frames.append(img.cpu().numpy().view(np.uint32).copy())  # (stream-ordered after the frame's kernel)
+        gr.check_exchange()  # no rank timed out
+        barrier = gr.render_peer_barrier_reduce_resolve(mine, spp)  # round-1 form: the same reduce kernel between two NCCL barriers
+        torch.cuda.synchronize(dev)
+        barrier = barrier.cpu().numpy().view(np.uint32).copy() if rank == 0 else None
         nccl = gr.render_reduce_resolve(mine, rank, spp)  # the NCCL exchange on the same share
         torch.cuda.synchronize(dev)
         if rank == 0:
-            np.savez(out_path, peer=np.stack(frames), nccl=nccl.cpu().numpy().view(np.uint32))
+            np.savez(out_path, peer=np.stack(frames), barrier=barrier, nccl=nccl.cpu().numpy().view(np.uint32))
         dist.barrier()
         ctx.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ngpu", [2, 4])
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
 def test_peer_exchange_one_process_per_gpu(ctx, scenes, tmp_path, ngpu):
     if _device_count() < ngpu:
-        pytest.skip(f"needs {ngpu} GPUs")
+        pytest.skip(f"needs {ngpu} GPUs, this box has {_device_count()}")
     import torch.multiprocessing as mp
 
     out = str(tmp_path / "peer.npz")
@@ -101,4 +106,5 @@ def test_peer_exchange_one_process_per_gpu(ctx, scenes, tmp_path, ngpu):
             c.close()
     for frame in got["peer"]:
         np.testing.assert_array_equal(frame, ref)
+    np.testing.assert_array_equal(got["barrier"], ref)
     assert np.abs(unpack_rgba(got["nccl"]) - unpack_rgba(ref)).max() <= 1  # NCCL's sum order is its own

@@ -319,11 +319,11 @@ def test_bvh_non_unit_directions_fall_back_to_the_scan(ctx, scenes):
 
 @pytest.mark.parametrize("kernel", ["pool", "mega"])
 @pytest.mark.parametrize("name,mode", [("c3", nat.MODE_SM), ("c2", nat.MODE_SM), ("planes", nat.MODE_SM), ("grid", nat.MODE_SM), ("grid", nat.MODE_MG)])
-def test_bvh_render_matches_linear_render(ctx, scenes, monkeypatch, name, mode, kernel):
+def test_bvh_render_matches_linear_render(ctx, scenes, knobs, name, mode, kernel):
     # Both BVH kernels trace exactly the linear scan's paths (same segment count).  "mega" (one segment per iteration) also
     # sums every pixel's samples in the same order -> bit-identical buffers; "pool" (warp-local ray pool, not the default) sums
     # them in completion order -> identical up to fp32 summation order, and deterministic.
-    monkeypatch.setenv("RTCU_BVH_KERNEL", kernel)
+    knobs(RTCU_BVH_KERNEL=kernel)
     sc = _grid() if name == "grid" else scenes[name][0]
     ctx.upload_scene(sc)
     for w, h, spp in ((192, 108, 4), (61, 37, 9)):  # the second size leaves partial 8x4 patches and partial CTAs
@@ -342,8 +342,8 @@ def test_bvh_render_matches_linear_render(ctx, scenes, monkeypatch, name, mode, 
             np.testing.assert_array_equal(bvh2, bvh)  # deterministic
 
 
-def test_bvh_pool_tiles_and_sample_ranges(ctx, scenes, monkeypatch):
-    monkeypatch.setenv("RTCU_BVH_KERNEL", "pool")
+def test_bvh_pool_tiles_and_sample_ranges(ctx, scenes, knobs):
+    knobs(RTCU_BVH_KERNEL="pool")
     sc = scenes["c3"][0]
     ctx.upload_scene(sc)
     kw = dict(samples_per_pixel=12, max_bounces=50, material_mode=nat.MODE_SM, flags=nat.ACCEL_BVH)
@@ -393,11 +393,11 @@ def test_render_matches_reference_build_fixtures(ctx, scenes):
 @pytest.mark.parametrize("name,mode,accel", [("c2", nat.MODE_SM, nat.ACCEL_LINEAR), ("c1", nat.MODE_MG, nat.ACCEL_LINEAR),
                                              ("planes", nat.MODE_SM, nat.ACCEL_LINEAR), ("c3", nat.MODE_SM, nat.ACCEL_BVH),
                                              ("c3", nat.MODE_MG, nat.ACCEL_LINEAR)])
-def test_wavefront_is_bit_identical_to_the_megakernel(ctx, scenes, monkeypatch, name, mode, accel):
+def test_wavefront_is_bit_identical_to_the_megakernel(ctx, scenes, knobs, name, mode, accel):
     # same paths, and per-pixel sums in sample order in both pipelines (the megakernel's straggler pass, which re-orders the
     # sum of the few pixels it takes over, is switched off for this comparison)
-    monkeypatch.setenv("RTCU_STRAGGLER_BUDGET", "0")
-    monkeypatch.setenv("RTCU_WF_RAYS", str(200 * 120 * 3))  # 3 samples per wave: 6 spp = 2 waves, 7 spp = 2 full + 1 partial
+    knobs(RTCU_STRAGGLER_BUDGET="0")
+    knobs(RTCU_WF_RAYS=str(200 * 120 * 3))  # 3 samples per wave: 6 spp = 2 waves, 7 spp = 2 full + 1 partial
     sc = scenes[name][0]
     ctx.upload_scene(sc)
     for spp in (6, 7):
@@ -457,17 +457,17 @@ def test_cheaper_exact_sqrt_rcp_div_equal_the_ieee_intrinsics_for_every_input(ct
     assert (r["sqrt"], r["rcp_of_sqrt"], r["div"]) == (0, 0, 0), r
 
 
-def test_tile_issue_order_never_changes_the_image(ctx, scenes, monkeypatch):
+def test_tile_issue_order_never_changes_the_image(ctx, scenes, knobs):
     """The library times row-major against cost-sorted tile order over the first frames of a view and keeps the faster
     (rtcu.cu: launch_render).  Whatever it picks, and whichever phase a frame falls in, accum and pixels are bit-identical."""
     for name, spp, flags in (("c2", 16, 0), ("c3", 8, 0), ("c3", 8, nat.ACCEL_LINEAR)):
         sc, depth = scenes[name]
         ctx.upload_scene(sc)  # resets the per-view history
         v = make_view(sc, 1280, 720, samples_per_pixel=spp, max_bounces=depth, material_mode=nat.MODE_SM, flags=flags)
-        monkeypatch.setenv("RTCU_TILE_ORDER", "0")
+        knobs(RTCU_TILE_ORDER="0")
         ref_rgba8, ref_accum = ctx.render(v, want_accum=True)
         segs = ctx.stats()["segments"]
-        monkeypatch.delenv("RTCU_TILE_ORDER")
+        knobs(RTCU_TILE_ORDER=None)
         launches = []
         for _ in range(5):  # row-major (timed), sorted (timed), then the winner
             rgba8, accum = ctx.render(v, want_accum=True)
@@ -476,14 +476,14 @@ def test_tile_issue_order_never_changes_the_image(ctx, scenes, monkeypatch):
             assert ctx.stats()["segments"] == segs
             launches.append(ctx.stats()["kernel_launches"])
         assert launches[0] == 2 and launches[1] == 3  # second frame: k_tile_order + megakernel + stragglers
-        monkeypatch.setenv("RTCU_TILE_ORDER", "1")
+        knobs(RTCU_TILE_ORDER="1")
         rgba8, accum = ctx.render(v, want_accum=True)
         np.testing.assert_array_equal(accum, ref_accum)
         assert ctx.stats()["kernel_launches"] == 3
-        monkeypatch.delenv("RTCU_TILE_ORDER")
+        knobs(RTCU_TILE_ORDER=None)
 
 
-def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes, monkeypatch):
+def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes, knobs):
     """From 16 samples per call a BVH scene is rendered with 16 or 8 lanes sharing each pixel's samples (k_render_stragglers in
     direct mode): same paths as the thread-per-pixel kernel (equal segment counts), per-pixel sums equal up to fp32 order, partial tiles / ragged 8x4 patches /
     sample ranges / accumulate-onto-a-device-buffer all behave like the other kernels, and the oracle agrees."""
@@ -498,10 +498,10 @@ def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes,
         rgba8, accum = ctx.render(v, want_accum=True)
         segs = ctx.stats()["segments"]
         assert ctx.stats()["kernel_launches"] == 1 and (accum[..., 3] == spp).all()
-        monkeypatch.setenv("RTCU_BVH_DIRECT", "0")
+        knobs(RTCU_BVH_DIRECT="0")
         rgba8_t, accum_t = ctx.render(v, want_accum=True)
         assert ctx.stats()["segments"] == segs and ctx.stats()["kernel_launches"] >= 2
-        monkeypatch.delenv("RTCU_BVH_DIRECT")
+        knobs(RTCU_BVH_DIRECT=None)
         np.testing.assert_allclose(accum[..., :3], accum_t[..., :3], rtol=4e-6, atol=1e-6)
         assert np.abs(unpack_rgba(rgba8) - unpack_rgba(rgba8_t)).max() <= 1
         r_rgba8, r_accum, r_segs = oracle.render(sc, v, threads=0)
@@ -516,9 +516,9 @@ def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes,
         tv = make_view(sc, tw, th, tile=tile, **tkw) if tile else make_view(sc, tw, th, **tkw)
         _, small = ctx.render(tv, want_accum=True)
         assert ctx.stats()["kernel_launches"] == 1
-        monkeypatch.setenv("RTCU_BVH_DIRECT", "0")
+        knobs(RTCU_BVH_DIRECT="0")
         _, small_t = ctx.render(tv, want_accum=True)
-        monkeypatch.delenv("RTCU_BVH_DIRECT")
+        knobs(RTCU_BVH_DIRECT=None)
         np.testing.assert_array_equal(small[..., 3], small_t[..., 3])
         np.testing.assert_allclose(small[..., :3], small_t[..., :3], rtol=4e-6, atol=1e-6)
         assert small[..., 3].sum() == 16 * (1 if tile else tw * th)

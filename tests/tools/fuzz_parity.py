@@ -59,11 +59,13 @@ for i in range(n_scenes):
                                   ("pool", nat.ACCEL_BVH, ("RTCU_BVH_KERNEL", "pool"))):
             if env:
                 os.environ[env[0]] = env[1]
+                ctx.reload_env()
             v = make_view(sc, w, h, material_mode=mode, seed=1000 + i, flags=flags)
             rgba8, accum = ctx.render(v, want_accum=True)
             segs = ctx.stats()["segments"]
             if env:
                 del os.environ[env[0]]
+                ctx.reload_env()
             if ref is None:
                 ref = oracle.render(sc, v)
             r_rgba8, r_accum, r_segs = ref
