@@ -62,6 +62,7 @@ struct RenderParams {
     uint32_t* tile_cost;          // += segments traced for the CTA's tile (nullable)
     const uint32_t* tile_order;   // CTA b renders tile tile_order[b] (nullable: CTA b renders tile b)
     int direct;                   // != 0: k_render_stragglers renders every pixel of the tile itself (no first pass, no queue)
+    int beam;                     // != 0 (direct mode): primary rays use their pixel's candidate leaf list (beam_collect)
 };
 
 #ifndef RTCU_PRIM_MISS
@@ -97,9 +98,12 @@ __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_p
         A = An;
         B = Bn;
     }
+    // A result counts as a hit when its distance is >= 0 (hit_result::operator bool, mg_ray_tracer.cpp:29-32): every accepted
+    // distance is >= 0.001 except a NaN -- S4 overflowing to inf - inf on coordinates around 1e19 and beyond -- which the scan's
+    // `best <= t` rule lets through and this rule then reports as a miss.  (is = -1 converts to RTCU_PRIM_MISS by itself.)
     Hit h;
     h.t = ts;
-    h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS;
+    h.prim = ts >= 0.0f ? (uint32_t)is : RTCU_PRIM_MISS;
     if (n_pl)
     {
         float tp = inf;
@@ -107,7 +111,7 @@ __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_p
         for (uint32_t i = 0; i < n_pl; i++)
             plane_test(s_pl[i], (int)i, r, tp, ip);
         // select(spheres, planes): the sphere wins when a.distance <= b.distance (:95-102)
-        if (ip >= 0 && !(is >= 0 && ts <= tp))
+        if (ip >= 0 && tp >= 0.0f && !(h.prim != RTCU_PRIM_MISS && ts <= tp))
         {
             h.t = tp;
             h.prim = RTCU_PRIM_PLANE | (uint32_t)ip;
@@ -188,6 +192,7 @@ struct Trav {
     int best_i;
     float ix, iy, iz; // 1 / d
     float kappa;      // margin factor, see above
+    float madd;       // margin added on top of kappa * E: 0 for a ray, the origin spread for a pixel beam (beam_collect)
 };
 
 // returns false when the ray direction is too far from unit length for the conservative margins, or the origin so far out
@@ -199,10 +204,15 @@ __device__ __forceinline__ bool trav_init(const Ray& r, Trav& tv)
     tv.best_t = __int_as_float(0x7f800000);
     tv.best_i = 0x7fffffff;
     const float eps_d = fabsf(dot3(r.d, r.d) - 1.0f);
-    tv.kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
-    tv.ix = __frcp_rn(r.d.x);
-    tv.iy = __frcp_rn(r.d.y);
-    tv.iz = __frcp_rn(r.d.z);
+    // kappa and 1 / d only feed the slab tests, whose margins carry 1 % of slack: MUFU approximations (2 ulp; the square root as
+    // x * rsqrt(x)) cost one instruction each where the IEEE forms expand to ten with a slow-path branch.  1.015 absorbs their
+    // error; a zero or denormal component gives +-inf like the exact reciprocal (the axis then does not cull)
+    const float k2 = 16.0f * 5.9604645e-8f + 2.0f * eps_d;
+    tv.kappa = 1.015f * k2 * mufu_rsq(k2);
+    tv.madd = 0.0f;
+    tv.ix = mufu_rcp(r.d.x);
+    tv.iy = mufu_rcp(r.d.y);
+    tv.iz = mufu_rcp(r.d.z);
     return eps_d <= 1e-3f && fabsf(r.o.x) <= 0x1p62f && fabsf(r.o.y) <= 0x1p62f && fabsf(r.o.z) <= 0x1p62f; // (false for a NaN)
 }
 
@@ -220,7 +230,7 @@ __device__ __forceinline__ void slab_pair(const float4 cx, const float4 cy, cons
     const float2 dcy = __fadd2_rn(make_float2(cy.x, cy.y), make_float2(-r.o.y, -r.o.y));
     const float2 dcz = __fadd2_rn(make_float2(cz.x, cz.y), make_float2(-r.o.z, -r.o.z));
     const float2 e3 = make_float2(fabsf(dcx.x) + fabsf(dcy.x) + fabsf(dcz.x), fabsf(dcx.y) + fabsf(dcy.y) + fabsf(dcz.y));
-    const float2 m = __fmul2_rn(__fadd2_rn(e3, make_float2(Ha, Hb)), make_float2(tv.kappa, tv.kappa));
+    const float2 m = __ffma2_rn(__fadd2_rn(e3, make_float2(Ha, Hb)), make_float2(tv.kappa, tv.kappa), make_float2(tv.madd, tv.madd));
     const float2 hx = __fadd2_rn(make_float2(cx.z, cx.w), m), hy = __fadd2_rn(make_float2(cy.z, cy.w), m), hz = __fadd2_rn(make_float2(cz.z, cz.w), m);
     const float2 tcx = __fmul2_rn(dcx, make_float2(tv.ix, tv.ix)), tcy = __fmul2_rn(dcy, make_float2(tv.iy, tv.iy)), tcz = __fmul2_rn(dcz, make_float2(tv.iz, tv.iz));
     const float2 ax = make_float2(fabsf(tv.ix), fabsf(tv.ix)), ay = make_float2(fabsf(tv.iy), fabsf(tv.iy)), az = make_float2(fabsf(tv.iz), fabsf(tv.iz));
@@ -315,20 +325,226 @@ __device__ __forceinline__ bool closest_sphere_bvh(const SceneDev& sc, const Ray
     return true;
 }
 
+// ---- traversal 2: node visits and leaf tests as separate, warp-converged phases ("if-if") -------------------------------------
+// The same tree, margins, culls and (t, index) rule as trav_step -- hence the same exact result -- with a different control
+// structure, chosen because the kernels are issue-bound at 19-23 of 32 active lanes and a quarter of their instructions were
+// branches:
+//   * a leaf child is no longer tested inside the node visit that found it (up to four divergent sub-branches per visit): it is
+//     ordered with the inner children -- the nearest hit child of any kind is processed next, the others go on the stack with
+//     their entry distance -- so the pop-time cull `tn <= best_t` now also drops leaves that a nearer hit has made irrelevant;
+//   * one loop iteration is { node visit, if the current item is an inner node } { leaf test, if it is (now) a leaf } { pop }:
+//     every phase is entered by all lanes that need it at the same time, a lane may pass through all three in one iteration;
+//   * the child bookkeeping is branch-free: the nearest child by three compare / selects, the other three by unconditional
+//     8-byte stack stores whose stack-pointer increments are predicated.
+// TOP > 0: the first TOP nodes of the breadth-first array (the top levels of the tree, which every ray visits) are read from
+// the copy the CTA staged in shared memory.
+struct TopNodes { const float4* nodes; uint32_t count; };
+
+template <bool USE_TOP, bool ANY_T = false>
+__device__ __forceinline__ bool closest_sphere_bvh2(const SceneDev& sc, const TopNodes top, const Ray& r, float& best_t, int& best_i, BvhStats& st)
+{
+    Trav tv;
+    if (!trav_init(r, tv))
+        return false;
+    uint2 stack[BVH_STACK + 1]; // {entry distance (bits), child reference}; one spare slot for the unconditional stores
+    int sp = 0;
+    const uint32_t NONE = 0xffffffffu;
+    const float inf = __int_as_float(0x7f800000);
+    uint32_t cur = 0; // the root; (int)cur >= 0: inner node, < -1: leaf, == -1: nothing in hand
+    for (;;)
+    {
+        if ((int)cur >= 0)
+        {
+            st.nodes++;
+            float4 nd[8];
+            if (USE_TOP && cur < top.count)
+            {
+                const float4* np = top.nodes + 8u * cur; // shared memory
+#pragma unroll
+                for (int k = 0; k < 8; k++) nd[k] = np[k];
+            }
+            else
+            {
+                const float4* np = sc.bvh_nodes + 8u * cur;
+#pragma unroll
+                for (int k = 0; k < 8; k++) nd[k] = __ldg(np + k);
+            }
+            const uint32_t ref[4] = { __float_as_uint(nd[6].x), __float_as_uint(nd[6].y), __float_as_uint(nd[6].z), __float_as_uint(nd[6].w) };
+            float tn[4];
+            bool hit[4];
+            slab_pair<ANY_T>(nd[0], nd[1], nd[2], nd[7].x, nd[7].y, r, tv, tn[0], tn[1], hit[0], hit[1]);
+            slab_pair<ANY_T>(nd[3], nd[4], nd[5], nd[7].z, nd[7].w, r, tv, tn[2], tn[3], hit[2], hit[3]);
+            // the nearest hit child is processed next (ties: the lower slot) ...
+            float nt = inf;
+            uint32_t nref = NONE;
+            int nslot = -1;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+            {
+                const bool nearer = hit[c] && (nslot < 0 || tn[c] < nt);
+                nt = nearer ? tn[c] : nt;
+                nref = nearer ? ref[c] : nref;
+                nslot = nearer ? c : nslot;
+            }
+            // ... the other hit children go on the stack in slot order: store always, keep the slot only when it counts
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+            {
+                stack[sp] = make_uint2(__float_as_uint(tn[c]), ref[c]);
+                sp += (hit[c] && c != nslot) ? 1 : 0;
+            }
+            cur = nref;
+        }
+        if ((int)cur < -1)
+        {
+            const uint32_t leaf = cur & 0x7fffffffu;
+            const float4* lp = sc.leaf_blk + 5u * leaf; // leaf < 2^29 (checked at upload): 32-bit index arithmetic
+            const float4 a0 = __ldg(lp), b0 = __ldg(lp + 1), a1 = __ldg(lp + 2), b1 = __ldg(lp + 3), idx = __ldg(lp + 4);
+            st.tests += 4; // sphere test slots (a leaf holds 1-4 spheres)
+            bvh_leaf_pair_test<ANY_T>(a0, b0, __float_as_int(idx.x), __float_as_int(idx.y), r, tv.best_t, tv.best_i);
+            bvh_leaf_pair_test<ANY_T>(a1, b1, __float_as_int(idx.z), __float_as_int(idx.w), r, tv.best_t, tv.best_i);
+            cur = NONE;
+        }
+        if (cur == NONE)
+        {
+            // pop, skipping entries that the current best already excludes
+            bool found = false;
+            while (sp > 0)
+            {
+                const uint2 e = stack[--sp];
+                if (__uint_as_float(e.x) <= tv.best_t)
+                {
+                    cur = e.y;
+                    found = true;
+                    break;
+                }
+            }
+            if (!found)
+                break;
+        }
+    }
+    best_t = tv.best_t;
+    best_i = tv.best_i == 0x7fffffff ? -1 : tv.best_i;
+    return true;
+}
+
+// ---- pixel beams: the primary rays of ONE pixel share their candidate leaves ---------------------------------------------------
+// More than half of all path segments are primary rays, and the reference's sample loop (mg_ray_tracer.cpp:187-194) sends all
+// of a pixel's samples through the same pixel: their rays differ by at most the pixel's footprint.  Where lanes share a pixel's
+// samples, the tree is therefore walked ONCE per pixel with the pixel's centre ray and margins widened by that footprint,
+// WITHOUT the closest-hit cull, collecting every leaf that any ray of the pixel could hit (up to BEAM_MAX, sorted by entry
+// distance).  A sample's primary ray then tests just those leaves -- S4, the (t, index) rule, exactly as a traversal would --
+// instead of descending from the root: the same result for a third of the instructions, and all lanes of the pixel run the
+// same short loop.  Pixels whose beam touches more leaves (grazing views over many spheres) keep the traversal.
+//
+// Why the list is complete.  Let R0 = (o0, d0) be the centre ray and R' = (o', d') any primary ray of the pixel, with
+// |o' - o0| <= rho and |d' - d0| <= sigma (both maximal at the pixel's corners: screen -> near / far points is affine when the
+// viewport's perspective divide is constant, and the angle to d0 is quasi-convex over the far-minus-near quad; the corners are
+// evaluated with the same arithmetic as the samples, plus slack for its rounding).  If S4 reports a hit of R' on a sphere
+// (c, r) at t' >= 0, the line of R' passes within r + kappa'|e'| of c (see above), and R0(t') lies within rho + sigma t' of
+// R'(t').  With E = the L1 distance from o0 to the far corner of a box around the sphere: |e'| <= E + rho and t' <= |e'| +
+// r + kappa'|e'| <= 2.01 E + 1.01 rho, so R0 meets the box inflated by (kappa_b + 2.01 sigma) E + 2 rho at parameter t' --
+// i.e. the slab test of the ordinary traversal with kappa := kappa_b + 2.01 sigma and an additive 2 rho passes for every
+// ancestor box of the sphere, and its entry distance tn0 <= t' (which makes `tn0 > best_t` a valid reason to stop early).
+// kappa_b is the margin factor of a ray that is unit length to within BEAM_EPS_D; a sample ray outside that (never seen:
+// primary directions are normalised) traverses.
+constexpr int BEAM_MAX = 8;                         // leaves per list
+constexpr int BEAM_MAX_VISITS = 48;                 // node visits after which a beam is given up
+constexpr float BEAM_EPS_D = 16.0f * 5.9604645e-8f; // |d.d - 1| bound of the rays that may use a list
+struct BeamList { float tn[BEAM_MAX]; uint32_t leaf[BEAM_MAX]; int n; int pad; }; // n < 0: no list, traverse
+
+// run by ONE lane per pixel (the list lives in shared memory)
+__device__ __noinline__ void beam_collect(const SceneDev& sc, const Ray& r0, const float sigma, const float rho, BeamList* __restrict__ out)
+{
+    out->n = -1;
+    Trav tv;
+    if (!trav_init(r0, tv) || !(fabsf(dot3(r0.d, r0.d) - 1.0f) <= BEAM_EPS_D))
+        return;
+    tv.kappa = 1.01f * (1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * BEAM_EPS_D) + 2.01f * sigma);
+    tv.madd = 2.02f * rho;
+    uint32_t stack[BVH_STACK];
+    int sp = 0, n = 0, visits = 0;
+    uint32_t node = 0;
+    for (;;)
+    {
+        if (++visits > BEAM_MAX_VISITS) return;
+        const float4* np = sc.bvh_nodes + 8u * node;
+        const float4 refs = __ldg(np + 6), hs = __ldg(np + 7);
+        const uint32_t ref[4] = { __float_as_uint(refs.x), __float_as_uint(refs.y), __float_as_uint(refs.z), __float_as_uint(refs.w) };
+        float tn[4];
+        bool hit[4];
+        slab_pair<false>(__ldg(np), __ldg(np + 1), __ldg(np + 2), hs.x, hs.y, r0, tv, tn[0], tn[1], hit[0], hit[1]); // (tv.best_t stays +inf: no cull)
+        slab_pair<false>(__ldg(np + 3), __ldg(np + 4), __ldg(np + 5), hs.z, hs.w, r0, tv, tn[2], tn[3], hit[2], hit[3]);
+        for (int c = 0; c < 4; c++)
+        {
+            if (!hit[c]) continue;
+            if (ref[c] & 0x80000000u)
+            {
+                if (n == BEAM_MAX) return;
+                int k = n++;
+                for (; k > 0 && out->tn[k - 1] > tn[c]; k--) // keep the list sorted by entry distance
+                {
+                    out->tn[k] = out->tn[k - 1];
+                    out->leaf[k] = out->leaf[k - 1];
+                }
+                out->tn[k] = tn[c];
+                out->leaf[k] = ref[c] & 0x7fffffffu;
+            }
+            else
+                stack[sp++] = ref[c];
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    out->n = n;
+}
+
+// closest sphere hit of a primary ray of the beam's pixel: the (t, index) minimum over the listed leaves
+__device__ __forceinline__ void beam_closest_sphere(const SceneDev& sc, const BeamList* __restrict__ beam, const Ray& r, float& best_t, int& best_i, BvhStats& st)
+{
+    best_t = __int_as_float(0x7f800000);
+    best_i = 0x7fffffff;
+    const int n = beam->n;
+    for (int k = 0; k < n; k++)
+    {
+        if (beam->tn[k] > best_t) break; // no ray of the pixel reaches this leaf (or a later one) before tn
+        const float4* lp = sc.leaf_blk + 5u * beam->leaf[k];
+        const float4 a0 = __ldg(lp), b0 = __ldg(lp + 1), a1 = __ldg(lp + 2), b1 = __ldg(lp + 3), idx = __ldg(lp + 4);
+        st.tests += 4;
+        bvh_leaf_pair_test<false>(a0, b0, __float_as_int(idx.x), __float_as_int(idx.y), r, best_t, best_i);
+        bvh_leaf_pair_test<false>(a1, b1, __float_as_int(idx.z), __float_as_int(idx.w), r, best_t, best_i);
+    }
+    best_i = best_i == 0x7fffffff ? -1 : best_i;
+}
+
 // sphere result of a traversal + the planes (linear) -> Hit, with the reference's select rule (mg_ray_tracer.cpp:95-102)
+// The BVH kernels are issue-bound and their hot loop (generate, traverse, leaf tests, shade) is ~22 KB of SASS against a 32 KB
+// L1.5 instruction cache (profiles/README.md: a variant whose loop grew to 40 KB spent 8x the cycles waiting for instructions).
+// Code that a BVH scene rarely runs is therefore kept OUT of the loop body as real functions: the plane loop (the large scenes
+// have no planes) and the scan that non-unit or far-away rays fall back to.
+__device__ __noinline__ void closest_plane_cold(const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray& r, float& tp, int& ip)
+{
+    tp = __int_as_float(0x7f800000);
+    ip = -1;
+    for (uint32_t i = 0; i < n_pl; i++)
+        plane_test(s_pl[i], (int)i, r, tp, ip);
+}
+__device__ __noinline__ Hit closest_hit_scan_cold(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r)
+{
+    return closest_hit_linear(sc.pairs, sc.n_spheres, s_pl, sc.n_planes, r);
+}
+
 __device__ __forceinline__ Hit combine_with_planes(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, const float ts, const int is)
 {
     Hit h;
     h.t = ts;
-    h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS;
+    h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS; // (a traversal never yields a NaN distance: trav_init sends such rays to the scan)
     if (sc.n_planes)
     {
-        const float inf = __int_as_float(0x7f800000);
-        float tp = inf;
-        int ip = -1;
-        for (uint32_t i = 0; i < sc.n_planes; i++)
-            plane_test(s_pl[i], (int)i, r, tp, ip);
-        if (ip >= 0 && !(is >= 0 && ts <= tp))
+        float tp;
+        int ip;
+        closest_plane_cold(s_pl, sc.n_planes, r, tp, ip);
+        if (ip >= 0 && tp >= 0.0f && !(is >= 0 && ts <= tp))
         {
             h.t = tp;
             h.prim = RTCU_PRIM_PLANE | (uint32_t)ip;
@@ -340,14 +556,17 @@ __device__ __forceinline__ Hit combine_with_planes(const SceneDev& sc, const flo
 }
 
 // closest hit: spheres through the BVH (or the global-memory linear scan when the ray is not unit length), planes linear
-__device__ __forceinline__ Hit closest_hit_bvh(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, BvhStats& st)
+// TRAV: 0 = trav_step (leaf children tested inside the node visit), 1 = closest_sphere_bvh2 (deferred leaves, if-if phases)
+//       2 = the same with the top levels of the tree read from shared memory (`top`)
+template <int TRAV = 1>
+__device__ __forceinline__ Hit closest_hit_bvh(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, BvhStats& st, const TopNodes top = TopNodes{ nullptr, 0u })
 {
     float ts;
     int is;
-    if (!closest_sphere_bvh(sc, r, ts, is, st))
+    if (!(TRAV == 0 ? closest_sphere_bvh(sc, r, ts, is, st) : closest_sphere_bvh2<TRAV == 2>(sc, top, r, ts, is, st)))
     {
         st.tests += sc.n_spheres;
-        return closest_hit_linear(sc.pairs, sc.n_spheres, s_pl, sc.n_planes, r);
+        return closest_hit_scan_cold(sc, s_pl, r);
     }
     return combine_with_planes(sc, s_pl, r, ts, is);
 }
@@ -407,12 +626,12 @@ __device__ __forceinline__ bool shade_segment(const SceneDev& sc, const RenderPa
 
 // One path segment (mg_ray_tracer.cpp:154-174, one level of the recursion): closest hit, then sky on a miss or one
 // scatter event on a hit.  Returns true when the path ended (miss, absorbed, or bounce budget exhausted).
-template <bool BVH>
+template <bool BVH, int TRAV = 1>
 __device__ __forceinline__ bool segment_step(const SceneDev& sc, const RenderParams& p, const float4* __restrict__ s_sph,
                                              const float4* __restrict__ s_pl, const RngKey& key, Ray& ray, V3& thr, V3& sum, uint32_t& seg,
-                                             BvhStats& bst)
+                                             BvhStats& bst, const TopNodes top = TopNodes{ nullptr, 0u })
 {
-    const Hit h = BVH ? closest_hit_bvh(sc, s_pl, ray, bst) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
+    const Hit h = BVH ? closest_hit_bvh<TRAV>(sc, s_pl, ray, bst, top) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
     return shade_segment<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, h);
 }
 
@@ -444,8 +663,8 @@ __device__ __forceinline__ bool shade_segment(const SceneDev& sc, const RenderPa
 // dominates).  !FLAT: plain per-thread loop, which the compiler nests as {generate; bounce until every lane's path
 // ended} -- generate and shade then run at full lane occupancy, best for tiny N where they dominate.
 // BVH: spheres are reached through the BVH (STAGE must be false; the structure lives in L1/L2).
-template <bool STAGE, bool FLAT, bool BVH>
-__global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_mega(const SceneDev sc, const RenderParams p)
+template <bool STAGE, bool FLAT, bool BVH, int TRAV = 1>
+__global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_mega(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p)
 {
     extern __shared__ float4 smem[];
     const float4* s_sph = sc.pairs;
@@ -518,7 +737,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
             if (live)
             {
                 segs++;
-                if (segment_step<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, bst))
+                if (segment_step<BVH, TRAV>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, bst))
                 {
                     live = false;
                     key.sample++;
@@ -538,7 +757,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
         for (;;)
         {
             segs++;
-            if (segment_step<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, bst))
+            if (segment_step<BVH, TRAV>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, bst))
             {
                 key.sample++;
                 if (key.sample >= p.sample_end)
@@ -674,9 +893,50 @@ __global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict_
 // 32 lanes share the pixel's remaining samples, each lane claiming the next unclaimed one as soon as its path ends; the 32
 // partial sums are combined in a fixed butterfly order and added to the pixel's partial result from the first pass --
 // deterministic, since which lane traces which sample depends only on the path lengths.  Primitives are read from global memory (L1-resident for the scenes that reach this path).
-template <bool BVH, int G_LANES = 32>
-__global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc, const RenderParams p)
+// TRAV = 2: the CTA first copies the top TOP_NODES nodes of the tree (breadth-first order: its top levels) into shared memory.
+constexpr uint32_t TOP_NODES = 21; // three levels of 4-wide nodes: 1 + 4 + 16, 2.7 KB
+// BEAM (direct mode): the primary rays of a pixel test the pixel's candidate leaves instead of traversing (beam_collect).
+// the pixel's footprint and its candidate list: centre ray against the rays through the four corners (lane k & 3 of the group
+// takes corner k), then one lane of the group walks the tree (beam_collect).  Called by all lanes of the warp; out of line: it
+// runs once per pixel, and its registers must not weigh on the sample loop
+template <uint32_t G>
+__device__ __noinline__ void beam_setup(const SceneDev& sc, const CameraConst& cam, const uint32_t px, const uint32_t py, const uint32_t lane, const bool has_work,
+                                        BeamList* __restrict__ beam)
 {
+    const uint32_t lg = lane & (G - 1u);
+    const float fx = __uint2float_rn(px), fy = __uint2float_rn(py);
+    const Ray rc = primary_ray(cam, __fadd_rn(fx, 0.5f), __fadd_rn(fy, 0.5f));
+    const Ray rk = primary_ray(cam, __fadd_rn(fx, (float)(lg & 1u)), __fadd_rn(fy, (float)((lg >> 1) & 1u)));
+    float dd = fabsf(rk.d.x - rc.d.x) + fabsf(rk.d.y - rc.d.y) + fabsf(rk.d.z - rc.d.z);
+    float oo = fabsf(rk.o.x - rc.o.x) + fabsf(rk.o.y - rc.o.y) + fabsf(rk.o.z - rc.o.z);
+    dd = fmaxf(dd, __shfl_xor_sync(0xffffffffu, dd, 1));
+    oo = fmaxf(oo, __shfl_xor_sync(0xffffffffu, oo, 1));
+    dd = fmaxf(dd, __shfl_xor_sync(0xffffffffu, dd, 2));
+    oo = fmaxf(oo, __shfl_xor_sync(0xffffffffu, oo, 2));
+    const float u16 = 16.0f * 5.9604645e-8f; // slack for the rounding of the ray arithmetic itself
+    const float sigma = 1.01f * dd + u16, rho = 1.01f * oo + u16 * (fabsf(rc.o.x) + fabsf(rc.o.y) + fabsf(rc.o.z) + 1.0f);
+    if (lg == 0u)
+    {
+        if (has_work) beam_collect(sc, rc, sigma, rho, beam);
+        else beam->n = -1;
+    }
+    __syncwarp();
+}
+
+template <bool BVH, int G_LANES = 32, int TRAV = 1, bool BEAM = false, int MINB = 8>
+__global__ void __launch_bounds__(128, MINB) k_render_stragglers(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p)
+{
+    __shared__ BeamList s_beam[BEAM ? 4 * (32 / G_LANES) : 1]; // one per lane group of the CTA
+    __shared__ float4 s_top[TRAV == 2 ? 8 * TOP_NODES : 1];
+    TopNodes top;
+    top.nodes = s_top;
+    top.count = 0;
+    if (BVH && TRAV == 2)
+    {
+        top.count = min(TOP_NODES, sc.n_bvh_nodes);
+        for (uint32_t i = threadIdx.x; i < 8u * top.count; i += blockDim.x) s_top[i] = __ldg(sc.bvh_nodes + i);
+        __syncthreads();
+    }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t tile_w = p.tile_x1 - p.tile_x0, tile_h = p.tile_y1 - p.tile_y0;
     // G lanes share one pixel (32 in queue mode; 16 or 8 in direct mode, so that every lane gets >= 2 samples): a warp works
@@ -717,6 +977,13 @@ __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc,
         Ray ray;
         ray.o = v3(0.0f, 0.0f, 0.0f);
         ray.d = v3(0.0f, 0.0f, 1.0f);
+        bool use_beam = false;
+        BeamList* beam = &s_beam[BEAM ? (threadIdx.x >> 5) * ppw + grp : 0];
+        if (BVH && BEAM && p.direct && p.cam.w_const && p.beam)
+        {
+            beam_setup<G>(sc, p.cam, px, py, lane, w.y < p.sample_end, beam);
+            use_beam = beam->n >= 0;
+        }
         // the lanes of a group share their pixel's remaining samples: a lane whose path ended takes the next unclaimed sample
         // at once (ballot rank in lane order -- deterministic), so lanes stay busy until the pixel runs out of samples
         uint32_t next = w.y;
@@ -725,7 +992,8 @@ __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc,
         {
             const unsigned idle = __ballot_sync(0xffffffffu, !live) & gmask;
             const uint32_t mine = next + __popc(idle & below);
-            if (!live && mine < p.sample_end)
+            const bool fresh = !live && mine < p.sample_end;
+            if (fresh)
             {
                 key.sample = mine;
                 seg = 0;
@@ -735,12 +1003,41 @@ __global__ void __launch_bounds__(128, 8) k_render_stragglers(const SceneDev sc,
             }
             next = min(p.sample_end, next + (uint32_t)__popc(idle));
             if (!__any_sync(0xffffffffu, live)) break;
-            if (live)
+            if (BVH && BEAM)
+            {
+                // Two passes over ONE copy of the segment code (the loop is kept rolled: instruction-cache footprint, see
+                // closest_plane_cold).  Pass 0: the lanes that have just started a sample of a pixel with a beam list find their
+                // primary hit in the list and shade it; pass 1: every lane in flight -- those lanes now with their first bounce --
+                // traverses.  One iteration thus advances a fresh lane by two segments and the traversal only ever sees
+                // secondary rays.
+                const bool listed = use_beam && fresh && fabsf(dot3(ray.d, ray.d) - 1.0f) <= BEAM_EPS_D;
+#pragma unroll 1
+                for (int pass = __any_sync(0xffffffffu, listed) ? 0 : 1; pass < 2; pass++)
+                {
+                    if (pass == 0 ? listed : live)
+                    {
+                        segs++;
+                        Hit h;
+                        if (pass == 0)
+                        {
+                            float ts;
+                            int is;
+                            beam_closest_sphere(sc, beam, ray, ts, is, bst);
+                            h = combine_with_planes(sc, sc.planes, ray, ts, is);
+                        }
+                        else
+                            h = closest_hit_bvh<TRAV>(sc, sc.planes, ray, bst, top);
+                        if (shade_segment<BVH>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, h)) live = false;
+                    }
+                }
+            }
+            else if (live)
             {
                 segs++;
-                if (segment_step<BVH>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst)) live = false;
+                if (segment_step<BVH, TRAV>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst, top)) live = false;
             }
         }
+        if (BEAM) __syncwarp(); // the list is rewritten for the next pixel only after every lane has left this one
         for (uint32_t off = G >> 1; off > 0; off >>= 1) // fixed butterfly inside the group
         {
             sum.x = __fadd_rn(sum.x, __shfl_xor_sync(0xffffffffu, sum.x, off));
@@ -909,8 +1206,8 @@ __global__ void __launch_bounds__(256) k_exchange_reduce_resolve(const PeerList 
 }
 
 // ---- step-wise parity kernels ----------------------------------------------------------------------
-template <bool STAGE, bool BVH>
-__global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, const float* __restrict__ o, const float* __restrict__ d,
+template <bool STAGE, bool BVH, int TRAV = 1>
+__global__ void __launch_bounds__(256) k_intersect_batch(const __grid_constant__ SceneDev sc, const float* __restrict__ o, const float* __restrict__ d,
                                                          uint32_t n, uint8_t* __restrict__ hit, uint32_t* __restrict__ prim,
                                                          float* __restrict__ t, float* __restrict__ nrm, unsigned long long* counters)
 {
@@ -936,7 +1233,7 @@ __global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, cons
         BvhStats bst;
         bst.nodes = 0;
         bst.tests = 0;
-        const Hit h = BVH ? closest_hit_bvh(sc, s_pl, r, bst) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, r);
+        const Hit h = BVH ? closest_hit_bvh<TRAV>(sc, s_pl, r, bst) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, r);
         hit[i] = h.prim != RTCU_PRIM_MISS;
         prim[i] = h.prim;
         t[i] = h.t;
@@ -968,7 +1265,7 @@ __global__ void k_primary_rays(const CameraConst cam, uint32_t width, const Phil
     d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z;
 }
 
-__global__ void k_scatter_batch(const SceneDev sc, uint32_t mode, const PhiloxKeys rk, uint32_t n, const uint32_t* __restrict__ material,
+__global__ void k_scatter_batch(const __grid_constant__ SceneDev sc, uint32_t mode, const PhiloxKeys rk, uint32_t n, const uint32_t* __restrict__ material,
                                 const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ t,
                                 const float* __restrict__ nrm, const uint32_t* __restrict__ pixel, const uint32_t* __restrict__ sample,
                                 const uint32_t* __restrict__ block, uint8_t* __restrict__ scattered, float* __restrict__ att,

@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned lanemask_lt()
     return m;
 }
 
-__global__ void __launch_bounds__(32 * POOL_WARPS, RTCU_POOL_BLOCKS) k_render_pool(const SceneDev sc, const RenderParams p)
+__global__ void __launch_bounds__(32 * POOL_WARPS, RTCU_POOL_BLOCKS) k_render_pool(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p)
 {
     __shared__ WarpPool pools[POOL_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, RTCU_POOL_BLOCKS) k_render_po
     ray.o = v3(0.0f, 0.0f, 0.0f);
     ray.d = v3(0.0f, 0.0f, 1.0f);
     Trav tv;
-    tv.node = 0; tv.sp = 0; tv.best_t = 0.0f; tv.best_i = -1; tv.ix = tv.iy = tv.iz = 0.0f; tv.kappa = 0.0f;
+    tv.node = 0; tv.sp = 0; tv.best_t = 0.0f; tv.best_i = -1; tv.ix = tv.iy = tv.iz = 0.0f; tv.kappa = 0.0f; tv.madd = 0.0f;
     uint32_t stack_ref[BVH_STACK];
     float stack_t[BVH_STACK];
 

@@ -60,6 +60,13 @@ int guarded(const char* what, F&& body) noexcept
     } while (0)
 
 constexpr size_t MAX_STAGE_BYTES = 200 * 1024; // dynamic shared memory budget for staged primitives
+#ifndef RTCU_DEFAULT_BEAM_MIN
+#define RTCU_DEFAULT_BEAM_MIN 16 // pixel beams from this many samples per lane (RTCU_BVH_BEAM overrides; 0 = never): the walk that
+                                 // builds a pixel's list costs about as much as eight primary traversals, and C4's 64 samples are below it
+#endif
+#ifndef RTCU_DEFAULT_TRAV
+#define RTCU_DEFAULT_TRAV 0 // traversal variant of the direct-mode BVH kernel (kernels.cuh, closest_hit_bvh); RTCU_BVH_TRAV overrides
+#endif
 
 template <typename T>
 struct DevBuf {
@@ -133,6 +140,8 @@ struct Knobs {
     uint32_t bvh_threshold = 32; // RTCU_BVH_THRESHOLD
     int bvh_trav = -1;         // RTCU_BVH_TRAV: traversal variant of the BVH kernels (-1 = default), see kernels.cuh
     int bvh_lanes = 0;         // RTCU_BVH_LANES: lanes per pixel in direct mode (8 / 16 / 32), 0 = by sample count
+    int bvh_minb = 7;          // RTCU_BVH_MINB: 6 / 7 / 8 CTAs per SM for the beam kernel (80 / 72 / 64 registers)
+    int bvh_beam = -1;         // RTCU_BVH_BEAM: samples per lane from which a pixel's primary rays share a candidate list (0 = never)
     void load()
     {
         *this = Knobs{};
@@ -147,7 +156,9 @@ struct Knobs {
         if (const char* e = getenv("RTCU_REGISTER_OUTPUT")) register_output = e[0] != '0';
         if (const char* e = getenv("RTCU_BVH_THRESHOLD")) bvh_threshold = (uint32_t)strtoul(e, nullptr, 10);
         if (const char* e = getenv("RTCU_BVH_TRAV")) bvh_trav = atoi(e);
-        if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) bvh_lanes = v; }
+        if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) bvh_lanes = v; }
+        if (const char* e = getenv("RTCU_BVH_MINB")) { const int v = atoi(e); if (v >= 6 && v <= 8) bvh_minb = v; }
+        if (const char* e = getenv("RTCU_BVH_BEAM")) bvh_beam = atoi(e) < 0 ? 0 : atoi(e);
     }
 };
 
@@ -270,6 +281,7 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     p.tile_cost = nullptr;
     p.tile_order = nullptr;
     p.direct = 0;
+    p.beam = 0;
     return RTCU_OK;
 }
 
@@ -444,7 +456,8 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
     if (pool) p.segment_budget = 0; // work is shared by the 32 lanes of a warp: no per-thread stragglers
     auto launch_mega = [&](const RenderParams& q) {
         if (pool) k_render_pool<<<grid, 32 * POOL_WARPS, 0, st>>>(ctx->scene, q);
-        else if (use_bvh) k_render_mega<false, true, true><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q); // flat loop (nested measures the same on C3/C4)
+        else if (use_bvh && ctx->knobs.bvh_trav == 0) k_render_mega<false, true, true, 0><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q);
+        else if (use_bvh) k_render_mega<false, true, true, 1><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q); // flat loop (nested measures the same on C3/C4)
         else if (sb > MAX_STAGE_BYTES) k_render_mega<false, true, false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q);
         else if (flat) k_render_mega<true, true, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, q);
         else k_render_mega<true, false, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, q);
@@ -469,15 +482,33 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
     {
         p.direct = 1;
         p.segment_budget = 0;
-        const unsigned long long n_items = (unsigned long long)((v->tile_x1 - v->tile_x0 + 7) / 8) * ((v->tile_y1 - v->tile_y0 + 3) / 4) * 16ull;
+        const unsigned long long n_items = (unsigned long long)((v->tile_x1 - v->tile_x0 + 7) / 8) * ((v->tile_y1 - v->tile_y0 + 3) / 4) * 32ull;
         if (n_items > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "tile too large");
         RenderParams q = p; // the kernel derives the item count from the tile (8x4 patches, ragged edges skipped)
         q.tile_cost = nullptr;
         // lanes per pixel: 16 (two pixels per warp) from 32 samples -- measured equal or better than 32 lanes on one pixel even
         // at 256 samples -- and 8 (four pixels per warp) below, so that every lane gets at least two samples
         const unsigned blocks = (unsigned)ctx->sm_count * 8;
-        if (n_samples >= 32) k_render_stragglers<true, 16><<<blocks, 128, 0, st>>>(ctx->scene, q);
-        else k_render_stragglers<true, 8><<<blocks, 128, 0, st>>>(ctx->scene, q);
+        // lanes per pixel.  Without beams: 16 (two pixels per warp) from 32 samples, 8 below, so that every lane gets at least two
+        // samples.  From 128 samples per call the pixel's primary rays share a candidate list (beams, below) and 8 lanes per pixel
+        // measure best (C3 41.2 -> 34.4 ms, the 512-sample share of C5 on 8 GPUs 321.6 -> 256.1 ms; 4 lanes the same, 16 lanes +10 %)
+        const int beam_min = ctx->knobs.bvh_beam >= 0 ? ctx->knobs.bvh_beam : RTCU_DEFAULT_BEAM_MIN;
+        const int lanes = ctx->knobs.bvh_lanes ? ctx->knobs.bvh_lanes : (beam_min > 0 && n_samples >= 8u * (uint32_t)beam_min ? 8 : n_samples >= 32 ? 16 : 8);
+        const int trav = ctx->knobs.bvh_trav >= 0 && ctx->knobs.bvh_trav <= 2 ? ctx->knobs.bvh_trav : RTCU_DEFAULT_TRAV;
+        // pixel beams (kernels.cuh, beam_collect): one walk per pixel replaces the primary rays' traversals; worth it once a lane
+        // traces several samples of the pixel (RTCU_BVH_BEAM: samples per lane from which beams are used, 0 = never)
+        const bool beam = beam_min > 0 && n_samples >= (uint32_t)(beam_min * lanes);
+        q.beam = beam ? 1 : 0;
+        const int minb = ctx->knobs.bvh_minb; // experiment: CTAs per SM the beam kernel is compiled for (8 = 64 registers, 6 = 80)
+#define RTCU_LAUNCH_DIRECT(G, T, B, M) k_render_stragglers<true, G, T, B, M><<<(unsigned)ctx->sm_count * M, 128, 0, st>>>(ctx->scene, q)
+#define RTCU_LAUNCH_BEAM(G) (minb == 6 ? RTCU_LAUNCH_DIRECT(G, 0, true, 6) : minb == 7 ? RTCU_LAUNCH_DIRECT(G, 0, true, 7) : RTCU_LAUNCH_DIRECT(G, 0, true, 8))
+        if (trav == 1 && lanes == 16) RTCU_LAUNCH_DIRECT(16, 1, false, 8); // (the traversal experiments: 16 lanes, no beams)
+        else if (trav == 2 && lanes == 16) RTCU_LAUNCH_DIRECT(16, 2, false, 8);
+        else if (lanes == 32) { if (beam) RTCU_LAUNCH_BEAM(32); else RTCU_LAUNCH_DIRECT(32, 0, false, 8); }
+        else if (lanes == 16) { if (beam) RTCU_LAUNCH_BEAM(16); else RTCU_LAUNCH_DIRECT(16, 0, false, 8); }
+        else if (lanes == 8) { if (beam) RTCU_LAUNCH_BEAM(8); else RTCU_LAUNCH_DIRECT(8, 0, false, 8); }
+        else { if (beam) RTCU_LAUNCH_BEAM(4); else RTCU_LAUNCH_DIRECT(4, 0, false, 8); }
+        (void)blocks;
         CU(cudaGetLastError());
         ctx->tile_hist_valid = false;
         ctx->stats.kernel_launches = 1;
@@ -546,7 +577,7 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
     {
         // the accumulate flag only applies to the first pass: the second adds onto what the first wrote
         const unsigned blocks = (unsigned)ctx->sm_count * 8;
-        if (use_bvh) k_render_stragglers<true><<<blocks, 128, 0, st>>>(ctx->scene, p);
+        if (use_bvh) k_render_stragglers<true, 32, 0><<<blocks, 128, 0, st>>>(ctx->scene, p);
         else k_render_stragglers<false><<<blocks, 128, 0, st>>>(ctx->scene, p);
         CU(cudaGetLastError());
         ctx->stats.kernel_launches++;
@@ -1734,8 +1765,10 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
     const size_t sb = stage_bytes(ctx);
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
     CU(cudaEventRecord(ctx->ev[0], st));
-    if (use_bvh)
-        k_intersect_batch<false, true><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
+    if (use_bvh && ctx->knobs.bvh_trav == 0)
+        k_intersect_batch<false, true, 0><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
+    else if (use_bvh)
+        k_intersect_batch<false, true, 1><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
     else if (sb <= MAX_STAGE_BYTES)
         k_intersect_batch<true, false><<<blocks, 256, sb, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
     else

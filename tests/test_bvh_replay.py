@@ -35,7 +35,14 @@ def build_replay(tmp_path_factory, *defines):
 
 @pytest.fixture(scope="module")
 def replay(tmp_path_factory):
+    """trav_step: leaf children tested inside the node visit (the preview renderer; RTCU_BVH_TRAV=0)"""
     return build_replay(tmp_path_factory)
+
+
+@pytest.fixture(scope="module")
+def replay2(tmp_path_factory):
+    """closest_sphere_bvh2: leaves deferred and ordered with the inner children (the path tracer's default)"""
+    return build_replay(tmp_path_factory, "-DBVH_REPLAY_TRAV2")
 
 
 def unit(v):
@@ -92,11 +99,13 @@ def cases():
 KNOBS = [{}, {"RTCU_BVH_LEAF_COST": "1"}, {"RTCU_BVH_COLLAPSE": "sah"}, {"RTCU_BVH_SWEEP": "512", "RTCU_BVH_LEAF_COST": "1", "RTCU_BVH_COLLAPSE": "sah"}]
 
 
+@pytest.mark.parametrize("trav", [2, 1], ids=["deferred-leaves", "leaves-in-visit"])
 @pytest.mark.parametrize("knobs", KNOBS, ids=["default", "leafcost", "sah-collapse", "sweep+leafcost+sah-collapse"])
 @pytest.mark.parametrize("name", ["rtiow", "cloud", "nested", "grid9601", "grid100k"])
-def test_replayed_traversal_equals_the_oracle_scan(replay, oracle, name, knobs, monkeypatch):
+def test_replayed_traversal_equals_the_oracle_scan(replay, replay2, oracle, name, knobs, trav, monkeypatch):
     if knobs and name == "grid100k":
         pytest.skip("variants: the smaller scenes")
+    replay = replay2 if trav == 2 else replay
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     sph, n = cases()[name]
@@ -150,10 +159,11 @@ def test_replayed_preview_traversal_equals_the_oracle_rasterizer(replay, oracle)
     assert (t[ref_hit] < 0).any() and len(np.unique(prim[ref_hit])) > 20  # negative distances do occur, and many spheres are seen
 
 
-def test_the_rays_need_the_margins(tmp_path_factory, oracle):
+@pytest.mark.parametrize("trav_define", [(), ("-DBVH_REPLAY_TRAV2",)], ids=["leaves-in-visit", "deferred-leaves"])
+def test_the_rays_need_the_margins(tmp_path_factory, oracle, trav_define):
     """the same traversal with the conservative margins switched off loses grazing hits on these rays: the equality above is the
     margins' doing, not the rays' leniency"""
-    no_margin = build_replay(tmp_path_factory, "-DBVH_REPLAY_NO_MARGIN")
+    no_margin = build_replay(tmp_path_factory, "-DBVH_REPLAY_NO_MARGIN", *trav_define)
     sph = np.ascontiguousarray(synth.rtiow_scene().spheres, np.float32)
     nodes, leaves, _ = R.bvh4_build_host(sph)
     o, d = rays_for(sph, 240000, np.random.default_rng(5))

@@ -57,8 +57,8 @@ def test_huge_coordinates_keep_the_reference_scan(ctx, oracle):
     sph = np.zeros((n, 4), np.float32)
     sph[:, :3] = rng.uniform(-3, 3, (n, 3))
     sph[:, 3] = rng.uniform(0.2, 0.6, n)
-    sph[7, :3] = [1e20, 0.5, -2e20]   # |e|^2 overflows to inf for this one: inf - inf = NaN in S4
-    sph[19, 3] = 3e19
+    sph[7, :3] = [6e18, 0.5, -8e18]   # beyond 2^62: one more order of magnitude and |e|^2 overflows
+    sph[19] = [0, -9e18, 0, 9e18]     # a "ground" whose r^2 is within a factor four of FLT_MAX
     base = synth.rtiow_scene()
     sc = dataclasses.replace(base, spheres=sph, sphere_material=(np.arange(n) % len(base.materials)).astype(np.uint32))
     ctx.upload_scene(sc)
@@ -68,15 +68,22 @@ def test_huge_coordinates_keep_the_reference_scan(ctx, oracle):
     assert st["accel"] == nat.ACCEL_LINEAR  # no BVH for this scene, although it has more than rtcu_bvh_threshold() spheres
     r_rgba8, r_accum, r_segs = oracle.render(sc, v)
     assert st["segments"] == r_segs
-    np.testing.assert_array_equal(np.isnan(accum), np.isnan(r_accum))
-    ok = ~np.isnan(r_accum[..., :3])
-    np.testing.assert_allclose(accum[..., :3][ok], r_accum[..., :3][ok], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(accum[..., :3], r_accum[..., :3], rtol=2e-5, atol=1e-6)
+    assert np.abs(unpack_rgba(rgba8) - unpack_rgba(r_rgba8)).max() <= 1
+    # where S4 does overflow (inf - inf = NaN distances, which the scan's `best <= t` rule accepts): still the scan's answer
+    sph[7, :3] = [1e20, 0.5, -2e20]
+    sph[19, 3] = 3e19
+    sc = dataclasses.replace(sc, spheres=sph)
+    ctx.upload_scene(sc)
     o, d = synth.random_rays(sc, 4096, seed=11)
-    o[::5] *= np.float32(1e19)  # origins outside the safe range fall back to the scan one by one
-    got = ctx.intersect_batch(o, d)
-    want = oracle.intersect_batch(sc, o, d)
-    np.testing.assert_array_equal(got[0], want[0])
-    np.testing.assert_array_equal(got[1], want[1])
+    o[::5] *= np.float32(1e19)
+    for accel in (nat.ACCEL_AUTO, nat.ACCEL_LINEAR):
+        got = ctx.intersect_batch(o, d, accel=accel)
+        want = oracle.intersect_batch(sc, o, d)
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+    with pytest.raises(nat.RtcuError, match="no BVH"):
+        ctx.intersect_batch(o, d, accel=nat.ACCEL_BVH)
 
 
 def test_far_origins_fall_back_to_the_scan_inside_a_bvh_scene(ctx, oracle, scenes):

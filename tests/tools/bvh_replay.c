@@ -23,6 +23,7 @@ int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], co
 {
     const float eps_d = fabsf(dot3(d, d) - 1.0f);
     if (!(eps_d <= 1e-3f)) return 0;
+    if (!(fabsf(o[0]) <= 0x1p62f && fabsf(o[1]) <= 0x1p62f && fabsf(o[2]) <= 0x1p62f)) return 0; /* S4 could overflow: the kernel scans */
     const float kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
     const float inv[3] = { 1.0f / d[0], 1.0f / d[1], 1.0f / d[2] };
     float best_t = start_t;
@@ -122,6 +123,136 @@ int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], co
     return 1;
 }
 
+/* ---- traversal 2 (kernels.cuh: closest_sphere_bvh2): leaf children are not tested inside the node visit but ordered with the
+ * inner ones -- the nearest hit child of either kind is processed next, the others are pushed in slot order with their entry
+ * distance, and the pop-time cull applies to leaves as well.  Same margins, same cull, same (t, index) rule. */
+static void slab4(const float* np, const float o[3], const float inv[3], float kappa, float best_t, int any_t, float tn[4], int hit[4])
+{
+    const float* H = np + 28;
+    for (int c = 0; c < 4; c++)
+    {
+        const int pair = c >> 1, slot = c & 1;
+        const float* ax = np + 12 * pair;
+        float dc[3];
+        for (int k = 0; k < 3; k++) dc[k] = ax[4 * k + slot] - o[k];
+        const float e3 = fabsf(dc[0]) + fabsf(dc[1]) + fabsf(dc[2]);
+#ifdef BVH_REPLAY_NO_MARGIN
+        const float m = 0.0f * (e3 + H[c]) * kappa;
+#else
+        const float m = (e3 + H[c]) * kappa;
+#endif
+        float near = -INFINITY, far = INFINITY;
+        for (int k = 0; k < 3; k++)
+        {
+            const float h = ax[4 * k + 2 + slot] + m, a = fabsf(inv[k]), tc = dc[k] * inv[k];
+            near = fmaxf(near, fmaf(-h, a, tc));
+            far = fminf(far, fmaf(h, a, tc));
+        }
+        tn[c] = near;
+        hit[c] = far >= (any_t ? near : fmaxf(near, 0.0f)) && near <= best_t;
+    }
+}
+
+int bvh_replay_ray2(const float* nodes, const float* leaves, const float o[3], const float d[3], int any_t, float start_t, int32_t start_i,
+                    float* t_out, int32_t* i_out, uint64_t* visits, uint64_t* leaf_visits, uint32_t* max_sp)
+{
+    const float eps_d = fabsf(dot3(d, d) - 1.0f);
+    if (!(eps_d <= 1e-3f)) return 0;
+    if (!(fabsf(o[0]) <= 0x1p62f && fabsf(o[1]) <= 0x1p62f && fabsf(o[2]) <= 0x1p62f)) return 0;
+    const float kappa = 1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * eps_d);
+    const float inv[3] = { 1.0f / d[0], 1.0f / d[1], 1.0f / d[2] };
+    float best_t = start_t;
+    int32_t best_i = start_i;
+    uint32_t stack_ref[STACK + 1];
+    float stack_t[STACK + 1];
+    uint32_t sp = 0, cur = 0;
+    const uint32_t NONE = 0xffffffffu;
+    for (;;)
+    {
+        if ((int32_t)cur >= 0)
+        {
+            const float* np = nodes + 32u * (size_t)cur;
+            uint32_t ref[4];
+            memcpy(ref, np + 24, sizeof ref);
+            float tn[4];
+            int hit[4];
+            (*visits)++;
+            slab4(np, o, inv, kappa, best_t, any_t, tn, hit);
+            float nt = INFINITY;
+            uint32_t nref = NONE;
+            int nslot = -1;
+            for (int c = 0; c < 4; c++)
+                if (hit[c] && (nslot < 0 || tn[c] < nt)) { nt = tn[c]; nref = ref[c]; nslot = c; }
+#ifdef BVH_REPLAY_SORTED_PUSH /* experiment: push the other children farthest first, so that they pop nearest first */
+            {
+                int ord[4] = { 0, 1, 2, 3 };
+                for (int i = 0; i < 4; i++)
+                    for (int j = i + 1; j < 4; j++)
+                        if (tn[ord[j]] > tn[ord[i]]) { const int x = ord[i]; ord[i] = ord[j]; ord[j] = x; }
+                for (int i = 0; i < 4; i++)
+                {
+                    const int c = ord[i];
+                    if (sp > STACK) return -1;
+                    stack_t[sp] = tn[c];
+                    stack_ref[sp] = ref[c];
+                    sp += (hit[c] && c != nslot) ? 1 : 0;
+                    if (sp > *max_sp) *max_sp = sp;
+                }
+            }
+#else
+            for (int c = 0; c < 4; c++)
+            {
+                if (sp > STACK) return -1;
+                stack_t[sp] = tn[c];
+                stack_ref[sp] = ref[c];
+                sp += (hit[c] && c != nslot) ? 1 : 0;
+                if (sp > *max_sp) *max_sp = sp;
+            }
+#endif
+            cur = nref;
+        }
+        if ((int32_t)cur < -1)
+        {
+            const float* lp = leaves + 20u * (size_t)(cur & 0x7fffffffu);
+            int32_t idx[4];
+            memcpy(idx, lp + 16, sizeof idx);
+            (*leaf_visits)++;
+            for (int k = 0; k < 4; k++)
+            {
+                const float* A = lp + 8 * (k >> 1);
+                const float* B = A + 4;
+                const int s = k & 1;
+                const float e[3] = { A[s] - o[0], A[2 + s] - o[1], B[s] - o[2] };
+                const float r2 = B[2 + s];
+                const float e2 = dot3(e, e), a = dot3(e, d);
+                const float disc = r2 - fmaf(-a, a, e2);
+                if (disc < 0.0f) continue;
+                const float f = sqrtf(disc);
+                const float t = (e2 < r2) ? a + f : a - f;
+                if ((any_t || !(t < 0.001f)) && (t < best_t || (t == best_t && idx[k] < best_i)))
+                {
+                    best_t = t;
+                    best_i = idx[k];
+                }
+            }
+            cur = NONE;
+        }
+        if (cur == NONE)
+        {
+            int found = 0;
+            while (sp > 0)
+            {
+                sp--;
+                if (stack_t[sp] <= best_t) { cur = stack_ref[sp]; found = 1; break; }
+            }
+            if (!found) break;
+        }
+    }
+    *t_out = best_t;
+    *i_out = best_i == 0x7fffffff ? -1 : best_i;
+    return 1;
+}
+
 /* n rays; hit[i] = 1 / 0, prim, t as the scan reports them (t = -1 on a miss), skipped[i] = 1 where the kernel would scan instead.
  * Returns the deepest stack use, or -1 on overflow. */
 int bvh_replay_batch(const float* nodes, const float* leaves, const float* o, const float* d, uint32_t n, uint8_t* hit, uint32_t* prim, float* t,
@@ -132,8 +263,13 @@ int bvh_replay_batch(const float* nodes, const float* leaves, const float* o, co
     {
         float tt = 0.0f;
         int32_t ii = -1;
+#ifdef BVH_REPLAY_TRAV2 /* the path tracer's default traversal; the preview renderer (any_t) uses the first one */
+        const int rc = bvh_replay_ray2(nodes, leaves, o + 3 * (size_t)i, d + 3 * (size_t)i, any_t, INFINITY, any_t ? -1 : 0x7fffffff, &tt, &ii,
+                                       &counters[0], &counters[1], &max_sp);
+#else
         const int rc = bvh_replay_ray(nodes, leaves, o + 3 * (size_t)i, d + 3 * (size_t)i, any_t, INFINITY, any_t ? -1 : 0x7fffffff, &tt, &ii,
                                       &counters[0], &counters[1], &max_sp);
+#endif
         if (rc < 0) return -1;
         skipped[i] = rc == 0;
         hit[i] = rc == 1 && ii >= 0;

@@ -24,7 +24,11 @@ def configs():
         "c3s": (c3, dict(width=1920, height=1080, spp=16, depth=50, mode=nat.MODE_SM)),  # short C3 for profiling
         "c4": (None, dict(width=3840, height=2160, spp=64, depth=10, mode=nat.MODE_SM)),
         "c4s": (None, dict(width=3840, height=2160, spp=4, depth=10, mode=nat.MODE_SM)),
+        # profiling sizes that take the default BVH path (lanes share a pixel's samples: from 16 samples per call, 16 lanes from 32)
+        "c3p": (c3, dict(width=1920, height=1080, spp=32, depth=50, mode=nat.MODE_SM)),
+        "c4p": (None, dict(width=1920, height=1080, spp=32, depth=10, mode=nat.MODE_SM)),
         "c5slice": (c3, dict(width=3840, height=2160, spp=4096, depth=50, mode=nat.MODE_SM, sample_range=(0, 64))),
+        "c5n8": (c3, dict(width=3840, height=2160, spp=4096, depth=50, mode=nat.MODE_SM, sample_range=(0, 512))),  # one GPU's share at N = 8
     }
 
 

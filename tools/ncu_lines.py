@@ -27,6 +27,7 @@ hdr = rows[hdr_i]; ci = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[hdr_i + 1:] if len(r) >= len(hdr) and r[0].startswith("0x")]
 base = int(data[0][0], 16)
 execd = {int(r[0], 16) - base: (int(r[ci["Instructions Executed"]]), int(r[ci["# Samples"]]), r[ci["Source"]].strip()) for r in data}
+threads = {int(r[0], 16) - base: int(r[ci["Thread Instructions Executed"]]) for r in data} if "Thread Instructions Executed" in ci else {}
 
 # ---- line info per offset from nvdisasm
 lines = open(dis_txt).read().split("\n")
@@ -75,7 +76,7 @@ def func_of(path, line):
             break
     return name
 
-agg = collections.Counter(); samp = collections.Counter()
+agg = collections.Counter(); samp = collections.Counter(); thr = collections.Counter()
 total = 0; tsamp = 0
 for off, (n, s, sass) in execd.items():
     loc = info.get(off)
@@ -85,7 +86,7 @@ for off, (n, s, sass) in execd.items():
         path, line = loc
         short = path.split("/")[-1]
         key = f"{short}:{line}" if by_line else f"{short}:{func_of(path, line)}"
-    agg[key] += n; samp[key] += s; total += n; tsamp += s
-print(f"total warp instructions {total}, stall samples {tsamp}")
+    agg[key] += n; samp[key] += s; total += n; tsamp += s; thr[key] += threads.get(off, 0)
+print(f"total warp instructions {total}, stall samples {tsamp}, active lanes per warp instruction {sum(thr.values()) / max(1, total):.2f}")
 for k, n in agg.most_common(45 if by_line else 30):
-    print(f"  {k:45s} {n:13d} {n / total:6.1%}   samples {samp[k] / max(1, tsamp):6.1%}")
+    print(f"  {k:45s} {n:13d} {n / total:6.1%}   samples {samp[k] / max(1, tsamp):6.1%}   lanes {thr[k] / max(1, n):5.1f}")
