@@ -72,6 +72,7 @@ class Oracle:
         L.rtref_u01.argtypes = [u32]
         L.rtref_intersect_batch.argtypes = [C.POINTER(SceneDesc), p, p, u32, p, p, p, p]
         L.rtref_primary_ray.argtypes = [C.POINTER(View), u32, u32, u32, p, p]
+        L.rtref_screen_ray.argtypes = [C.POINTER(View), C.c_float, C.c_float, p, p]
         L.rtref_scatter.argtypes = [C.POINTER(SceneDesc), u32, u32, p, p, C.c_float, p, u64, u32, u32, u32, p, p, p]
         L.rtref_pack_pixel.restype = u32
         L.rtref_pack_pixel.argtypes = [C.c_float, C.c_float, C.c_float, u32]
@@ -129,6 +130,17 @@ class Oracle:
         oo = (C.c_float * 3)(); dd = (C.c_float * 3)()
         for i in range(n):
             self.lib.rtref_primary_ray(C.byref(v), int(px[i]), int(py[i]), int(sample[i]), oo, dd)
+            o[i] = list(oo); d[i] = list(dd)
+        return o, d
+
+    def screen_rays(self, view, sx, sy):
+        """primary rays through explicit screen positions (pixel corners, edges, ...)"""
+        v = self.view_from(view)
+        n = len(sx)
+        o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32)
+        oo = (C.c_float * 3)(); dd = (C.c_float * 3)()
+        for i in range(n):
+            self.lib.rtref_screen_ray(C.byref(v), float(sx[i]), float(sy[i]), oo, dd)
             o[i] = list(oo); d[i] = list(dd)
         return o, d
 

@@ -457,6 +457,17 @@ void rtref_primary_ray(const rtref_view* v, uint32_t px, uint32_t py, uint32_t s
     d[0] = r.d.x; d[1] = r.d.y; d[2] = r.d.z;
 }
 
+/* the primary ray through an explicit screen position (what primary_ray computes once the jitter is known): lets a test place
+ * rays on a pixel's corners and edges */
+void rtref_screen_ray(const rtref_view* v, float sx, float sy, float o[3], float d[3])
+{
+    const v3 near_p = screen_to_world(v, sx, sy, 0.0f);
+    const v3 far_p = screen_to_world(v, sx, sy, 1.0f);
+    const v3 dir = normalize3(v3_sub(far_p, near_p));
+    o[0] = near_p.x; o[1] = near_p.y; o[2] = near_p.z;
+    d[0] = dir.x; d[1] = dir.y; d[2] = dir.z;
+}
+
 int rtref_scatter(const rtref_scene* s, uint32_t mode, uint32_t material, const float o[3], const float d[3], float t,
                   const float n[3], uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t block, float att[3],
                   float o_out[3], float d_out[3])

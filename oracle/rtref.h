@@ -81,6 +81,8 @@ int rtref_intersect_batch(const rtref_scene* s, const float* o, const float* d, 
 /* --- unit entry points for step-wise parity --------------------------------------------- */
 void rtref_primary_ray(const rtref_view* v, uint32_t px, uint32_t py, uint32_t sample,
                        float o[3], float d[3]);
+/* the same for an explicit screen position (sx, sy) instead of pixel + sample jitter */
+void rtref_screen_ray(const rtref_view* v, float sx, float sy, float o[3], float d[3]);
 /* returns 1 if scattered, 0 if absorbed; block = philox block index (segment+1) */
 int  rtref_scatter(const rtref_scene* s, uint32_t mode, uint32_t material,
                    const float o[3], const float d[3], float t, const float n[3],

@@ -247,11 +247,13 @@ inline Result build(const float* spheres, uint32_t n, Pool& pool)
         return out;
     }
 
-    // Builder experiments, both off by default ("Tree quality": measured with tools/bvh_visits.cpp, waiting
-    // for a device measurement): RTCU_BVH_SWEEP=N evaluates every split position exactly for ranges of <= N spheres instead of
-    // binning them; RTCU_BVH_LEAF_COST=1 counts a side in 4-sphere leaf blocks (ceil(n / 4)) instead of spheres.
-    uint32_t sweep_below = 0;
-    bool leaf_block_cost = false;
+    // Split rules beyond the 16-bin SAH, measured on the device in round 2 (profiles/README.md): ranges of <= sweep_below spheres
+    // evaluate every split position exactly instead of binning (a 484-sphere scene is swept whole: C3 -4 %; a large scene only at
+    // the bottom of the tree, where 64 is as good as 512 and costs no measurable build time); from 8192 spheres a side's cost counts
+    // 4-sphere leaf blocks, ceil(n / 4), instead of spheres, which packs the leaves of a dense field (C4 -2 %; +1 % on C3, hence the
+    // threshold).  RTCU_BVH_SWEEP=N and RTCU_BVH_LEAF_COST=0/1 override.
+    uint32_t sweep_below = n <= 4096u ? 512u : 64u;
+    bool leaf_block_cost = n >= 8192u;
     if (const char* e = std::getenv("RTCU_BVH_SWEEP")) sweep_below = (uint32_t)std::min(4096, std::max(0, std::atoi(e)));
     if (const char* e = std::getenv("RTCU_BVH_LEAF_COST")) leaf_block_cost = std::atoi(e) != 0;
     auto side_cost = [&](float half_area, uint32_t count) { return half_area * (float)(leaf_block_cost ? (count + MAX_LEAF - 1) / MAX_LEAF : count); };

@@ -81,8 +81,11 @@ __host__ __device__ __forceinline__ uint32_t pair_float4_count(uint32_t n_sphere
 __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_pairs, const uint32_t n_sph,
                                                   const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray& r)
 {
-    const float inf = __int_as_float(0x7f800000);
-    float ts = inf;
+    // "nothing found yet" is a NaN: `!(best <= t)` then accepts the first candidate whatever its distance -- +inf included, which
+    // the reference's `have && hit_dist <= t` (mg_ray_tracer.cpp:74) accepts too (a sphere whose r * r overflows) -- and the final
+    // `distance >= 0` test reads it as a miss
+    const float none = __int_as_float(0x7fc00000);
+    float ts = none;
     int is = -1;
     // software pipeline: the next pair is loaded (warp-uniform LDS.128 x2) before the current one is tested, so the
     // shared-memory latency hides behind ~20 arithmetic instructions.  The array ends with never-hit pairs (r2 = -inf),
@@ -106,7 +109,7 @@ __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_p
     h.prim = ts >= 0.0f ? (uint32_t)is : RTCU_PRIM_MISS;
     if (n_pl)
     {
-        float tp = inf;
+        float tp = none;
         int ip = -1;
         for (uint32_t i = 0; i < n_pl; i++)
             plane_test(s_pl[i], (int)i, r, tp, ip);
@@ -524,7 +527,7 @@ __device__ __forceinline__ void beam_closest_sphere(const SceneDev& sc, const Be
 // have no planes) and the scan that non-unit or far-away rays fall back to.
 __device__ __noinline__ void closest_plane_cold(const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray& r, float& tp, int& ip)
 {
-    tp = __int_as_float(0x7f800000);
+    tp = __int_as_float(0x7fc00000); // NaN = nothing found yet, see closest_hit_linear
     ip = -1;
     for (uint32_t i = 0; i < n_pl; i++)
         plane_test(s_pl[i], (int)i, r, tp, ip);

@@ -442,7 +442,7 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
     p.straggler_count = ctx->straggler_count.p;
     CU(cudaMemsetAsync(ctx->straggler_count.p, 0, sizeof(unsigned int), st));
 
-    CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), st));
     ctx->stats.accel = use_bvh ? RTCU_ACCEL_BVH : RTCU_ACCEL_LINEAR;
     ctx->stats.samples = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0) * (v->sample_end - v->sample_begin);
     if (pipe == RTCU_PIPE_WAVEFRONT)
@@ -798,13 +798,13 @@ void pack_bvh4(const rtcu_bvh::Result& bvh, const std::vector<float4>& sph, std:
     wide[0].depth = 1;
     uint32_t n_leaves = 0;
     depth4 = 0;
-    // Which binary nodes fold into a 4-wide node.  Default: greedy -- replace the inner child of largest area by its two children
-    // until four slots are filled.  RTCU_BVH_COLLAPSE=sah (experiment, off by default; DESIGN.md section 8, "Tree quality"): the
-    // collapse of least SAH cost by dynamic programming (after Ylitie et al. 2017) -- C(e, i) = cheapest way to cover the subtree
-    // of child entry e with at most i slots of its parent's wide node: as one wide node of its own (i = 1: area x node cost + the
-    // best distribution of ITS four slots over its two children), or dissolved into the parent (its children share the i slots).
+    // Which binary nodes fold into a 4-wide node: the collapse of least SAH cost by dynamic programming (after Ylitie et al. 2017) --
+    // C(e, i) = cheapest way to cover the subtree of child entry e with at most i slots of its parent's wide node: as one wide node
+    // of its own (i = 1: area x node cost + the best distribution of ITS four slots over its two children), or dissolved into the
+    // parent (its children share the i slots).  Measured against the greedy rule (replace the inner child of largest area by its two
+    // children until four slots are filled; RTCU_BVH_COLLAPSE=greedy): C4 28 % fewer nodes, 95.8 -> 92.8 ms; C3 41.2 -> 41.0 ms.
     const char* collapse_env = getenv("RTCU_BVH_COLLAPSE");
-    const bool sah_collapse = collapse_env && strcmp(collapse_env, "sah") == 0;
+    const bool sah_collapse = !(collapse_env && strcmp(collapse_env, "greedy") == 0);
     const size_t n_binary = bvh.nodes.size();
     std::vector<float> cost_entry, cost_split; // C[(2 * node + side) * 5 + i], D[node * 5 + j]
     std::vector<uint8_t> split_left;           // slots given to the left child by the best distribution D[node][j]
@@ -1112,7 +1112,7 @@ rtcu_ctx* rtcu_create(int device)
         ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_launch, cudaEventDisableTiming) == cudaSuccess;
     ctx->knobs.load();
-    ok = ok && ctx->counters.reserve(4) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess && ctx->straggler_count.reserve(1) == cudaSuccess;
+    ok = ok && ctx->counters.reserve(8) == cudaSuccess && ctx->h_counters.reserve(4) == cudaSuccess && ctx->straggler_count.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_render_mega<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess
          && cudaFuncSetAttribute(k_render_mega<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_wf_intersect<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_STAGE_BYTES) == cudaSuccess
@@ -1571,7 +1571,7 @@ int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* vi
             if (rc) return rc;
         }
         else
-            CU(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream)); // not the counters of an earlier frame
+            CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream)); // not the counters of an earlier frame
         CU(cudaEventRecord(c->ev[3], c->stream));
     }
     // root waits for every peer, then sums their buffers through peer loads inside the resolve kernel
@@ -1763,7 +1763,7 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
     CU(cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     const unsigned blocks = (unsigned)((n + 255) / 256 < (uint32_t)ctx->sm_count * 8 ? (n + 255) / 256 : ctx->sm_count * 8);
     const size_t sb = stage_bytes(ctx);
-    CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), st));
     CU(cudaEventRecord(ctx->ev[0], st));
     if (use_bvh && ctx->knobs.bvh_trav == 0)
         k_intersect_batch<false, true, 0><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);

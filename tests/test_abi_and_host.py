@@ -195,8 +195,10 @@ def test_bvh_builder_invariants(lib, n):
 
 # ---- the 4-wide device tree (collapsed on upload), built on the host: same invariants in the device layout ---------
 @pytest.mark.parametrize("knobs", [{}, {"RTCU_BVH_SWEEP": "512"}, {"RTCU_BVH_LEAF_COST": "1"}, {"RTCU_BVH_SWEEP": "64", "RTCU_BVH_LEAF_COST": "1"},
-                                   {"RTCU_BVH_COLLAPSE": "sah"}, {"RTCU_BVH_COLLAPSE": "sah", "RTCU_BVH_LEAF_COST": "1"}],
-                         ids=["default", "sweep", "leafcost", "sweep+leafcost", "sah-collapse", "sah-collapse+leafcost"])
+                                   {"RTCU_BVH_COLLAPSE": "sah"}, {"RTCU_BVH_COLLAPSE": "sah", "RTCU_BVH_LEAF_COST": "1"},
+                                   {"RTCU_BVH_SWEEP": "0", "RTCU_BVH_LEAF_COST": "0", "RTCU_BVH_COLLAPSE": "greedy"},  # round 1's tree
+                                   {"RTCU_BVH_SWEEP": "0", "RTCU_BVH_LEAF_COST": "0"}, {"RTCU_BVH_COLLAPSE": "greedy"}],
+                         ids=["default", "sweep", "leafcost", "sweep+leafcost", "sah-collapse", "sah-collapse+leafcost", "binned-greedy", "binned", "greedy"])
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 9, 33, 484, 5000, 100001])
 def test_bvh4_device_tree_invariants(lib, n, knobs, monkeypatch):
     """every tree the builder can produce -- the default and the experimental split / collapse rules (bvh.h: RTCU_BVH_SWEEP,
@@ -300,10 +302,10 @@ def test_bvh_build_is_independent_of_thread_count(lib, case, monkeypatch):
         centres = rng.uniform(-200, 200, (30, 3))
         sph = np.concatenate([centres[rng.integers(0, 30, 30000)] + rng.normal(0, 0.5, (30000, 3)), rng.uniform(0.01, 0.2, (30000, 1))],
                              axis=1).astype(np.float32)
-    if case in ("grid100k", "clusters30k"):  # the experimental split rules are order-independent as well
-        monkeypatch.setenv("RTCU_BVH_SWEEP", "64" if case == "grid100k" else "0")
-        monkeypatch.setenv("RTCU_BVH_LEAF_COST", "1")
-        monkeypatch.setenv("RTCU_BVH_COLLAPSE", "sah")
+    if case in ("grid100k", "clusters30k"):  # the other split / collapse rules are order-independent as well
+        monkeypatch.setenv("RTCU_BVH_SWEEP", "512" if case == "grid100k" else "0")
+        monkeypatch.setenv("RTCU_BVH_LEAF_COST", "0" if case == "grid100k" else "1")
+        monkeypatch.setenv("RTCU_BVH_COLLAPSE", "greedy")
         check_threads(sph, monkeypatch, ("8",))
         monkeypatch.delenv("RTCU_BVH_SWEEP")
         monkeypatch.delenv("RTCU_BVH_LEAF_COST")

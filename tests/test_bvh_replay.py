@@ -96,11 +96,12 @@ def cases():
             "grid9601": (synth.grid_scene(nx=120, nz=80).spheres, 24000), "grid100k": (synth.grid_scene().spheres, 4000)}
 
 
-KNOBS = [{}, {"RTCU_BVH_LEAF_COST": "1"}, {"RTCU_BVH_COLLAPSE": "sah"}, {"RTCU_BVH_SWEEP": "512", "RTCU_BVH_LEAF_COST": "1", "RTCU_BVH_COLLAPSE": "sah"}]
+KNOBS = [{}, {"RTCU_BVH_LEAF_COST": "1"}, {"RTCU_BVH_SWEEP": "0", "RTCU_BVH_LEAF_COST": "0", "RTCU_BVH_COLLAPSE": "greedy"},
+         {"RTCU_BVH_SWEEP": "512", "RTCU_BVH_LEAF_COST": "1", "RTCU_BVH_COLLAPSE": "sah"}]
 
 
 @pytest.mark.parametrize("trav", [2, 1], ids=["deferred-leaves", "leaves-in-visit"])
-@pytest.mark.parametrize("knobs", KNOBS, ids=["default", "leafcost", "sah-collapse", "sweep+leafcost+sah-collapse"])
+@pytest.mark.parametrize("knobs", KNOBS, ids=["default", "leafcost", "binned-greedy", "sweep+leafcost+sah-collapse"])
 @pytest.mark.parametrize("name", ["rtiow", "cloud", "nested", "grid9601", "grid100k"])
 def test_replayed_traversal_equals_the_oracle_scan(replay, replay2, oracle, name, knobs, trav, monkeypatch):
     if knobs and name == "grid100k":
@@ -171,3 +172,117 @@ def test_the_rays_need_the_margins(tmp_path_factory, oracle, trav_define):
     ref_hit, ref_prim, _, _ = oracle.intersect_batch(scene_of(sph), o, d)
     wrong = int((hit != ref_hit).sum() + ((prim != ref_prim) & (hit == 1) & (ref_hit == 1)).sum())
     assert 0 < wrong < 200, wrong
+
+
+# ---- pixel beams ----------------------------------------------------------------------------------------------------------------
+def build_beam_replay(tmp_path_factory, *defines):
+    so = tmp_path_factory.mktemp("bvh_beam") / "libbvh_beam.so"
+    subprocess.run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fno-fast-math", "-ffp-contract=off", "-mfma", *defines, "-o", str(so),
+                    str(ROOT / "tests" / "tools" / "bvh_replay.c"), "-lm"], check=True)
+    lib = C.CDLL(str(so))
+    lib.bvh_replay_beam_collect.restype = C.c_int
+    lib.bvh_replay_beam_collect.argtypes = [C.c_void_p] * 4
+    lib.bvh_replay_beam_closest.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_uint32] + [C.c_void_p] * 4
+    return lib
+
+
+def beam_pixel_rays(oracle, view, px, py, rng, n_random):
+    """screen positions of one pixel: centre, the four corners (the far ones are the closed end of the jitter range), points on the
+    edges, the largest jitter a sample can draw (1 - 2^-24), random jitters; and the primary rays through them"""
+    top = np.float32(1.0) - np.float32(2.0) ** -24
+    offs = [(0.5, 0.5), (0, 0), (1, 0), (0, 1), (1, 1), (top, top), (0, top), (top, 0), (0.5, 0), (0, 0.5), (top, 0.5), (0.5, top)]
+    offs += [tuple(x) for x in rng.random((n_random, 2)).astype(np.float32)]
+    sx = np.float32(px) + np.array([a for a, _ in offs], np.float32)
+    sy = np.float32(py) + np.array([b for _, b in offs], np.float32)
+    return oracle.screen_rays(view, sx, sy)
+
+
+def beam_cases():
+    from rt_b200.scene import Camera
+
+    rtiow, grid = synth.rtiow_scene(), synth.grid_scene(nx=120, nz=80)
+    rng = np.random.default_rng(21)
+    cloud = np.concatenate([rng.uniform(-8, 8, (900, 3)), rng.uniform(0.05, 0.7, (900, 1))], axis=1).astype(np.float32)
+    cloud[0] = [0, -1000, 0, 1000]
+    cloud[1] = cloud[2]  # identical spheres: the lower index wins, in a list as in a scan
+    # (spheres, camera, image size): fine pixels (the benchmark's 4K), coarse pixels (fat beams), the camera inside / between spheres
+    return {
+        "rtiow-4k": (rtiow.spheres, rtiow.camera, (3840, 2160)),
+        "rtiow-coarse": (rtiow.spheres, rtiow.camera, (160, 90)),
+        "rtiow-low": (rtiow.spheres, Camera(position=(3.0, 0.45, 2.0), direction=(-1.0, -0.05, -0.6)), (640, 360)),
+        "grid-4k": (grid.spheres, grid.camera, (3840, 2160)),
+        "cloud": (cloud, Camera(position=(0.3, 0.2, 0.1), direction=(0.2, -0.1, -1.0)), (320, 200)),
+    }
+
+
+@pytest.mark.parametrize("name", ["rtiow-4k", "rtiow-coarse", "rtiow-low", "grid-4k", "cloud"])
+def test_replayed_pixel_beams_equal_the_oracle_scan(tmp_path_factory, oracle, name):
+    """every primary ray of a pixel -- corners, edges, extreme and random jitters -- finds in the pixel's candidate list exactly what
+    the reference's scan over ALL spheres finds: hit flag, sphere index and t, bit for bit"""
+    from rt_b200.renderer import make_view
+
+    lib = build_beam_replay(tmp_path_factory)
+    sph, cam, (w, h) = beam_cases()[name]
+    sph = np.ascontiguousarray(sph, np.float32)
+    sc = scene_of(sph)
+    sc.camera = cam
+    view = make_view(sc, w, h)
+    nodes, leaves, _ = R.bvh4_build_host(sph)
+    rng = np.random.default_rng(abs(hash(name)) % 1000)
+    n_pixels = 260 if len(sph) < 2000 else 120
+    px = rng.integers(0, w, n_pixels)
+    py = np.concatenate([rng.integers(0, h, n_pixels // 2), rng.integers(h // 3, h, n_pixels - n_pixels // 2)])  # sky is boring: favour the lower rows
+    lists, tested, lengths = 0, 0, []
+    list_tn, list_leaf = np.zeros(8, np.float32), np.zeros(8, np.uint32)
+    for x, y in zip(px, py):
+        o, d = beam_pixel_rays(oracle, view, int(x), int(y), rng, 12)
+        rays5 = np.ascontiguousarray(np.concatenate([o[:5], d[:5]], axis=1).reshape(5, 2, 3), np.float32)  # centre + corners as (o, d)
+        n_list = lib.bvh_replay_beam_collect(nodes.ctypes.data, rays5.ctypes.data, list_tn.ctypes.data, list_leaf.ctypes.data)
+        if n_list < 0:
+            continue  # this pixel traverses
+        lists += 1
+        lengths.append(n_list)
+        n = len(o)
+        hit, prim, t, usable = np.zeros(n, np.uint8), np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        lib.bvh_replay_beam_closest(leaves.ctypes.data, list_tn.ctypes.data, list_leaf.ctypes.data, n_list, o.ctypes.data, d.ctypes.data, n,
+                                    hit.ctypes.data, prim.ctypes.data, t.ctypes.data, usable.ctypes.data)
+        ref_hit, ref_prim, ref_t, _ = oracle.intersect_batch(sc, o, d)
+        ok = usable.astype(bool)
+        assert ok.all()  # normalised directions are always within BEAM_EPS_D of unit length
+        assert np.array_equal(hit[ok], ref_hit[ok]), (name, int(x), int(y))
+        assert np.array_equal(prim[ok], ref_prim[ok]), (name, int(x), int(y))
+        assert np.array_equal(t[ok].view(np.uint32), ref_t[ok].view(np.uint32)), (name, int(x), int(y))
+        tested += int(ok.sum())
+    assert lists >= n_pixels // 4, (lists, n_pixels)  # the lists are used, not just declined
+    assert tested > 1000 and max(lengths) >= 2
+
+
+def test_the_beams_need_the_footprint_margins(tmp_path_factory, oracle):
+    """with the pixel-footprint terms of the margin switched off (the centre ray's own margins only), coarse pixels lose hits of
+    their corner rays: the equality above is the margins' doing"""
+    from rt_b200.renderer import make_view
+
+    lib = build_beam_replay(tmp_path_factory, "-DBVH_REPLAY_NO_BEAM_MARGIN")
+    sph, cam, _ = beam_cases()["rtiow-coarse"]
+    w, h = 64, 36  # pixels a quarter of a small sphere wide: the corner rays see spheres the centre ray passes by
+    sph = np.ascontiguousarray(sph, np.float32)
+    sc = scene_of(sph)
+    sc.camera = cam
+    view = make_view(sc, w, h)
+    nodes, leaves, _ = R.bvh4_build_host(sph)
+    rng = np.random.default_rng(4)
+    wrong = 0
+    list_tn, list_leaf = np.zeros(8, np.float32), np.zeros(8, np.uint32)
+    for x, y in zip(rng.integers(0, w, 500), rng.integers(h // 3, h, 500)):
+        o, d = beam_pixel_rays(oracle, view, int(x), int(y), rng, 4)
+        rays5 = np.ascontiguousarray(np.concatenate([o[:5], d[:5]], axis=1).reshape(5, 2, 3), np.float32)
+        n_list = lib.bvh_replay_beam_collect(nodes.ctypes.data, rays5.ctypes.data, list_tn.ctypes.data, list_leaf.ctypes.data)
+        if n_list < 0:
+            continue
+        n = len(o)
+        hit, prim, t, usable = np.zeros(n, np.uint8), np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        lib.bvh_replay_beam_closest(leaves.ctypes.data, list_tn.ctypes.data, list_leaf.ctypes.data, n_list, o.ctypes.data, d.ctypes.data, n,
+                                    hit.ctypes.data, prim.ctypes.data, t.ctypes.data, usable.ctypes.data)
+        ref_hit, ref_prim, _, _ = oracle.intersect_batch(sc, o, d)
+        wrong += int((hit != ref_hit).sum() + ((prim != ref_prim) & (hit == 1) & (ref_hit == 1)).sum())
+    assert wrong > 0

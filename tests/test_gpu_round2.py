@@ -162,7 +162,7 @@ def test_pageable_destination_is_registered_once_and_survives_a_remap(scenes, na
         if name == "c2":
             assert later < 0.05, (first, later)  # the kernels store into the image themselves: nothing follows them
         # the application frees its image and the allocator maps NEW pages at the same address: the registration is stale
-        fixed = libc.mmap(addr, nbytes, prot, flags_ | mmap.MAP_FIXED, -1, 0)
+        fixed = libc.mmap(addr, nbytes, prot, flags_ | 0x10, -1, 0)  # MAP_FIXED (Linux): replaces the mapping in place
         assert fixed == addr
         img = np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint32)), shape=(h, w))
         assert not img.any()

@@ -253,6 +253,131 @@ int bvh_replay_ray2(const float* nodes, const float* leaves, const float o[3], c
     return 1;
 }
 
+/* ---- pixel beams (kernels.cuh: beam_setup, beam_collect, beam_closest_sphere): ONE conservative walk per pixel with the centre
+ * ray, margins widened by the pixel's footprint and no closest-hit cull, collects the leaves any primary ray of the pixel could
+ * hit; a sample's primary ray then takes the (t, index) minimum over those leaves only.  rays: 5 x (o, d) = the centre ray and the
+ * rays through the pixel's four corners.  Returns the list length, or -1 when the pixel keeps the traversal (too many leaves or
+ * node visits, centre ray not unit length). */
+#define BEAM_MAX 8
+#define BEAM_MAX_VISITS 48
+#define BEAM_EPS_D (16.0f * 5.9604645e-8f)
+int bvh_replay_beam_collect(const float* nodes, const float* rays, float* list_tn, uint32_t* list_leaf)
+{
+    const float* o = rays;
+    const float* d = rays + 3;
+    float dd = 0.0f, oo = 0.0f;
+    for (int k = 1; k < 5; k++)
+    {
+        const float* ok = rays + 6 * k;
+        const float* dk = ok + 3;
+        dd = fmaxf(dd, fabsf(dk[0] - d[0]) + fabsf(dk[1] - d[1]) + fabsf(dk[2] - d[2]));
+        oo = fmaxf(oo, fabsf(ok[0] - o[0]) + fabsf(ok[1] - o[1]) + fabsf(ok[2] - o[2]));
+    }
+    const float u16 = 16.0f * 5.9604645e-8f;
+    const float sigma = 1.01f * dd + u16, rho = 1.01f * oo + u16 * (fabsf(o[0]) + fabsf(o[1]) + fabsf(o[2]) + 1.0f);
+    const float eps_d = fabsf(dot3(d, d) - 1.0f);
+    if (!(eps_d <= 1e-3f) || !(eps_d <= BEAM_EPS_D)) return -1;
+    if (!(fabsf(o[0]) <= 0x1p62f && fabsf(o[1]) <= 0x1p62f && fabsf(o[2]) <= 0x1p62f)) return -1;
+#ifdef BVH_REPLAY_NO_BEAM_MARGIN /* what the footprint terms are for: the centre ray's own margins lose hits of the pixel's other rays */
+    const float kappa = 1.01f * (1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * BEAM_EPS_D)), madd = 0.0f;
+    (void)sigma; (void)rho;
+#else
+    const float kappa = 1.01f * (1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * BEAM_EPS_D) + 2.01f * sigma), madd = 2.02f * rho;
+#endif
+    const float inv[3] = { 1.0f / d[0], 1.0f / d[1], 1.0f / d[2] };
+    uint32_t stack[STACK];
+    int sp = 0, n = 0, visits = 0;
+    uint32_t node = 0;
+    for (;;)
+    {
+        if (++visits > BEAM_MAX_VISITS) return -1;
+        const float* np = nodes + 32u * (size_t)node;
+        uint32_t ref[4];
+        memcpy(ref, np + 24, sizeof ref);
+        const float* H = np + 28;
+        for (int c = 0; c < 4; c++)
+        {
+            const int pair = c >> 1, slot = c & 1;
+            const float* ax = np + 12 * pair;
+            float dc[3];
+            for (int k = 0; k < 3; k++) dc[k] = ax[4 * k + slot] - o[k];
+            const float e3 = fabsf(dc[0]) + fabsf(dc[1]) + fabsf(dc[2]);
+            const float m = fmaf(e3 + H[c], kappa, madd);
+            float near = -INFINITY, far = INFINITY;
+            for (int k = 0; k < 3; k++)
+            {
+                const float h = ax[4 * k + 2 + slot] + m, a = fabsf(inv[k]), tc = dc[k] * inv[k];
+                near = fmaxf(near, fmaf(-h, a, tc));
+                far = fminf(far, fmaf(h, a, tc));
+            }
+            if (!(far >= fmaxf(near, 0.0f))) continue; /* no closest-hit cull: best_t stays +inf */
+            if (ref[c] & 0x80000000u)
+            {
+                if (n == BEAM_MAX) return -1;
+                int k = n++;
+                for (; k > 0 && list_tn[k - 1] > near; k--)
+                {
+                    list_tn[k] = list_tn[k - 1];
+                    list_leaf[k] = list_leaf[k - 1];
+                }
+                list_tn[k] = near;
+                list_leaf[k] = ref[c] & 0x7fffffffu;
+            }
+            else
+            {
+                if (sp >= STACK) return -1;
+                stack[sp++] = ref[c];
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return n;
+}
+
+/* closest hit of n rays of the pixel over the listed leaves; usable[i] = 0 where the kernel would traverse instead (the ray is not
+ * unit length to within BEAM_EPS_D) */
+void bvh_replay_beam_closest(const float* leaves, const float* list_tn, const uint32_t* list_leaf, int n_list, const float* o, const float* d,
+                             uint32_t n, uint8_t* hit, uint32_t* prim, float* t, uint8_t* usable)
+{
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const float* oi = o + 3 * (size_t)i;
+        const float* di = d + 3 * (size_t)i;
+        usable[i] = fabsf(dot3(di, di) - 1.0f) <= BEAM_EPS_D;
+        float best_t = INFINITY;
+        int32_t best_i = 0x7fffffff;
+        for (int k = 0; k < n_list; k++)
+        {
+            if (list_tn[k] > best_t) break;
+            const float* lp = leaves + 20u * (size_t)list_leaf[k];
+            int32_t idx[4];
+            memcpy(idx, lp + 16, sizeof idx);
+            for (int q = 0; q < 4; q++)
+            {
+                const float* A = lp + 8 * (q >> 1);
+                const float* B = A + 4;
+                const int s = q & 1;
+                const float e[3] = { A[s] - oi[0], A[2 + s] - oi[1], B[s] - oi[2] };
+                const float r2 = B[2 + s];
+                const float e2 = dot3(e, e), a = dot3(e, di);
+                const float disc = r2 - fmaf(-a, a, e2);
+                if (disc < 0.0f) continue;
+                const float f = sqrtf(disc);
+                const float tt = (e2 < r2) ? a + f : a - f;
+                if (!(tt < 0.001f) && (tt < best_t || (tt == best_t && idx[q] < best_i)))
+                {
+                    best_t = tt;
+                    best_i = idx[q];
+                }
+            }
+        }
+        hit[i] = best_i != 0x7fffffff;
+        prim[i] = hit[i] ? (uint32_t)best_i : 0xffffffffu;
+        t[i] = hit[i] ? best_t : -1.0f;
+    }
+}
+
 /* n rays; hit[i] = 1 / 0, prim, t as the scan reports them (t = -1 on a miss), skipped[i] = 1 where the kernel would scan instead.
  * Returns the deepest stack use, or -1 on overflow. */
 int bvh_replay_batch(const float* nodes, const float* leaves, const float* o, const float* d, uint32_t n, uint8_t* hit, uint32_t* prim, float* t,
