@@ -56,6 +56,13 @@ enum {
     RTCU_PIPE_WAVEFRONT = 2 << 4   /* generate / intersect / shade / compact over HBM queues  */
 };
 
+/* bit 8 of rtcu_view.flags, rtcu_render only: progressive refinement.  The call's samples [sample_begin, sample_end) are ADDED to
+ * the fp32 sums the context keeps on the device from its previous rtcu_render calls of the same image size, and rgba8_out is
+ * resolved over samples_per_pixel (pass the total so far).  Because sample indices are global under the counter-based RNG, k
+ * calls of n samples equal one call of k n samples up to fp32 summation order.  The sums never leave the device unless
+ * accum_out / rtcu_accum_download asks for them. */
+#define RTCU_FLAG_ACCUMULATE 0x100u
+
 /* primitive ids reported by rtcu_intersect_batch / rtcu_rasterize: a sphere index, or one of these */
 #define RTCU_PRIM_MISS  0xFFFFFFFFu
 #define RTCU_PRIM_PLANE 0x80000000u /* | plane index */
@@ -160,6 +167,11 @@ int rtcu_upload_scene_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_sc
  *   and then written by the kernels (zero-copy) or by one DMA; each frame is verified to have landed in the caller's pages, so a
  *   buffer that was freed and re-allocated at the same address costs one staged frame, never a wrong image. */
 int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out);
+
+/* the fp32 sums {sum_r, sum_g, sum_b, n} the context holds from its last rtcu_render (width*height*4 floats): read them back
+ * (checkpoint of a progressive render) or replace them (resume; the next RTCU_FLAG_ACCUMULATE call adds onto them) */
+int rtcu_accum_download(rtcu_ctx* ctx, uint32_t width, uint32_t height, float* accum_out);
+int rtcu_accum_upload(rtcu_ctx* ctx, uint32_t width, uint32_t height, const float* accum_in);
 
 /* ---- preview: replaces rasterizer::render (reference src/renderers/rasterizer.cpp:22-88): one ray per pixel through the
  * pixel centre, nearest of planes, boxes, spheres (strict '<' in that order, no minimum distance), N.L shading against

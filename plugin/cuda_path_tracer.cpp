@@ -16,6 +16,10 @@
 //  * every B200 of the box is used (RT_CUDA_DEVICES=n caps it): a frame with at least 16 samples per pixel and device is split
 //    by sample range over the devices (rtcu_render_multi: one context per device, the fp32 sums added over NVLink inside the
 //    resolve kernel of device 0); smaller frames, and boxes without peer access, render on device 0.
+//  * RT_CUDA_PROGRESSIVE=1: a frame whose scene, camera, size and sampling equal the previous frame's is not traced again from
+//    sample 0 but REFINED -- the next samples_per_pixel samples are added to the fp32 sums the library keeps on the device and
+//    the image is resolved over all samples so far (RTCU_FLAG_ACCUMULATE).  Off by default: the reference's app renders only
+//    when something changed (window.cpp:213-217), and a drop-in must return the same image for the same call.
 //  * image_view memory is pageable (image.cpp:9-13): the library page-locks it once per (pointer, size) and writes later
 //    frames into it directly (rtcu.h, rtcu_render), so no staging copy follows the kernels.
 #ifdef RTCU_PLUGIN_STUB_CHECK
@@ -58,6 +62,7 @@ namespace
 		std::vector<uint32_t> sphere_mat_, plane_mat_, box_mat_;
 		std::vector<rtcu_material> materials_;
 		bool uploaded_ = false;
+		uint32_t scene_uploads_ = 0, uploads_seen_ = 0; // counts scene changes (a progressive render restarts on one)
 
 		explicit cuda_renderer(const char* name, bool all_devices = false)
 		{
@@ -137,6 +142,7 @@ namespace
 			desc.n_boxes		 = static_cast<uint32_t>(box_mat_.size());
 			// validated and built (BVH) once, copied to every device in use
 			uploaded_ = rtcu_upload_scene_multi(ctxs_.data(), static_cast<uint32_t>(ctxs_.size()), &desc) == RTCU_OK;
+			scene_uploads_++;
 			return uploaded_;
 		}
 
@@ -167,11 +173,16 @@ namespace
 	struct cuda_path_tracer final : cuda_renderer
 	{
 		uint32_t material_mode_ = RTCU_MODE_SM;
+		bool progressive_		= false;
+		rtcu_view last_view_{}; // the frame the sums on the device belong to
+		uint32_t samples_done_ = 0;
 
 		cuda_path_tracer() : cuda_renderer{ "cuda_path_tracer", true }
 		{
 			if (const char* mode = std::getenv("RT_CUDA_MATERIAL_MODE"); mode && std::strcmp(mode, "mg") == 0)
 				material_mode_ = RTCU_MODE_MG;
+			if (const char* prog = std::getenv("RT_CUDA_PROGRESSIVE"); prog && prog[0] == '1')
+				progressive_ = true;
 		}
 
 		void render(const rt::scene& scene, image_view& pixels, muu::thread_pool& /*threads*/) noexcept override
@@ -181,8 +192,33 @@ namespace
 				std::fprintf(stderr, "cuda_path_tracer: %s\n", rtcu_last_error());
 				return;
 			}
-			rtcu_view v		= make_view(scene, pixels);
-			v.material_mode = material_mode_;
+			const bool scene_changed = scene_uploads_ != uploads_seen_;
+			uploads_seen_			 = scene_uploads_;
+			rtcu_view v				 = make_view(scene, pixels);
+			v.material_mode			 = material_mode_;
+
+			if (progressive_)
+			{
+				// the same scene through the same view as the sums on the device: add the next samples instead of starting over
+				const bool same = !scene_changed && samples_done_ > 0 && std::memcmp(&v, &last_view_, sizeof v) == 0;
+				last_view_ = v;
+				if (!same)
+					samples_done_ = 0;
+				v.sample_begin		= samples_done_;
+				v.sample_end		= samples_done_ + scene.samples_per_pixel;
+				v.samples_per_pixel = v.sample_end;
+				if (same)
+					v.flags |= RTCU_FLAG_ACCUMULATE;
+				if (rtcu_render(ctx_, &v, pixels.data(), nullptr) != RTCU_OK)
+				{
+					std::fprintf(stderr, "cuda_path_tracer: %s\n", rtcu_last_error());
+					samples_done_ = 0;
+					return;
+				}
+				samples_done_ = v.sample_end;
+				rtcu_get_stats(ctx_, &g_last_stats);
+				return;
+			}
 
 			// sample-range split over the devices while every device keeps at least 16 samples per pixel (below that the
 			// per-device kernels are too short to pay for the exchange)

@@ -18,6 +18,7 @@ RTCU_OK, RTCU_ERR_INVALID, RTCU_ERR_CUDA, RTCU_ERR_STATE, RTCU_ERR_NOMEM = 0, -1
 MODE_MG, MODE_SM = 0, 1
 ACCEL_AUTO, ACCEL_LINEAR, ACCEL_BVH = 0, 1, 2
 PIPE_AUTO, PIPE_MEGAKERNEL, PIPE_WAVEFRONT = 0 << 4, 1 << 4, 2 << 4
+FLAG_ACCUMULATE = 0x100
 PRIM_MISS, PRIM_PLANE, PRIM_BOX = 0xFFFFFFFF, 0x80000000, 0x40000000
 
 # every symbol include/rtcu.h declares (tests check the .so exports exactly these)
@@ -28,6 +29,7 @@ EXPORTS = (
     "rtcu_rasterize", "rtcu_rasterize_device", "rtcu_selftest_math",
     "rtcu_ipc_alloc", "rtcu_ipc_open", "rtcu_ipc_release", "rtcu_reduce_resolve_rows", "rtcu_bvh4_build_host",
     "rtcu_reload_env", "rtcu_upload_scene_multi", "rtcu_exchange_reduce_resolve", "rtcu_exchange_check",
+    "rtcu_accum_download", "rtcu_accum_upload",
 )
 
 
@@ -118,6 +120,8 @@ def load_library() -> C.CDLL:
         "rtcu_upload_scene_multi": (i, [C.POINTER(p), u32, C.POINTER(SceneDesc)]),
         "rtcu_exchange_reduce_resolve": (i, [p, C.POINTER(p), C.POINTER(p), u32, u32, u32, u32, u32, u32, u32, u32, p, p]),
         "rtcu_exchange_check": (i, [p, p, p]),
+        "rtcu_accum_download": (i, [p, u32, u32, p]),
+        "rtcu_accum_upload": (i, [p, u32, u32, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -1182,8 +1182,8 @@ __global__ void __launch_bounds__(256) k_exchange_reduce_resolve(const PeerList 
     }
     if (threadIdx.x < (unsigned)bufs.n && !wait_epoch(&mine->ready[threadIdx.x], epoch, timeout)) atomicExch(&mine->error, 1u);
     __syncthreads();
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < count)
+    // (a grid of a few CTAs per SM striding over the band: the handshake, the fence and the completion count are per CTA)
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
     {
         const uint32_t i = first + k;
         float4 a = bufs.ptr[0][i];
@@ -1194,8 +1194,9 @@ __global__ void __launch_bounds__(256) k_exchange_reduce_resolve(const PeerList 
         }
         rgba8[i] = pack_pixel(a.x, a.y, a.z, spp);
     }
-    __threadfence_system(); // the pixel stores (peer stores when the image lives on another GPU) before the completion count
     __syncthreads();
+    if (threadIdx.x == 0)
+        __threadfence_system(); // cumulative: the CTA's pixel stores (peer stores when the image lives on another GPU) before the count
     if (threadIdx.x == 0 && atomicAdd(&mine->finished, 1u) == gridDim.x - 1u)
     {
         __threadfence_system();

@@ -198,6 +198,7 @@ struct rtcu_ctx {
     bool have_scene = false;
 
     // frame buffers owned by the host entry points
+    uint32_t accum_w = 0, accum_h = 0; // image size of the sums in `accum` (RTCU_FLAG_ACCUMULATE adds onto them)
     DevBuf<float4> accum;
     DevBuf<uint32_t> rgba8;
     PinnedBuf<uint32_t> h_rgba8;
@@ -1459,8 +1460,14 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     CU(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)view->width * view->height;
     if (npix == 0) return fail(RTCU_ERR_INVALID, "empty image");
+    // progressive refinement: this call's samples are added to the sums of the previous calls, which stay on the device
+    const int accumulate = (view->flags & RTCU_FLAG_ACCUMULATE) ? 1 : 0;
+    if (accumulate && (ctx->accum_w != view->width || ctx->accum_h != view->height || !ctx->accum.p))
+        return fail(RTCU_ERR_STATE, "RTCU_FLAG_ACCUMULATE: the context holds no sums of a %ux%u image", view->width, view->height);
     CU(ctx->accum.reserve(npix));
     CU(ctx->rgba8.reserve(npix));
+    ctx->accum_w = view->width;
+    ctx->accum_h = view->height;
     const bool full = view->tile_x0 == 0 && view->tile_y0 == 0 && view->tile_x1 == view->width && view->tile_y1 == view->height;
 
     // Zero-copy output: when the caller's image is pinned / registered host memory and the whole frame is rendered, the
@@ -1482,7 +1489,7 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     }
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int rc = launch_render(ctx, view, ctx->accum.p, d_out, 0, ctx->stream);
+    int rc = launch_render(ctx, view, ctx->accum.p, d_out, accumulate, ctx->stream);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 
@@ -1545,6 +1552,30 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     return RTCU_OK;
 }
 
+int rtcu_accum_download(rtcu_ctx* ctx, uint32_t width, uint32_t height, float* accum_out)
+{
+    if (!ctx || !accum_out) return fail(RTCU_ERR_INVALID, "null argument");
+    if (!ctx->accum.p || ctx->accum_w != width || ctx->accum_h != height || !width || !height)
+        return fail(RTCU_ERR_STATE, "the context holds no sums of a %ux%u image", width, height);
+    CU(cudaSetDevice(ctx->device));
+    return copy_out(ctx, accum_out, reinterpret_cast<const float*>(ctx->accum.p), (size_t)width * height * 4, ctx->h_accum);
+}
+
+int rtcu_accum_upload(rtcu_ctx* ctx, uint32_t width, uint32_t height, const float* accum_in)
+{
+    if (!ctx || !accum_in || !width || !height) return fail(RTCU_ERR_INVALID, "bad argument");
+    if ((uint64_t)width * height > 0xFFFFFFFFull) return fail(RTCU_ERR_INVALID, "image too large");
+    CU(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)width * height;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(ctx->accum.reserve(npix));
+    CU(cudaMemcpyAsync(ctx->accum.p, accum_in, npix * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->accum_w = width;
+    ctx->accum_h = height;
+    return RTCU_OK;
+}
+
 int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out)
 {
     if (!ctxs || n_ctx == 0 || n_ctx > 8 || !view) return fail(RTCU_ERR_INVALID, "bad argument");
@@ -1558,6 +1589,8 @@ int rtcu_render_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_view* vi
         if (!c) return fail(RTCU_ERR_INVALID, "null context %u", g);
         CU(cudaSetDevice(c->device));
         CU(c->accum.reserve(npix));
+        c->accum_w = view->width;
+        c->accum_h = view->height;
         CU(cudaMemsetAsync(c->accum.p, 0, npix * sizeof(float4), c->stream)); // pixels outside the tile must add 0
         rtcu_view v = *view;
         v.sample_begin = s0 + (uint32_t)((uint64_t)total * g / n_ctx);
@@ -1719,7 +1752,8 @@ int rtcu_exchange_reduce_resolve(rtcu_ctx* ctx, const float* const* d_accums, vo
     }
     CU(cudaSetDevice(ctx->device));
     const uint32_t count = width * rows;
-    const unsigned blocks = count ? (count + 255) / 256 : 1u; // a rank without rows still takes part in the handshake
+    // a rank without rows still takes part in the handshake; otherwise at most eight CTAs per SM, striding over the band
+    const unsigned blocks = count ? std::min<unsigned>((count + 255) / 256, (unsigned)ctx->sm_count * 8u) : 1u;
     const long long timeout = 20ll * 2000000000ll;            // ~20 s of SM clock cycles
     k_exchange_reduce_resolve<<<blocks, 256, 0, (cudaStream_t)stream>>>(bufs, flags, (int)rank, (int)dst_rank, epoch, width * row0, count, (float)spp, d_rgba8, timeout);
     CU(cudaGetLastError());

@@ -224,6 +224,16 @@ class Context:
     def resolve_device(self, d_accum_ptr: int, width: int, height: int, spp: int, d_rgba8_ptr: int, stream: int = 0) -> None:
         nat.check(self._lib.rtcu_resolve_device(self._h, d_accum_ptr, width, height, spp, d_rgba8_ptr, stream or None))
 
+    def accum_download(self, width: int, height: int) -> np.ndarray:
+        """the fp32 sums the context holds from its last render(s): (H, W, 4) {sum_r, sum_g, sum_b, n}"""
+        out = np.zeros((height, width, 4), np.float32)
+        nat.check(self._lib.rtcu_accum_download(self._h, width, height, nat.ptr(out)))
+        return out
+
+    def accum_upload(self, accum: np.ndarray) -> None:
+        a = nat.contiguous(accum, np.float32)
+        nat.check(self._lib.rtcu_accum_upload(self._h, a.shape[1], a.shape[0], nat.ptr(a)))
+
     def sync(self) -> None:
         nat.check(self._lib.rtcu_sync(self._h))
 
@@ -367,10 +377,11 @@ def render_multi(contexts: Sequence[Context], view: nat.View, want_accum: bool =
 
 class ProgressiveRenderer:
     """Progressive refinement behind the same boundary: every `refine()` call traces the next
-    `samples_per_step` global samples of the frame into the context's fp32 accumulation buffer and returns the image
-    resolved over the samples so far -- what an interactive `render()` would show while the camera rests.  Because sample
-    indices are global (counter-based RNG), the image after k steps equals a single render of k*samples_per_step samples
-    up to fp32 summation order."""
+    `samples_per_step` global samples of the frame and returns the image resolved over the samples so far -- what an
+    interactive `render()` would show while the camera rests.  The fp32 sums stay ON THE DEVICE (RTCU_FLAG_ACCUMULATE):
+    a step moves a few hundred bytes in and the packed image out, and the divide / sqrt / pack runs in the kernels.  Because
+    sample indices are global (counter-based RNG), the image after k steps equals a single render of k*samples_per_step
+    samples up to fp32 summation order.  `accum` reads the sums back on demand (checkpoints, tests)."""
 
     def __init__(self, ctx: "Context", scene: Scene, width: int, height: int, *, samples_per_step: int = 4, max_bounces: Optional[int] = None,
                  material_mode: int = nat.MODE_SM, seed: int = DEFAULT_SEED, flags: int = 0):
@@ -378,21 +389,38 @@ class ProgressiveRenderer:
         self.samples_per_step, self.max_bounces = samples_per_step, max_bounces
         self.material_mode, self.seed, self.flags = material_mode, seed, flags
         self.samples_done = 0
-        self.accum = np.zeros((height, width, 4), np.float32)
+        # a Context keeps the sums on its device; anything else (the CPU stand-in of the host-logic tests) is summed here
+        self._on_device = hasattr(ctx, "accum_download")
+        self._host_accum = None if self._on_device else np.zeros((height, width, 4), np.float32)
+        self._image = np.zeros((height, width), np.uint32)
         ctx.upload_scene(scene)
+
+    @property
+    def accum(self) -> np.ndarray:
+        if not self._on_device:
+            return self._host_accum
+        if self.samples_done == 0:
+            return np.zeros((self.height, self.width, 4), np.float32)
+        return self.ctx.accum_download(self.width, self.height)
 
     def reset(self) -> None:
         """camera moved / scene reloaded (main.cpp:233-313): start over"""
         self.samples_done = 0
-        self.accum[...] = 0
+        if not self._on_device:
+            self._host_accum[...] = 0
         self.ctx.upload_scene(self.scene)
 
     def refine(self) -> np.ndarray:
         begin, end = self.samples_done, self.samples_done + self.samples_per_step
+        flags = self.flags | (nat.FLAG_ACCUMULATE if self._on_device and begin > 0 else 0)
         view = make_view(self.scene, self.width, self.height, samples_per_pixel=end, max_bounces=self.max_bounces,
-                         sample_range=(begin, end), seed=self.seed, material_mode=self.material_mode, flags=self.flags)
+                         sample_range=(begin, end), seed=self.seed, material_mode=self.material_mode, flags=flags)
+        if self._on_device:
+            self.ctx.render(view, rgba8=self._image, want_accum=False)  # sums added and resolved on the device
+            self.samples_done = end
+            return self._image.copy()
         _, part = self.ctx.render(view, want_rgba8=False, want_accum=True)
-        self.accum += part
+        self._host_accum += part
         self.samples_done = end
         return self.resolve()
 
@@ -431,14 +459,18 @@ class ProgressiveRenderer:
         differs = sorted(k for k in mine if identity.get(k) != mine[k])
         if differs:
             raise ValueError(f"checkpoint {path} belongs to a different render ({', '.join(differs)} differ)")
-        if accum.shape != self.accum.shape or accum.dtype != np.float32 or done < 0:
+        if accum.shape != (self.height, self.width, 4) or accum.dtype != np.float32 or done < 0:
             raise ValueError(f"checkpoint {path} is malformed")
-        self.accum[...] = accum
+        if self._on_device:
+            self.ctx.accum_upload(accum)
+        else:
+            self._host_accum[...] = accum
         self.samples_done = done
         return done
 
     def resolve(self) -> np.ndarray:
-        """divide / sqrt / pack over the samples so far (mg_ray_tracer.cpp:195-200), on the host copy"""
+        """divide / sqrt / pack over the samples so far (mg_ray_tracer.cpp:195-200) from a host copy of the sums (refine() returns
+        the image the device resolved; this is the same arithmetic for a stand-in context and for checks)"""
         n = np.float32(max(self.samples_done, 1))
         c = np.sqrt(self.accum[..., :3] / n, dtype=np.float32)
         c = np.minimum(np.maximum(c, np.float32(0)), np.float32(1))

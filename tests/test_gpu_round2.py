@@ -273,3 +273,51 @@ def test_plugin_splits_the_frame_over_all_gpus(monkeypatch, ngpu):
         assert ref.plugin_last_stats()["kernel_launches"] <= 3
     finally:
         ref.close(handle)
+
+
+def test_plugin_refines_an_unchanged_view_when_asked_to(monkeypatch):
+    """RT_CUDA_PROGRESSIVE=1 (f-3): frames of an unchanged scene and camera add their samples to the sums on the device; any change
+    starts over.  k frames of n samples equal one frame of k n samples (global sample indices), within fp32 summation order."""
+    monkeypatch.setenv("RT_CUDA_DEVICES", "1")
+    monkeypatch.setenv("RT_CUDA_PROGRESSIVE", "1")
+    monkeypatch.delenv("RT_CUDA_MATERIAL_MODE", raising=False)
+    ref = _plugin()
+    sc = S.load("scenes/dielectric.toml")
+    w, h, spp, depth = 320, 200, 8, 50
+    one, _ = ref.render(sc, w, h, spp, depth, 0x5EED, "sm_ray_tracer", threads=0)
+    three, _ = ref.render(sc, w, h, 3 * spp, depth, 0x5EED, "sm_ray_tracer", threads=0)
+    handle = ref.open("cuda_path_tracer")
+    try:
+        img = np.zeros((h, w), np.uint32)
+        ref.render_with(handle, sc, img, spp, depth, 0x5EED)
+        assert np.abs(unpack_rgba(img) - unpack_rgba(one)).max() <= 1      # frame 1: samples [0, 8)
+        ref.render_with(handle, sc, img, spp, depth, 0x5EED)
+        ref.render_with(handle, sc, img, spp, depth, 0x5EED)
+        assert np.abs(unpack_rgba(img) - unpack_rgba(three)).max() <= 1    # frame 3: the mean over samples [0, 24)
+        moved = dataclasses.replace(sc, camera=dataclasses.replace(sc.camera, position=(0.5, 1.2, 3.5)))
+        moved_one, _ = ref.render(moved, w, h, spp, depth, 0x5EED, "sm_ray_tracer", threads=0)
+        ref.render_with(handle, moved, img, spp, depth, 0x5EED)
+        assert np.abs(unpack_rgba(img) - unpack_rgba(moved_one)).max() <= 1  # the camera moved: samples [0, 8) of the new view
+        edited = dataclasses.replace(moved, spheres=moved.spheres * np.float32([1, 1, 1, 0.8]))
+        edited_one, _ = ref.render(edited, w, h, spp, depth, 0x5EED, "sm_ray_tracer", threads=0)
+        ref.render_with(handle, edited, img, spp, depth, 0x5EED)
+        assert np.abs(unpack_rgba(img) - unpack_rgba(edited_one)).max() <= 1  # the scene changed: start over too
+    finally:
+        ref.close(handle)
+
+
+def test_accumulate_flag_needs_sums_of_the_same_size(ctx, scenes):
+    sc = scenes["c2"][0]
+    ctx.upload_scene(sc)
+    kw = dict(samples_per_pixel=8, max_bounces=20, material_mode=nat.MODE_SM)
+    whole, whole_accum = ctx.render(make_view(sc, 200, 120, **kw), want_accum=True)
+    ctx.render(make_view(sc, 200, 120, **{**kw, "samples_per_pixel": 3}, sample_range=(0, 3)))
+    img, accum = ctx.render(make_view(sc, 200, 120, sample_range=(3, 8), flags=nat.FLAG_ACCUMULATE, **kw), want_accum=True)
+    np.testing.assert_allclose(accum, whole_accum, rtol=2e-6, atol=1e-7)   # [0,3) + [3,8) == [0,8)
+    assert np.abs(unpack_rgba(img) - unpack_rgba(whole)).max() <= 1
+    np.testing.assert_array_equal(ctx.accum_download(200, 120), accum)
+    with pytest.raises(nat.RtcuError, match="holds no sums"):
+        ctx.render(make_view(sc, 160, 120, flags=nat.FLAG_ACCUMULATE, **kw))
+    ctx.accum_upload(np.zeros((120, 200, 4), np.float32))
+    img0, accum0 = ctx.render(make_view(sc, 200, 120, flags=nat.FLAG_ACCUMULATE, **kw), want_accum=True)
+    np.testing.assert_array_equal(accum0, whole_accum)                      # onto zeros: the plain frame
