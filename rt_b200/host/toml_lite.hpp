@@ -324,8 +324,20 @@ class parser {
         return n;
     }
 
+    // arrays and inline tables nest by recursion: bounded like toml++'s parser (TOML_MAX_NESTED_VALUES = 256), so that a document of
+    // 200 000 opening brackets is a parse error (main.cpp:370-379: "error: ...", exit 1), not a stack overflow
+    static constexpr int max_nesting = 256;
+    int depth_ = 0;
+    struct depth_guard {
+        int& d;
+        explicit depth_guard(int& depth) : d(depth) { ++d; }
+        ~depth_guard() { --d; }
+    };
+
     node_ptr parse_value()
     {
+        const depth_guard nested{ depth_ };
+        if (depth_ > max_nesting) fail("exceeded maximum nested value depth of " + std::to_string(max_nesting));
         skip_ws();
         auto n = std::make_shared<node>();
         n->line = line_;

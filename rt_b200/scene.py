@@ -258,12 +258,27 @@ def make_materials(rows: Sequence[tuple]) -> np.ndarray:
     return m
 
 
+def _nesting(value) -> int:
+    """levels of arrays / tables below and including `value` (iterative: the point is documents nested hundreds deep)"""
+    deepest, todo = 0, [(value, 1)]
+    while todo:
+        v, d = todo.pop()
+        if isinstance(v, (list, dict)):
+            deepest = max(deepest, d)
+            todo.extend((c, d + 1) for c in (v.values() if isinstance(v, dict) else v))
+    return deepest
+
+
 def loads(text: str, path: str = "") -> Scene:
     """scene::load on TOML text (src/scene.cpp:527-618)."""
     try:
         cfg = tomllib.loads(text)
     except tomllib.TOMLDecodeError as e:
         raise SceneError(f"TOML parse error: {e}") from None
+    except RecursionError:  # arrays / inline tables nested thousands deep: a parse error in toml++ too (256 levels)
+        raise SceneError("TOML parse error: exceeded maximum nested value depth of 256") from None
+    if _nesting(cfg) > 256 + 1:  # (+1: the document itself is a table) -- the limit of toml++ and of the C++ twin's parser
+        raise SceneError("TOML parse error: exceeded maximum nested value depth of 256")
 
     s = Scene(path=path)
     s.samples_per_pixel = min(max(_unsigned(cfg.get("samples_per_pixel"), 30, "samples_per_pixel"), 1), 1000)

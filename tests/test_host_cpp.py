@@ -278,6 +278,22 @@ def test_documents_must_be_utf8(cli, tmp_path):
             bad.decode("utf-8")
 
 
+def test_deeply_nested_values_are_a_parse_error_not_a_crash(cli, tmp_path):
+    """arrays / inline tables nested 200 000 deep used to overflow the C++ parser's stack (exit 139); toml++ caps nesting at 256
+    and reports a parse error, which main.cpp:370-379 prints as `error: ...` with exit code 1"""
+    from rt_b200 import scene as S
+
+    p = tmp_path / "deep.toml"
+    for doc in ("x = " + "[" * 200000 + "]" * 200000 + "\n", "x = " + "{a = " * 100000 + "1" + "}" * 100000 + "\n", "x = " + "[" * 300 + "]" * 300 + "\n"):
+        p.write_text(doc)
+        r = run(cli, "--scene", str(p), "--dump-scene", check=False)
+        assert r.returncode == 1 and "nested" in r.stderr and r.stderr.strip().splitlines()[-1].startswith("error: "), (r.returncode, r.stderr[-200:])
+    with pytest.raises(S.SceneError, match="nested"):
+        S.loads("x = " + "[" * 200000 + "]" * 200000)
+    p.write_text("x = " + "[" * 200 + "]" * 200 + "\n[[spheres]]\nradius = 2\n")  # within the limit: an ordinary document
+    assert dumped(cli, p)["spheres"][0][3] == 2.0 and len(S.loads(p.read_text()).spheres) == 1
+
+
 def test_dump_keeps_signed_zeros_and_non_finite_values(cli, tmp_path):
     p = tmp_path / "z.toml"
     p.write_text("planes = [ {normal = -0.6}, {normal = [0, 0, 0]}, {position = [0, 2, 0]} ]\nspheres = [ {position = [-0.0, 0, 1e-46]} ]\n")

@@ -225,6 +225,9 @@ def mutate(text: str, r: random.Random) -> str:
             b[i:i] = b[j:j + r.randint(1, 12)]
         else:
             b.insert(i, r.choice(b"[]{}=,\"'\n"))
+    if r.random() < 0.02:  # values nested beyond any parser's patience (toml++ gives up at 256 levels): a parse error on both sides
+        depth = r.choice([257, 300, 5000, 200000])
+        b += ("\ndeep = " + ("[" * depth + "]" * depth if r.random() < 0.5 else "{a = " * depth + "1" + "}" * depth) + "\n").encode()
     return b.decode("utf-8", errors="surrogateescape")
 
 
