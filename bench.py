@@ -487,6 +487,7 @@ def run_gpu(args):
     host_t = torch.from_numpy(host_img.view(np.int32))
     scene_bytes = int(scene.spheres.nbytes + scene.sphere_material.nbytes + scene.planes.nbytes + scene.plane_material.nbytes + scene.materials.nbytes)
     prepared = ctx.prepare_scene(scene)  # the descriptor over the host arrays; the upload itself happens every step
+    ctx.set_output_pinning(True)  # as plugin/cuda_path_tracer.cpp does: the frame's image is page-locked once, on first sight
 
     def step_e2e(i, dst=host_img):
         set_seed(i)
@@ -595,7 +596,7 @@ def run_gpu(args):
                        "seed": f"{base_seed} + step index", "l2": "flushed between steps (256 MiB fill, outside the per-step CUDA events)",
                        "pipeline": "megakernel", "accel": "bvh" if is_bvh else "linear", "timed_region_s": round(total_ms * 1e-3, 3)},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": scene_bytes * world, "d2h_bytes_per_step": W * H * 4,
-                    "destination": "pageable 64-byte aligned host memory (as image.cpp:9-13), page-locked by the library on first sight" if world == 1
+                    "destination": "pageable 64-byte aligned host memory (as image.cpp:9-13), page-locked on first sight (rtcu_set_output_pinning, as the plugin does)" if world == 1
                                    else "pageable host memory on rank 0 (torch copy from the reduced device image)",
                     "steps": e2e_steps, "value_pinned_destination": e2e_pinned,
                     "ms_d2h_last_frame": round(e2e_stats["ms_d2h"], 4) if e2e_stats else None},

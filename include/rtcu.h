@@ -162,11 +162,20 @@ int rtcu_upload_scene_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_sc
  *   mg_ray_tracer.cpp:187-194, except where several lanes share a pixel (BVH scenes from 16 samples per call, pixels handed
  *   to the second pass, multi-GPU sample splits): there it is a fixed tree of partial sums -- deterministic, equal to the
  *   sequential sum up to fp32 rounding.
- * rgba8_out may be pageable (the reference's image, image.cpp:9-13): a full-frame destination is page-locked once per
- *   (pointer, size) -- cudaHostRegister, undone when another image arrives or in rtcu_destroy; RTCU_REGISTER_OUTPUT=0 disables --
- *   and then written by the kernels (zero-copy) or by one DMA; each frame is verified to have landed in the caller's pages, so a
- *   buffer that was freed and re-allocated at the same address costs one staged frame, never a wrong image. */
+ * rgba8_out may be pinned or pageable.  A pinned image is written by the kernels themselves (zero-copy) or by one DMA; a pageable
+ *   one (the reference's, image.cpp:9-13) is staged through a bounce buffer -- unless the caller has opted in with
+ *   rtcu_set_output_pinning, see there. */
 int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float* accum_out);
+/* Opt-in for callers whose image outlives the frame, like the reference's back buffer (back_buffer.hpp: one rt::image per
+ * window size, handed to render() frame after frame): with enable != 0 a pageable full-frame rgba8_out of rtcu_render /
+ * rtcu_rasterize / rtcu_render_multi is page-locked once per (pointer, size) -- cudaHostRegister, undone when another image
+ * arrives, on enable = 0 and in rtcu_destroy -- and from then on treated like pinned memory (no staging copy: C2's frame is
+ * complete 0.9 ms earlier).  Every frame is verified to have landed in the caller's pages, so an image that was freed and
+ * re-allocated at the same address costs one staged frame, never a wrong picture.  Off by default: a page-locked range that
+ * the application has freed stays registered until the next frame notices, and other CUDA calls of the process that touch
+ * re-used parts of it would fail -- acceptable for a renderer plugin that owns the process's CUDA use, not for a library
+ * default. */
+int rtcu_set_output_pinning(rtcu_ctx* ctx, int enable);
 
 /* the fp32 sums {sum_r, sum_g, sum_b, n} the context holds from its last rtcu_render (width*height*4 floats): read them back
  * (checkpoint of a progressive render) or replace them (resume; the next RTCU_FLAG_ACCUMULATE call adds onto them) */

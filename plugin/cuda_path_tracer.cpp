@@ -20,8 +20,9 @@
 //    sample 0 but REFINED -- the next samples_per_pixel samples are added to the fp32 sums the library keeps on the device and
 //    the image is resolved over all samples so far (RTCU_FLAG_ACCUMULATE).  Off by default: the reference's app renders only
 //    when something changed (window.cpp:213-217), and a drop-in must return the same image for the same call.
-//  * image_view memory is pageable (image.cpp:9-13): the library page-locks it once per (pointer, size) and writes later
-//    frames into it directly (rtcu.h, rtcu_render), so no staging copy follows the kernels.
+//  * image_view memory is pageable (image.cpp:9-13) and lives as long as the window's back buffer: the plugin opts in to
+//    rtcu_set_output_pinning, so the library page-locks it once per (pointer, size) and writes later frames into it directly --
+//    no staging copy follows the kernels.
 #ifdef RTCU_PLUGIN_STUB_CHECK
 	#include "rt_stub.hpp" // minimal stand-ins for the accessors used below (compile check without muu)
 #else
@@ -70,6 +71,9 @@ namespace
 			if (!ctx_)
 				throw std::runtime_error{ std::string{ name } + ": " + rtcu_last_error() };
 			ctxs_.push_back(ctx_);
+			// the application's image lives as long as its back buffer and arrives frame after frame: let the library page-lock
+			// it once per (pointer, size) and write into it directly (rtcu.h, rtcu_set_output_pinning)
+			rtcu_set_output_pinning(ctx_, 1);
 			int devices = all_devices ? rtcu_device_count() : 1;
 			if (const char* cap = std::getenv("RT_CUDA_DEVICES"); cap && std::atoi(cap) >= 1)
 				devices = std::min(devices, std::atoi(cap));

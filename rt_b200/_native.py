@@ -29,7 +29,7 @@ EXPORTS = (
     "rtcu_rasterize", "rtcu_rasterize_device", "rtcu_selftest_math",
     "rtcu_ipc_alloc", "rtcu_ipc_open", "rtcu_ipc_release", "rtcu_reduce_resolve_rows", "rtcu_bvh4_build_host",
     "rtcu_reload_env", "rtcu_upload_scene_multi", "rtcu_exchange_reduce_resolve", "rtcu_exchange_check",
-    "rtcu_accum_download", "rtcu_accum_upload",
+    "rtcu_accum_download", "rtcu_accum_upload", "rtcu_set_output_pinning",
 )
 
 
@@ -122,6 +122,7 @@ def load_library() -> C.CDLL:
         "rtcu_exchange_check": (i, [p, p, p]),
         "rtcu_accum_download": (i, [p, u32, u32, p]),
         "rtcu_accum_upload": (i, [p, u32, u32, p]),
+        "rtcu_set_output_pinning": (i, [p, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

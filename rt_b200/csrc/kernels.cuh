@@ -62,7 +62,7 @@ struct RenderParams {
     uint32_t* tile_cost;          // += segments traced for the CTA's tile (nullable)
     const uint32_t* tile_order;   // CTA b renders tile tile_order[b] (nullable: CTA b renders tile b)
     int direct;                   // != 0: k_render_stragglers renders every pixel of the tile itself (no first pass, no queue)
-    int beam;                     // != 0 (direct mode): primary rays use their pixel's candidate leaf list (beam_collect)
+    const struct BeamList* beam;  // non-null (direct mode): per 8x4 patch, the leaves its primary rays can hit (k_beam_lists)
 };
 
 #ifndef RTCU_PRIM_MISS
@@ -431,17 +431,20 @@ __device__ __forceinline__ bool closest_sphere_bvh2(const SceneDev& sc, const To
     return true;
 }
 
-// ---- pixel beams: the primary rays of ONE pixel share their candidate leaves ---------------------------------------------------
+// ---- patch beams: the primary rays of an 8x4-pixel patch share their candidate leaves ----------------------------------------
 // More than half of all path segments are primary rays, and the reference's sample loop (mg_ray_tracer.cpp:187-194) sends all
-// of a pixel's samples through the same pixel: their rays differ by at most the pixel's footprint.  Where lanes share a pixel's
-// samples, the tree is therefore walked ONCE per pixel with the pixel's centre ray and margins widened by that footprint,
-// WITHOUT the closest-hit cull, collecting every leaf that any ray of the pixel could hit (up to BEAM_MAX, sorted by entry
-// distance).  A sample's primary ray then tests just those leaves -- S4, the (t, index) rule, exactly as a traversal would --
-// instead of descending from the root: the same result for a third of the instructions, and all lanes of the pixel run the
-// same short loop.  Pixels whose beam touches more leaves (grazing views over many spheres) keep the traversal.
+// of a pixel's samples through the same pixel: their rays differ by at most the pixel's footprint, and a handful of neighbouring
+// pixels by little more.  Before a frame of a BVH scene is traced, k_beam_lists therefore walks the tree ONCE per 8x4-pixel
+// patch with the patch's centre ray and margins widened by the patch's footprint, WITHOUT the closest-hit cull, and records
+// every leaf that any primary ray of the patch could hit (up to BEAM_MAX, sorted by entry distance).  A sample's primary ray
+// then tests just those leaves -- S4, the (t, index) rule, exactly as a traversal would -- instead of descending from the
+// root: the same result for a third of the instructions, and all lanes of a pixel run the same short loop.  Patches whose beam
+// touches more leaves (grazing views over many spheres) keep the traversal.  (Measured: the median patch of C4 lists 4 leaves,
+// 86 % of them at most 16; C3 / C5: median 2, none above 16.  One walk per patch serves 32 pixels x all their samples, so it
+// pays even at C4's 64 samples per pixel, where a walk per pixel -- the first form of this -- did not.)
 //
-// Why the list is complete.  Let R0 = (o0, d0) be the centre ray and R' = (o', d') any primary ray of the pixel, with
-// |o' - o0| <= rho and |d' - d0| <= sigma (both maximal at the pixel's corners: screen -> near / far points is affine when the
+// Why the list is complete.  Let R0 = (o0, d0) be the centre ray and R' = (o', d') any primary ray of the patch, with
+// |o' - o0| <= rho and |d' - d0| <= sigma (both maximal at the patch's corners: screen -> near / far points is affine when the
 // viewport's perspective divide is constant, and the angle to d0 is quasi-convex over the far-minus-near quad; the corners are
 // evaluated with the same arithmetic as the samples, plus slack for its rounding).  If S4 reports a hit of R' on a sphere
 // (c, r) at t' >= 0, the line of R' passes within r + kappa'|e'| of c (see above), and R0(t') lies within rho + sigma t' of
@@ -450,14 +453,15 @@ __device__ __forceinline__ bool closest_sphere_bvh2(const SceneDev& sc, const To
 // i.e. the slab test of the ordinary traversal with kappa := kappa_b + 2.01 sigma and an additive 2 rho passes for every
 // ancestor box of the sphere, and its entry distance tn0 <= t' (which makes `tn0 > best_t` a valid reason to stop early).
 // kappa_b is the margin factor of a ray that is unit length to within BEAM_EPS_D; a sample ray outside that (never seen:
-// primary directions are normalised) traverses.
-constexpr int BEAM_MAX = 8;                         // leaves per list
-constexpr int BEAM_MAX_VISITS = 48;                 // node visits after which a beam is given up
+// primary directions are normalised) traverses.  tests/test_bvh_replay.py replays this on the CPU against the oracle's scan.
+constexpr int BEAM_MAX = 16;                        // leaves per list
+constexpr int BEAM_MAX_VISITS = 96;                 // node visits after which a beam is given up
 constexpr float BEAM_EPS_D = 16.0f * 5.9604645e-8f; // |d.d - 1| bound of the rays that may use a list
-struct BeamList { float tn[BEAM_MAX]; uint32_t leaf[BEAM_MAX]; int n; int pad; }; // n < 0: no list, traverse
+constexpr uint32_t BEAM_PATCH_W = 8, BEAM_PATCH_H = 4; // the patches k_render_stragglers enumerates in direct mode
+struct BeamEntry { float tn; uint32_t leaf; };
+struct BeamList { int n; int pad; BeamEntry e[BEAM_MAX]; }; // n < 0: no list, traverse
 
-// run by ONE lane per pixel (the list lives in shared memory)
-__device__ __noinline__ void beam_collect(const SceneDev& sc, const Ray& r0, const float sigma, const float rho, BeamList* __restrict__ out)
+__device__ __forceinline__ void beam_collect(const float4* __restrict__ bvh_nodes, const Ray& r0, const float sigma, const float rho, BeamList* __restrict__ out)
 {
     out->n = -1;
     Trav tv;
@@ -466,12 +470,13 @@ __device__ __noinline__ void beam_collect(const SceneDev& sc, const Ray& r0, con
     tv.kappa = 1.01f * (1.01f * sqrtf(16.0f * 5.9604645e-8f + 2.0f * BEAM_EPS_D) + 2.01f * sigma);
     tv.madd = 2.02f * rho;
     uint32_t stack[BVH_STACK];
+    BeamEntry list[BEAM_MAX];
     int sp = 0, n = 0, visits = 0;
     uint32_t node = 0;
     for (;;)
     {
         if (++visits > BEAM_MAX_VISITS) return;
-        const float4* np = sc.bvh_nodes + 8u * node;
+        const float4* np = bvh_nodes + 8u * node;
         const float4 refs = __ldg(np + 6), hs = __ldg(np + 7);
         const uint32_t ref[4] = { __float_as_uint(refs.x), __float_as_uint(refs.y), __float_as_uint(refs.z), __float_as_uint(refs.w) };
         float tn[4];
@@ -485,13 +490,10 @@ __device__ __noinline__ void beam_collect(const SceneDev& sc, const Ray& r0, con
             {
                 if (n == BEAM_MAX) return;
                 int k = n++;
-                for (; k > 0 && out->tn[k - 1] > tn[c]; k--) // keep the list sorted by entry distance
-                {
-                    out->tn[k] = out->tn[k - 1];
-                    out->leaf[k] = out->leaf[k - 1];
-                }
-                out->tn[k] = tn[c];
-                out->leaf[k] = ref[c] & 0x7fffffffu;
+                for (; k > 0 && list[k - 1].tn > tn[c]; k--) // keep the list sorted by entry distance
+                    list[k] = list[k - 1];
+                list[k].tn = tn[c];
+                list[k].leaf = ref[c] & 0x7fffffffu;
             }
             else
                 stack[sp++] = ref[c];
@@ -499,19 +501,22 @@ __device__ __noinline__ void beam_collect(const SceneDev& sc, const Ray& r0, con
         if (sp == 0) break;
         node = stack[--sp];
     }
+    for (int k = 0; k < n; k++) out->e[k] = list[k];
     out->n = n;
 }
 
-// closest sphere hit of a primary ray of the beam's pixel: the (t, index) minimum over the listed leaves
-__device__ __forceinline__ void beam_closest_sphere(const SceneDev& sc, const BeamList* __restrict__ beam, const Ray& r, float& best_t, int& best_i, BvhStats& st)
+// closest sphere hit of a primary ray of the beam's patch: the (t, index) minimum over the listed leaves (read from global memory:
+// the loads are uniform across the lanes of a pixel)
+__device__ __forceinline__ void beam_closest_sphere(const SceneDev& sc, const BeamList* __restrict__ beam, const int n, const Ray& r, float& best_t, int& best_i,
+                                                    BvhStats& st)
 {
     best_t = __int_as_float(0x7f800000);
     best_i = 0x7fffffff;
-    const int n = beam->n;
     for (int k = 0; k < n; k++)
     {
-        if (beam->tn[k] > best_t) break; // no ray of the pixel reaches this leaf (or a later one) before tn
-        const float4* lp = sc.leaf_blk + 5u * beam->leaf[k];
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(&beam->e[k]));
+        if (__uint_as_float(e.x) > best_t) break; // no ray of the patch reaches this leaf (or a later one) before tn
+        const float4* lp = sc.leaf_blk + 5u * e.y;
         const float4 a0 = __ldg(lp), b0 = __ldg(lp + 1), a1 = __ldg(lp + 2), b1 = __ldg(lp + 3), idx = __ldg(lp + 4);
         st.tests += 4;
         bvh_leaf_pair_test<false>(a0, b0, __float_as_int(idx.x), __float_as_int(idx.y), r, best_t, best_i);
@@ -525,16 +530,22 @@ __device__ __forceinline__ void beam_closest_sphere(const SceneDev& sc, const Be
 // L1.5 instruction cache (profiles/README.md: a variant whose loop grew to 40 KB spent 8x the cycles waiting for instructions).
 // Code that a BVH scene rarely runs is therefore kept OUT of the loop body as real functions: the plane loop (the large scenes
 // have no planes) and the scan that non-unit or far-away rays fall back to.
-__device__ __noinline__ void closest_plane_cold(const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray& r, float& tp, int& ip)
+struct PlaneHit { float t; int i; };
+__device__ __noinline__ PlaneHit closest_plane_cold(const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray r)
 {
-    tp = __int_as_float(0x7fc00000); // NaN = nothing found yet, see closest_hit_linear
-    ip = -1;
+    PlaneHit h;
+    h.t = __int_as_float(0x7fc00000); // NaN = nothing found yet, see closest_hit_linear
+    h.i = -1;
     for (uint32_t i = 0; i < n_pl; i++)
-        plane_test(s_pl[i], (int)i, r, tp, ip);
+        plane_test(s_pl[i], (int)i, r, h.t, h.i);
+    return h;
 }
-__device__ __noinline__ Hit closest_hit_scan_cold(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r)
+// (arguments by value: a reference to the kernel's SceneDev / RenderParams parameter would make the compiler keep a copy of the
+// whole parameter in local memory and read it from there everywhere)
+__device__ __noinline__ Hit closest_hit_scan_cold(const float4* __restrict__ pairs, const uint32_t n_spheres, const float4* __restrict__ s_pl, const uint32_t n_planes,
+                                                  const Ray r)
 {
-    return closest_hit_linear(sc.pairs, sc.n_spheres, s_pl, sc.n_planes, r);
+    return closest_hit_linear(pairs, n_spheres, s_pl, n_planes, r);
 }
 
 __device__ __forceinline__ Hit combine_with_planes(const SceneDev& sc, const float4* __restrict__ s_pl, const Ray& r, const float ts, const int is)
@@ -544,9 +555,9 @@ __device__ __forceinline__ Hit combine_with_planes(const SceneDev& sc, const flo
     h.prim = is >= 0 ? (uint32_t)is : RTCU_PRIM_MISS; // (a traversal never yields a NaN distance: trav_init sends such rays to the scan)
     if (sc.n_planes)
     {
-        float tp;
-        int ip;
-        closest_plane_cold(s_pl, sc.n_planes, r, tp, ip);
+        const PlaneHit ph = closest_plane_cold(s_pl, sc.n_planes, r);
+        const float tp = ph.t;
+        const int ip = ph.i;
         if (ip >= 0 && tp >= 0.0f && !(is >= 0 && ts <= tp))
         {
             h.t = tp;
@@ -569,7 +580,7 @@ __device__ __forceinline__ Hit closest_hit_bvh(const SceneDev& sc, const float4*
     if (!(TRAV == 0 ? closest_sphere_bvh(sc, r, ts, is, st) : closest_sphere_bvh2<TRAV == 2>(sc, top, r, ts, is, st)))
     {
         st.tests += sc.n_spheres;
-        return closest_hit_scan_cold(sc, s_pl, r);
+        return closest_hit_scan_cold(sc.pairs, sc.n_spheres, s_pl, sc.n_planes, r);
     }
     return combine_with_planes(sc, s_pl, r, ts, is);
 }
@@ -667,7 +678,7 @@ __device__ __forceinline__ bool shade_segment(const SceneDev& sc, const RenderPa
 // ended} -- generate and shade then run at full lane occupancy, best for tiny N where they dominate.
 // BVH: spheres are reached through the BVH (STAGE must be false; the structure lives in L1/L2).
 template <bool STAGE, bool FLAT, bool BVH, int TRAV = 1>
-__global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_mega(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p)
+__global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_mega(const SceneDev sc, const RenderParams p)
 {
     extern __shared__ float4 smem[];
     const float4* s_sph = sc.pairs;
@@ -718,6 +729,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
         Ray ray;
         ray.o = v3(0.0f, 0.0f, 0.0f);
         ray.d = v3(0.0f, 0.0f, 1.0f);
+        // the candidate leaves of the warp's 8x4 patch (k_beam_lists; the warp's patch IS one of its patches): n < 0 = traverse
+        const BeamList* beam = nullptr;
+        int beam_n = -1;
+        if (BVH && p.beam && in_tile)
+        {
+            const uint32_t patches_x = (p.tile_x1 - p.tile_x0 + BEAM_PATCH_W - 1u) / BEAM_PATCH_W;
+            beam = p.beam + ((py - p.tile_y0) / BEAM_PATCH_H) * patches_x + (px - p.tile_x0) / BEAM_PATCH_W;
+            beam_n = __ldg(&beam->n);
+        }
         for (;;)
         {
             // (1) regeneration, decided by a warp vote so every lane reconverges here each iteration: lanes whose path
@@ -726,6 +746,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
             const unsigned flying = __ballot_sync(0xffffffffu, live);
             if (!idle && !flying)
                 break;
+            bool fresh = false;
             if (idle && (!flying || __popc(idle) >= (int)p.regen_threshold))
             {
                 if (more && !live)
@@ -734,21 +755,39 @@ __global__ void __launch_bounds__(MEGA_THREADS, RTCU_MEGA_MIN_BLOCKS) k_render_m
                     thr = v3(1.0f, 1.0f, 1.0f);
                     ray = generate(p.cam, key, px, py);
                     live = true;
+                    fresh = true;
                 }
             }
-            // (2) one path segment for every lane in flight
-            if (live)
+            // (2) one path segment for every lane in flight -- two for a lane that has just started a sample in a patch with a
+            // beam list: its primary hit comes from the list (pass 0), then it traverses with the others (pass 1).  One rolled
+            // copy of the segment code serves both passes (instruction-cache footprint, see closest_plane_cold).
+            const bool listed = BVH && fresh && beam_n >= 0 && fabsf(dot3(ray.d, ray.d) - 1.0f) <= BEAM_EPS_D;
+#pragma unroll 1
+            for (int pass = (BVH && __any_sync(0xffffffffu, listed)) ? 0 : 1; pass < 2; pass++)
             {
-                segs++;
-                if (segment_step<BVH, TRAV>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, bst))
+                if (pass == 0 ? listed : live)
                 {
-                    live = false;
-                    key.sample++;
-                    more = key.sample < p.sample_end;
-                    if (more && p.segment_budget && segs >= p.segment_budget)
+                    segs++;
+                    Hit h;
+                    if (BVH && pass == 0)
                     {
-                        p.stragglers[atomicAdd(p.straggler_count, 1u)] = make_uint2(key.pixel, key.sample);
-                        more = false;
+                        float ts;
+                        int is;
+                        beam_closest_sphere(sc, beam, beam_n, ray, ts, is, bst);
+                        h = combine_with_planes(sc, s_pl, ray, ts, is);
+                    }
+                    else
+                        h = BVH ? closest_hit_bvh<TRAV>(sc, s_pl, ray, bst) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
+                    if (shade_segment<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, h))
+                    {
+                        live = false;
+                        key.sample++;
+                        more = key.sample < p.sample_end;
+                        if (more && p.segment_budget && segs >= p.segment_budget)
+                        {
+                            p.stragglers[atomicAdd(p.straggler_count, 1u)] = make_uint2(key.pixel, key.sample);
+                            more = false;
+                        }
                     }
                 }
             }
@@ -898,38 +937,35 @@ __global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict_
 // deterministic, since which lane traces which sample depends only on the path lengths.  Primitives are read from global memory (L1-resident for the scenes that reach this path).
 // TRAV = 2: the CTA first copies the top TOP_NODES nodes of the tree (breadth-first order: its top levels) into shared memory.
 constexpr uint32_t TOP_NODES = 21; // three levels of 4-wide nodes: 1 + 4 + 16, 2.7 KB
-// BEAM (direct mode): the primary rays of a pixel test the pixel's candidate leaves instead of traversing (beam_collect).
-// the pixel's footprint and its candidate list: centre ray against the rays through the four corners (lane k & 3 of the group
-// takes corner k), then one lane of the group walks the tree (beam_collect).  Called by all lanes of the warp; out of line: it
-// runs once per pixel, and its registers must not weigh on the sample loop
-template <uint32_t G>
-__device__ __noinline__ void beam_setup(const SceneDev& sc, const CameraConst& cam, const uint32_t px, const uint32_t py, const uint32_t lane, const bool has_work,
-                                        BeamList* __restrict__ beam)
+// BEAM (direct mode): primary rays test their patch's candidate leaves instead of traversing (k_beam_lists).
+// One thread per 8x4-pixel patch of the tile (the patches k_render_stragglers enumerates in direct mode, row-major): the patch's
+// footprint -- centre ray against the rays through its four corners -- and its candidate leaf list (beam_collect).
+__global__ void __launch_bounds__(128) k_beam_lists(const SceneDev sc, const RenderParams p, BeamList* __restrict__ lists)
 {
-    const uint32_t lg = lane & (G - 1u);
-    const float fx = __uint2float_rn(px), fy = __uint2float_rn(py);
-    const Ray rc = primary_ray(cam, __fadd_rn(fx, 0.5f), __fadd_rn(fy, 0.5f));
-    const Ray rk = primary_ray(cam, __fadd_rn(fx, (float)(lg & 1u)), __fadd_rn(fy, (float)((lg >> 1) & 1u)));
-    float dd = fabsf(rk.d.x - rc.d.x) + fabsf(rk.d.y - rc.d.y) + fabsf(rk.d.z - rc.d.z);
-    float oo = fabsf(rk.o.x - rc.o.x) + fabsf(rk.o.y - rc.o.y) + fabsf(rk.o.z - rc.o.z);
-    dd = fmaxf(dd, __shfl_xor_sync(0xffffffffu, dd, 1));
-    oo = fmaxf(oo, __shfl_xor_sync(0xffffffffu, oo, 1));
-    dd = fmaxf(dd, __shfl_xor_sync(0xffffffffu, dd, 2));
-    oo = fmaxf(oo, __shfl_xor_sync(0xffffffffu, oo, 2));
+    const uint32_t tile_w = p.tile_x1 - p.tile_x0, tile_h = p.tile_y1 - p.tile_y0;
+    const uint32_t patches_x = (tile_w + BEAM_PATCH_W - 1u) / BEAM_PATCH_W, patches_y = (tile_h + BEAM_PATCH_H - 1u) / BEAM_PATCH_H;
+    const uint32_t patch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (patch >= patches_x * patches_y) return;
+    const uint32_t x0 = p.tile_x0 + (patch % patches_x) * BEAM_PATCH_W, y0 = p.tile_y0 + (patch / patches_x) * BEAM_PATCH_H;
+    const uint32_t x1 = min(x0 + BEAM_PATCH_W, p.tile_x1), y1 = min(y0 + BEAM_PATCH_H, p.tile_y1);
+    const float fx0 = __uint2float_rn(x0), fy0 = __uint2float_rn(y0), fx1 = __uint2float_rn(x1), fy1 = __uint2float_rn(y1);
+    const Ray rc = primary_ray(p.cam, 0.5f * (fx0 + fx1), 0.5f * (fy0 + fy1));
+    float dd = 0.0f, oo = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++)
+    {
+        const Ray rk = primary_ray(p.cam, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0);
+        dd = fmaxf(dd, fabsf(rk.d.x - rc.d.x) + fabsf(rk.d.y - rc.d.y) + fabsf(rk.d.z - rc.d.z));
+        oo = fmaxf(oo, fabsf(rk.o.x - rc.o.x) + fabsf(rk.o.y - rc.o.y) + fabsf(rk.o.z - rc.o.z));
+    }
     const float u16 = 16.0f * 5.9604645e-8f; // slack for the rounding of the ray arithmetic itself
     const float sigma = 1.01f * dd + u16, rho = 1.01f * oo + u16 * (fabsf(rc.o.x) + fabsf(rc.o.y) + fabsf(rc.o.z) + 1.0f);
-    if (lg == 0u)
-    {
-        if (has_work) beam_collect(sc, rc, sigma, rho, beam);
-        else beam->n = -1;
-    }
-    __syncwarp();
+    beam_collect(sc.bvh_nodes, rc, sigma, rho, lists + patch);
 }
 
 template <bool BVH, int G_LANES = 32, int TRAV = 1, bool BEAM = false, int MINB = 8>
-__global__ void __launch_bounds__(128, MINB) k_render_stragglers(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p)
+__global__ void __launch_bounds__(128, MINB) k_render_stragglers(const SceneDev sc, const RenderParams p)
 {
-    __shared__ BeamList s_beam[BEAM ? 4 * (32 / G_LANES) : 1]; // one per lane group of the CTA
     __shared__ float4 s_top[TRAV == 2 ? 8 * TOP_NODES : 1];
     TopNodes top;
     top.nodes = s_top;
@@ -980,13 +1016,15 @@ __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const __grid_co
         Ray ray;
         ray.o = v3(0.0f, 0.0f, 0.0f);
         ray.d = v3(0.0f, 0.0f, 1.0f);
-        bool use_beam = false;
-        BeamList* beam = &s_beam[BEAM ? (threadIdx.x >> 5) * ppw + grp : 0];
-        if (BVH && BEAM && p.direct && p.cam.w_const && p.beam)
+        // the candidate leaves of this pixel's 8x4 patch (k_beam_lists): n < 0 = the patch traverses
+        const BeamList* beam = nullptr;
+        int beam_n = -1;
+        if (BVH && BEAM && p.direct && p.beam)
         {
-            beam_setup<G>(sc, p.cam, px, py, lane, w.y < p.sample_end, beam);
-            use_beam = beam->n >= 0;
+            beam = p.beam + item / G; // direct mode: item / G is the patch
+            beam_n = __ldg(&beam->n);
         }
+        const bool use_beam = beam_n >= 0;
         // the lanes of a group share their pixel's remaining samples: a lane whose path ended takes the next unclaimed sample
         // at once (ballot rank in lane order -- deterministic), so lanes stay busy until the pixel runs out of samples
         uint32_t next = w.y;
@@ -1025,7 +1063,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const __grid_co
                         {
                             float ts;
                             int is;
-                            beam_closest_sphere(sc, beam, ray, ts, is, bst);
+                            beam_closest_sphere(sc, beam, beam_n, ray, ts, is, bst);
                             h = combine_with_planes(sc, sc.planes, ray, ts, is);
                         }
                         else
@@ -1040,7 +1078,6 @@ __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const __grid_co
                 if (segment_step<BVH, TRAV>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst, top)) live = false;
             }
         }
-        if (BEAM) __syncwarp(); // the list is rewritten for the next pixel only after every lane has left this one
         for (uint32_t off = G >> 1; off > 0; off >>= 1) // fixed butterfly inside the group
         {
             sum.x = __fadd_rn(sum.x, __shfl_xor_sync(0xffffffffu, sum.x, off));
@@ -1211,7 +1248,7 @@ __global__ void __launch_bounds__(256) k_exchange_reduce_resolve(const PeerList 
 
 // ---- step-wise parity kernels ----------------------------------------------------------------------
 template <bool STAGE, bool BVH, int TRAV = 1>
-__global__ void __launch_bounds__(256) k_intersect_batch(const __grid_constant__ SceneDev sc, const float* __restrict__ o, const float* __restrict__ d,
+__global__ void __launch_bounds__(256) k_intersect_batch(const SceneDev sc, const float* __restrict__ o, const float* __restrict__ d,
                                                          uint32_t n, uint8_t* __restrict__ hit, uint32_t* __restrict__ prim,
                                                          float* __restrict__ t, float* __restrict__ nrm, unsigned long long* counters)
 {
@@ -1269,7 +1306,7 @@ __global__ void k_primary_rays(const CameraConst cam, uint32_t width, const Phil
     d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z;
 }
 
-__global__ void k_scatter_batch(const __grid_constant__ SceneDev sc, uint32_t mode, const PhiloxKeys rk, uint32_t n, const uint32_t* __restrict__ material,
+__global__ void k_scatter_batch(const SceneDev sc, uint32_t mode, const PhiloxKeys rk, uint32_t n, const uint32_t* __restrict__ material,
                                 const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ t,
                                 const float* __restrict__ nrm, const uint32_t* __restrict__ pixel, const uint32_t* __restrict__ sample,
                                 const uint32_t* __restrict__ block, uint8_t* __restrict__ scattered, float* __restrict__ att,

@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned lanemask_lt()
     return m;
 }
 
-__global__ void __launch_bounds__(32 * POOL_WARPS, RTCU_POOL_BLOCKS) k_render_pool(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p)
+__global__ void __launch_bounds__(32 * POOL_WARPS, RTCU_POOL_BLOCKS) k_render_pool(const SceneDev sc, const RenderParams p)
 {
     __shared__ WarpPool pools[POOL_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;

@@ -60,10 +60,6 @@ int guarded(const char* what, F&& body) noexcept
     } while (0)
 
 constexpr size_t MAX_STAGE_BYTES = 200 * 1024; // dynamic shared memory budget for staged primitives
-#ifndef RTCU_DEFAULT_BEAM_MIN
-#define RTCU_DEFAULT_BEAM_MIN 16 // pixel beams from this many samples per lane (RTCU_BVH_BEAM overrides; 0 = never): the walk that
-                                 // builds a pixel's list costs about as much as eight primary traversals, and C4's 64 samples are below it
-#endif
 #ifndef RTCU_DEFAULT_TRAV
 #define RTCU_DEFAULT_TRAV 0 // traversal variant of the direct-mode BVH kernel (kernels.cuh, closest_hit_bvh); RTCU_BVH_TRAV overrides
 #endif
@@ -136,12 +132,13 @@ struct Knobs {
     bool direct = true;        // RTCU_BVH_DIRECT=0 disables the lanes-share-a-pixel BVH path
     int tile_order = -1;       // RTCU_TILE_ORDER: 0 row-major, 1 sorted, -1 measured per view
     bool zero_copy = true;     // RTCU_ZERO_COPY=0: always stage the image
-    bool register_output = true; // RTCU_REGISTER_OUTPUT=0: never page-lock the caller's image
+    bool register_output = false; // rtcu_set_output_pinning / RTCU_REGISTER_OUTPUT=1: page-lock the caller's pageable image
     uint32_t bvh_threshold = 32; // RTCU_BVH_THRESHOLD
-    int bvh_trav = -1;         // RTCU_BVH_TRAV: traversal variant of the BVH kernels (-1 = default), see kernels.cuh
+    int bvh_trav = -1;         // RTCU_BVH_TRAV: traversal variant of the BVH kernels (kernels.cuh, closest_hit_bvh): 0 = leaves tested
+                               // inside the node visit (default, measured faster), 1 = deferred leaves, 2 = 1 + top levels in shared memory
     int bvh_lanes = 0;         // RTCU_BVH_LANES: lanes per pixel in direct mode (8 / 16 / 32), 0 = by sample count
-    int bvh_minb = 7;          // RTCU_BVH_MINB: 6 / 7 / 8 CTAs per SM for the beam kernel (80 / 72 / 64 registers)
-    int bvh_beam = -1;         // RTCU_BVH_BEAM: samples per lane from which a pixel's primary rays share a candidate list (0 = never)
+    int bvh_minb = 8;          // RTCU_BVH_MINB: 6 / 7 / 8 CTAs per SM for the beam kernel (80 / 72 / 64 registers)
+    int bvh_beam = -1;         // RTCU_BVH_BEAM=0: no patch beams (every primary ray traverses)
     void load()
     {
         *this = Knobs{};
@@ -153,7 +150,7 @@ struct Knobs {
         if (const char* e = getenv("RTCU_BVH_DIRECT")) direct = e[0] != '0';
         if (const char* e = getenv("RTCU_TILE_ORDER")) tile_order = e[0] == '0' ? 0 : e[0] == '1' ? 1 : -1;
         if (const char* e = getenv("RTCU_ZERO_COPY")) zero_copy = e[0] != '0';
-        if (const char* e = getenv("RTCU_REGISTER_OUTPUT")) register_output = e[0] != '0';
+        if (const char* e = getenv("RTCU_REGISTER_OUTPUT")) register_output = e[0] == '1';
         if (const char* e = getenv("RTCU_BVH_THRESHOLD")) bvh_threshold = (uint32_t)strtoul(e, nullptr, 10);
         if (const char* e = getenv("RTCU_BVH_TRAV")) bvh_trav = atoi(e);
         if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) bvh_lanes = v; }
@@ -214,6 +211,7 @@ struct rtcu_ctx {
     int tile_sorted_wins = 0;
     float tile_ms[2] = { 0.0f, 0.0f };
     cudaEvent_t tile_ev[2] = {};
+    DevBuf<BeamList> beam_lists;         // per 8x4 patch of the last direct-mode frame: candidate leaves of its primary rays
     DevBuf<uint2> stragglers;            // straggler queue of the last render (width*height entries)
     DevBuf<unsigned int> straggler_count;
     PinnedBuf<unsigned long long> h_counters;
@@ -282,7 +280,7 @@ int make_params(const rtcu_ctx* ctx, const rtcu_view* v, RenderParams& p)
     p.tile_cost = nullptr;
     p.tile_order = nullptr;
     p.direct = 0;
-    p.beam = 0;
+    p.beam = nullptr;
     return RTCU_OK;
 }
 
@@ -457,7 +455,7 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
     if (pool) p.segment_budget = 0; // work is shared by the 32 lanes of a warp: no per-thread stragglers
     auto launch_mega = [&](const RenderParams& q) {
         if (pool) k_render_pool<<<grid, 32 * POOL_WARPS, 0, st>>>(ctx->scene, q);
-        else if (use_bvh && ctx->knobs.bvh_trav == 0) k_render_mega<false, true, true, 0><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q);
+        else if (use_bvh && ctx->knobs.bvh_trav != 1) k_render_mega<false, true, true, 0><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q);
         else if (use_bvh) k_render_mega<false, true, true, 1><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q); // flat loop (nested measures the same on C3/C4)
         else if (sb > MAX_STAGE_BYTES) k_render_mega<false, true, false><<<grid, MEGA_THREADS, 0, st>>>(ctx->scene, q);
         else if (flat) k_render_mega<true, true, false><<<grid, MEGA_THREADS, sb, st>>>(ctx->scene, q);
@@ -490,16 +488,25 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
         // lanes per pixel: 16 (two pixels per warp) from 32 samples -- measured equal or better than 32 lanes on one pixel even
         // at 256 samples -- and 8 (four pixels per warp) below, so that every lane gets at least two samples
         const unsigned blocks = (unsigned)ctx->sm_count * 8;
-        // lanes per pixel.  Without beams: 16 (two pixels per warp) from 32 samples, 8 below, so that every lane gets at least two
-        // samples.  From 128 samples per call the pixel's primary rays share a candidate list (beams, below) and 8 lanes per pixel
-        // measure best (C3 41.2 -> 34.4 ms, the 512-sample share of C5 on 8 GPUs 321.6 -> 256.1 ms; 4 lanes the same, 16 lanes +10 %)
-        const int beam_min = ctx->knobs.bvh_beam >= 0 ? ctx->knobs.bvh_beam : RTCU_DEFAULT_BEAM_MIN;
-        const int lanes = ctx->knobs.bvh_lanes ? ctx->knobs.bvh_lanes : (beam_min > 0 && n_samples >= 8u * (uint32_t)beam_min ? 8 : n_samples >= 32 ? 16 : 8);
+        // Patch beams (kernels.cuh, k_beam_lists): one walk per 8x4-pixel patch before the frame replaces the primary rays'
+        // traversals by a scan of the patch's candidate leaves.  Needs a viewport whose perspective divide is constant (every
+        // camera::viewport, camera.hpp:122-137); RTCU_BVH_BEAM=0 disables.
+        const bool beam = ctx->knobs.bvh_beam != 0 && p.cam.w_const;
+        // lanes per pixel: 16 (two pixels per warp) from 32 samples per call, 8 (four pixels per warp) below, so that every lane gets
+        // at least two samples (RTCU_BVH_LANES to measure: with the beams 16 and 8 are within 2 % of each other, 4 is 3-7 % behind)
+        const int lanes = ctx->knobs.bvh_lanes ? ctx->knobs.bvh_lanes : (n_samples >= 32 ? 16 : 8);
         const int trav = ctx->knobs.bvh_trav >= 0 && ctx->knobs.bvh_trav <= 2 ? ctx->knobs.bvh_trav : RTCU_DEFAULT_TRAV;
         // pixel beams (kernels.cuh, beam_collect): one walk per pixel replaces the primary rays' traversals; worth it once a lane
         // traces several samples of the pixel (RTCU_BVH_BEAM: samples per lane from which beams are used, 0 = never)
-        const bool beam = beam_min > 0 && n_samples >= (uint32_t)(beam_min * lanes);
-        q.beam = beam ? 1 : 0;
+        q.beam = nullptr;
+        if (beam)
+        {
+            const uint32_t n_patches = ((v->tile_x1 - v->tile_x0 + BEAM_PATCH_W - 1) / BEAM_PATCH_W) * ((v->tile_y1 - v->tile_y0 + BEAM_PATCH_H - 1) / BEAM_PATCH_H);
+            CU(ctx->beam_lists.reserve(n_patches));
+            k_beam_lists<<<(n_patches + 127) / 128, 128, 0, st>>>(ctx->scene, q, ctx->beam_lists.p);
+            CU(cudaGetLastError());
+            q.beam = ctx->beam_lists.p;
+        }
         const int minb = ctx->knobs.bvh_minb; // experiment: CTAs per SM the beam kernel is compiled for (8 = 64 registers, 6 = 80)
 #define RTCU_LAUNCH_DIRECT(G, T, B, M) k_render_stragglers<true, G, T, B, M><<<(unsigned)ctx->sm_count * M, 128, 0, st>>>(ctx->scene, q)
 #define RTCU_LAUNCH_BEAM(G) (minb == 6 ? RTCU_LAUNCH_DIRECT(G, 0, true, 6) : minb == 7 ? RTCU_LAUNCH_DIRECT(G, 0, true, 7) : RTCU_LAUNCH_DIRECT(G, 0, true, 8))
@@ -512,9 +519,19 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
         (void)blocks;
         CU(cudaGetLastError());
         ctx->tile_hist_valid = false;
-        ctx->stats.kernel_launches = 1;
+        ctx->stats.kernel_launches = beam ? 2 : 1;
         ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
         return RTCU_OK;
+    }
+    // thread-per-pixel BVH frames (fewer than 16 samples per call: interactive refinement) use the patch beams too: a warp of
+    // k_render_mega covers exactly one 8x4 patch
+    if (use_bvh && !pool && ctx->knobs.bvh_beam != 0 && p.cam.w_const)
+    {
+        const uint32_t n_patches = ((v->tile_x1 - v->tile_x0 + BEAM_PATCH_W - 1) / BEAM_PATCH_W) * ((v->tile_y1 - v->tile_y0 + BEAM_PATCH_H - 1) / BEAM_PATCH_H);
+        CU(ctx->beam_lists.reserve(n_patches));
+        k_beam_lists<<<(n_patches + 127) / 128, 128, 0, st>>>(ctx->scene, p, ctx->beam_lists.p);
+        CU(cudaGetLastError());
+        p.beam = ctx->beam_lists.p;
     }
     const uint32_t n_tiles = grid.x * grid.y;
     const bool lpt = !pool && n_tiles >= 2u * 8u * (uint32_t)ctx->sm_count && ctx->knobs.tile_order != 0;
@@ -574,6 +591,7 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
         ctx->tile_hist_valid = false;
     launch_mega(p);
     CU(cudaGetLastError());
+    if (p.beam) ctx->stats.kernel_launches++;
     if (p.segment_budget)
     {
         // the accumulate flag only applies to the first pass: the second adds onto what the first wrote
@@ -1059,7 +1077,23 @@ uint32_t rtcu_bvh_threshold(void)
 int rtcu_reload_env(rtcu_ctx* ctx)
 {
     if (!ctx) return fail(RTCU_ERR_INVALID, "null context");
+    const bool pin = ctx->knobs.register_output;
     ctx->knobs.load();
+    ctx->knobs.register_output = ctx->knobs.register_output || pin; // (a caller's rtcu_set_output_pinning survives)
+    return RTCU_OK;
+}
+
+int rtcu_set_output_pinning(rtcu_ctx* ctx, int enable)
+{
+    if (!ctx) return fail(RTCU_ERR_INVALID, "null context");
+    CU(cudaSetDevice(ctx->device));
+    ctx->knobs.register_output = enable != 0;
+    if (!enable)
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        drop_registration(ctx);
+        ctx->out_reg = HostReg{};
+    }
     return RTCU_OK;
 }
 
@@ -1139,7 +1173,7 @@ void rtcu_destroy(rtcu_ctx* ctx)
     ctx->wf_rad.release(); ctx->wf_sum.release(); ctx->wf_hit.release(); ctx->wf_counts.release(); ctx->h_wf_counts.release();
     ctx->raster_prim.release(); ctx->raster_depth.release();
     ctx->h_raster_prim.release(); ctx->h_raster_depth.release();
-    ctx->tile_cost.release(); ctx->tile_order.release();
+    ctx->tile_cost.release(); ctx->tile_order.release(); ctx->beam_lists.release();
     ctx->counters.release(); ctx->stragglers.release(); ctx->straggler_count.release(); ctx->h_counters.release(); ctx->scratch.release();
     for (auto& e : ctx->tile_ev)
         if (e) cudaEventDestroy(e);
@@ -1799,7 +1833,7 @@ int rtcu_intersect_batch(rtcu_ctx* ctx, const float* o, const float* d, uint32_t
     const size_t sb = stage_bytes(ctx);
     CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), st));
     CU(cudaEventRecord(ctx->ev[0], st));
-    if (use_bvh && ctx->knobs.bvh_trav == 0)
+    if (use_bvh && ctx->knobs.bvh_trav != 1)
         k_intersect_batch<false, true, 0><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);
     else if (use_bvh)
         k_intersect_batch<false, true, 1><<<blocks, 256, 0, st>>>(ctx->scene, d_o, d_d, n, d_hit, d_prim, d_t, normal ? d_n : nullptr, ctx->counters.p);

@@ -38,7 +38,7 @@ struct WfWave {
 
 enum { WF_MISS = 0, WF_LAMBERT = 1, WF_METAL = 2, WF_DIELECTRIC = 3 };
 
-__global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ RenderParams p, const WfQueues q, const WfWave w)
+__global__ void __launch_bounds__(256) k_wf_generate(const RenderParams p, const WfQueues q, const WfWave w)
 {
     const uint32_t npix = w.tile_w * w.tile_h, n = npix * w.n_slots;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -93,7 +93,7 @@ __device__ __forceinline__ void wf_append_sorted(const WfQueues& q, int kind, ui
 }
 
 template <bool STAGE, bool BVH>
-__global__ void __launch_bounds__(256) k_wf_intersect(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p, const WfQueues q, const int cur)
+__global__ void __launch_bounds__(256) k_wf_intersect(const SceneDev sc, const RenderParams p, const WfQueues q, const int cur)
 {
     extern __shared__ float4 smem[];
     const float4* s_sph = sc.pairs;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) k_wf_intersect(const __grid_constant__ Sc
     }
 }
 
-__global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ SceneDev sc, const __grid_constant__ RenderParams p, const WfQueues q, const WfWave w)
+__global__ void __launch_bounds__(256) k_wf_shade(const SceneDev sc, const RenderParams p, const WfQueues q, const WfWave w)
 {
     const uint32_t c0 = q.counts[2], c1 = q.counts[3], c2 = q.counts[4], c3 = q.counts[5];
     const uint32_t total = c0 + c1 + c2 + c3;
@@ -234,7 +234,7 @@ __global__ void k_wf_advance(const WfQueues q)
 }
 
 // frame_sum[pixel] (+)= rad[0][pixel] + rad[1][pixel] + ... in ascending sample order; `first` starts the sum at 0
-__global__ void __launch_bounds__(256) k_wf_accumulate(const __grid_constant__ RenderParams p, const WfQueues q, const WfWave w, float4* __restrict__ frame_sum, int first)
+__global__ void __launch_bounds__(256) k_wf_accumulate(const RenderParams p, const WfQueues q, const WfWave w, float4* __restrict__ frame_sum, int first)
 {
     const uint32_t npix = w.tile_w * w.tile_h;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += gridDim.x * blockDim.x)
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) k_wf_accumulate(const __grid_constant__ R
 }
 
 // frame_sum -> accum (optionally on top of the previous contents) and the packed image, over the tile
-__global__ void __launch_bounds__(256) k_wf_finish(const __grid_constant__ RenderParams p, const float4* __restrict__ frame_sum, uint32_t tile_w, uint32_t tile_h)
+__global__ void __launch_bounds__(256) k_wf_finish(const RenderParams p, const float4* __restrict__ frame_sum, uint32_t tile_w, uint32_t tile_h)
 {
     const uint32_t npix = tile_w * tile_h;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += gridDim.x * blockDim.x)

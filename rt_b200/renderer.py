@@ -237,6 +237,10 @@ class Context:
     def sync(self) -> None:
         nat.check(self._lib.rtcu_sync(self._h))
 
+    def set_output_pinning(self, enable: bool) -> None:
+        """rtcu_set_output_pinning: page-lock a pageable image that is handed over frame after frame (what the plugin does)"""
+        nat.check(self._lib.rtcu_set_output_pinning(self._h, int(enable)))
+
     def reload_env(self) -> None:
         """the RTCU_* knobs are read at rtcu_create; re-read them for this context (A/B tests that change os.environ)"""
         nat.check(self._lib.rtcu_reload_env(self._h))

@@ -475,11 +475,12 @@ def test_tile_issue_order_never_changes_the_image(ctx, scenes, knobs):
             np.testing.assert_array_equal(rgba8, ref_rgba8)
             assert ctx.stats()["segments"] == segs
             launches.append(ctx.stats()["kernel_launches"])
-        assert launches[0] == 2 and launches[1] == 3  # second frame: k_tile_order + megakernel + stragglers
+        beams = 1 if ctx.stats()["accel"] == nat.ACCEL_BVH else 0  # a BVH frame is preceded by k_beam_lists
+        assert launches[0] == 2 + beams and launches[1] == 3 + beams  # second frame: k_tile_order + megakernel + stragglers
         knobs(RTCU_TILE_ORDER="1")
         rgba8, accum = ctx.render(v, want_accum=True)
         np.testing.assert_array_equal(accum, ref_accum)
-        assert ctx.stats()["kernel_launches"] == 3
+        assert ctx.stats()["kernel_launches"] == 3 + beams
         knobs(RTCU_TILE_ORDER=None)
 
 
@@ -497,7 +498,16 @@ def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes,
         v = make_view(sc, w, h, **kw)
         rgba8, accum = ctx.render(v, want_accum=True)
         segs = ctx.stats()["segments"]
-        assert ctx.stats()["kernel_launches"] == 1 and (accum[..., 3] == spp).all()
+        assert ctx.stats()["kernel_launches"] == 2 and (accum[..., 3] == spp).all()  # k_beam_lists + the trace kernel
+        # without the patch beams every primary ray traverses: the same hits, hence the same paths (equal segment counts); which
+        # lane traces which sample shifts (a lane with a list advances two segments per iteration), so the sums agree to fp32 order
+        knobs(RTCU_BVH_BEAM="0")
+        rgba8_nb, accum_nb = ctx.render(v, want_accum=True)
+        assert ctx.stats()["segments"] == segs and ctx.stats()["kernel_launches"] == 1
+        knobs(RTCU_BVH_BEAM=None)
+        np.testing.assert_array_equal(accum_nb[..., 3], accum[..., 3])
+        np.testing.assert_allclose(accum_nb[..., :3], accum[..., :3], rtol=4e-6, atol=1e-6)
+        assert np.abs(unpack_rgba(rgba8_nb) - unpack_rgba(rgba8)).max() <= 1
         knobs(RTCU_BVH_DIRECT="0")
         rgba8_t, accum_t = ctx.render(v, want_accum=True)
         assert ctx.stats()["segments"] == segs and ctx.stats()["kernel_launches"] >= 2
@@ -515,18 +525,20 @@ def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes,
         tkw = dict(samples_per_pixel=16, max_bounces=depth, material_mode=nat.MODE_SM)
         tv = make_view(sc, tw, th, tile=tile, **tkw) if tile else make_view(sc, tw, th, **tkw)
         _, small = ctx.render(tv, want_accum=True)
-        assert ctx.stats()["kernel_launches"] == 1
+        assert ctx.stats()["kernel_launches"] == 2
         knobs(RTCU_BVH_DIRECT="0")
         _, small_t = ctx.render(tv, want_accum=True)
         knobs(RTCU_BVH_DIRECT=None)
         np.testing.assert_array_equal(small[..., 3], small_t[..., 3])
         np.testing.assert_allclose(small[..., :3], small_t[..., :3], rtol=4e-6, atol=1e-6)
         assert small[..., 3].sum() == 16 * (1 if tile else tw * th)
-    # a partial tile writes only the tile, and equals the same pixels of the frame bit for bit (per-pixel work is independent)
+    # a partial tile writes only the tile, and equals the same pixels of the frame (same paths; the tile's 8x4 patches start at
+    # the tile's corner, so which patches have a beam list -- and with it the order of a pixel's partial sums -- may differ)
     img = np.full((h, w), 0xDEADBEEF, np.uint32)
     tv = make_view(sc, w, h, tile=(13, 9, 150, 100), **kw)
     part, pacc = ctx.render(tv, rgba8=img, want_accum=True)
-    np.testing.assert_array_equal(pacc[9:100, 13:150], accum[9:100, 13:150])
+    np.testing.assert_array_equal(pacc[9:100, 13:150, 3], accum[9:100, 13:150, 3])
+    np.testing.assert_allclose(pacc[9:100, 13:150, :3], accum[9:100, 13:150, :3], rtol=4e-6, atol=1e-6)
     assert (part[:9] == 0xDEADBEEF).all() and (part[:, 150:] == 0xDEADBEEF).all()
     # rtcu_render_device with accumulate: two calls of 64 samples onto one device buffer = one call of 128 (fp32 order)
     dev = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda:0")

@@ -148,6 +148,7 @@ def test_pageable_destination_is_registered_once_and_survives_a_remap(scenes, na
     addr = libc.mmap(None, nbytes, prot, flags_, -1, 0)
     assert addr not in (None, C.c_void_p(-1).value)
     with Context(0) as c:  # its own context: registrations are per context
+        c.set_output_pinning(True)  # what the plugin does: the image is handed over frame after frame
         c.upload_scene(sc)
         v = make_view(sc, w, h, samples_per_pixel=spp, max_bounces=20, material_mode=nat.MODE_SM)
         want, _ = c.render(v, rgba8=np.zeros((h, w), np.uint32))  # a throw-away pageable array: staged or registered, either way right

@@ -253,13 +253,13 @@ int bvh_replay_ray2(const float* nodes, const float* leaves, const float o[3], c
     return 1;
 }
 
-/* ---- pixel beams (kernels.cuh: beam_setup, beam_collect, beam_closest_sphere): ONE conservative walk per pixel with the centre
- * ray, margins widened by the pixel's footprint and no closest-hit cull, collects the leaves any primary ray of the pixel could
- * hit; a sample's primary ray then takes the (t, index) minimum over those leaves only.  rays: 5 x (o, d) = the centre ray and the
- * rays through the pixel's four corners.  Returns the list length, or -1 when the pixel keeps the traversal (too many leaves or
- * node visits, centre ray not unit length). */
-#define BEAM_MAX 8
-#define BEAM_MAX_VISITS 48
+/* ---- patch beams (kernels.cuh: k_beam_lists, beam_collect, beam_closest_sphere): ONE conservative walk per patch of pixels with
+ * the patch's centre ray, margins widened by the patch's footprint and no closest-hit cull, collects the leaves any primary ray
+ * of the patch could hit; a sample's primary ray then takes the (t, index) minimum over those leaves only.  rays: 5 x (o, d) =
+ * the centre ray and the rays through the patch's four corners.  Returns the list length, or -1 when the patch keeps the
+ * traversal (too many leaves or node visits, centre ray not unit length). */
+#define BEAM_MAX 16
+#define BEAM_MAX_VISITS 96
 #define BEAM_EPS_D (16.0f * 5.9604645e-8f)
 int bvh_replay_beam_collect(const float* nodes, const float* rays, float* list_tn, uint32_t* list_leaf)
 {
