@@ -454,8 +454,11 @@ __device__ __forceinline__ bool closest_sphere_bvh2(const SceneDev& sc, const To
 // ancestor box of the sphere, and its entry distance tn0 <= t' (which makes `tn0 > best_t` a valid reason to stop early).
 // kappa_b is the margin factor of a ray that is unit length to within BEAM_EPS_D; a sample ray outside that (never seen:
 // primary directions are normalised) traverses.  tests/test_bvh_replay.py replays this on the CPU against the oracle's scan.
-constexpr int BEAM_MAX = 16;                        // leaves per list
-constexpr int BEAM_MAX_VISITS = 96;                 // node visits after which a beam is given up
+#ifndef RTCU_BEAM_MAX
+#define RTCU_BEAM_MAX 16
+#endif
+constexpr int BEAM_MAX = RTCU_BEAM_MAX;             // leaves per list
+constexpr int BEAM_MAX_VISITS = 6 * BEAM_MAX;       // node visits after which a beam is given up
 constexpr float BEAM_EPS_D = 16.0f * 5.9604645e-8f; // |d.d - 1| bound of the rays that may use a list
 constexpr uint32_t BEAM_PATCH_W = 8, BEAM_PATCH_H = 4; // the patches k_render_stragglers enumerates in direct mode
 struct BeamEntry { float tn; uint32_t leaf; };

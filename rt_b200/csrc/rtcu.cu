@@ -436,7 +436,10 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
     // straggler hand-off (see k_render_stragglers): budget = 3x the samples of this call + 64 segments per pixel
     const uint32_t n_samples = v->sample_end - v->sample_begin;
     p.segment_budget = straggler_budget_for(ctx, n_samples, use_bvh);
-    CU(ctx->stragglers.reserve((size_t)v->width * v->height));
+    // the queue of the second pass: one entry per pixel of the tile at most -- and none at all where no thread can hand over (no
+    // budget, or the frame takes the lanes-share-a-pixel path, which has no second pass)
+    if (p.segment_budget && !uses_direct_mode(ctx, v))
+        CU(ctx->stragglers.reserve((size_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0)));
     p.stragglers = ctx->stragglers.p;
     p.straggler_count = ctx->straggler_count.p;
     CU(cudaMemsetAsync(ctx->straggler_count.p, 0, sizeof(unsigned int), st));
