@@ -63,6 +63,7 @@ struct RenderParams {
     const uint32_t* tile_order;   // CTA b renders tile tile_order[b] (nullable: CTA b renders tile b)
     int direct;                   // != 0: k_render_stragglers renders every pixel of the tile itself (no first pass, no queue)
     const struct BeamList* beam;  // non-null (direct mode): per 8x4 patch, the leaves its primary rays can hit (k_beam_lists)
+    float* run_scratch;           // k_render_runs: per lane group, RUN x 3 x G partial sums (lanes' shares of the run's pixels)
 };
 
 #ifndef RTCU_PRIM_MISS
@@ -1113,6 +1114,177 @@ __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const SceneDev 
             atomicAdd(p.counters + 1, nodes);
             atomicAdd(p.counters + 2, tests);
         }
+    }
+}
+
+// ---- direct mode without the end-of-pixel stall: lanes move on to the group's next pixel -------------------------------------
+// k_render_stragglers in direct mode lets G lanes share ONE pixel's samples and ends the pixel with a reduction: when the pixel
+// has no unclaimed sample left, its lanes idle until the slowest path is done.  With 4 samples per lane (C4: 64 spp, 16 lanes)
+// that idling is 18 of 32 lanes active (ncu) -- the compaction tools/bvh_warp_sim.cpp priced at 9 %.  Here a warp takes a whole
+// 8x4 patch and each of its 32 / G lane groups a RUN of G pixels of it; a lane whose path has ended claims the next unclaimed
+// (pixel, sample) of the run in lexicographic order -- by ballot rank, so the assignment depends on path lengths only and is
+// deterministic -- and simply carries on into the next pixel.  A lane visits the run's pixels in ascending order, so it adds
+// to each pixel at most one partial sum: on leaving a pixel it parks that sum in a scratch slot (run pixel, lane), and when the
+// run is done lane k adds up pixel k's slots in lane order (a fixed order: same paths, same segment counts, sums equal to the
+// other kernels' up to fp32 order).  The stall now happens once per G pixels instead of once per pixel.
+// Beams: the warp's patch is one beam list.  The scratch slots live in global memory (L2; a few accesses per lane and run).
+// A warp item is GROUPS x RUN pixels of a patch (RUN <= G); shorter runs keep the item count high enough for the tail.
+// MEASURED (B200, RTCU_BVH_RUNS=1), against k_render_stragglers direct mode: RUN 8: C3 33.1 vs 30.5 ms, C4 79.6 vs 80.5 ms, C5/8 241.5 vs
+// 231.7 ms; RUN 4: 32.7 / 83.2 / 242.6; RUN 16 (a whole patch per warp): 38.9 / 84.0 / 248.8.  The stall it removes is real (C4) but at
+// >= 256 samples per pixel there is little stall to remove and the claim bookkeeping, the lanes of a group straddling two pixels and
+// the 172 B of spills (128 B there) cost more.  Kept as an experiment, not the default.
+template <int G_LANES, bool BEAM, int RUN_PIXELS>
+__global__ void __launch_bounds__(128, 8) k_render_runs(const SceneDev sc, const RenderParams p)
+{
+    // a warp item is GROUPS x RUN consecutive pixels of a patch (in the patch's row-major order); SUBS items make a patch
+    constexpr uint32_t G = G_LANES, GROUPS = 32u / G, RUN = RUN_PIXELS, SUBS = 32u / (GROUPS * RUN);
+    static_assert(RUN <= G && GROUPS * RUN * SUBS == 32u, "a run is at most G pixels (lane k sums pixel k) and runs tile the patch");
+    const uint32_t lane = threadIdx.x & 31u, lg = lane & (G - 1u), grp = lane / G;
+    const uint32_t gmask = ((G == 32u) ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G), below = gmask & ((1u << lane) - 1u);
+    const uint32_t tile_w = p.tile_x1 - p.tile_x0, tile_h = p.tile_y1 - p.tile_y0;
+    const uint32_t patches_x = (tile_w + 7u) >> 3, count = patches_x * ((tile_h + 3u) >> 2) * SUBS;
+    const uint32_t spp = p.sample_end - p.sample_begin; // >= 16 >= G: a claim wraps into the next pixel at most once
+    float* const slots = p.run_scratch + ((size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + grp) * (RUN * 3u * G);
+    unsigned long long segs = 0;
+    BvhStats bst;
+    bst.nodes = 0;
+    bst.tests = 0;
+    const TopNodes top = TopNodes{ nullptr, 0u };
+    for (;;)
+    {
+        uint32_t item = 0;
+        if (lane == 0) item = (uint32_t)atomicAdd(p.counters + 3, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= count) break;
+        const uint32_t patch = item / SUBS, first = (item % SUBS) * GROUPS * RUN + grp * RUN; // the run's first pixel within the patch
+        const uint32_t patch_x0 = (patch % patches_x) * 8u, patch_y0 = (patch / patches_x) * 4u;
+        // the run's pixels that lie inside the tile (ragged patches at the right and bottom edge), as a bit mask over the run
+        uint32_t valid = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < RUN; k++)
+        {
+            const uint32_t in_patch = first + k;
+            valid |= (patch_x0 + (in_patch & 7u) < tile_w && patch_y0 + (in_patch >> 3) < tile_h) ? (1u << k) : 0u;
+        }
+        const uint32_t n_valid = __popc(valid);
+        for (uint32_t k = 0; k < RUN * 3u; k++) __stcg(slots + k * G + lg, 0.0f);
+        const BeamList* beam = nullptr;
+        int beam_n = -1;
+        if (BEAM && p.beam)
+        {
+            beam = p.beam + patch;
+            beam_n = __ldg(&beam->n);
+        }
+        const bool use_beam = beam_n >= 0;
+
+        RngKey key;
+        key.ks = &p.rk;
+        key.pixel = 0;
+        key.sample = 0;
+        V3 sum = v3(0.0f, 0.0f, 0.0f);
+        V3 thr = v3(1.0f, 1.0f, 1.0f);
+        uint32_t seg = 0, px = 0, py = 0;
+        int cur = -1; // the valid pixel of the run this lane is adding to
+        Ray ray;
+        ray.o = v3(0.0f, 0.0f, 0.0f);
+        ray.d = v3(0.0f, 0.0f, 1.0f);
+        uint32_t next_j = 0, next_s = 0; // the next unclaimed (valid pixel, sample) of the run; uniform within the group
+        bool live = false;
+        for (;;)
+        {
+            const unsigned idle = __ballot_sync(0xffffffffu, !live) & gmask;
+            uint32_t j = next_j, smp = next_s + __popc(idle & below);
+            if (smp >= spp) { smp -= spp; j++; }
+            const bool fresh = !live && j < n_valid;
+            if (fresh)
+            {
+                if ((int)j != cur)
+                {
+                    if (cur >= 0) // leaving a pixel: park this lane's share of it
+                    {
+                        __stcg(slots + (cur * 3u + 0u) * G + lg, sum.x);
+                        __stcg(slots + (cur * 3u + 1u) * G + lg, sum.y);
+                        __stcg(slots + (cur * 3u + 2u) * G + lg, sum.z);
+                    }
+                    cur = (int)j;
+                    sum = v3(0.0f, 0.0f, 0.0f);
+                    const uint32_t in_patch = first + __fns(valid, 0u, (int)j + 1); // the j-th valid pixel of the run
+                    px = p.tile_x0 + patch_x0 + (in_patch & 7u);
+                    py = p.tile_y0 + patch_y0 + (in_patch >> 3);
+                    key.pixel = py * p.width + px;
+                }
+                key.sample = p.sample_begin + smp;
+                seg = 0;
+                thr = v3(1.0f, 1.0f, 1.0f);
+                ray = generate(p.cam, key, px, py);
+                live = true;
+            }
+            next_s += (uint32_t)__popc(idle);
+            if (next_s >= spp) { next_s -= spp; next_j++; }
+            if (next_j > n_valid) next_j = n_valid; // (all claimed: stay put)
+            if (!__any_sync(0xffffffffu, live)) break;
+            // pass 0: the lanes that have just started a sample find their primary hit in the patch's list; pass 1: every lane in
+            // flight traverses (one rolled copy of the segment code, see k_render_stragglers)
+            const bool listed = BEAM && use_beam && fresh && fabsf(dot3(ray.d, ray.d) - 1.0f) <= BEAM_EPS_D;
+#pragma unroll 1
+            for (int pass = (BEAM && __any_sync(0xffffffffu, listed)) ? 0 : 1; pass < 2; pass++)
+            {
+                if (pass == 0 ? listed : live)
+                {
+                    segs++;
+                    Hit h;
+                    if (BEAM && pass == 0)
+                    {
+                        float ts;
+                        int is;
+                        beam_closest_sphere(sc, beam, beam_n, ray, ts, is, bst);
+                        h = combine_with_planes(sc, sc.planes, ray, ts, is);
+                    }
+                    else
+                        h = closest_hit_bvh<0>(sc, sc.planes, ray, bst, top);
+                    if (shade_segment<true>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, h)) live = false;
+                }
+            }
+        }
+        if (cur >= 0)
+        {
+            __stcg(slots + (cur * 3u + 0u) * G + lg, sum.x);
+            __stcg(slots + (cur * 3u + 1u) * G + lg, sum.y);
+            __stcg(slots + (cur * 3u + 2u) * G + lg, sum.z);
+        }
+        __syncwarp();
+        if (lg < n_valid) // lane k of the group adds up the run's k-th valid pixel, shares in lane order
+        {
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+            for (uint32_t l = 0; l < G; l++)
+            {
+                sx = __fadd_rn(sx, __ldcg(slots + (lg * 3u + 0u) * G + l));
+                sy = __fadd_rn(sy, __ldcg(slots + (lg * 3u + 1u) * G + l));
+                sz = __fadd_rn(sz, __ldcg(slots + (lg * 3u + 2u) * G + l));
+            }
+            const uint32_t in_patch = first + __fns(valid, 0u, (int)lg + 1);
+            const uint32_t pix = (p.tile_y0 + patch_y0 + (in_patch >> 3)) * p.width + p.tile_x0 + patch_x0 + (in_patch & 7u);
+            float4 acc = p.accumulate ? p.accum[pix] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            acc.x = __fadd_rn(acc.x, sx); acc.y = __fadd_rn(acc.y, sy); acc.z = __fadd_rn(acc.z, sz);
+            acc.w = __fadd_rn(acc.w, (float)spp);
+            p.accum[pix] = acc;
+            if (p.rgba8)
+                p.rgba8[pix] = pack_pixel(acc.x, acc.y, acc.z, p.spp_resolve);
+        }
+        __syncwarp(); // the slots are zeroed again for the next patch only after they have been read
+    }
+    unsigned long long nodes = bst.nodes, tests = bst.tests;
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        segs += __shfl_down_sync(0xffffffffu, segs, off);
+        nodes += __shfl_down_sync(0xffffffffu, nodes, off);
+        tests += __shfl_down_sync(0xffffffffu, tests, off);
+    }
+    if (lane == 0 && segs)
+    {
+        atomicAdd(p.counters, segs);
+        atomicAdd(p.counters + 1, nodes);
+        atomicAdd(p.counters + 2, tests);
     }
 }
 

@@ -322,3 +322,47 @@ def test_accumulate_flag_needs_sums_of_the_same_size(ctx, scenes):
     ctx.accum_upload(np.zeros((120, 200, 4), np.float32))
     img0, accum0 = ctx.render(make_view(sc, 200, 120, flags=nat.FLAG_ACCUMULATE, **kw), want_accum=True)
     np.testing.assert_array_equal(accum0, whole_accum)                      # onto zeros: the plain frame
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("run", ["4", "8"])
+def test_runs_kernel_traces_the_same_paths_as_direct_mode(ctx, oracle, scenes, knobs, run):
+    """k_render_runs (RTCU_BVH_RUNS=1, an experiment that is not the default): lane groups walk runs of pixels instead of one
+    pixel at a time.  Same paths (equal segment counts), per-pixel sums equal up to fp32 order, deterministic, ragged patches /
+    sub-patch tiles / sample ranges included, and the oracle agrees."""
+    sc, depth = scenes["c3"]
+    ctx.upload_scene(sc)
+    w, h = 203, 117  # ragged against the 8x4 patches
+    for spp, rng in ((20, None), (96, None), (64, (7, 40))):  # 8 lanes per pixel, 16 lanes per pixel, a sample range
+        kw = dict(samples_per_pixel=spp, max_bounces=depth, material_mode=nat.MODE_SM)
+        if rng:
+            kw["sample_range"] = rng
+        v = make_view(sc, w, h, **kw)
+        _, want = ctx.render(v, want_accum=True)
+        segs = ctx.stats()["segments"]
+        knobs(RTCU_BVH_RUNS="1", RTCU_BVH_RUN=run)
+        img, got = ctx.render(v, want_accum=True)
+        assert ctx.stats()["segments"] == segs and ctx.stats()["kernel_launches"] == 2
+        _, again = ctx.render(v, want_accum=True)
+        np.testing.assert_array_equal(again, got)
+        knobs(RTCU_BVH_BEAM="0")
+        _, nobeam = ctx.render(v, want_accum=True)
+        assert ctx.stats()["segments"] == segs and ctx.stats()["kernel_launches"] == 1
+        knobs(RTCU_BVH_RUNS=None, RTCU_BVH_RUN=None, RTCU_BVH_BEAM=None)
+        np.testing.assert_array_equal(got[..., 3], want[..., 3])
+        np.testing.assert_allclose(got[..., :3], want[..., :3], rtol=4e-6, atol=1e-6)
+        np.testing.assert_allclose(nobeam[..., :3], want[..., :3], rtol=4e-6, atol=1e-6)
+        if rng is None:
+            r_rgba8, r_accum, r_segs = oracle.render(sc, v, threads=0)
+            assert r_segs == segs
+            assert np.abs(unpack_rgba(img) - unpack_rgba(r_rgba8)).max() <= 1
+    knobs(RTCU_BVH_RUNS="1", RTCU_BVH_RUN=run)
+    for tw, th, tile in ((3, 2, None), (40, 30, (17, 11, 18, 12)), (w, h, (13, 9, 150, 100))):
+        tkw = dict(samples_per_pixel=16, max_bounces=depth, material_mode=nat.MODE_SM)
+        tv = make_view(sc, tw, th, tile=tile, **tkw) if tile else make_view(sc, tw, th, **tkw)
+        knobs(RTCU_BVH_RUNS="1", RTCU_BVH_RUN=run)
+        _, small = ctx.render(tv, want_accum=True)
+        knobs(RTCU_BVH_RUNS=None)
+        _, small_d = ctx.render(tv, want_accum=True)
+        np.testing.assert_array_equal(small[..., 3], small_d[..., 3])
+        np.testing.assert_allclose(small[..., :3], small_d[..., :3], rtol=4e-6, atol=1e-6)
