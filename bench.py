@@ -549,7 +549,8 @@ def run_gpu(args):
         is_bvh = stats["accel"] == nat.ACCEL_BVH
         facts = kernel_facts(cfg.key)
         roofline = {
-            "bound": "fp32", "kernel": "k_render_bvh (lanes share a pixel's samples)" if is_bvh else "k_render_mega",
+            "bound": "fp32", "kernel": ("k_render_bvh (lanes share a pixel's samples)" if is_bvh else
+                                       "k_render_scan_shared (small frame: lanes share a pixel's samples)" if int(stats.get("kernel_launches") or 0) == 1 else "k_render_mega"),
             "achieved": round(achieved, 3), "peak": round(peak_nominal, 2), "unit": "TFLOP/s", "frac": round(achieved / peak_nominal, 4),
             "traffic": facts.get("dram_bytes_per_launch") if world == 1 else None,
             "traffic_source": facts.get("source") if world == 1 else None,

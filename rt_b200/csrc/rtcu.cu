@@ -137,6 +137,8 @@ struct Knobs {
     int bvh_trav = -1;         // RTCU_BVH_TRAV: traversal variant of the BVH kernels (kernels.cuh, closest_hit_bvh): 0 = leaves tested
                                // inside the node visit (default, measured faster), 1 = deferred leaves, 2 = 1 + top levels in shared memory
     int bvh_lanes = 0;         // RTCU_BVH_LANES: lanes per pixel in direct mode (8 / 16 / 32), 0 = by sample count
+    int scan_direct = -1;      // RTCU_SCAN_DIRECT: scan (non-BVH) scenes rendered with G lanes sharing a pixel: G = 2 / 4 / 8 / 16 always,
+                               // 0 never, default: frames of fewer than 8 waves of tiles (launch_render_on)
     int bvh_run_pixels = 8;    // RTCU_BVH_RUN: pixels per lane-group run (4 / 8)
     bool bvh_runs = false;     // RTCU_BVH_RUNS=1: k_render_runs (lane groups walk runs of pixels) instead of k_render_stragglers'
                                // direct mode.  Measured, not default: C3 33.1 vs 30.5 ms, C4 79.6 vs 80.5 ms
@@ -158,6 +160,7 @@ struct Knobs {
         if (const char* e = getenv("RTCU_BVH_TRAV")) bvh_trav = atoi(e);
         if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) bvh_lanes = v; }
         if (const char* e = getenv("RTCU_BVH_RUNS")) bvh_runs = e[0] != '0';
+        if (const char* e = getenv("RTCU_SCAN_DIRECT")) { const int v = atoi(e); scan_direct = (v == 2 || v == 4 || v == 8 || v == 16) ? v : (e[0] == '0' ? 0 : -1); }
         if (const char* e = getenv("RTCU_BVH_RUN")) { const int v = atoi(e); if (v == 4 || v == 8) bvh_run_pixels = v; }
         if (const char* e = getenv("RTCU_BVH_MINB")) { const int v = atoi(e); if (v >= 6 && v <= 8) bvh_minb = v; }
         if (const char* e = getenv("RTCU_BVH_BEAM")) bvh_beam = atoi(e) < 0 ? 0 : atoi(e);
@@ -405,7 +408,17 @@ bool uses_direct_mode(const rtcu_ctx* ctx, const rtcu_view* v)
 {
     const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
     const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= ctx->knobs.bvh_threshold);
-    return use_bvh && ctx->have_bvh && pipe != RTCU_PIPE_WAVEFRONT && !ctx->knobs.pool && v->sample_end - v->sample_begin >= 16 && ctx->knobs.direct;
+    if (pipe == RTCU_PIPE_WAVEFRONT || ctx->knobs.pool || v->sample_end - v->sample_begin < 16) return false;
+    if (!(use_bvh && ctx->have_bvh))
+    {
+        // scan scenes: the thread-per-pixel grid wins once it has enough tiles to balance itself (measured crossover between
+        // 1280x720 and 1920x1080, i.e. 6 and 14 waves of 16x8 tiles); smaller frames take pixel-sized dynamic work items
+        const int sd = ctx->knobs.scan_direct;
+        if (sd >= 0) return sd != 0 && v->sample_end - v->sample_begin >= 2u * (uint32_t)sd;
+        const uint64_t n_tiles = (uint64_t)((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W) * ((v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
+        return n_tiles < 8ull * 8ull * (uint64_t)ctx->sm_count;
+    }
+    return ctx->knobs.direct;
 }
 
 int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_t* d_rgba8, int accumulate, cudaStream_t st);
@@ -501,6 +514,24 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
         // Patch beams (kernels.cuh, k_beam_lists): one walk per 8x4-pixel patch before the frame replaces the primary rays'
         // traversals by a scan of the patch's candidate leaves.  Needs a viewport whose perspective divide is constant (every
         // camera::viewport, camera.hpp:122-137); RTCU_BVH_BEAM=0 disables.
+        if (!use_bvh)
+        {
+            // lanes per pixel as for the BVH kernels: 16 once every lane gets four samples, else 8 (320x240 .. 1280x720 at 16 / 30 / 64 /
+            // 256 samples: 8 lanes win below 64 samples, 16 from there; 4 and 2 lanes are behind everywhere).  The primitives are read
+            // through L1: staging them in shared memory as k_render_mega does measures the same (C1 0.405 vs 0.406 ms).
+            switch (ctx->knobs.scan_direct > 0 ? ctx->knobs.scan_direct : (n_samples >= 64 ? 16 : 8))
+            {
+            case 2: k_render_stragglers<false, 2><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
+            case 4: k_render_stragglers<false, 4><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
+            case 8: k_render_stragglers<false, 8><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
+            default: k_render_stragglers<false, 16><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
+            }
+            CU(cudaGetLastError());
+            ctx->tile_hist_valid = false;
+            ctx->stats.kernel_launches = 1;
+            ctx->stats.pipeline = RTCU_PIPE_MEGAKERNEL;
+            return RTCU_OK;
+        }
         const bool beam = ctx->knobs.bvh_beam != 0 && p.cam.w_const;
         // lanes per pixel: 16 (two pixels per warp) from 32 samples per call, 8 (four pixels per warp) below, so that every lane gets
         // at least two samples (RTCU_BVH_LANES to measure: with the beams 16 and 8 are within 2 % of each other, 4 is 3-7 % behind)

@@ -79,11 +79,14 @@ def test_c4_full_size(ctx, c4, knobs):
     np.testing.assert_array_equal(acc_bvh[..., 3], acc_lin[..., 3])
     np.testing.assert_allclose(acc_bvh[..., :3], acc_lin[..., :3], rtol=4e-6, atol=1e-6)
     assert np.abs(unpack_rgba(rgba_lin[1200:1232, 1900:1964]) - unpack_rgba(rgba_a[1200:1232, 1900:1964])).max() <= 1
-    # with the thread-per-pixel kernel on both sides the buffers are bit-identical
-    knobs(RTCU_BVH_DIRECT="0")
+    # with the thread-per-pixel kernel on both sides the buffers are bit-identical (a tile this small would otherwise take the
+    # lanes-share-a-pixel kernel on the scan side too)
+    knobs(RTCU_BVH_DIRECT="0", RTCU_SCAN_DIRECT="0")
     _, acc_bvh_tpp = ctx.render(make_view(c4, 3840, 2160, tile=tile, flags=nat.ACCEL_BVH, **kw), want_accum=True)
-    knobs(RTCU_BVH_DIRECT=None)
-    np.testing.assert_array_equal(acc_bvh_tpp, acc_lin)
+    _, acc_lin_tpp = ctx.render(make_view(c4, 3840, 2160, tile=tile, flags=nat.ACCEL_LINEAR, **kw), want_accum=True)
+    knobs(RTCU_BVH_DIRECT=None, RTCU_SCAN_DIRECT=None)
+    np.testing.assert_array_equal(acc_bvh_tpp, acc_lin_tpp)
+    np.testing.assert_allclose(acc_lin[..., :3], acc_lin_tpp[..., :3], rtol=4e-6, atol=1e-6)
     # closest hits of 2^16 random + 2^16 silhouette-grazing rays: BVH == scan
     for o, d in (synth.random_rays(c4, 1 << 16, seed=3, spread=60.0), synth.grazing_rays(c4, 1 << 16, seed=4)):
         lin = ctx.intersect_batch(o, d, accel=nat.ACCEL_LINEAR)

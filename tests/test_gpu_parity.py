@@ -172,7 +172,7 @@ def test_render_c1_default_frame_vs_oracle(ctx, oracle, scenes):
     assert_images_match(rgba8, accum, r_rgba8, r_accum, 30)
 
 
-def test_render_c2_full_size_properties(ctx, oracle, scenes):
+def test_render_c2_full_size_properties(ctx, oracle, scenes, knobs):
     # BASELINE configs[1] at full size (1920x1080, 64 spp, depth 50, sm table): size-independent properties
     sc = scenes["c2"][0]
     ctx.upload_scene(sc)
@@ -185,9 +185,19 @@ def test_render_c2_full_size_properties(ctx, oracle, scenes):
     np.testing.assert_array_equal(rgba_a, rgba_b)
     assert ctx.stats()["segments"] == segs_a
     assert (accum_a[..., 3] == 64).all() and np.isfinite(accum_a).all() and ((rgba_a & 0xFF) == 0xFF).all()
-    # (2) tiles compose exactly: a tile render equals the same pixels of the full frame
+    # (2) tiles compose: a tile render equals the same pixels of the full frame -- the same paths; a tile this small is rendered
+    # with lanes sharing a pixel (launch_render_on: frames of fewer than 8 waves of tiles), so the sums differ in fp32 order only,
+    # and bit for bit when the tile is made to take the frame's kernel
     vt = make_view(sc, 1920, 1080, samples_per_pixel=64, max_bounces=50, material_mode=nat.MODE_SM, tile=(1000, 500, 1100, 540))
     rgba_t, accum_t = ctx.render(vt, want_accum=True)
+    assert ctx.stats()["kernel_launches"] == 1
+    np.testing.assert_array_equal(accum_t[500:540, 1000:1100, 3], accum_a[500:540, 1000:1100, 3])
+    np.testing.assert_allclose(accum_t[500:540, 1000:1100, :3], accum_a[500:540, 1000:1100, :3], rtol=4e-6, atol=1e-6)
+    assert np.abs(unpack_rgba(rgba_t[500:540, 1000:1100]) - unpack_rgba(rgba_a[500:540, 1000:1100])).max() <= 1
+    assert (rgba_t[:500] == 0).all()
+    knobs(RTCU_SCAN_DIRECT="0")
+    rgba_t, accum_t = ctx.render(vt, want_accum=True)
+    knobs(RTCU_SCAN_DIRECT=None)
     np.testing.assert_array_equal(accum_t[500:540, 1000:1100], accum_a[500:540, 1000:1100])
     np.testing.assert_array_equal(rgba_t[500:540, 1000:1100], rgba_a[500:540, 1000:1100])
     assert (rgba_t[:500] == 0).all()
@@ -460,6 +470,7 @@ def test_cheaper_exact_sqrt_rcp_div_equal_the_ieee_intrinsics_for_every_input(ct
 def test_tile_issue_order_never_changes_the_image(ctx, scenes, knobs):
     """The library times row-major against cost-sorted tile order over the first frames of a view and keeps the faster
     (rtcu.cu: launch_render).  Whatever it picks, and whichever phase a frame falls in, accum and pixels are bit-identical."""
+    knobs(RTCU_SCAN_DIRECT="0")  # (a scan frame of 1280x720 at 16 spp would take the kernel that has no tile order)
     for name, spp, flags in (("c2", 16, 0), ("c3", 8, 0), ("c3", 8, nat.ACCEL_LINEAR)):
         sc, depth = scenes[name]
         ctx.upload_scene(sc)  # resets the per-view history

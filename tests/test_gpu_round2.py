@@ -366,3 +366,54 @@ def test_runs_kernel_traces_the_same_paths_as_direct_mode(ctx, oracle, scenes, k
         _, small_d = ctx.render(tv, want_accum=True)
         np.testing.assert_array_equal(small[..., 3], small_d[..., 3])
         np.testing.assert_allclose(small[..., :3], small_d[..., :3], rtol=4e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,mode", [("c1", nat.MODE_MG), ("c2", nat.MODE_SM), ("planes", nat.MODE_SM)])
+def test_small_scan_frames_share_pixels_between_lanes(ctx, oracle, scenes, knobs, name, mode):
+    """Scan (non-BVH) scenes: a frame of fewer than 8 waves of 16x8 tiles, from 16 samples per call, is rendered by
+    k_render_stragglers in direct mode (8 or 16 lanes share a pixel's samples, pixel-sized work items handed out dynamically)
+    instead of the thread-per-pixel grid, which cannot balance so few tiles (C1 0.55 -> 0.41 ms).  Same paths (segment counts equal
+    the oracle's and the other kernel's), sums equal up to fp32 order, deterministic; tiles of such a frame compose bit for bit."""
+    sc, depth = scenes[name]
+    ctx.upload_scene(sc)
+    w, h = 203, 117
+    for spp in (20, 70):  # 8 lanes per pixel, 16 lanes per pixel
+        kw = dict(samples_per_pixel=spp, max_bounces=depth, material_mode=mode)
+        v = make_view(sc, w, h, **kw)
+        rgba8, accum = ctx.render(v, want_accum=True)
+        st = ctx.stats()
+        assert st["kernel_launches"] == 1 and st["accel"] == nat.ACCEL_LINEAR and (accum[..., 3] == spp).all()
+        rgba8_b, accum_b = ctx.render(v, want_accum=True)
+        np.testing.assert_array_equal(accum_b, accum)
+        np.testing.assert_array_equal(rgba8_b, rgba8)
+        r_rgba8, r_accum, r_segs = oracle.render(sc, v, threads=0)
+        assert r_segs == st["segments"]
+        np.testing.assert_allclose(accum[..., :3], r_accum[..., :3], rtol=2e-5, atol=1e-6)
+        assert np.abs(unpack_rgba(rgba8) - unpack_rgba(r_rgba8)).max() <= 1
+        knobs(RTCU_SCAN_DIRECT="0")  # the thread-per-pixel grid: sequential sums, bit-identical to the oracle's order
+        rgba8_t, accum_t = ctx.render(v, want_accum=True)
+        assert ctx.stats()["segments"] == st["segments"] and ctx.stats()["kernel_launches"] >= 2
+        knobs(RTCU_SCAN_DIRECT=None)
+        np.testing.assert_allclose(accum[..., :3], accum_t[..., :3], rtol=4e-6, atol=1e-6)
+        assert np.abs(unpack_rgba(rgba8) - unpack_rgba(rgba8_t)).max() <= 1
+        # a tile of the frame (ragged against the 8x4 patches) equals the frame's pixels bit for bit and leaves the rest alone
+        img = np.full((h, w), 0xDEADBEEF, np.uint32)
+        part, pacc = ctx.render(make_view(sc, w, h, tile=(13, 9, 150, 100), **kw), rgba8=img, want_accum=True)
+        np.testing.assert_array_equal(pacc[9:100, 13:150], accum[9:100, 13:150])
+        np.testing.assert_array_equal(part[9:100, 13:150], rgba8[9:100, 13:150])
+        assert (part[:9] == 0xDEADBEEF).all() and (part[:, :13] == 0xDEADBEEF).all() and (part[100:] == 0xDEADBEEF).all()
+        # sample ranges: the same paths, partitioned; accumulated on the device they resolve to the frame
+        lo = spp // 3
+        ctx.render(make_view(sc, w, h, sample_range=(0, lo), **kw))
+        segs_lo = ctx.stats()["segments"]
+        img2, acc2 = ctx.render(make_view(sc, w, h, sample_range=(lo, spp), flags=nat.FLAG_ACCUMULATE, **kw), want_accum=True)
+        assert segs_lo + ctx.stats()["segments"] == st["segments"]
+        np.testing.assert_array_equal(acc2[..., 3], accum[..., 3])
+        np.testing.assert_allclose(acc2[..., :3], accum[..., :3], rtol=4e-6, atol=1e-6)
+        assert np.abs(unpack_rgba(img2) - unpack_rgba(rgba8)).max() <= 1
+    # below 16 samples per call, and from 8 waves of tiles, the thread-per-pixel grid stays
+    ctx.render(make_view(sc, w, h, samples_per_pixel=15, max_bounces=depth, material_mode=mode))
+    assert ctx.stats()["kernel_launches"] >= 2
+    ctx.render(make_view(sc, 1920, 1080, samples_per_pixel=16, max_bounces=depth, material_mode=mode))
+    assert ctx.stats()["kernel_launches"] >= 2

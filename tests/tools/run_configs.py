@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--depth", type=int, default=0, help="override max_bounces (0 = the config's own)")
+    ap.add_argument("--size", default="", help="override the frame size, WxH")
+    ap.add_argument("--spp", type=int, default=0, help="override the samples per pixel")
     args = ap.parse_args()
     cfgs = configs()
     ctx = Context(0)
@@ -52,6 +54,10 @@ def main():
         upload_ms = (time.perf_counter() - t0) * 1e3
         if args.depth:
             c = dict(c, depth=args.depth)
+        if args.size:
+            c = dict(c, width=int(args.size.split("x")[0]), height=int(args.size.split("x")[1]))
+        if args.spp:
+            c = dict(c, spp=args.spp)
         v = make_view(sc, c["width"], c["height"], samples_per_pixel=c["spp"], max_bounces=c["depth"], material_mode=c["mode"],
                       sample_range=c.get("sample_range"), flags=args.flags)
         best, st = None, None
