@@ -139,6 +139,8 @@ struct Knobs {
     int bvh_lanes = 0;         // RTCU_BVH_LANES: lanes per pixel in direct mode (8 / 16 / 32), 0 = by sample count
     int scan_direct = -1;      // RTCU_SCAN_DIRECT: scan (non-BVH) scenes rendered with G lanes sharing a pixel: G = 2 / 4 / 8 / 16 always,
                                // 0 never, default: frames of fewer than 8 waves of tiles (launch_render_on)
+    bool zero_copy_direct = true; // RTCU_ZERO_COPY_DIRECT=0: no zero-copy output from the lanes-share-a-pixel kernels (their stores cross
+                                  // PCIe 8 or 16 bytes at a time; measured, that still beats a copy after the frame: C1 e2e 0.483 -> 0.438 ms)
     int bvh_run_pixels = 8;    // RTCU_BVH_RUN: pixels per lane-group run (4 / 8)
     bool bvh_runs = false;     // RTCU_BVH_RUNS=1: k_render_runs (lane groups walk runs of pixels) instead of k_render_stragglers'
                                // direct mode.  Measured, not default: C3 33.1 vs 30.5 ms, C4 79.6 vs 80.5 ms
@@ -160,6 +162,7 @@ struct Knobs {
         if (const char* e = getenv("RTCU_BVH_TRAV")) bvh_trav = atoi(e);
         if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) bvh_lanes = v; }
         if (const char* e = getenv("RTCU_BVH_RUNS")) bvh_runs = e[0] != '0';
+        if (const char* e = getenv("RTCU_ZERO_COPY_DIRECT")) zero_copy_direct = e[0] != '0';
         if (const char* e = getenv("RTCU_SCAN_DIRECT")) { const int v = atoi(e); scan_direct = (v == 2 || v == 4 || v == 8 || v == 16) ? v : (e[0] == '0' ? 0 : -1); }
         if (const char* e = getenv("RTCU_BVH_RUN")) { const int v = atoi(e); if (v == 4 || v == 8) bvh_run_pixels = v; }
         if (const char* e = getenv("RTCU_BVH_MINB")) { const int v = atoi(e); if (v >= 6 && v <= 8) bvh_minb = v; }
@@ -1569,8 +1572,7 @@ int rtcu_render(rtcu_ctx* ctx, const rtcu_view* view, uint32_t* rgba8_out, float
     // verified (see output_alias).
     uint32_t* d_out = rgba8_out ? ctx->rgba8.p : nullptr;
     bool zero_copy = false, verify = false;
-    // (not in direct mode: there one lane per pixel stores 4 bytes at a time, which would cross PCIe as single-pixel writes)
-    if (rgba8_out && full && ctx->knobs.zero_copy && !uses_direct_mode(ctx, view))
+    if (rgba8_out && full && ctx->knobs.zero_copy && (ctx->knobs.zero_copy_direct || !uses_direct_mode(ctx, view)))
     {
         if (uint32_t* alias = output_alias(ctx, rgba8_out, npix, &verify))
         {
