@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(128) k_beam_lists(const SceneDev sc, const Ren
     beam_collect(sc.bvh_nodes, rc, sigma, rho, lists + patch);
 }
 
-template <bool BVH, int G_LANES = 32, int TRAV = 1, bool BEAM = false, int MINB = 8>
+template <bool BVH, int G_LANES = 32, int TRAV = 1, bool BEAM = false, int MINB = 8, bool NESTED = false>
 __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const SceneDev sc, const RenderParams p)
 {
     __shared__ float4 s_top[TRAV == 2 ? 8 * TOP_NODES : 1];
@@ -1033,6 +1033,30 @@ __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const SceneDev 
         // at once (ballot rank in lane order -- deterministic), so lanes stay busy until the pixel runs out of samples
         uint32_t next = w.y;
         bool live = false;
+        if (!BVH && NESTED)
+        {
+            // scan scenes with a handful of primitives: generate and shade dominate, and they run fullest when a lane simply loops
+            // over its own share of the pixel's samples (lane l of the group: samples l, l + G, ...; cf. k_render_mega's plain loop)
+            key.sample = w.y + (lane & (G - 1u));
+            if (key.sample < p.sample_end)
+            {
+                ray = generate(p.cam, key, px, py);
+                for (;;)
+                {
+                    segs++;
+                    if (segment_step<BVH, TRAV>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst, top))
+                    {
+                        key.sample += G;
+                        if (key.sample >= p.sample_end) break;
+                        seg = 0;
+                        thr = v3(1.0f, 1.0f, 1.0f);
+                        ray = generate(p.cam, key, px, py);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        else
         for (;;)
         {
             const unsigned idle = __ballot_sync(0xffffffffu, !live) & gmask;

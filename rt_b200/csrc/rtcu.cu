@@ -138,9 +138,10 @@ struct Knobs {
                                // inside the node visit (default, measured faster), 1 = deferred leaves, 2 = 1 + top levels in shared memory
     int bvh_lanes = 0;         // RTCU_BVH_LANES: lanes per pixel in direct mode (8 / 16 / 32), 0 = by sample count
     int scan_direct = -1;      // RTCU_SCAN_DIRECT: scan (non-BVH) scenes rendered with G lanes sharing a pixel: G = 2 / 4 / 8 / 16 always,
-                               // 0 never, default: frames of fewer than 8 waves of tiles (launch_render_on)
+                               // 0 never, default: by frame size and sample count (scan_direct_lanes)
     bool zero_copy_direct = true; // RTCU_ZERO_COPY_DIRECT=0: no zero-copy output from the lanes-share-a-pixel kernels (their stores cross
                                   // PCIe 8 or 16 bytes at a time; measured, that still beats a copy after the frame: C1 e2e 0.483 -> 0.438 ms)
+    bool scan_nested = true;   // RTCU_SCAN_NESTED=0: that kernel with samples claimed by ballot rank instead of a static split and a plain loop
     int bvh_run_pixels = 8;    // RTCU_BVH_RUN: pixels per lane-group run (4 / 8)
     bool bvh_runs = false;     // RTCU_BVH_RUNS=1: k_render_runs (lane groups walk runs of pixels) instead of k_render_stragglers'
                                // direct mode.  Measured, not default: C3 33.1 vs 30.5 ms, C4 79.6 vs 80.5 ms
@@ -162,6 +163,7 @@ struct Knobs {
         if (const char* e = getenv("RTCU_BVH_TRAV")) bvh_trav = atoi(e);
         if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) bvh_lanes = v; }
         if (const char* e = getenv("RTCU_BVH_RUNS")) bvh_runs = e[0] != '0';
+        if (const char* e = getenv("RTCU_SCAN_NESTED")) scan_nested = e[0] != '0';
         if (const char* e = getenv("RTCU_ZERO_COPY_DIRECT")) zero_copy_direct = e[0] != '0';
         if (const char* e = getenv("RTCU_SCAN_DIRECT")) { const int v = atoi(e); scan_direct = (v == 2 || v == 4 || v == 8 || v == 16) ? v : (e[0] == '0' ? 0 : -1); }
         if (const char* e = getenv("RTCU_BVH_RUN")) { const int v = atoi(e); if (v == 4 || v == 8) bvh_run_pixels = v; }
@@ -405,22 +407,37 @@ int launch_wavefront(rtcu_ctx* ctx, const rtcu_view* v, RenderParams p, bool use
     return RTCU_OK;
 }
 
+// Scan (non-BVH) scenes: lanes per pixel of the lanes-share-a-pixel kernel (k_render_stragglers in direct mode), or 0 for the
+// thread-per-pixel grid (k_render_mega).  The grid hands a 16x8 tile to a CTA for the whole frame and cannot balance tiles whose
+// cost differs several-fold unless it has very many of them; pixel-sized work items taken from an atomic cursor can, and G lanes
+// sharing a pixel shorten the longest item G-fold.  Measured on B200 (tools/sweep_scan_sizes.py, profiles/r2_scan_frame_sizes.txt;
+// basic.toml and dielectric.toml with both scatter tables, 320x240 .. 3840x2160, 16 .. 256 samples): up to 1280x720 the shared
+// kernel wins by 1.1x .. 4x with 8 lanes (16 from 64 samples); at 1920x1080 by 1 .. 25 % with 4 lanes (8 from 64 samples); at
+// 3840x2160 the two are within 2 % and the grid -- sequential per-pixel sums, row-coalesced stores -- stays.  Below 16 samples
+// (progressive refinement steps): 4 lanes from 8 samples, 2 from 4 -- up to 2.7x at 800x600, even at 1920x1080 (r2_scan_low_spp.txt).
+// Thresholds are in pixels per resident thread (8 CTAs x 128 threads per SM), so they follow the SM count.
+int scan_direct_lanes(const rtcu_ctx* ctx, const rtcu_view* v)
+{
+    const uint32_t n = v->sample_end - v->sample_begin;
+    const int sd = ctx->knobs.scan_direct;
+    if (sd >= 0) return (sd != 0 && n >= 2u * (uint32_t)sd) ? sd : 0;
+    if (n < 4) return 0;
+    const uint64_t pixels = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0), threads = 1024ull * (uint64_t)ctx->sm_count;
+    if (pixels >= 27 * threads) return 0;
+    if (n < 16) return n >= 8 ? 4 : 2; // a lane gets at least two samples
+    if (pixels >= 10 * threads) return n >= 64 ? 8 : 4;
+    return n >= 64 ? 16 : 8;
+}
+
 // launches the trace kernels of one view on `st`; accum/rgba8 are device pointers
 // whether launch_render will take the warp-per-pixel path (k_render_stragglers in direct mode) for this view
 bool uses_direct_mode(const rtcu_ctx* ctx, const rtcu_view* v)
 {
     const uint32_t accel = v->flags & 0xFu, pipe = v->flags & 0xF0u;
     const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= ctx->knobs.bvh_threshold);
-    if (pipe == RTCU_PIPE_WAVEFRONT || ctx->knobs.pool || v->sample_end - v->sample_begin < 16) return false;
-    if (!(use_bvh && ctx->have_bvh))
-    {
-        // scan scenes: the thread-per-pixel grid wins once it has enough tiles to balance itself (measured crossover between
-        // 1280x720 and 1920x1080, i.e. 6 and 14 waves of 16x8 tiles); smaller frames take pixel-sized dynamic work items
-        const int sd = ctx->knobs.scan_direct;
-        if (sd >= 0) return sd != 0 && v->sample_end - v->sample_begin >= 2u * (uint32_t)sd;
-        const uint64_t n_tiles = (uint64_t)((v->tile_x1 - v->tile_x0 + MEGA_TILE_W - 1) / MEGA_TILE_W) * ((v->tile_y1 - v->tile_y0 + MEGA_TILE_H - 1) / MEGA_TILE_H);
-        return n_tiles < 8ull * 8ull * (uint64_t)ctx->sm_count;
-    }
+    if (pipe == RTCU_PIPE_WAVEFRONT) return false;
+    if (!(use_bvh && ctx->have_bvh)) return scan_direct_lanes(ctx, v) != 0;
+    if (ctx->knobs.pool || v->sample_end - v->sample_begin < 16) return false;
     return ctx->knobs.direct;
 }
 
@@ -519,15 +536,29 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
         // camera::viewport, camera.hpp:122-137); RTCU_BVH_BEAM=0 disables.
         if (!use_bvh)
         {
-            // lanes per pixel as for the BVH kernels: 16 once every lane gets four samples, else 8 (320x240 .. 1280x720 at 16 / 30 / 64 /
-            // 256 samples: 8 lanes win below 64 samples, 16 from there; 4 and 2 lanes are behind everywhere).  The primitives are read
-            // through L1: staging them in shared memory as k_render_mega does measures the same (C1 0.405 vs 0.406 ms).
-            switch (ctx->knobs.scan_direct > 0 ? ctx->knobs.scan_direct : (n_samples >= 64 ? 16 : 8))
+            // Each lane loops over its own share of the pixel's samples (lane l: samples l, l + G, ...), the plain loop that is fastest for
+            // a handful of primitives (RTCU_SCAN_NESTED=0: lanes claim samples by ballot rank as in the BVH kernels -- 5-13 % behind on
+            // basic.toml and dielectric.toml, ahead only where a few paths are very long: dielectric.toml with the mg table below
+            // 1280x720).  The primitives are read through L1: staging them in shared memory as k_render_mega does measures the same
+            // (C1 0.405 vs 0.406 ms).
+            switch (scan_direct_lanes(ctx, v))
             {
-            case 2: k_render_stragglers<false, 2><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
-            case 4: k_render_stragglers<false, 4><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
-            case 8: k_render_stragglers<false, 8><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
-            default: k_render_stragglers<false, 16><<<blocks, 128, 0, st>>>(ctx->scene, q); break;
+            case 2:
+                if (ctx->knobs.scan_nested) k_render_stragglers<false, 2, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                else k_render_stragglers<false, 2><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                break;
+            case 4:
+                if (ctx->knobs.scan_nested) k_render_stragglers<false, 4, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                else k_render_stragglers<false, 4><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                break;
+            case 8:
+                if (ctx->knobs.scan_nested) k_render_stragglers<false, 8, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                else k_render_stragglers<false, 8><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                break;
+            default:
+                if (ctx->knobs.scan_nested) k_render_stragglers<false, 16, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                else k_render_stragglers<false, 16><<<blocks, 128, 0, st>>>(ctx->scene, q);
+                break;
             }
             CU(cudaGetLastError());
             ctx->tile_hist_valid = false;

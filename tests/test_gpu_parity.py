@@ -185,9 +185,9 @@ def test_render_c2_full_size_properties(ctx, oracle, scenes, knobs):
     np.testing.assert_array_equal(rgba_a, rgba_b)
     assert ctx.stats()["segments"] == segs_a
     assert (accum_a[..., 3] == 64).all() and np.isfinite(accum_a).all() and ((rgba_a & 0xFF) == 0xFF).all()
-    # (2) tiles compose: a tile render equals the same pixels of the full frame -- the same paths; a tile this small is rendered
-    # with lanes sharing a pixel (launch_render_on: frames of fewer than 8 waves of tiles), so the sums differ in fp32 order only,
-    # and bit for bit when the tile is made to take the frame's kernel
+    # (2) tiles compose: a tile render equals the same pixels of the full frame -- the same paths; a tile this small shares a pixel
+    # between 16 lanes and the frame between 8 (rtcu.cu, scan_direct_lanes), so the sums differ in fp32 order only, and bit for bit
+    # when tile and frame are rendered the same way
     vt = make_view(sc, 1920, 1080, samples_per_pixel=64, max_bounces=50, material_mode=nat.MODE_SM, tile=(1000, 500, 1100, 540))
     rgba_t, accum_t = ctx.render(vt, want_accum=True)
     assert ctx.stats()["kernel_launches"] == 1
@@ -195,12 +195,16 @@ def test_render_c2_full_size_properties(ctx, oracle, scenes, knobs):
     np.testing.assert_allclose(accum_t[500:540, 1000:1100, :3], accum_a[500:540, 1000:1100, :3], rtol=4e-6, atol=1e-6)
     assert np.abs(unpack_rgba(rgba_t[500:540, 1000:1100]) - unpack_rgba(rgba_a[500:540, 1000:1100])).max() <= 1
     assert (rgba_t[:500] == 0).all()
-    knobs(RTCU_SCAN_DIRECT="0")
-    rgba_t, accum_t = ctx.render(vt, want_accum=True)
-    knobs(RTCU_SCAN_DIRECT=None)
-    np.testing.assert_array_equal(accum_t[500:540, 1000:1100], accum_a[500:540, 1000:1100])
-    np.testing.assert_array_equal(rgba_t[500:540, 1000:1100], rgba_a[500:540, 1000:1100])
-    assert (rgba_t[:500] == 0).all()
+    for how in ("8", "0"):  # 8 lanes per pixel; the thread-per-pixel grid
+        knobs(RTCU_SCAN_DIRECT=how)
+        rgba_f, accum_f = ctx.render(v, want_accum=True)
+        assert ctx.stats()["segments"] == segs_a
+        rgba_t, accum_t = ctx.render(vt, want_accum=True)
+        knobs(RTCU_SCAN_DIRECT=None)
+        np.testing.assert_array_equal(accum_t[500:540, 1000:1100], accum_f[500:540, 1000:1100])
+        np.testing.assert_array_equal(rgba_t[500:540, 1000:1100], rgba_f[500:540, 1000:1100])
+        assert (rgba_t[:500] == 0).all()
+        np.testing.assert_allclose(accum_f[..., :3], accum_a[..., :3], rtol=4e-6, atol=1e-6)
     # (3) a strided row subset against the oracle at the full spp / depth
     r_rgba8, r_accum, r_segs = oracle.render(sc, v, row_step=90)
     rows = np.arange(0, 1080, 90)
@@ -332,8 +336,9 @@ def test_bvh_non_unit_directions_fall_back_to_the_scan(ctx, scenes):
 def test_bvh_render_matches_linear_render(ctx, scenes, knobs, name, mode, kernel):
     # Both BVH kernels trace exactly the linear scan's paths (same segment count).  "mega" (one segment per iteration) also
     # sums every pixel's samples in the same order -> bit-identical buffers; "pool" (warp-local ray pool, not the default) sums
-    # them in completion order -> identical up to fp32 summation order, and deterministic.
-    knobs(RTCU_BVH_KERNEL=kernel)
+    # them in completion order -> identical up to fp32 summation order, and deterministic.  (The scan side is held to its
+    # thread-per-pixel kernel: frames this small otherwise share each pixel between lanes, which re-orders the sums.)
+    knobs(RTCU_BVH_KERNEL=kernel, RTCU_SCAN_DIRECT="0")
     sc = _grid() if name == "grid" else scenes[name][0]
     ctx.upload_scene(sc)
     for w, h, spp in ((192, 108, 4), (61, 37, 9)):  # the second size leaves partial 8x4 patches and partial CTAs
@@ -406,7 +411,7 @@ def test_render_matches_reference_build_fixtures(ctx, scenes):
 def test_wavefront_is_bit_identical_to_the_megakernel(ctx, scenes, knobs, name, mode, accel):
     # same paths, and per-pixel sums in sample order in both pipelines (the megakernel's straggler pass, which re-orders the
     # sum of the few pixels it takes over, is switched off for this comparison)
-    knobs(RTCU_STRAGGLER_BUDGET="0")
+    knobs(RTCU_STRAGGLER_BUDGET="0", RTCU_SCAN_DIRECT="0")  # (and so is the lanes-share-a-pixel kernel small scan frames take)
     knobs(RTCU_WF_RAYS=str(200 * 120 * 3))  # 3 samples per wave: 6 spp = 2 waves, 7 spp = 2 full + 1 partial
     sc = scenes[name][0]
     ctx.upload_scene(sc)

@@ -371,10 +371,11 @@ def test_runs_kernel_traces_the_same_paths_as_direct_mode(ctx, oracle, scenes, k
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,mode", [("c1", nat.MODE_MG), ("c2", nat.MODE_SM), ("planes", nat.MODE_SM)])
 def test_small_scan_frames_share_pixels_between_lanes(ctx, oracle, scenes, knobs, name, mode):
-    """Scan (non-BVH) scenes: a frame of fewer than 8 waves of 16x8 tiles, from 16 samples per call, is rendered by
-    k_render_stragglers in direct mode (8 or 16 lanes share a pixel's samples, pixel-sized work items handed out dynamically)
-    instead of the thread-per-pixel grid, which cannot balance so few tiles (C1 0.55 -> 0.41 ms).  Same paths (segment counts equal
-    the oracle's and the other kernel's), sums equal up to fp32 order, deterministic; tiles of such a frame compose bit for bit."""
+    """Scan (non-BVH) scenes: below 3840x2160, from 16 samples per call, a frame is rendered by k_render_stragglers in direct mode
+    (4 / 8 / 16 lanes share a pixel's samples, pixel-sized work items handed out dynamically) instead of the thread-per-pixel grid,
+    which cannot balance a few thousand tiles (C1 0.55 -> 0.35 ms).  Same paths (segment counts equal the oracle's and the other
+    kernel's), sums equal up to fp32 order, deterministic; tiles of such a frame compose bit for bit while the lane count is the
+    same.  RTCU_SCAN_NESTED=0 (lanes claim samples by ballot rank, as the BVH kernels do) is held to the same."""
     sc, depth = scenes[name]
     ctx.upload_scene(sc)
     w, h = 203, 117
@@ -412,8 +413,34 @@ def test_small_scan_frames_share_pixels_between_lanes(ctx, oracle, scenes, knobs
         np.testing.assert_array_equal(acc2[..., 3], accum[..., 3])
         np.testing.assert_allclose(acc2[..., :3], accum[..., :3], rtol=4e-6, atol=1e-6)
         assert np.abs(unpack_rgba(img2) - unpack_rgba(rgba8)).max() <= 1
-    # below 16 samples per call, and from 8 waves of tiles, the thread-per-pixel grid stays
-    ctx.render(make_view(sc, w, h, samples_per_pixel=15, max_bounces=depth, material_mode=mode))
-    assert ctx.stats()["kernel_launches"] >= 2
+    # the other sample-to-lane assignment, and the lane counts the bigger frames take (forced here on the small frame)
+    v = make_view(sc, w, h, samples_per_pixel=70, max_bounces=depth, material_mode=mode)
+    _, want = ctx.render(v, want_accum=True)
+    segs = ctx.stats()["segments"]
+    for kn in (dict(RTCU_SCAN_NESTED="0"), dict(RTCU_SCAN_DIRECT="4"), dict(RTCU_SCAN_DIRECT="8"), dict(RTCU_SCAN_DIRECT="8", RTCU_SCAN_NESTED="0"),
+               dict(RTCU_SCAN_DIRECT="2")):
+        knobs(**kn)
+        _, got = ctx.render(v, want_accum=True)
+        assert ctx.stats()["segments"] == segs and ctx.stats()["kernel_launches"] == 1
+        _, again = ctx.render(v, want_accum=True)
+        knobs(**{k: None for k in kn})
+        np.testing.assert_array_equal(again, got)
+        np.testing.assert_array_equal(got[..., 3], want[..., 3])
+        np.testing.assert_allclose(got[..., :3], want[..., :3], rtol=4e-6, atol=1e-6)
+    # 1920x1080: 4 lanes per pixel below 64 samples, still one launch; 4 / 2 lanes for 8 / 4 samples per call; below 4 samples
+    # per call, and from 3840x2160, the thread-per-pixel grid stays
     ctx.render(make_view(sc, 1920, 1080, samples_per_pixel=16, max_bounces=depth, material_mode=mode))
+    assert ctx.stats()["kernel_launches"] == 1
+    for spp in (5, 9):
+        v = make_view(sc, w, h, samples_per_pixel=spp, max_bounces=depth, material_mode=mode)
+        rgba8, accum = ctx.render(v, want_accum=True)
+        assert ctx.stats()["kernel_launches"] == 1
+        r_rgba8, r_accum, r_segs = oracle.render(sc, v, threads=0)
+        assert r_segs == ctx.stats()["segments"]
+        np.testing.assert_array_equal(accum[..., 3], r_accum[..., 3])
+        np.testing.assert_allclose(accum[..., :3], r_accum[..., :3], rtol=2e-5, atol=1e-6)
+        assert np.abs(unpack_rgba(rgba8) - unpack_rgba(r_rgba8)).max() <= 1
+    ctx.render(make_view(sc, w, h, samples_per_pixel=3, max_bounces=depth, material_mode=mode))
+    assert ctx.stats()["kernel_launches"] >= 2
+    ctx.render(make_view(sc, 3840, 2160, samples_per_pixel=16, max_bounces=depth, material_mode=mode))
     assert ctx.stats()["kernel_launches"] >= 2
