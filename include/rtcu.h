@@ -159,9 +159,10 @@ int rtcu_upload_scene_multi(rtcu_ctx* const* ctxs, uint32_t n_ctx, const rtcu_sc
  *   packed as colour::operator uint32_t (colour.hpp:100-106); only the tile is written.
  * accum_out (nullable): width*height*4 floats {sum_r,sum_g,sum_b,n_samples}; only the tile is written.  The paths are the
  *   reference's (same segments per sample for the same seed); the per-pixel sum runs in ascending sample order as in
- *   mg_ray_tracer.cpp:187-194, except where several lanes share a pixel (BVH scenes from 16 samples per call, pixels handed
- *   to the second pass, multi-GPU sample splits): there it is a fixed tree of partial sums -- deterministic, equal to the
- *   sequential sum up to fp32 rounding.
+ *   mg_ray_tracer.cpp:187-194, except where several lanes share a pixel (from 4 samples per call: BVH scenes, and scenes
+ *   without a BVH below 3840x2160; pixels handed to the second pass; multi-GPU sample splits): there it is a fixed tree of
+ *   partial sums -- deterministic, equal to the sequential sum up to fp32 rounding, and independent of the tile only while the
+ *   tile takes the same lane count as the frame (RTCU_SCAN_DIRECT=0 RTCU_BVH_DIRECT=0: always the sequential sum).
  * rgba8_out may be pinned or pageable.  A pinned image is written by the kernels themselves (zero-copy) or by one DMA; a pageable
  *   one (the reference's, image.cpp:9-13) is staged through a bounce buffer -- unless the caller has opted in with
  *   rtcu_set_output_pinning, see there. */

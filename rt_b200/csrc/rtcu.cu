@@ -161,7 +161,7 @@ struct Knobs {
         if (const char* e = getenv("RTCU_REGISTER_OUTPUT")) register_output = e[0] == '1';
         if (const char* e = getenv("RTCU_BVH_THRESHOLD")) bvh_threshold = (uint32_t)strtoul(e, nullptr, 10);
         if (const char* e = getenv("RTCU_BVH_TRAV")) bvh_trav = atoi(e);
-        if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) bvh_lanes = v; }
+        if (const char* e = getenv("RTCU_BVH_LANES")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) bvh_lanes = v; }
         if (const char* e = getenv("RTCU_BVH_RUNS")) bvh_runs = e[0] != '0';
         if (const char* e = getenv("RTCU_SCAN_NESTED")) scan_nested = e[0] != '0';
         if (const char* e = getenv("RTCU_ZERO_COPY_DIRECT")) zero_copy_direct = e[0] != '0';
@@ -437,7 +437,9 @@ bool uses_direct_mode(const rtcu_ctx* ctx, const rtcu_view* v)
     const bool use_bvh = accel == RTCU_ACCEL_BVH || (accel == RTCU_ACCEL_AUTO && ctx->have_bvh && ctx->scene.n_spheres >= ctx->knobs.bvh_threshold);
     if (pipe == RTCU_PIPE_WAVEFRONT) return false;
     if (!(use_bvh && ctx->have_bvh)) return scan_direct_lanes(ctx, v) != 0;
-    if (ctx->knobs.pool || v->sample_end - v->sample_begin < 16) return false;
+    if (ctx->knobs.pool) return false;
+    const uint32_t min_samples = ctx->knobs.bvh_lanes ? 2u * (uint32_t)ctx->knobs.bvh_lanes : 4u; // a lane gets at least two samples
+    if (v->sample_end - v->sample_begin < min_samples) return false;
     return ctx->knobs.direct;
 }
 
@@ -514,12 +516,12 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
     // stream, and the faster order is kept until the view or the scene changes.  It is a scheduling decision only: every
     // sample is traced every frame and the image is bit-identical whatever the order.  RTCU_TILE_ORDER=0: always
     // row-major; =1: always sorted once a cost map exists.
-    // BVH scenes with at least 16 samples per call skip the thread-per-pixel kernel altogether: k_render_stragglers in direct
-    // mode lets 16 (or 8) lanes share ONE pixel's samples.  The samples of a pixel start from (almost) the same ray and their
+    // BVH scenes with at least 4 samples per call skip the thread-per-pixel kernel altogether: k_render_stragglers in direct
+    // mode lets 16 (or 8 / 4 / 2: every lane gets at least two samples) lanes share ONE pixel's samples.  The samples of a pixel start from (almost) the same ray and their
     // first bounces from (almost) the same point, so the warp traverses far more coherently than 32 neighbouring pixels do,
     // and pixel-sized work items leave no grid tail (C4 -19 %, C3 -6 %; at 30 spp -18 % / -8 %).  The per-pixel sum is then a
     // fixed butterfly over the lane sums instead of the sequential sum (same paths, same segment count; fp32 summation
-    // order only).  Below 16 samples the lanes would run dry.  RTCU_BVH_DIRECT=0 disables.
+    // order only).  RTCU_BVH_DIRECT=0 disables.  Scan scenes: see scan_direct_lanes.
     if (uses_direct_mode(ctx, v))
     {
         p.direct = 1;
@@ -569,7 +571,9 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
         const bool beam = ctx->knobs.bvh_beam != 0 && p.cam.w_const;
         // lanes per pixel: 16 (two pixels per warp) from 32 samples per call, 8 (four pixels per warp) below, so that every lane gets
         // at least two samples (RTCU_BVH_LANES to measure: with the beams 16 and 8 are within 2 % of each other, 4 is 3-7 % behind)
-        const int lanes = ctx->knobs.bvh_lanes ? ctx->knobs.bvh_lanes : (n_samples >= 32 ? 16 : 8);
+        // Below 16 samples (progressive refinement steps): 4 lanes from 8 samples, 2 lanes from 4 -- C3 / C4 at 800x600 .. 3840x2160:
+        // 4-48 % faster than the thread-per-pixel kernel with its second pass (profiles/r2_bvh_low_spp.txt).
+        const int lanes = ctx->knobs.bvh_lanes ? ctx->knobs.bvh_lanes : (n_samples >= 32 ? 16 : n_samples >= 16 ? 8 : n_samples >= 8 ? 4 : 2);
         const int trav = ctx->knobs.bvh_trav >= 0 && ctx->knobs.bvh_trav <= 2 ? ctx->knobs.bvh_trav : RTCU_DEFAULT_TRAV;
         // pixel beams (kernels.cuh, beam_collect): one walk per pixel replaces the primary rays' traversals; worth it once a lane
         // traces several samples of the pixel (RTCU_BVH_BEAM: samples per lane from which beams are used, 0 = never)
@@ -601,13 +605,21 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
         }
         const int minb = ctx->knobs.bvh_minb; // experiment: CTAs per SM the beam kernel is compiled for (8 = 64 registers, 6 = 80)
 #define RTCU_LAUNCH_DIRECT(G, T, B, M) k_render_stragglers<true, G, T, B, M><<<(unsigned)ctx->sm_count * M, 128, 0, st>>>(ctx->scene, q)
-#define RTCU_LAUNCH_BEAM(G) (minb == 6 ? RTCU_LAUNCH_DIRECT(G, 0, true, 6) : minb == 7 ? RTCU_LAUNCH_DIRECT(G, 0, true, 7) : RTCU_LAUNCH_DIRECT(G, 0, true, 8))
+#define RTCU_LAUNCH_BEAM(G) RTCU_LAUNCH_DIRECT(G, 0, true, 8)
         if (trav == 1 && lanes == 16) RTCU_LAUNCH_DIRECT(16, 1, false, 8); // (the traversal experiments: 16 lanes, no beams)
         else if (trav == 2 && lanes == 16) RTCU_LAUNCH_DIRECT(16, 2, false, 8);
         else if (lanes == 32) { if (beam) RTCU_LAUNCH_BEAM(32); else RTCU_LAUNCH_DIRECT(32, 0, false, 8); }
-        else if (lanes == 16) { if (beam) RTCU_LAUNCH_BEAM(16); else RTCU_LAUNCH_DIRECT(16, 0, false, 8); }
+        else if (lanes == 16)
+        {
+            // (the register-budget experiment, RTCU_BVH_MINB: 6 / 7 CTAs per SM = 80 / 72 registers, 16 lanes only)
+            if (beam && minb == 6) RTCU_LAUNCH_DIRECT(16, 0, true, 6);
+            else if (beam && minb == 7) RTCU_LAUNCH_DIRECT(16, 0, true, 7);
+            else if (beam) RTCU_LAUNCH_BEAM(16);
+            else RTCU_LAUNCH_DIRECT(16, 0, false, 8);
+        }
         else if (lanes == 8) { if (beam) RTCU_LAUNCH_BEAM(8); else RTCU_LAUNCH_DIRECT(8, 0, false, 8); }
-        else { if (beam) RTCU_LAUNCH_BEAM(4); else RTCU_LAUNCH_DIRECT(4, 0, false, 8); }
+        else if (lanes == 4) { if (beam) RTCU_LAUNCH_BEAM(4); else RTCU_LAUNCH_DIRECT(4, 0, false, 8); }
+        else { if (beam) RTCU_LAUNCH_BEAM(2); else RTCU_LAUNCH_DIRECT(2, 0, false, 8); }
         (void)blocks;
         CU(cudaGetLastError());
         ctx->tile_hist_valid = false;

@@ -338,7 +338,7 @@ def test_bvh_render_matches_linear_render(ctx, scenes, knobs, name, mode, kernel
     # sums every pixel's samples in the same order -> bit-identical buffers; "pool" (warp-local ray pool, not the default) sums
     # them in completion order -> identical up to fp32 summation order, and deterministic.  (The scan side is held to its
     # thread-per-pixel kernel: frames this small otherwise share each pixel between lanes, which re-orders the sums.)
-    knobs(RTCU_BVH_KERNEL=kernel, RTCU_SCAN_DIRECT="0")
+    knobs(RTCU_BVH_KERNEL=kernel, RTCU_SCAN_DIRECT="0", RTCU_BVH_DIRECT="0")
     sc = _grid() if name == "grid" else scenes[name][0]
     ctx.upload_scene(sc)
     for w, h, spp in ((192, 108, 4), (61, 37, 9)):  # the second size leaves partial 8x4 patches and partial CTAs
@@ -411,7 +411,7 @@ def test_render_matches_reference_build_fixtures(ctx, scenes):
 def test_wavefront_is_bit_identical_to_the_megakernel(ctx, scenes, knobs, name, mode, accel):
     # same paths, and per-pixel sums in sample order in both pipelines (the megakernel's straggler pass, which re-orders the
     # sum of the few pixels it takes over, is switched off for this comparison)
-    knobs(RTCU_STRAGGLER_BUDGET="0", RTCU_SCAN_DIRECT="0")  # (and so is the lanes-share-a-pixel kernel small scan frames take)
+    knobs(RTCU_STRAGGLER_BUDGET="0", RTCU_SCAN_DIRECT="0", RTCU_BVH_DIRECT="0")  # (and so are the lanes-share-a-pixel kernels)
     knobs(RTCU_WF_RAYS=str(200 * 120 * 3))  # 3 samples per wave: 6 spp = 2 waves, 7 spp = 2 full + 1 partial
     sc = scenes[name][0]
     ctx.upload_scene(sc)
@@ -475,7 +475,7 @@ def test_cheaper_exact_sqrt_rcp_div_equal_the_ieee_intrinsics_for_every_input(ct
 def test_tile_issue_order_never_changes_the_image(ctx, scenes, knobs):
     """The library times row-major against cost-sorted tile order over the first frames of a view and keeps the faster
     (rtcu.cu: launch_render).  Whatever it picks, and whichever phase a frame falls in, accum and pixels are bit-identical."""
-    knobs(RTCU_SCAN_DIRECT="0")  # (a scan frame of 1280x720 at 16 spp would take the kernel that has no tile order)
+    knobs(RTCU_SCAN_DIRECT="0", RTCU_BVH_DIRECT="0")  # (these frames would otherwise take the kernels that have no tile order)
     for name, spp, flags in (("c2", 16, 0), ("c3", 8, 0), ("c3", 8, nat.ACCEL_LINEAR)):
         sc, depth = scenes[name]
         ctx.upload_scene(sc)  # resets the per-view history
@@ -501,7 +501,7 @@ def test_tile_issue_order_never_changes_the_image(ctx, scenes, knobs):
 
 
 def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes, knobs):
-    """From 16 samples per call a BVH scene is rendered with 16 or 8 lanes sharing each pixel's samples (k_render_stragglers in
+    """From 4 samples per call a BVH scene is rendered with 2 .. 16 lanes sharing each pixel's samples (k_render_stragglers in
     direct mode): same paths as the thread-per-pixel kernel (equal segment counts), per-pixel sums equal up to fp32 order, partial tiles / ragged 8x4 patches /
     sample ranges / accumulate-onto-a-device-buffer all behave like the other kernels, and the oracle agrees."""
     import torch
@@ -509,7 +509,7 @@ def test_bvh_direct_mode_tiles_ranges_and_device_accumulate(ctx, oracle, scenes,
     sc, depth = scenes["c3"]
     ctx.upload_scene(sc)
     w, h = 203, 117  # ragged against the 8x4 patches
-    for spp in (20, 96):  # 8 lanes per pixel (four pixels per warp), 16 lanes per pixel (two pixels per warp)
+    for spp in (5, 9, 20, 96):  # 2 / 4 / 8 / 16 lanes per pixel (16 / 8 / 4 / 2 pixels per warp)
         kw = dict(samples_per_pixel=spp, max_bounces=depth, material_mode=nat.MODE_SM)
         v = make_view(sc, w, h, **kw)
         rgba8, accum = ctx.render(v, want_accum=True)
