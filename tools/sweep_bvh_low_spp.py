@@ -1,5 +1,8 @@
+#!/usr/bin/env python3
+"""Device A/B of the BVH kernels at progressive-refinement sample counts (4 .. 12 per call): the default against 2 / 4 lanes sharing
+a pixel forced (RTCU_BVH_LANES).  gpurun -- 'python tools/sweep_bvh_low_spp.py'   (profiles/r2_bvh_low_spp.txt)"""
 import os, sys, pathlib
-ROOT = pathlib.Path(__file__).resolve().parent.parent.parent; sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests" / "tools"))
+ROOT = pathlib.Path(__file__).resolve().parent.parent; sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests" / "tools"))
 from rt_b200 import _native as nat, synth
 from rt_b200.renderer import Context, make_view
 import run_configs
