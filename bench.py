@@ -102,6 +102,28 @@ def measured_peaks() -> dict:
     return {}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version banner on fd 1 when the box
+    sets NCCL_DEBUG=VERSION).  From here on everything written to fd 1 goes to stderr; emit() writes the line to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def kernel_facts(cfg_key: str) -> dict:
     """What only a profiler sees (DRAM bytes per launch, active lanes per warp instruction) for the dominant kernel of a config:
     read from profiles/kernel_facts.json, which names the ncu capture and the git commit it was taken at.  Absent -> nulls."""
@@ -263,7 +285,7 @@ def run_reference(args):
         "e2e": {"value": round(mean_v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -616,7 +638,7 @@ def run_gpu(args):
             "segments_per_sample": round(segments_all / samples_per_step, 4),
             "configs": others,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
@@ -641,6 +663,7 @@ def main():
     args = ap.parse_args()
     if args.steps < 1:
         ap.error("--steps must be >= 1")
+    claim_stdout()
     return run_reference(args) if args.impl == "reference" else run_gpu(args)
 
 

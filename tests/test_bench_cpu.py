@@ -59,3 +59,13 @@ def test_kernel_facts_name_their_capture():
         assert f["dram_bytes_per_launch"] == f["dram_read_bytes"] + f["dram_write_bytes"] > 0
         assert 1.0 <= f["active_lanes"] <= 32.0 and "git" in f["source"] and f["kernel"].startswith("k_render_")
         assert bench.kernel_facts(key) == f
+
+
+def test_only_the_json_line_reaches_stdout():
+    """Libraries write to fd 1 behind Python's back (NCCL's version banner under NCCL_DEBUG=VERSION): bench.py moves fd 1 to stderr
+    and writes its one line to the original stdout."""
+    code = "import os, bench; bench.claim_stdout(); os.write(1, b'NCCL version x.y\\n'); print('python noise'); bench.emit({'a': 1})"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert "NCCL version x.y" in r.stderr and "python noise" in r.stderr
