@@ -186,6 +186,19 @@ __device__ __forceinline__ void bvh_leaf_pair_test(const float4 A, const float4 
     }
 }
 
+// A leaf block pads its 1-4 spheres to two packed pairs, padding last (pack_bvh4 sorts a leaf by original index and fills up with
+// never-hit spheres): when the third slot is padding the second pair holds nothing and its test can be skipped.  Every scene
+// with one sphere far larger than the rest -- a ground sphere -- has such a leaf right under the root, and nearly every ray visits it
+// (CPU proxy tools/bvh_visits.cpp: 46 % of the leaf visits of C3 / C5, 34 % of C4's).  RTCU_LEAF_SKIP_PAD: bit 0 = skip in the
+// traversal, bit 1 = skip in the beam-list scan of the primary rays (where the branch is uniform over the lanes of a pixel).
+#ifndef RTCU_LEAF_SKIP_PAD
+#define RTCU_LEAF_SKIP_PAD 3 // measured (B200): C3 30.46 -> 29.78 ms, C4 80.45 -> 79.65 ms, a 32-sample slice of C5 32.85 -> 32.45 ms
+#endif
+__device__ __forceinline__ bool leaf_second_pair(const float4 idx, const bool skip_padding)
+{
+    return !skip_padding || __float_as_int(idx.z) != 0x7fffffff;
+}
+
 constexpr int BVH_STACK = 64; // entries; a visit pushes at most 3, so trees up to 20 levels of 4-wide nodes (4^20 leaves)
 
 // traversal state of one ray; the node stack lives in (L1-cached) local memory of the calling kernel
@@ -276,9 +289,14 @@ __device__ __forceinline__ bool trav_step(const SceneDev& sc, const Ray& r, Trav
             const uint32_t leaf = ref[c] & 0x7fffffffu;
             const float4* lp = sc.leaf_blk + 5u * leaf; // leaf < 2^29 (checked at upload): 32-bit index arithmetic
             const float4 a0 = __ldg(lp), b0 = __ldg(lp + 1), a1 = __ldg(lp + 2), b1 = __ldg(lp + 3), idx = __ldg(lp + 4);
-            st.tests += 4; // sphere test slots (a leaf holds 1-4 spheres)
             bvh_leaf_pair_test<ANY_T>(a0, b0, __float_as_int(idx.x), __float_as_int(idx.y), r, tv.best_t, tv.best_i);
-            bvh_leaf_pair_test<ANY_T>(a1, b1, __float_as_int(idx.z), __float_as_int(idx.w), r, tv.best_t, tv.best_i);
+            if (leaf_second_pair(idx, (RTCU_LEAF_SKIP_PAD & 1) != 0)) // sphere test slots: a leaf holds 1-4 spheres
+            {
+                st.tests += 4;
+                bvh_leaf_pair_test<ANY_T>(a1, b1, __float_as_int(idx.z), __float_as_int(idx.w), r, tv.best_t, tv.best_i);
+            }
+            else
+                st.tests += 2;
         }
         else if (next == 0xffffffffu)
         {
@@ -456,7 +474,7 @@ __device__ __forceinline__ bool closest_sphere_bvh2(const SceneDev& sc, const To
 // kappa_b is the margin factor of a ray that is unit length to within BEAM_EPS_D; a sample ray outside that (never seen:
 // primary directions are normalised) traverses.  tests/test_bvh_replay.py replays this on the CPU against the oracle's scan.
 #ifndef RTCU_BEAM_MAX
-#define RTCU_BEAM_MAX 16
+#define RTCU_BEAM_MAX 32 // capacity 8 / 16 / 24 / 32: C4 82.7 / 80.5 / 79.7 / 79.2 ms, C3 and C5 unchanged (no list above 16 there)
 #endif
 constexpr int BEAM_MAX = RTCU_BEAM_MAX;             // leaves per list
 constexpr int BEAM_MAX_VISITS = 6 * BEAM_MAX;       // node visits after which a beam is given up
@@ -522,9 +540,14 @@ __device__ __forceinline__ void beam_closest_sphere(const SceneDev& sc, const Be
         if (__uint_as_float(e.x) > best_t) break; // no ray of the patch reaches this leaf (or a later one) before tn
         const float4* lp = sc.leaf_blk + 5u * e.y;
         const float4 a0 = __ldg(lp), b0 = __ldg(lp + 1), a1 = __ldg(lp + 2), b1 = __ldg(lp + 3), idx = __ldg(lp + 4);
-        st.tests += 4;
         bvh_leaf_pair_test<false>(a0, b0, __float_as_int(idx.x), __float_as_int(idx.y), r, best_t, best_i);
-        bvh_leaf_pair_test<false>(a1, b1, __float_as_int(idx.z), __float_as_int(idx.w), r, best_t, best_i);
+        if (leaf_second_pair(idx, (RTCU_LEAF_SKIP_PAD & 2) != 0))
+        {
+            st.tests += 4;
+            bvh_leaf_pair_test<false>(a1, b1, __float_as_int(idx.z), __float_as_int(idx.w), r, best_t, best_i);
+        }
+        else
+            st.tests += 2;
     }
     best_i = best_i == 0x7fffffff ? -1 : best_i;
 }

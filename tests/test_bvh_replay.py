@@ -239,7 +239,7 @@ def test_replayed_patch_beams_equal_the_oracle_scan(tmp_path_factory, oracle, na
     px = rng.integers(0, w - pw + 1, n_pixels)
     py = np.concatenate([rng.integers(0, h - ph + 1, n_pixels // 2), rng.integers(h // 3, h - ph + 1, n_pixels - n_pixels // 2)])  # sky is boring: favour the lower rows
     lists, tested, lengths = 0, 0, []
-    list_tn, list_leaf = np.zeros(16, np.float32), np.zeros(16, np.uint32)
+    list_tn, list_leaf = np.zeros(32, np.float32), np.zeros(32, np.uint32)
     for x, y in zip(px, py):
         o, d = beam_pixel_rays(oracle, view, int(x), int(y), rng, 12, pw, ph)
         rays5 = np.ascontiguousarray(np.concatenate([o[:5], d[:5]], axis=1).reshape(5, 2, 3), np.float32)  # centre + corners as (o, d)
@@ -278,7 +278,7 @@ def test_the_beams_need_the_footprint_margins(tmp_path_factory, oracle):
     nodes, leaves, _ = R.bvh4_build_host(sph)
     rng = np.random.default_rng(4)
     wrong = 0
-    list_tn, list_leaf = np.zeros(16, np.float32), np.zeros(16, np.uint32)
+    list_tn, list_leaf = np.zeros(32, np.float32), np.zeros(32, np.uint32)
     for x, y in zip(rng.integers(0, w, 500), rng.integers(h // 3, h, 500)):
         o, d = beam_pixel_rays(oracle, view, int(x), int(y), rng, 4, 1, 1)
         rays5 = np.ascontiguousarray(np.concatenate([o[:5], d[:5]], axis=1).reshape(5, 2, 3), np.float32)

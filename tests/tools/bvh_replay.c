@@ -258,8 +258,8 @@ int bvh_replay_ray2(const float* nodes, const float* leaves, const float o[3], c
  * of the patch could hit; a sample's primary ray then takes the (t, index) minimum over those leaves only.  rays: 5 x (o, d) =
  * the centre ray and the rays through the patch's four corners.  Returns the list length, or -1 when the patch keeps the
  * traversal (too many leaves or node visits, centre ray not unit length). */
-#define BEAM_MAX 16
-#define BEAM_MAX_VISITS 96
+#define BEAM_MAX 32
+#define BEAM_MAX_VISITS 192
 #define BEAM_EPS_D (16.0f * 5.9604645e-8f)
 int bvh_replay_beam_collect(const float* nodes, const float* rays, float* list_tn, uint32_t* list_leaf)
 {
