@@ -79,6 +79,10 @@ __host__ __device__ __forceinline__ uint32_t pair_float4_count(uint32_t n_sphere
 
 // closest hit over planes then spheres with the reference's tie rules
 // (mg_ray_tracer.cpp:35-102, :160-162).  s_pairs / s_pl may point to shared or global memory.
+// NP > 0: the scene has at most 2 NP spheres (the reference's own scenes: basic.toml 3, dielectric.toml 7) and the pair array,
+// padded with never-hit pairs, is swept as exactly NP pairs -- no loop counter, no remainder loop, no prefetch bookkeeping: the
+// generic loop spends 38 instructions per segment on those (tools/ncu_phases.py on C2), as many as two pair tests.
+template <int NP = 0>
 __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_pairs, const uint32_t n_sph,
                                                   const float4* __restrict__ s_pl, const uint32_t n_pl, const Ray& r)
 {
@@ -92,15 +96,29 @@ __device__ __forceinline__ Hit closest_hit_linear(const float4* __restrict__ s_p
     // shared-memory latency hides behind ~20 arithmetic instructions.  The array ends with never-hit pairs (r2 = -inf),
     // so the prefetch of the pair after the last one is always in bounds.  (Testing two pairs per iteration with a
     // two-pair prefetch was measured slower: 16 more live registers under the 64-register cap.)
-    const uint32_t n_pairs = (n_sph + 1u) >> 1;
-    float4 A = s_pairs[0], B = s_pairs[1];
-#pragma unroll 4
-    for (uint32_t j = 0; j < n_pairs; j++)
+    if (NP > 0)
     {
-        const float4 An = s_pairs[2 * j + 2], Bn = s_pairs[2 * j + 3];
-        sphere_pair_test(A, B, (int)j, r, ts, is);
-        A = An;
-        B = Bn;
+        // two pairs per iteration of a rolled loop: fully unrolled, ptxas issues all 2 NP loads up front and spills 200 bytes around
+        // them under the 64-register cap (C2 2.65 -> 3.03 ms); one pair per iteration with a prefetch spills 108 bytes
+#pragma unroll 1
+        for (int j = 0; j < NP; j += 2)
+        {
+            sphere_pair_test(s_pairs[2 * j], s_pairs[2 * j + 1], j, r, ts, is);
+            sphere_pair_test(s_pairs[2 * j + 2], s_pairs[2 * j + 3], j + 1, r, ts, is);
+        }
+    }
+    else
+    {
+        const uint32_t n_pairs = (n_sph + 1u) >> 1;
+        float4 A = s_pairs[0], B = s_pairs[1];
+#pragma unroll 4
+        for (uint32_t j = 0; j < n_pairs; j++)
+        {
+            const float4 An = s_pairs[2 * j + 2], Bn = s_pairs[2 * j + 3];
+            sphere_pair_test(A, B, (int)j, r, ts, is);
+            A = An;
+            B = Bn;
+        }
     }
     // A result counts as a hit when its distance is >= 0 (hit_result::operator bool, mg_ray_tracer.cpp:29-32): every accepted
     // distance is >= 0.001 except a NaN -- S4 overflowing to inf - inf on coordinates around 1e19 and beyond -- which the scan's
@@ -667,12 +685,12 @@ __device__ __forceinline__ bool shade_segment(const SceneDev& sc, const RenderPa
 
 // One path segment (mg_ray_tracer.cpp:154-174, one level of the recursion): closest hit, then sky on a miss or one
 // scatter event on a hit.  Returns true when the path ended (miss, absorbed, or bounce budget exhausted).
-template <bool BVH, int TRAV = 1>
+template <bool BVH, int TRAV = 1, int NP = 0>
 __device__ __forceinline__ bool segment_step(const SceneDev& sc, const RenderParams& p, const float4* __restrict__ s_sph,
                                              const float4* __restrict__ s_pl, const RngKey& key, Ray& ray, V3& thr, V3& sum, uint32_t& seg,
                                              BvhStats& bst, const TopNodes top = TopNodes{ nullptr, 0u })
 {
-    const Hit h = BVH ? closest_hit_bvh<TRAV>(sc, s_pl, ray, bst, top) : closest_hit_linear(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
+    const Hit h = BVH ? closest_hit_bvh<TRAV>(sc, s_pl, ray, bst, top) : closest_hit_linear<NP>(s_sph, sc.n_spheres, s_pl, sc.n_planes, ray);
     return shade_segment<BVH>(sc, p, s_sph, s_pl, key, ray, thr, sum, seg, h);
 }
 
@@ -990,7 +1008,7 @@ __global__ void __launch_bounds__(128) k_beam_lists(const SceneDev sc, const Ren
     beam_collect(sc.bvh_nodes, rc, sigma, rho, lists + patch);
 }
 
-template <bool BVH, int G_LANES = 32, int TRAV = 1, bool BEAM = false, int MINB = 8, bool NESTED = false>
+template <bool BVH, int G_LANES = 32, int TRAV = 1, bool BEAM = false, int MINB = 8, bool NESTED = false, int NP = 0>
 __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const SceneDev sc, const RenderParams p)
 {
     __shared__ float4 s_top[TRAV == 2 ? 8 * TOP_NODES : 1];
@@ -1067,7 +1085,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_stragglers(const SceneDev 
                 for (;;)
                 {
                     segs++;
-                    if (segment_step<BVH, TRAV>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst, top))
+                    if (segment_step<BVH, TRAV, NP>(sc, p, sc.pairs, sc.planes, key, ray, thr, sum, seg, bst, top))
                     {
                         key.sample += G;
                         if (key.sample >= p.sample_end) break;

@@ -147,6 +147,8 @@ struct Knobs {
                                // direct mode.  Measured, not default: C3 33.1 vs 30.5 ms, C4 79.6 vs 80.5 ms
     int bvh_minb = 8;          // RTCU_BVH_MINB: 6 / 7 / 8 CTAs per SM for the beam kernel (80 / 72 / 64 registers)
     int bvh_beam = -1;         // RTCU_BVH_BEAM=0: no patch beams (every primary ray traverses)
+    bool scan_fixed_pairs = true; // RTCU_SCAN_FIXED_PAIRS=0: scan scenes of at most 8 spheres use the generic pair loop too
+    int scan_minb = 0;            // RTCU_SCAN_MINB=6 / 8: CTAs per SM (80 / 64 registers) of the fixed-pair kernels, 0 = by pair count
     void load()
     {
         *this = Knobs{};
@@ -169,6 +171,8 @@ struct Knobs {
         if (const char* e = getenv("RTCU_BVH_RUN")) { const int v = atoi(e); if (v == 4 || v == 8) bvh_run_pixels = v; }
         if (const char* e = getenv("RTCU_BVH_MINB")) { const int v = atoi(e); if (v >= 6 && v <= 8) bvh_minb = v; }
         if (const char* e = getenv("RTCU_BVH_BEAM")) bvh_beam = atoi(e) < 0 ? 0 : atoi(e);
+        if (const char* e = getenv("RTCU_SCAN_FIXED_PAIRS")) scan_fixed_pairs = e[0] != '0';
+        if (const char* e = getenv("RTCU_SCAN_MINB")) { const int v = atoi(e); scan_minb = (v == 6 || v == 8) ? v : 0; }
     }
 };
 
@@ -543,24 +547,28 @@ int launch_render_on(rtcu_ctx* ctx, const rtcu_view* v, float4* d_accum, uint32_
             // basic.toml and dielectric.toml, ahead only where a few paths are very long: dielectric.toml with the mg table below
             // 1280x720).  The primitives are read through L1: staging them in shared memory as k_render_mega does measures the same
             // (C1 0.405 vs 0.406 ms).
+            // Scenes of at most 8 spheres (the reference's own: basic.toml 3, dielectric.toml 7) sweep a fixed number of packed pairs
+            // (closest_hit_linear<NP>: the pair array is padded to an even pair count with never-hit pairs).  Measured (B200, kernel ms,
+            // generic loop / fixed pairs at 64 registers / at 80 registers and 6 CTAs per SM): C1 0.356 / 0.336 / 0.322, C2 2.656 / 2.579 /
+            // 2.674, C2 with the mg table 2.606 / 2.520 / 2.492 -- two pairs take 80 registers (104 bytes of spills at 64), four pairs 64.
+            const uint32_t np = !ctx->knobs.scan_fixed_pairs ? 0u : ctx->scene.n_spheres <= 4 ? 2u : ctx->scene.n_spheres <= 8 ? 4u : 0u;
+            const int scan_minb = ctx->knobs.scan_minb ? ctx->knobs.scan_minb : (np == 2u ? 6 : 8);
+#define RTCU_LAUNCH_SCAN(G)                                                                                                         \
+    do {                                                                                                                            \
+        const unsigned b6 = (unsigned)ctx->sm_count * 6;                                                                            \
+        if (!ctx->knobs.scan_nested) k_render_stragglers<false, G><<<blocks, 128, 0, st>>>(ctx->scene, q);                          \
+        else if (np == 2u && scan_minb == 8) k_render_stragglers<false, G, 1, false, 8, true, 2><<<blocks, 128, 0, st>>>(ctx->scene, q); \
+        else if (np == 2u) k_render_stragglers<false, G, 1, false, 6, true, 2><<<b6, 128, 0, st>>>(ctx->scene, q);                  \
+        else if (np == 4u && scan_minb == 8) k_render_stragglers<false, G, 1, false, 8, true, 4><<<blocks, 128, 0, st>>>(ctx->scene, q); \
+        else if (np == 4u) k_render_stragglers<false, G, 1, false, 6, true, 4><<<b6, 128, 0, st>>>(ctx->scene, q);                  \
+        else k_render_stragglers<false, G, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);                               \
+    } while (0)
             switch (scan_direct_lanes(ctx, v))
             {
-            case 2:
-                if (ctx->knobs.scan_nested) k_render_stragglers<false, 2, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                else k_render_stragglers<false, 2><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                break;
-            case 4:
-                if (ctx->knobs.scan_nested) k_render_stragglers<false, 4, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                else k_render_stragglers<false, 4><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                break;
-            case 8:
-                if (ctx->knobs.scan_nested) k_render_stragglers<false, 8, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                else k_render_stragglers<false, 8><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                break;
-            default:
-                if (ctx->knobs.scan_nested) k_render_stragglers<false, 16, 1, false, 8, true><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                else k_render_stragglers<false, 16><<<blocks, 128, 0, st>>>(ctx->scene, q);
-                break;
+            case 2: RTCU_LAUNCH_SCAN(2); break;
+            case 4: RTCU_LAUNCH_SCAN(4); break;
+            case 8: RTCU_LAUNCH_SCAN(8); break;
+            default: RTCU_LAUNCH_SCAN(16); break;
             }
             CU(cudaGetLastError());
             ctx->tile_hist_valid = false;

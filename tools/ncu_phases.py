@@ -85,6 +85,14 @@ def phase(chain):
         return "traversal: node loads, child bookkeeping, stack"
     if k("trav_init"):
         return "traversal: init"
+    if k("closest_hit_linear"):  # scan scenes
+        if s("sphere_candidate"):
+            return "scan: sphere candidates (sqrt, t, acceptance)"
+        if s("sphere_pair_test"):
+            return "scan: packed pair tests"
+        if s("plane_test"):
+            return "scan: planes"
+        return "scan: loop, loads, select"
     if k("generate"):
         return "generate: Philox" if philox else "generate: primary ray"
     if k("shade_segment"):
