@@ -427,7 +427,15 @@ int scan_direct_lanes(const rtcu_ctx* ctx, const rtcu_view* v)
     if (sd >= 0) return (sd != 0 && n >= 2u * (uint32_t)sd) ? sd : 0;
     if (n < 4) return 0;
     const uint64_t pixels = (uint64_t)(v->tile_x1 - v->tile_x0) * (v->tile_y1 - v->tile_y0), threads = 1024ull * (uint64_t)ctx->sm_count;
-    if (pixels >= 27 * threads) return 0;
+    if (pixels >= 27 * threads)
+    {
+        // 3840x2160 and up: the thread-per-pixel grid (sequential sums, row-coalesced stores) ties with the generic shared-pixel kernel,
+        // but not with the fixed-pair ones of scenes of at most 8 spheres (launch_render): basic.toml / dielectric.toml sm / mg at 4K,
+        // grid vs 4 lanes: 9.33 / 10.10 / 9.44 vs 8.47 / 9.87 / 9.14 ms at 64 samples, 36.3 / 40.4 / 37.3 vs 33.1 / 38.9 / 36.0 at 256; at 16
+        // samples 2 lanes: 2.40 / 2.56 / 2.46 vs 2.18 / 2.51 / 2.49
+        const bool fixed_pairs = ctx->knobs.scan_fixed_pairs && ctx->knobs.scan_nested && ctx->scene.n_spheres <= 8;
+        return fixed_pairs && n >= 16 ? (n >= 64 ? 4 : 2) : 0;
+    }
     if (n < 16) return n >= 8 ? 4 : 2; // a lane gets at least two samples
     if (pixels >= 10 * threads) return n >= 64 ? 8 : 4;
     return n >= 64 ? 16 : 8;

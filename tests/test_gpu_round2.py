@@ -428,7 +428,7 @@ def test_small_scan_frames_share_pixels_between_lanes(ctx, oracle, scenes, knobs
         np.testing.assert_array_equal(got[..., 3], want[..., 3])
         np.testing.assert_allclose(got[..., :3], want[..., :3], rtol=4e-6, atol=1e-6)
     # 1920x1080: 4 lanes per pixel below 64 samples, still one launch; 4 / 2 lanes for 8 / 4 samples per call; below 4 samples
-    # per call, and from 3840x2160, the thread-per-pixel grid stays
+    # per call the thread-per-pixel grid stays
     ctx.render(make_view(sc, 1920, 1080, samples_per_pixel=16, max_bounces=depth, material_mode=mode))
     assert ctx.stats()["kernel_launches"] == 1
     for spp in (5, 9):
@@ -442,5 +442,17 @@ def test_small_scan_frames_share_pixels_between_lanes(ctx, oracle, scenes, knobs
         assert np.abs(unpack_rgba(rgba8) - unpack_rgba(r_rgba8)).max() <= 1
     ctx.render(make_view(sc, w, h, samples_per_pixel=3, max_bounces=depth, material_mode=mode))
     assert ctx.stats()["kernel_launches"] >= 2
-    ctx.render(make_view(sc, 3840, 2160, samples_per_pixel=16, max_bounces=depth, material_mode=mode))
-    assert ctx.stats()["kernel_launches"] >= 2
+    # 3840x2160: scenes of at most 8 spheres (fixed-pair kernels) share pixels there too, the others keep the grid
+    v4k = make_view(sc, 3840, 2160, samples_per_pixel=16, max_bounces=depth, material_mode=mode)
+    rgba8_4k, _ = ctx.render(v4k, want_accum=True)
+    segs_4k = ctx.stats()["segments"]
+    assert (ctx.stats()["kernel_launches"] == 1) == (len(sc.spheres) <= 8)
+    knobs(RTCU_SCAN_FIXED_PAIRS="0")  # the generic pair loop: the grid at 4K, the same paths everywhere
+    rgba8_g, _ = ctx.render(v4k, want_accum=True)
+    assert ctx.stats()["kernel_launches"] >= 2 and ctx.stats()["segments"] == segs_4k
+    assert np.abs(unpack_rgba(rgba8_g) - unpack_rgba(rgba8_4k)).max() <= 1
+    v = make_view(sc, w, h, samples_per_pixel=70, max_bounces=depth, material_mode=mode)
+    _, got = ctx.render(v, want_accum=True)
+    knobs(RTCU_SCAN_FIXED_PAIRS=None)
+    assert ctx.stats()["segments"] == segs
+    np.testing.assert_array_equal(got, want)  # fixed or generic pair loop: the same tests in the same order, bit for bit
