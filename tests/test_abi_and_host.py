@@ -261,6 +261,7 @@ def test_bvh4_device_tree_invariants(lib, n, knobs, monkeypatch):
                 idx = blk[4].view(np.uint32)
                 real = idx[idx != 0x7FFFFFFF]
                 assert 1 <= len(real) <= 4 and list(real) == sorted(real)
+                assert (idx[:len(real)] != 0x7FFFFFFF).all()  # padding comes last: a padded third slot means an empty second pair (leaf_second_pair)
                 # the packed pairs hold exactly those spheres: {cx0,cx1,cy0,cy1},{cz0,cz1,r2_0,r2_1}, padding r2 = -inf
                 for k, i in enumerate(idx):
                     a, b = blk[2 * (k // 2)], blk[2 * (k // 2) + 1]

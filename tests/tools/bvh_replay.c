@@ -74,7 +74,8 @@ int bvh_replay_ray(const float* nodes, const float* leaves, const float o[3], co
                 int32_t idx[4];
                 memcpy(idx, lp + 16, sizeof idx);
                 (*leaf_visits)++;
-                for (int k = 0; k < 4; k++)
+                const int n_slots = idx[2] == 0x7fffffff ? 2 : 4; /* kernels.cuh leaf_second_pair: padding is last, a padded third slot = no second pair */
+                for (int k = 0; k < n_slots; k++)
                 {
                     const float* A = lp + 8 * (k >> 1);
                     const float* B = A + 4;
@@ -353,7 +354,8 @@ void bvh_replay_beam_closest(const float* leaves, const float* list_tn, const ui
             const float* lp = leaves + 20u * (size_t)list_leaf[k];
             int32_t idx[4];
             memcpy(idx, lp + 16, sizeof idx);
-            for (int q = 0; q < 4; q++)
+            const int n_slots = idx[2] == 0x7fffffff ? 2 : 4; /* as the device's list scan */
+            for (int q = 0; q < n_slots; q++)
             {
                 const float* A = lp + 8 * (q >> 1);
                 const float* B = A + 4;
