@@ -226,7 +226,7 @@ int rtcu_scatter_batch(rtcu_ctx* ctx, uint32_t material_mode, uint64_t seed, uin
                        const uint32_t* material, const float* o, const float* d, const float* t,
                        const float* normal, const uint32_t* pixel, const uint32_t* sample,
                        const uint32_t* block, uint8_t* scattered, float* att, float* o_out, float* d_out);
-/* Philox4x32-10 blocks for n counters (ctr n x 4, out n x 4) under one key */
+/* blocks of the SPEC's random stream (Philox4x32, 7 rounds) for n counters (ctr n x 4, out n x 4) under one key */
 int rtcu_philox_batch(rtcu_ctx* ctx, const uint32_t* ctr, uint32_t n, uint64_t key, uint32_t* out);
 
 int rtcu_get_stats(rtcu_ctx* ctx, rtcu_stats* out);

@@ -67,7 +67,8 @@ class Oracle:
     def __init__(self, flavour: str = "strict"):
         self.lib = C.CDLL(str(build(flavour)))
         L, p, u32, u64, i = self.lib, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
-        L.rtref_philox4x32_10.argtypes = [p, p, p]
+        L.rtref_philox_stream.argtypes = [p, p, p]
+        L.rtref_philox4x32_r.argtypes = [p, p, C.c_int, p]
         L.rtref_u01.restype = C.c_float
         L.rtref_u01.argtypes = [u32]
         L.rtref_intersect_batch.argtypes = [C.POINTER(SceneDesc), p, p, u32, p, p, p, p]
@@ -107,7 +108,15 @@ class Oracle:
         c = (C.c_uint32 * 4)(*[int(x) for x in ctr])
         k = (C.c_uint32 * 2)(key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF)
         o = (C.c_uint32 * 4)()
-        self.lib.rtref_philox4x32_10(c, k, o)
+        self.lib.rtref_philox_stream(c, k, o)
+        return np.array(list(o), np.uint32)
+
+    def philox_rounds(self, ctr, key: int, rounds: int) -> np.ndarray:
+        """Philox4x32 with an explicit round count (the published vectors exist for 7 and 10)"""
+        c = (C.c_uint32 * 4)(*[int(x) for x in ctr])
+        k = (C.c_uint32 * 2)(key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF)
+        o = (C.c_uint32 * 4)()
+        self.lib.rtref_philox4x32_r(c, k, int(rounds), o)
         return np.array(list(o), np.uint32)
 
     def u01(self, x: int) -> float:

@@ -3,7 +3,7 @@
 // src/renderer.cpp, which are used where they lie and never copied.
 //
 //  * rt::detail::random_float() (declared in the reference's random.hpp:27-28, defined in random.cpp which is NOT
-//    compiled) is replaced by the counter-based stream of SPEC S9: Philox4x32-10, counter (pixel, sample, block, retry).
+//    compiled) is replaced by the counter-based stream of SPEC S9: Philox4x32-7, counter (pixel, sample, block, retry).
 //    The reference calls it without any context, so the stand-in math library reports the call sites that delimit
 //    the coordinates: thread_pool::for_range (pixel), vec3::operator+= in the per-pixel worker (sample end),
 //    transform_position(depth 1) (primary ray built -> block 1), ray::at after draws (a scatter event closed).
@@ -22,7 +22,7 @@
 #include <memory>
 #include <string>
 
-extern "C" void rtref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); // oracle/rtref.c
+extern "C" void rtref_philox_stream(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); // oracle/rtref.c
 extern "C" float rtref_u01(uint32_t x);
 
 namespace
@@ -83,7 +83,7 @@ namespace rt::detail
 		if (std::memcmp(ctr, g_rng.cached_ctr, sizeof ctr) != 0)
 		{
 			const uint32_t key[2] = { static_cast<uint32_t>(g_seed), static_cast<uint32_t>(g_seed >> 32) };
-			rtref_philox4x32_10(ctr, key, g_rng.cached_out);
+			rtref_philox_stream(ctr, key, g_rng.cached_out);
 			std::memcpy(g_rng.cached_ctr, ctr, sizeof ctr);
 		}
 		return rtref_u01(g_rng.cached_out[n % 3u]);

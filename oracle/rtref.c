@@ -35,7 +35,7 @@
  *                     p = h.xyz * (1.0f / h.w)                (camera.hpp:42-48)
  *  S8  sky            a = 0.5f*(d.y + 1.0f); c = fma(sky_k, a, 1.0f*(1.0f - a)), sky=(0.5,0.7,1.0)
  *                     (muu lerp = start*(1-alpha) + finish*alpha)  (mg_ray_tracer.cpp:163-164)
- *  S9  RNG            Philox4x32-10, key = (seed_lo, seed_hi), ctr = (pixel, sample, block, retry);
+ *  S9  RNG            Philox4x32-7, key = (seed_lo, seed_hi), ctr = (pixel, sample, block, retry);
  *                     block 0 = pixel jitter (out[0], out[1]); block k+1 = scatter at the end of
  *                     segment k (lambert/metal out[0..2] = x,y,z; dielectric out[0]).
  *                     float = (x >> 8) * 2^-24.  retry increments only when a unit-vector draw is
@@ -88,12 +88,16 @@ static inline v3 ray_at(v3 o, v3 d, float t) { return v3_make(FMA(d.x, t, o.x), 
 
 typedef struct { v3 o, d; } ray_t;
 
-/* ---- S9: Philox4x32-10 (Salmon et al., SC'11; Random123 constants) ----------------------- */
-void rtref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+/* ---- S9: Philox4x32-R (Salmon et al., SC'11; Random123 constants).  The stream of the SPEC uses R = 7 rounds, the fewest
+ * the paper certifies as Crush-resistant (Random123's philox4x32_7; its default of 10 is a safety margin): the path tracer draws
+ * one block per sample and one per scatter event, and the generator is 8-15 % of the device's instructions.  Both round
+ * counts are pinned against Random123's kat_vectors (tests/test_oracle_kat.py). ----------------------- */
+#define RTREF_PHILOX_ROUNDS 7
+void rtref_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4])
 {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int round = 0; round < 10; round++)
+    for (int round = 0; round < rounds; round++)
     {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -107,6 +111,11 @@ void rtref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t 
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+/* one block of the SPEC's stream */
+void rtref_philox_stream(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    rtref_philox4x32_r(ctr, key, RTREF_PHILOX_ROUNDS, out);
+}
 
 float rtref_u01(uint32_t x) { return (float)(x >> 8) * 0x1.0p-24f; }
 
@@ -117,7 +126,7 @@ static void rng_block(const rng_key* k, uint32_t block, uint32_t retry, float u[
     const uint32_t ctr[4] = { k->pixel, k->sample, block, retry };
     const uint32_t key[2] = { (uint32_t)k->seed, (uint32_t)(k->seed >> 32) };
     uint32_t out[4];
-    rtref_philox4x32_10(ctr, key, out);
+    rtref_philox_stream(ctr, key, out);
     for (int i = 0; i < 4; i++)
         u[i] = rtref_u01(out[i]);
 }

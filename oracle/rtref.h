@@ -12,7 +12,7 @@
  * images of that build bit for bit (tests/test_reference_build.py, tests/test_raster_oracle.py; fixtures
  * tests/golden/refbuild_*.npz, raster_*.npz).  What stays unpinned is muu's own arithmetic, restated from
  * its published algorithms as the numbered SPEC in rtref.c.  Further pins: hand-derived known-answer
- * vectors and the published Philox4x32-10 vectors.
+ * vectors and the published Philox4x32 vectors (7 rounds = the SPEC's stream, and 10).
  *
  * The data structures deliberately mirror include/rtcu.h field by field so one harness can feed
  * both sides, but the two headers are independent files.
@@ -69,7 +69,8 @@ typedef struct rtref_view {
 } rtref_view;
 
 /* --- RNG (replaces src/random.cpp on both sides) --------------------------------------- */
-void  rtref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void  rtref_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
+void  rtref_philox_stream(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); /* the SPEC's stream: 7 rounds */
 float rtref_u01(uint32_t x);                          /* (x >> 8) * 2^-24, in [0,1) */
 
 /* --- level-1 parity entry point: closest hit over planes + spheres ---------------------- */

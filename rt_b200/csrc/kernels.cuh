@@ -1575,7 +1575,7 @@ __global__ void k_philox_batch(const uint4* __restrict__ ctr, uint32_t n, const 
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
-        out[i] = philox4x32_10(ctr[i], rk);
+        out[i] = philox4x32(ctr[i], rk);
 }
 
 

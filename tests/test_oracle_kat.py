@@ -1,6 +1,6 @@
 """Known-answer tests that pin the CPU oracle (SURVEY.md section 8c "pins the new repo must create").
 
-The reference has no tests or golden vectors, so these are: published Philox4x32-10 vectors (Random123
+The reference has no tests or golden vectors, so these are: published Philox4x32 vectors for 7 rounds -- the SPEC's stream -- and 10 (Random123
 kat_vectors), hand-derived intersection cases, and pack / colour identities read off the reference source.
 """
 import math
@@ -14,8 +14,14 @@ from rt_b200.renderer import make_view
 from conftest import GOLDEN
 
 
-# ---- RNG: Philox4x32-10, Random123 kat_vectors ------------------------------------------------------
+# ---- RNG: Philox4x32, Random123 kat_vectors (`philox4x32 7 ...` and `philox4x32 10 ...` lines) -----------------
+# PHILOX_KAT = the SPEC's stream (7 rounds); the 10-round vectors pin the same round function a second time.
 PHILOX_KAT = [
+    ((0, 0, 0, 0), (0, 0), (0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48)),
+    ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662)),
+    ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A)),
+]
+PHILOX_KAT_10 = [
     ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
     ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
     ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
@@ -26,6 +32,12 @@ PHILOX_KAT = [
 def test_philox_published_vectors(oracle, ctr, key, expect):
     out = oracle.philox(ctr, key[0] | (key[1] << 32))
     assert tuple(int(x) for x in out) == expect
+    assert tuple(int(x) for x in oracle.philox_rounds(ctr, key[0] | (key[1] << 32), 7)) == expect
+
+
+@pytest.mark.parametrize("ctr,key,expect", PHILOX_KAT_10)
+def test_philox_published_vectors_ten_rounds(oracle, ctr, key, expect):
+    assert tuple(int(x) for x in oracle.philox_rounds(ctr, key[0] | (key[1] << 32), 10)) == expect
 
 
 def test_u01_mapping(oracle):

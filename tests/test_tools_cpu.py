@@ -19,11 +19,11 @@ def test_phase_functions_are_found_in_the_sources():
         assert lo < hi and name in text[lo - 1], name
     # shade_segment is declared before segment_step and defined after it: the range must be the definition's
     assert K["shade_segment"][0] > K["segment_step"][0]
-    for name in ("philox4x32_10", "rng_block", "sphere_candidate", "sphere_pair_test", "plane_test", "sky", "scatter", "schlick", "random_unit_vector"):
+    for name in ("philox4x32", "rng_block", "sphere_candidate", "sphere_pair_test", "plane_test", "sky", "scatter", "schlick", "random_unit_vector"):
         lo, hi = S[name]
         assert lo < hi, name
     # a chain through trav_step and slab_pair is a slab test; through shade_segment and philox a shade Philox
     mid = lambda r: (r[0] + r[1]) // 2
     assert mod.phase([("sm_100_rt.hpp", 108), ("kernels.cuh", mid(K["slab_pair"])), ("kernels.cuh", mid(K["trav_step"]))], K, S) == "traversal: slab tests"
-    assert mod.phase([("spec.cuh", mid(S["philox4x32_10"])), ("kernels.cuh", mid(K["shade_segment"]))], K, S) == "shade: Philox"
+    assert mod.phase([("spec.cuh", mid(S["philox4x32"])), ("kernels.cuh", mid(K["shade_segment"]))], K, S) == "shade: Philox"
     assert mod.phase([("kernels.cuh", mid(K["k_render_stragglers"]))], K, S) == "kernel loop: claim, ballots, epilogue"

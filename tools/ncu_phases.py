@@ -35,7 +35,7 @@ def phase(chain, K, S):
         return any(f == fname and any(tab[n][0] <= ln <= tab[n][1] for n in names if n in tab) for f, ln in chain)
     k = lambda *n: has(K, "kernels.cuh", *n)
     s = lambda *n: has(S, "spec.cuh", *n)
-    philox = s("philox4x32_10", "rng_block", "philox_keys")
+    philox = s("philox4x32", "rng_block", "philox_keys")
     if k("beam_closest_sphere"):
         return "primary list scan: leaf pair tests" if k("bvh_leaf_pair_test", "bvh_leaf_candidate") else "primary list scan: loop, loads"
     if k("trav_step", "closest_sphere_bvh"):
