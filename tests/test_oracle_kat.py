@@ -40,6 +40,21 @@ def test_philox_published_vectors_ten_rounds(oracle, ctr, key, expect):
     assert tuple(int(x) for x in oracle.philox_rounds(ctr, key[0] | (key[1] << 32), 10)) == expect
 
 
+def test_stream_is_uniform_over_the_counters_a_pixel_uses(oracle):
+    """the renderer walks the counter (pixel, sample, block, retry) sequentially in `sample`; the seven-round stream must look
+    uniform and uncorrelated along exactly that axis (chi-square over 64 bins per output word, lag-1 correlation, and the
+    correlation between the two jitter words of a sample)"""
+    n = 1 << 14
+    u = np.array([[oracle.u01(int(w)) for w in oracle.philox((12345, s, 0, 0), 0x5EED)] for s in range(n)])
+    for w in range(4):
+        counts = np.bincount((u[:, w] * 64).astype(int), minlength=64)
+        chi2 = float(((counts - n / 64) ** 2 / (n / 64)).sum())
+        assert chi2 < 120.0, (w, chi2)  # 63 degrees of freedom: mean 63, 99.99th percentile ~ 113
+        assert abs(np.corrcoef(u[:-1, w], u[1:, w])[0, 1]) < 0.04  # lag 1 along the sample index (sigma = 1 / sqrt(n) ~ 0.008)
+    assert abs(np.corrcoef(u[:, 0], u[:, 1])[0, 1]) < 0.04
+    assert abs(u.mean() - 0.5) < 0.01
+
+
 def test_u01_mapping(oracle):
     assert oracle.u01(0) == 0.0
     assert oracle.u01(0xFF) == 0.0  # low 8 bits dropped
